@@ -1,0 +1,583 @@
+// libemotivoice_b200.so -- context, weight binding, layer orchestration and the C ABI
+// (include/emotivoice_b200.h).  All math runs in the hand-written sm_100a kernels of
+// conv1d_tm.cu / am_kernels.cu / voc_kernels.cu; this file only sequences launches on the
+// caller's stream and carves the caller-provided workspace.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ev_common.cuh"
+
+namespace ev {
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+struct Tensor {
+  const float* p = nullptr;
+  uint64_t numel = 0;
+};
+
+struct EncLayerW {
+  const float *ln1w, *ln1b, *wqkv, *bqkv, *wo, *bo, *ln2w, *ln2b, *w1, *b1, *w2, *b2;
+};
+struct StackW {
+  const float* alpha;
+  std::vector<EncLayerW> layers;
+  const float *lnfw, *lnfb;
+};
+struct PredW {
+  std::vector<const float*> w, b, lnw, lnb;
+  const float *linw, *linb;
+};
+struct ConvW {
+  const float *w, *b;
+  int K, dil, cin, cout;
+};
+struct UpW {
+  const float *w, *b;
+  int K, cin, cout_packed, rate, cout;
+};
+
+}  // namespace ev
+
+struct ev_ctx {
+  ev_config cfg;
+  int device = 0;
+  bool bound = false;
+  bool has_am = false, has_voc = false;   // a blob may carry only one half (PromptTTS / Generator used alone)
+  std::unordered_map<std::string, ev::Tensor> tensors;
+  const float* pe = nullptr;
+  int pe_len = 0;
+  // resolved weights
+  const float *emb_word = nullptr, *emb_spk = nullptr;
+  ev::StackW enc, dec;
+  const float *cond_wx, *cond_wc, *cond_b;
+  ev::PredW dur, pitch, energy;
+  const float *pemb_w, *pemb_b, *eemb_w, *eemb_b;
+  const float *mel_w, *mel_b;
+  ev::ConvW pre;
+  std::vector<ev::UpW> ups;
+  std::vector<ev::ConvW> rb_c1, rb_c2;   // [(stage*n_resk + j)*n_dil + l]
+  const float *post_w, *post_b;
+  int post_k = 7;
+  int total_up = 1;
+  int max_stage_width = 0;   // max over stages of prod(rates so far) * channels
+};
+
+namespace ev {
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace (counts in floats, 256-byte aligned blocks)
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<char*>(p)) {}
+  float* take(size_t n_floats) {
+    float* r = reinterpret_cast<float*>(base + off);
+    off += align_up(n_floats * sizeof(float), 256);
+    return r;
+  }
+};
+
+struct Phase1Bufs {
+  float *x, *y, *qkv, *ctx, *h, *cond_in, *cond_bias, *hs, *pm, *p1, *p2, *centers, *ds_f;
+};
+struct Phase2Bufs {
+  float *x, *y, *qkv, *ctx, *h;
+};
+struct VocBufs {
+  float *X, *Tm, *R1, *R2, *ACC;
+};
+
+static void carve_phase1(const ev_ctx* c, Carver& cv, int B, int T, Phase1Bufs* o) {
+  const size_t H = c->cfg.hidden, n = (size_t)B * T;
+  o->x = cv.take(n * H);
+  o->y = cv.take(n * H);
+  o->qkv = cv.take(n * 3 * H);
+  o->ctx = cv.take(n * H);
+  o->h = cv.take(n * 4 * H);
+  o->cond_in = cv.take((size_t)B * (H + 2 * c->cfg.bert_dim));
+  o->cond_bias = cv.take((size_t)B * H);
+  o->hs = cv.take(n * H);
+  o->pm = cv.take(n * H);
+  o->p1 = cv.take(n * H);
+  o->p2 = cv.take(n * H);
+  o->centers = cv.take(n);
+  o->ds_f = cv.take(n);
+}
+static void carve_phase2(const ev_ctx* c, Carver& cv, int B, int F, Phase2Bufs* o) {
+  const size_t H = c->cfg.hidden, n = (size_t)B * F;
+  o->x = cv.take(n * H);
+  o->y = cv.take(n * H);
+  o->qkv = cv.take(n * 3 * H);
+  o->ctx = cv.take(n * H);
+  o->h = cv.take(n * 4 * H);
+}
+static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
+  const size_t n = (size_t)B * F * (size_t)c->max_stage_width;
+  o->X = cv.take(n);
+  o->Tm = cv.take(n);
+  o->R1 = cv.take(n);
+  o->R2 = cv.take(n);
+  o->ACC = cv.take(n);
+}
+
+static int find(ev_ctx* c, const std::string& name, uint64_t expect, const float** out) {
+  auto it = c->tensors.find(name);
+  if (it == c->tensors.end()) {
+    set_error("weight '%s' missing from the bound blob", name.c_str());
+    return EV_ENOWEIGHT;
+  }
+  if (expect && it->second.numel != expect) {
+    set_error("weight '%s' has %llu elements, expected %llu", name.c_str(), (unsigned long long)it->second.numel,
+              (unsigned long long)expect);
+    return EV_EINVAL;
+  }
+  *out = it->second.p;
+  return EV_OK;
+}
+
+static int resolve_stack(ev_ctx* c, const char* pre, int n_layers, StackW* s) {
+  const uint64_t H = c->cfg.hidden, K = c->cfg.ffn_kernel;
+  std::string p(pre);
+  EV_TRY(find(c, p + ".alpha", 1, &s->alpha));
+  s->layers.resize(n_layers);
+  for (int i = 0; i < n_layers; ++i) {
+    std::string q = p + "." + std::to_string(i);
+    EncLayerW& l = s->layers[i];
+    EV_TRY(find(c, q + ".ln1.w", H, &l.ln1w));
+    EV_TRY(find(c, q + ".ln1.b", H, &l.ln1b));
+    EV_TRY(find(c, q + ".wqkv", H * 3 * H, &l.wqkv));
+    EV_TRY(find(c, q + ".bqkv", 3 * H, &l.bqkv));
+    EV_TRY(find(c, q + ".wo", H * H, &l.wo));
+    EV_TRY(find(c, q + ".bo", H, &l.bo));
+    EV_TRY(find(c, q + ".ln2.w", H, &l.ln2w));
+    EV_TRY(find(c, q + ".ln2.b", H, &l.ln2b));
+    EV_TRY(find(c, q + ".w1", K * H * 4 * H, &l.w1));
+    EV_TRY(find(c, q + ".b1", 4 * H, &l.b1));
+    EV_TRY(find(c, q + ".w2", K * 4 * H * H, &l.w2));
+    EV_TRY(find(c, q + ".b2", H, &l.b2));
+  }
+  EV_TRY(find(c, p + ".lnf.w", H, &s->lnfw));
+  EV_TRY(find(c, p + ".lnf.b", H, &s->lnfb));
+  return EV_OK;
+}
+
+static int resolve_pred(ev_ctx* c, const char* pre, int n_layers, PredW* s) {
+  const uint64_t H = c->cfg.hidden, K = c->cfg.pred_kernel;
+  std::string p(pre);
+  s->w.resize(n_layers); s->b.resize(n_layers); s->lnw.resize(n_layers); s->lnb.resize(n_layers);
+  for (int i = 0; i < n_layers; ++i) {
+    std::string q = p + "." + std::to_string(i);
+    EV_TRY(find(c, q + ".w", K * H * H, &s->w[i]));
+    EV_TRY(find(c, q + ".b", H, &s->b[i]));
+    EV_TRY(find(c, q + ".ln.w", H, &s->lnw[i]));
+    EV_TRY(find(c, q + ".ln.b", H, &s->lnb[i]));
+  }
+  EV_TRY(find(c, p + ".lin.w", H, &s->linw));
+  EV_TRY(find(c, p + ".lin.b", 1, &s->linb));
+  return EV_OK;
+}
+
+static int resolve_voc(ev_ctx* c);
+
+static int resolve_all(ev_ctx* c) {
+  c->has_am = c->tensors.count("emb.word") != 0;
+  c->has_voc = c->tensors.count("voc.pre.w") != 0;
+  if (!c->has_am && !c->has_voc) {
+    set_error("ev_bind_weights: blob holds neither the acoustic model ('emb.word') nor the vocoder ('voc.pre.w')");
+    return EV_ENOWEIGHT;
+  }
+  if (c->has_voc) EV_TRY(resolve_voc(c));
+  if (!c->has_am) return EV_OK;
+  const ev_config& g = c->cfg;
+  const uint64_t H = g.hidden;
+  EV_TRY(find(c, "emb.word", (uint64_t)g.n_vocab * H, &c->emb_word));
+  EV_TRY(find(c, "emb.spk", (uint64_t)g.n_speaker * H, &c->emb_spk));
+  EV_TRY(resolve_stack(c, "enc", g.enc_layers, &c->enc));
+  EV_TRY(resolve_stack(c, "dec", g.dec_layers, &c->dec));
+  EV_TRY(find(c, "cond.wx", H * H, &c->cond_wx));
+  EV_TRY(find(c, "cond.wc", (H + 2 * (uint64_t)g.bert_dim) * H, &c->cond_wc));
+  EV_TRY(find(c, "cond.b", H, &c->cond_b));
+  EV_TRY(resolve_pred(c, "dur", g.dur_layers, &c->dur));
+  EV_TRY(resolve_pred(c, "pitch", g.pitch_layers, &c->pitch));
+  EV_TRY(resolve_pred(c, "energy", g.energy_layers, &c->energy));
+  EV_TRY(find(c, "pitch_emb.w", (uint64_t)g.embed_kernel * H, &c->pemb_w));
+  EV_TRY(find(c, "pitch_emb.b", H, &c->pemb_b));
+  EV_TRY(find(c, "energy_emb.w", (uint64_t)g.embed_kernel * H, &c->eemb_w));
+  EV_TRY(find(c, "energy_emb.b", H, &c->eemb_b));
+  EV_TRY(find(c, "to_mel.w", H * g.n_mels, &c->mel_w));
+  EV_TRY(find(c, "to_mel.b", g.n_mels, &c->mel_b));
+  return EV_OK;
+}
+
+static int resolve_voc(ev_ctx* c) {
+  const ev_config& g = c->cfg;
+  c->pre.K = 7; c->pre.dil = 1; c->pre.cin = g.n_mels; c->pre.cout = g.voc_c0;
+  EV_TRY(find(c, "voc.pre.w", (uint64_t)7 * g.n_mels * g.voc_c0, &c->pre.w));
+  EV_TRY(find(c, "voc.pre.b", g.voc_c0, &c->pre.b));
+  c->ups.resize(g.n_ups);
+  c->rb_c1.clear(); c->rb_c2.clear();
+  int ch = g.voc_c0, mul = 1;
+  c->max_stage_width = g.voc_c0;
+  for (int s = 0; s < g.n_ups; ++s) {
+    UpW& u = c->ups[s];
+    u.rate = g.up_rates[s]; u.cin = ch; u.cout = ch / 2; u.cout_packed = u.cout * u.rate;
+    std::string q = "voc.up." + std::to_string(s);
+    auto it = c->tensors.find(q + ".w");
+    if (it == c->tensors.end()) { set_error("weight '%s.w' missing", q.c_str()); return EV_ENOWEIGHT; }
+    const uint64_t per_tap = (uint64_t)u.cin * u.cout_packed;
+    if (it->second.numel % per_tap != 0 || ((it->second.numel / per_tap) & 1) == 0) {
+      set_error("weight '%s.w': %llu elements is not an odd number of (%d x %d) taps", q.c_str(),
+                (unsigned long long)it->second.numel, u.cin, u.cout_packed);
+      return EV_EINVAL;
+    }
+    u.K = (int)(it->second.numel / per_tap);
+    u.w = it->second.p;
+    EV_TRY(find(c, q + ".b", u.cout_packed, &u.b));
+    ch = u.cout; mul *= u.rate;
+    if (mul * ch > c->max_stage_width) c->max_stage_width = mul * ch;
+    for (int j = 0; j < g.n_resk; ++j)
+      for (int l = 0; l < g.n_dil; ++l) {
+        const int k = g.res_kernels[j];
+        std::string r = "voc.rb." + std::to_string(s * g.n_resk + j);
+        ConvW c1{nullptr, nullptr, k, g.res_dils[j][l], ch, ch}, c2{nullptr, nullptr, k, 1, ch, ch};
+        EV_TRY(find(c, r + ".c1." + std::to_string(l) + ".w", (uint64_t)k * ch * ch, &c1.w));
+        EV_TRY(find(c, r + ".c1." + std::to_string(l) + ".b", ch, &c1.b));
+        EV_TRY(find(c, r + ".c2." + std::to_string(l) + ".w", (uint64_t)k * ch * ch, &c2.w));
+        EV_TRY(find(c, r + ".c2." + std::to_string(l) + ".b", ch, &c2.b));
+        c->rb_c1.push_back(c1); c->rb_c2.push_back(c2);
+      }
+  }
+  c->total_up = mul;
+  c->post_k = 7;
+  EV_TRY(find(c, "voc.post.w", (uint64_t)7 * ch, &c->post_w));
+  EV_TRY(find(c, "voc.post.b", 1, &c->post_b));
+  return EV_OK;
+}
+
+static int conv(const float* x, const float* w, const float* bias, long long bias_bs, const float* res, float* out,
+                int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens, int lens_mul, int in_act,
+                float in_slope, int out_act, int acc, float div, cudaStream_t st) {
+  ConvParams p;
+  p.x = x; p.w = w; p.bias = bias; p.res = res; p.out = out; p.bias_bs = bias_bs;
+  p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil;
+  p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope;
+  p.out_act = out_act; p.acc = acc; p.div = div;
+  return launch_conv1d(p, st);
+}
+
+// Encoder.forward (encoder.py:316-324) minus the positional prologue (done by the caller of this
+// function): n x [ x += W_o Attn(LN1 x) ; x += Conv2(GELU(Conv1(LN2 x))) ], then after_norm -> y.
+static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float* qkv, float* ctxb, float* h,
+                     int B, int L, const int32_t* key_lens, const int32_t* conv_lens, bool first_ln_done,
+                     cudaStream_t st) {
+  const int H = c->cfg.hidden, K = c->cfg.ffn_kernel, heads = c->cfg.n_heads;
+  for (size_t i = 0; i < s.layers.size(); ++i) {
+    const EncLayerW& l = s.layers[i];
+    if (!(i == 0 && first_ln_done))
+      EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln1w, l.ln1b, y, B * L, L, H, st));
+    EV_TRY(conv(y, l.wqkv, l.bqkv, 0, nullptr, qkv, B, L, H, 3 * H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
+                EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+    EV_TRY(launch_attention(qkv, key_lens, ctxb, B, L, H, heads, st));
+    EV_TRY(conv(ctxb, l.wo, l.bo, 0, x, x, B, L, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
+                EV_ACC_STORE, 1.f, st));
+    EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln2w, l.ln2b, y, B * L, L, H, st));
+    EV_TRY(conv(y, l.w1, l.b1, 0, nullptr, h, B, L, H, 4 * H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_GELU,
+                EV_ACC_STORE, 1.f, st));
+    EV_TRY(conv(h, l.w2, l.b2, 0, x, x, B, L, 4 * H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
+                EV_ACC_STORE, 1.f, st));
+  }
+  EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, s.lnfw, s.lnfb, y, B * L, L, H, st));
+  return EV_OK;
+}
+
+// [conv k -> ReLU -> channel LN] x n -> Linear(H -> 1) (variance.py:36-56, :101-124)
+static int run_predictor(const ev_ctx* c, const PredW& p, const float* in, float* t1, float* t2, int B, int T,
+                         const int32_t* lens, const int32_t* conv_lens, int mode, float* out_f, int64_t* out_i,
+                         cudaStream_t st) {
+  const int H = c->cfg.hidden, K = c->cfg.pred_kernel;
+  const float* cur = in;
+  for (size_t i = 0; i < p.w.size(); ++i) {
+    EV_TRY(conv(cur, p.w[i], p.b[i], 0, nullptr, t1, B, T, H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_RELU,
+                EV_ACC_STORE, 1.f, st));
+    EV_TRY(launch_layernorm(t1, nullptr, nullptr, nullptr, nullptr, nullptr, p.lnw[i], p.lnb[i], t2, B * T, T, H, st));
+    cur = t2;
+  }
+  return launch_rowdot(cur, p.linw, p.linb, lens, B, T, H, mode, out_f, out_i, st);
+}
+
+}  // namespace ev
+
+using namespace ev;
+
+extern "C" {
+
+int ev_abi_version(void) { return EV_ABI_VERSION; }
+const char* ev_last_error(void) { return g_err.c_str(); }
+uint64_t ev_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ev_create(ev_ctx** out, int device, const ev_config* cfg) {
+  EV_CHECK_ARG(out && cfg, "ev_create: null argument");
+  *out = nullptr;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { set_error("ev_create: cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e)); return EV_ECUDA; }
+  if (prop.major != 10) {
+    set_error("ev_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return EV_EARCH;
+  }
+  EV_CHECK_ARG(cfg->hidden % 128 == 0 && cfg->hidden <= 512, "ev_create: hidden=%d unsupported", cfg->hidden);
+  EV_CHECK_ARG(cfg->n_heads > 0 && cfg->hidden % cfg->n_heads == 0, "ev_create: heads=%d", cfg->n_heads);
+  EV_CHECK_ARG((cfg->ffn_kernel & 1) && (cfg->pred_kernel & 1) && (cfg->embed_kernel & 1) && cfg->embed_kernel <= 15,
+               "ev_create: kernel sizes must be odd");
+  EV_CHECK_ARG(cfg->n_ups >= 1 && cfg->n_ups <= 8 && cfg->n_resk >= 1 && cfg->n_resk <= 4 && cfg->n_dil >= 1 && cfg->n_dil <= 4,
+               "ev_create: vocoder shape out of range");
+  EV_CHECK_ARG(cfg->n_mels % 16 == 0 && cfg->bert_dim % 8 == 0, "ev_create: n_mels must be a multiple of 16");
+  ev_ctx* c = new ev_ctx();
+  c->cfg = *cfg;
+  c->device = device;
+  *out = c;
+  return EV_OK;
+}
+
+void ev_destroy(ev_ctx* ctx) { delete ctx; }
+
+int ev_bind_weights(ev_ctx* ctx, const float* blob, size_t n_floats, const ev_weight_entry* index, int n_entries) {
+  EV_CHECK_ARG(ctx && blob && index && n_entries > 0, "ev_bind_weights: null argument");
+  ctx->tensors.clear();
+  ctx->bound = false;
+  for (int i = 0; i < n_entries; ++i) {
+    const ev_weight_entry& e = index[i];
+    EV_CHECK_ARG(e.offset + e.numel <= n_floats, "ev_bind_weights: entry '%.55s' exceeds the blob", e.name);
+    EV_CHECK_ARG(e.offset % 4 == 0, "ev_bind_weights: entry '%.55s' is not 16-byte aligned", e.name);
+    Tensor t;
+    t.p = blob + e.offset;
+    t.numel = e.numel;
+    char nm[57];
+    memcpy(nm, e.name, 56);
+    nm[56] = 0;
+    ctx->tensors[std::string(nm)] = t;
+  }
+  EV_TRY(resolve_all(ctx));
+  ctx->bound = true;
+  return EV_OK;
+}
+
+int ev_bind_pe(ev_ctx* ctx, const float* pe, int pe_len) {
+  EV_CHECK_ARG(ctx && pe && pe_len > 0, "ev_bind_pe: bad argument");
+  ctx->pe = pe;
+  ctx->pe_len = pe_len;
+  return EV_OK;
+}
+
+size_t ev_phase1_workspace_bytes(const ev_ctx* ctx, int B, int T) {
+  if (!ctx || !ctx->bound || !ctx->has_am || B <= 0 || T <= 0) return 0;
+  Carver cv(nullptr);
+  Phase1Bufs p1;
+  carve_phase1(ctx, cv, B, T, &p1);
+  return cv.off + 256;
+}
+
+size_t ev_phase2_workspace_bytes(const ev_ctx* ctx, int B, int F) {
+  if (!ctx || !ctx->bound || B <= 0 || F <= 0) return 0;
+  // the vocoder runs after phase 2 on the same stream and re-carves the buffer from its start
+  Carver am(nullptr), voc(nullptr);
+  Phase2Bufs p2;
+  VocBufs vb;
+  if (ctx->has_am) carve_phase2(ctx, am, B, F, &p2);
+  if (ctx->has_voc) carve_voc(ctx, voc, B, F, &vb);
+  return (am.off > voc.off ? am.off : voc.off) + 256;
+}
+
+static int use_device(const ev_ctx* ctx) {
+  int cur = -1;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e == cudaSuccess && cur != ctx->device) e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e)); return EV_ECUDA; }
+  return EV_OK;
+}
+
+int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const int64_t* spk, const float* style,
+                 const float* content, int B, int T, int invariant, int64_t* dur_out, float* pitch_out,
+                 float* energy_out, int32_t* lens32_out, int32_t* mel_lens_out, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  EV_CHECK_ARG(ctx && ctx->bound && ctx->has_am, "ev_am_phase1: acoustic-model weights not bound");
+  EV_CHECK_ARG(ling && lens64 && spk && style && content && dur_out && pitch_out && energy_out && lens32_out &&
+                   mel_lens_out && workspace,
+               "ev_am_phase1: null argument");
+  EV_CHECK_ARG(B > 0 && T > 0, "ev_am_phase1: B=%d T=%d", B, T);
+  if (!ctx->pe || ctx->pe_len < T) { set_error("ev_am_phase1: positional table has %d rows, need %d", ctx->pe_len, T); return EV_EPELEN; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const ev_config& g = ctx->cfg;
+  const int H = g.hidden;
+  Carver cv(workspace);
+  Phase1Bufs b;
+  carve_phase1(ctx, cv, B, T, &b);
+  if (cv.off > workspace_bytes) { set_error("ev_am_phase1: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
+  EV_TRY(use_device(ctx));
+  EV_TRY(launch_lens_to_i32(lens64, lens32_out, B, T, st));
+  const int32_t* lens = lens32_out;
+  const int32_t* conv_lens = invariant ? lens : nullptr;
+
+  // encoder: x = word_emb[ids] + alpha*pe (model_open_source.py:107, encoder.py:257-261), fused with LN1 of layer 0
+  EV_TRY(launch_layernorm(nullptr, ling, ctx->emb_word, ctx->pe, ctx->enc.alpha, b.x, ctx->enc.layers[0].ln1w,
+                          ctx->enc.layers[0].ln1b, b.y, B * T, T, H, st));
+  EV_TRY(run_stack(ctx, ctx->enc, b.x, b.y, b.qkv, b.ctx, b.h, B, T, lens, conv_lens, true, st));
+  // conditioning (model_open_source.py:109-111): per-utterance bias + W_x x
+  EV_TRY(launch_cond_gather(spk, ctx->emb_spk, style, content, b.cond_in, B, H, g.bert_dim, st));
+  EV_TRY(conv(b.cond_in, ctx->cond_wc, ctx->cond_b, 0, nullptr, b.cond_bias, 1, B, H + 2 * g.bert_dim, H, 1, 1, nullptr,
+              1, EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+  EV_TRY(conv(b.y, ctx->cond_wx, b.cond_bias, H, nullptr, b.hs, B, T, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
+              EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+  // predictors (model_open_source.py:120-121,130)
+  const float* pin = b.hs;
+  if (!invariant) {   // literal batch: masked_fill on the input only (variance.py:38-39); pads of hs are live data
+    EV_TRY(launch_mask_rows(b.hs, lens, b.pm, B, T, H, st));
+    pin = b.pm;
+  }
+  EV_TRY(run_predictor(ctx, ctx->pitch, pin, b.p1, b.p2, B, T, lens, conv_lens, 0, pitch_out, nullptr, st));
+  EV_TRY(run_predictor(ctx, ctx->energy, pin, b.p1, b.p2, B, T, lens, conv_lens, 0, energy_out, nullptr, st));
+  EV_TRY(run_predictor(ctx, ctx->dur, pin, b.p1, b.p2, B, T, lens, conv_lens, 1, nullptr, dur_out, st));
+  // x = x + pitch_embed + energy_embed (model_open_source.py:131-134)
+  EV_TRY(launch_var_embed_add(b.hs, pitch_out, energy_out, ctx->pemb_w, ctx->pemb_b, ctx->eemb_w, ctx->eemb_b, B, T, H,
+                              g.embed_kernel, st));
+  // duration bookkeeping for the length regulator (alignment.py:183-199)
+  EV_TRY(launch_duration_scan(dur_out, lens, invariant, B, T, b.centers, b.ds_f, mel_lens_out, st));
+  return EV_OK;
+}
+
+int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens, const int32_t* mel_lens, int B, int T,
+                 int F, int invariant, float* mel_out, void* workspace, size_t workspace_bytes, void* stream) {
+  EV_CHECK_ARG(ctx && ctx->bound && ctx->has_am, "ev_am_phase2: acoustic-model weights not bound");
+  EV_CHECK_ARG(phase1_workspace && lens && mel_lens && mel_out && workspace, "ev_am_phase2: null argument");
+  EV_CHECK_ARG(B > 0 && T > 0 && F > 0, "ev_am_phase2: B=%d T=%d F=%d", B, T, F);
+  if (!ctx->pe || ctx->pe_len < F) { set_error("ev_am_phase2: positional table has %d rows, need %d", ctx->pe_len, F); return EV_EPELEN; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const ev_config& g = ctx->cfg;
+  const int H = g.hidden;
+  EV_TRY(use_device(ctx));
+  Carver cv1(const_cast<void*>(phase1_workspace)), cv(workspace);
+  Phase1Bufs b1;
+  Phase2Bufs b;
+  carve_phase1(ctx, cv1, B, T, &b1);
+  carve_phase2(ctx, cv, B, F, &b);
+  if (cv.off > workspace_bytes) { set_error("ev_am_phase2: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
+  const int32_t* flens = invariant ? mel_lens : nullptr;
+  // length regulator + the decoder's positional encoding (alignment.py:198-211, encoder.py:257-261)
+  EV_TRY(launch_gauss_upsample(b1.hs, b1.centers, lens, mel_lens, B, T, H, F, invariant, ctx->pe, ctx->dec.alpha, b.x, st));
+  // decoder (model_open_source.py:146: mask None in the reference; per-item lengths under the invariant contract)
+  EV_TRY(run_stack(ctx, ctx->dec, b.x, b.y, b.qkv, b.ctx, b.h, B, F, flens, flens, false, st));
+  // to_mel (model_open_source.py:147)
+  EV_TRY(conv(b.y, ctx->mel_w, ctx->mel_b, 0, nullptr, mel_out, B, F, H, g.n_mels, 1, 1, flens, 1, EV_ACT_NONE, 0.f,
+              EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+  return EV_OK;
+}
+
+int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t* mel_lens, int B, int F, float* wav_out,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  EV_CHECK_ARG(ctx && ctx->bound && ctx->has_voc, "ev_vocoder: vocoder weights not bound");
+  EV_CHECK_ARG(mel && wav_out && workspace, "ev_vocoder: null argument");
+  EV_CHECK_ARG(B > 0 && F > 0, "ev_vocoder: B=%d F=%d", B, F);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const ev_config& g = ctx->cfg;
+  EV_TRY(use_device(ctx));
+  Carver cv(workspace);
+  VocBufs v;
+  carve_voc(ctx, cv, B, F, &v);
+  if (cv.off > workspace_bytes) { set_error("ev_vocoder: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
+  const float* m = mel;
+  if (!mel_time_major) {
+    EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm, B, g.n_mels, F, st));
+    m = v.Tm;
+  }
+  // conv_pre (hifigan/models.py:116)
+  EV_TRY(conv(m, ctx->pre.w, ctx->pre.b, 0, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1, mel_lens, 1,
+              EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+  int L = F, mul = 1;
+  size_t rb = 0;
+  for (int s = 0; s < g.n_ups; ++s) {
+    const UpW& u = ctx->ups[s];
+    // x = ups[i](leaky_relu(x, 0.1)) (:118-119): polyphase-packed transposed conv, output viewed (L, rate*Cout)
+    EV_TRY(conv(v.ACC, u.w, u.b, 0, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+                EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+    L *= u.rate; mul *= u.rate;
+    const int C = u.cout;
+    for (int j = 0; j < g.n_resk; ++j) {
+      const float* src = v.X;
+      for (int l = 0; l < g.n_dil; ++l, ++rb) {
+        const ConvW& c1 = ctx->rb_c1[rb];
+        const ConvW& c2 = ctx->rb_c2[rb];
+        // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
+        EV_TRY(conv(src, c1.w, c1.b, 0, nullptr, v.Tm, B, L, C, C, c1.K, c1.dil, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+                    EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+        const bool last = (l == g.n_dil - 1);
+        float* dst = last ? v.ACC : ((l & 1) ? v.R2 : v.R1);
+        int acc = EV_ACC_STORE;
+        if (last && j > 0) acc = (j == g.n_resk - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;   // xs += ...; x = xs / n (:120-126)
+        const float div = (float)g.n_resk;
+        if (last && g.n_resk == 1) acc = EV_ACC_STORE;
+        EV_TRY(conv(v.Tm, c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f, EV_ACT_NONE,
+                    acc, div, st));
+        src = dst;
+      }
+    }
+  }
+  // x = leaky_relu(x) [slope 0.01]; conv_post; tanh (:127-129)
+  EV_CHECK_ARG(mul == ctx->total_up, "ev_vocoder: internal rate mismatch");
+  const int Cl = ctx->ups.back().cout;
+  EV_TRY(launch_conv_post(v.ACC, ctx->post_w, ctx->post_b, mel_lens, mul, B, L, Cl, ctx->post_k, 0.01f, wav_out, st));
+  return EV_OK;
+}
+
+int ev_wav_to_pcm16(const float* wav, int16_t* pcm, size_t n, void* stream) {
+  EV_CHECK_ARG(wav && pcm, "ev_wav_to_pcm16: null argument");
+  return launch_pcm16(wav, pcm, n, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_conv1d(const float* x, const float* w, const float* bias, size_t bias_bstride, const float* res, float* out,
+                 int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens, int lens_mul, int in_act,
+                 float in_slope, int out_act, int acc, float div, void* stream) {
+  EV_CHECK_ARG(x && w && out, "ev_op_conv1d: null argument");
+  return conv(x, w, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul, in_act, in_slope,
+              out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int C, void* stream) {
+  EV_CHECK_ARG(x && w && b && y, "ev_op_layernorm: null argument");
+  return launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, w, b, y, rows, rows, C,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_attention(const float* qkv, const int32_t* key_lens, float* ctx_out, int B, int L, int H, int n_heads,
+                    void* stream) {
+  EV_CHECK_ARG(qkv && ctx_out, "ev_op_attention: null argument");
+  return launch_attention(qkv, key_lens, ctx_out, B, L, H, n_heads, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_gauss_upsample(const float* hs, const int64_t* dur, const int32_t* lens, int B, int T, int H, int F,
+                         int invariant, const float* pe, const float* alpha, float* centers_tmp, int32_t* mel_lens_tmp,
+                         float* out, void* stream) {
+  EV_CHECK_ARG(hs && dur && centers_tmp && mel_lens_tmp && out, "ev_op_gauss_upsample: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // centers_tmp holds 2*B*T floats: centres then float durations
+  EV_TRY(launch_duration_scan(dur, lens, invariant, B, T, centers_tmp, centers_tmp + (size_t)B * T, mel_lens_tmp, st));
+  return launch_gauss_upsample(hs, centers_tmp, lens, mel_lens_tmp, B, T, H, F, invariant, pe, alpha, out, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Shared declarations of the sm_100a engine (internal; the public ABI is include/emotivoice_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/emotivoice_b200.h"
+
+namespace ev {
+
+// thread-local error string behind ev_last_error()
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define EV_CHECK_ARG(cond, ...)                      \
+  do {                                               \
+    if (!(cond)) {                                   \
+      ev::set_error(__VA_ARGS__);                    \
+      return EV_EINVAL;                              \
+    }                                                \
+  } while (0)
+
+#define EV_CUDA_LAUNCH_CHECK(what)                                                        \
+  do {                                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess) {                                                             \
+      ev::set_error("%s: %s", what, cudaGetErrorString(e__));                             \
+      return EV_ECUDA;                                                                    \
+    }                                                                                     \
+    ev::count_launch();                                                                   \
+  } while (0)
+
+#define EV_TRY(expr)                 \
+  do {                               \
+    int rc__ = (expr);               \
+    if (rc__ != EV_OK) return rc__;  \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// generic time-major conv (conv1d_tm.cu)
+// ---------------------------------------------------------------------------------
+struct ConvParams {
+  const float* x;      // (B, L, Cin)
+  const float* w;      // (K, Cin, Cout)
+  const float* bias;   // (Cout) or per item (bias_bs floats apart); may be null
+  const float* res;    // (B, L, Cout) or null
+  float* out;          // (B, L, Cout)
+  long long bias_bs;
+  int B, L, Cin, Cout, K, dil;
+  const int32_t* lens; // valid rows per item = lens[b]*lens_mul (null: L)
+  int lens_mul;
+  int in_act;          // EV_ACT_NONE / EV_ACT_LRELU
+  float in_slope;
+  int out_act;         // EV_ACT_*
+  int acc;             // EV_ACC_*
+  float div;
+};
+int launch_conv1d(const ConvParams& p, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------
+// acoustic-model kernels (am_kernels.cu)
+// ---------------------------------------------------------------------------------
+// y = LN(x) over C; optional prologue x = emb[ids] + alpha*pe[t] (written to x_out).
+int launch_layernorm(const float* x, const int64_t* ids, const float* emb, const float* pe, const float* alpha,
+                     float* x_out, const float* w, const float* b, float* y, int rows, int L, int C,
+                     cudaStream_t st);
+int launch_attention(const float* qkv, const int32_t* key_lens, float* ctx, int B, int L, int H, int heads,
+                     cudaStream_t st);
+int launch_cond_gather(const int64_t* spk, const float* spk_emb, const float* style, const float* content,
+                       float* out, int B, int H, int bert, cudaStream_t st);
+// y[row] = dot(x[row,:], w) + b ; masked rows (t >= lens[b]) -> 0.  mode 0: float out; mode 1: duration int64
+int launch_rowdot(const float* x, const float* w, const float* b, const int32_t* lens, int B, int T, int C,
+                  int mode, float* out_f, int64_t* out_i, cudaStream_t st);
+int launch_lens_to_i32(const int64_t* lens, int32_t* out, int B, int T, cudaStream_t st);
+// zero rows t >= lens[b] of x (B,T,C) into y (masked_fill of the predictors' input)
+int launch_mask_rows(const float* x, const int32_t* lens, float* y, int B, int T, int C, cudaStream_t st);
+int launch_var_embed_add(float* x, const float* pitch, const float* energy, const float* wp, const float* bp,
+                         const float* we, const float* be, int B, int T, int C, int K, cudaStream_t st);
+int launch_duration_scan(const int64_t* dur, const int32_t* lens, int invariant, int B, int T, float* centers,
+                         float* ds_f, int32_t* mel_lens, cudaStream_t st);
+int launch_gauss_upsample(const float* hs, const float* centers, const int32_t* lens, const int32_t* mel_lens,
+                          int B, int T, int H, int F, int invariant, const float* pe, const float* alpha,
+                          float* out, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------
+// vocoder kernels (voc_kernels.cu)
+// ---------------------------------------------------------------------------------
+int launch_transpose_cf_to_tm(const float* in, float* out, int B, int C, int L, cudaStream_t st);
+// wav[b,t] = tanh(bias + sum_j sum_c w[j][c] * lrelu_slope(x[b,t+j-K/2,c])); rows >= len -> 0
+int launch_conv_post(const float* x, const float* w, const float* bias, const int32_t* lens, int lens_mul, int B,
+                     int L, int C, int K, float slope, float* wav, cudaStream_t st);
+int launch_pcm16(const float* wav, int16_t* pcm, size_t n, cudaStream_t st);
+
+__device__ __forceinline__ float act_apply(float v, int act, float slope) {
+  switch (act) {
+    case EV_ACT_LRELU: return v > 0.f ? v : v * slope;
+    case EV_ACT_RELU: return v > 0.f ? v : 0.f;
+    case EV_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    case EV_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+}  // namespace ev

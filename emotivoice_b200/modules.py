@@ -1,0 +1,354 @@
+"""Host-side mirror of the reference's model boundary.
+
+Same class names, constructor arguments, ``state_dict`` keys, ``forward()`` keyword
+signature and returned dict as
+
+* ``JETSGenerator``  -- models/prompt_tts_modified/jets.py:26-71
+* ``PromptTTS``      -- models/prompt_tts_modified/model_open_source.py:14-163
+* ``Generator``      -- models/hifigan/models.py:90-140
+
+so the reference's callers (inference_am_vocoder_joint.py:70-74,120-129, demo_page.py:88-92,
+openaiapi.py:78-82) run unchanged: ``JETSGenerator(conf).to(device)``,
+``.load_state_dict(torch.load(path)['generator'])``, ``.eval()``, call under ``no_grad``.
+
+The modules hold ``nn.Parameter`` trees only (for state-dict compatibility); every FLOP
+of ``forward`` runs in libemotivoice_b200.so (hand-written sm_100a kernels) through the C
+ABI in include/emotivoice_b200.h.  PyTorch provides device memory and the stream.  There
+is no CPU path: calling ``forward`` on CPU tensors raises.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _abi, packing, synth
+
+
+class _Holder(nn.Module):
+    """Parameter container; never called."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter holder: compute happens in libemotivoice_b200.so")
+
+
+def _register(root, dotted, tensor):
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Holder())
+        mod = mod._modules[p]
+    mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+def _legacy_weight_norm_hook(module, state_dict, prefix, *args):
+    """Checkpoints written by torch < 2.1 carry weight_g / weight_v instead of
+    parametrizations.weight.original0/1 (checkpoint row): accept both."""
+    for k in list(state_dict.keys()):
+        if not k.startswith(prefix):
+            continue
+        if k.endswith(".weight_g"):
+            state_dict[k[:-len("weight_g")] + "parametrizations.weight.original0"] = state_dict.pop(k)
+        elif k.endswith(".weight_v"):
+            state_dict[k[:-len("weight_v")] + "parametrizations.weight.original1"] = state_dict.pop(k)
+
+
+def _dirty_post_hook(module, incompatible_keys):
+    for m in module.modules():
+        if isinstance(m, _EngineOwner):
+            m._ev_dirty = True
+
+
+class _Engine:
+    """One ev_ctx + its packed weight blob and positional table on one device."""
+
+    def __init__(self, conf, packed, device):
+        self.lib = _abi.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("emotivoice_b200 runs on CUDA (sm_100a) only; got device %s. "
+                               "There is no CPU fallback." % (self.device,))
+        self.index_dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.cfg = _abi.make_config(conf)
+        self.hidden = int(self.cfg.hidden)
+        handle = ctypes.c_void_p()
+        _abi.check(self.lib.ev_create(ctypes.byref(handle), self.index_dev, ctypes.byref(self.cfg)))
+        self.handle = handle
+        blob, self.index = packing.make_blob(packed)
+        self.blob = blob.to(self.device)
+        _abi.check(self.lib.ev_bind_weights(self.handle, self.blob.data_ptr(), self.blob.numel(),
+                                            ctypes.cast(self.index, ctypes.c_void_p), len(self.index)))
+        self.pe = None
+        self.ensure_pe(5000)          # PositionalEncoding max_len=5000 (encoder.py:206)
+        self.total_up = int(np.prod([self.cfg.up_rates[i] for i in range(self.cfg.n_ups)]))
+
+    def ensure_pe(self, n):
+        if self.pe is not None and self.pe.shape[0] >= n:
+            return
+        n = max(n, 2 * (self.pe.shape[0] if self.pe is not None else 0))
+        self.pe = packing.build_pe_table(n, self.hidden).to(self.device)
+        _abi.check(self.lib.ev_bind_pe(self.handle, self.pe.data_ptr(), n))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.ev_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- calls ------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def acoustic(self, ling, lens, spk, style, content, invariant):
+        lib, dev = self.lib, self.device
+        B, T = ling.shape
+        self.ensure_pe(T)
+        dur = torch.empty((B, T), dtype=torch.int64, device=dev)
+        pitch = torch.empty((B, T), dtype=torch.float32, device=dev)
+        energy = torch.empty((B, T), dtype=torch.float32, device=dev)
+        meta = torch.empty((2 * B + 1,), dtype=torch.int32, device=dev)      # lens32 | mel_lens (B+1)
+        n1 = lib.ev_phase1_workspace_bytes(self.handle, B, T)
+        ws1 = torch.empty((n1,), dtype=torch.uint8, device=dev)
+        st = self._stream()
+        lens32_ptr = meta.data_ptr()
+        mel_lens_ptr = meta.data_ptr() + 4 * B
+        _abi.check(lib.ev_am_phase1(self.handle, ling.data_ptr(), lens.data_ptr(), spk.data_ptr(), style.data_ptr(),
+                                    content.data_ptr(), B, T, int(invariant), dur.data_ptr(), pitch.data_ptr(),
+                                    energy.data_ptr(), lens32_ptr, mel_lens_ptr, ws1.data_ptr(), n1, st))
+        # the path's single host sync: the output length is data dependent (alignment.py:194-195)
+        mel_lens_host = meta[B:].cpu()
+        F = int(mel_lens_host[B])
+        self.ensure_pe(F)
+        n2 = lib.ev_phase2_workspace_bytes(self.handle, B, F)
+        ws2 = torch.empty((n2,), dtype=torch.uint8, device=dev)
+        mel = torch.empty((B, F, int(self.cfg.n_mels)), dtype=torch.float32, device=dev)
+        _abi.check(lib.ev_am_phase2(self.handle, ws1.data_ptr(), lens32_ptr, mel_lens_ptr, B, T, F, int(invariant),
+                                    mel.data_ptr(), ws2.data_ptr(), n2, st))
+        return dict(mel=mel, dur=dur, pitch=pitch, energy=energy, meta=meta, mel_lens=meta[B:2 * B],
+                    mel_lens_host=mel_lens_host[:B], F=F, ws2=ws2, n2=n2)
+
+    def vocode(self, mel, time_major, mel_lens_ptr, ws=None, n=0):
+        lib, dev = self.lib, self.device
+        if time_major:
+            B, F, _ = mel.shape
+        else:
+            B, _, F = mel.shape
+        if ws is None:
+            n = lib.ev_phase2_workspace_bytes(self.handle, B, F)
+            ws = torch.empty((n,), dtype=torch.uint8, device=dev)
+        wav = torch.empty((B, 1, F * self.total_up), dtype=torch.float32, device=dev)
+        _abi.check(lib.ev_vocoder(self.handle, mel.data_ptr(), int(bool(time_major)), mel_lens_ptr, B, F,
+                                  wav.data_ptr(), ws.data_ptr(), n, self._stream()))
+        return wav
+
+
+class _EngineOwner(nn.Module):
+    """Lazy (re)packing of the parameter tree into an engine on the parameters' device."""
+
+    def __init__(self):
+        super().__init__()
+        self._ev_engine = None
+        self._ev_dirty = True
+        self._ev_lock = threading.Lock()
+        self.register_load_state_dict_post_hook(_dirty_post_hook)
+
+    def _mark_dirty(self):
+        self._ev_dirty = True
+
+    def _apply(self, fn, *a, **k):          # .to() / .cuda() / .float() ...
+        r = super()._apply(fn, *a, **k)
+        self._ev_dirty = True
+        return r
+
+    def refresh_weights(self):
+        """Call after modifying parameters in place (load_state_dict / .to() do it for you)."""
+        self._ev_dirty = True
+
+    def _pack(self):
+        raise NotImplementedError
+
+    def _engine(self):
+        eng = self._ev_engine
+        dev = next(self.parameters()).device
+        if eng is not None and not self._ev_dirty and eng.device == dev:
+            return eng
+        with self._ev_lock:
+            if self._ev_engine is None or self._ev_dirty or self._ev_engine.device != dev:
+                self._ev_engine = _Engine(self.config, self._pack(), dev)
+                self._ev_dirty = False
+            return self._ev_engine
+
+
+def _prep(t, dtype, device):
+    if t.device != device:
+        raise RuntimeError("input tensor on %s but the module is on %s" % (t.device, device))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _seeded_init(conf):
+    seed = int(torch.randint(0, 2 ** 31 - 1, ()).item())
+    return synth.make_state_dict(conf, seed=seed)
+
+
+class Generator(_EngineOwner):
+    """HiFi-GAN generator (hifigan/models.py:90-140).  ``Generator(h)`` takes the ``model``
+    node of the config, like the reference.  forward: (B, 80, F) -> (B, 1, 256 F)."""
+
+    def __init__(self, h, _init=None):
+        super().__init__()
+        self.h = h
+        self.num_kernels = len(h.resblock_kernel_sizes)
+        self.num_upsamples = len(h.upsample_rates)
+        self.upsample_factor = int(np.prod(h.upsample_rates))
+        if str(h.resblock) != "1":
+            raise NotImplementedError("only resblock '1' (config.yaml:87)")
+        from .config import AttrDict
+        self.config = AttrDict(model=h, n_mels=int(h.initial_channel), segment_size=32, n_vocab=1, n_speaker=1)
+        if _init is None:
+            full = AttrDict(model=h, n_mels=int(h.initial_channel), n_vocab=2, n_speaker=2)
+            _init = {k[len("generator."):]: v for k, v in _seeded_init(full).items() if k.startswith("generator.")}
+        for k, v in _init.items():
+            _register(self, k, v.clone())
+        self._register_load_state_dict_pre_hook(_legacy_weight_norm_hook, with_module=True)
+
+    def _pack(self):
+        return packing.pack_vocoder({"generator." + k: v for k, v in self.state_dict().items()}, self.h)
+
+    @torch.no_grad()
+    def forward(self, x):
+        eng = self._engine()
+        x = _prep(x, torch.float32, eng.device)
+        return eng.vocode(x, time_major=False, mel_lens_ptr=None)
+
+    def remove_weight_norm(self):
+        """hifigan/models.py:133-140 (broken on torch >= 2.1 in the reference):
+        replaces every (g, v) pair by the folded ``weight``."""
+        print('Removing weight norm...')
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        for mod, _, _ in synth.vocoder_conv_shapes(self.h):
+            if mod + ".parametrizations.weight.original0" not in sd:
+                continue
+            w = packing.fold_weight_norm(sd, mod)
+            holder = self
+            for p in mod.split("."):
+                holder = holder._modules[p]
+            del holder._modules["parametrizations"]
+            holder.register_parameter("weight", nn.Parameter(w.to(next(self.parameters()).device), requires_grad=False))
+        self._mark_dirty()
+
+
+class PromptTTS(_EngineOwner):
+    """Acoustic model (model_open_source.py:14-163), inference branch only."""
+
+    def __init__(self, config, _init=None):
+        super().__init__()
+        self.config = config
+        if _init is None:
+            _init = {k[len("am."):]: v for k, v in _seeded_init(config).items() if k.startswith("am.")}
+        for k, v in _init.items():
+            _register(self, k, v.clone())
+        self.compat_padded_batch = False
+
+    def _pack(self):
+        sd = {"am." + k: v for k, v in self.state_dict().items()}
+        packed = packing.pack_state_dict_am(sd, self.config)
+        return packed
+
+    @torch.no_grad()
+    def forward(self, inputs_ling, input_lengths, inputs_speaker, inputs_style_embedding, inputs_content_embedding,
+                mel_targets=None, output_lengths=None, pitch_targets=None, energy_targets=None, alpha=1.0):
+        if mel_targets is not None:
+            raise NotImplementedError("training-mode forward (teacher forcing) is out of scope for this engine")
+        eng = self._engine()
+        return _am_forward(eng, inputs_ling, input_lengths, inputs_speaker, inputs_style_embedding,
+                           inputs_content_embedding, not self.compat_padded_batch)[0]
+
+
+def _am_forward(eng, inputs_ling, input_lengths, inputs_speaker, style, content, invariant):
+    dev = eng.device
+    ling = _prep(inputs_ling, torch.int64, dev)
+    lens = _prep(input_lengths, torch.int64, dev)
+    spk = _prep(inputs_speaker, torch.int64, dev)
+    style = _prep(style, torch.float32, dev)
+    content = _prep(content, torch.float32, dev)
+    if ling.dim() != 2 or lens.shape[0] != ling.shape[0] or spk.shape[0] != ling.shape[0]:
+        raise RuntimeError("shape mismatch: inputs_ling %s, input_lengths %s, inputs_speaker %s"
+                           % (tuple(ling.shape), tuple(lens.shape), tuple(spk.shape)))
+    r = eng.acoustic(ling, lens, spk, style, content, invariant)
+    out = {
+        "mel_targets": None,
+        "dec_outputs": r["mel"],
+        "postnet_outputs": None,
+        "pitch_predictions": r["pitch"].squeeze(),     # model_open_source.py:153
+        "pitch_targets": None,
+        "energy_predictions": r["energy"].squeeze(),   # :155
+        "energy_targets": None,
+        "log_duration_predictions": r["dur"],          # linear-domain integer frames despite the name (:157)
+        "duration_targets": None,
+        "input_lengths": input_lengths,
+        "output_lengths": None,
+        "log_p_attn": None,
+        "bin_loss": None,
+        "mel_lengths": r["mel_lens"],                  # extension: per-item frame counts (B,) int32
+    }
+    return out, r
+
+
+class JETSGenerator(_EngineOwner):
+    """Joint acoustic model + vocoder (jets.py:26-71).
+
+    ``compat_padded_batch`` (default False): with B > 1 the reference's padded forward leaks
+    padding into the shorter items (decoder runs unmasked, convolutions run across pad frames;
+    SURVEY.md s4 item 4).  By default every item of a batch is computed exactly like the
+    reference's B=1 call for that item (what every reference caller runs); set the attribute
+    to True to reproduce the literal padded-batch forward instead.  For B=1 both agree.
+    """
+
+    def __init__(self, config):
+        super().__init__()
+        self.upsample_factor = int(np.prod(config.model.upsample_rates))
+        self.segment_size = config.segment_size
+        init = _seeded_init(config)
+        self.am = PromptTTS(config, _init={k[3:]: v for k, v in init.items() if k.startswith("am.")})
+        self.generator = Generator(config.model, _init={k[10:]: v for k, v in init.items() if k.startswith("generator.")})
+        self.config = config
+        self.compat_padded_batch = False
+        self._register_load_state_dict_pre_hook(_legacy_weight_norm_hook, with_module=True)
+
+    def _pack(self):
+        return packing.pack_state_dict(self.state_dict(), self.config)
+
+    @torch.no_grad()
+    def forward(self, inputs_ling, input_lengths, inputs_speaker, inputs_style_embedding, inputs_content_embedding,
+                mel_targets=None, output_lengths=None, pitch_targets=None, energy_targets=None, alpha=1.0,
+                cut_flag=True):
+        if mel_targets is not None:
+            raise NotImplementedError("training-mode forward (teacher forcing / random segments) is out of scope")
+        eng = self._engine()
+        invariant = not self.compat_padded_batch
+        outputs, r = _am_forward(eng, inputs_ling, input_lengths, inputs_speaker, inputs_style_embedding,
+                                 inputs_content_embedding, invariant)
+        B = r["mel"].shape[0]
+        mel_lens_ptr = (r["meta"].data_ptr() + 4 * B) if invariant else None
+        # jets.py:62-66: z = dec_outputs.transpose(1, 2); wav = generator(z).  dec_outputs is already the
+        # vocoder's time-major input layout: no transpose, no copy.
+        wav = eng.vocode(r["mel"], time_major=True, mel_lens_ptr=mel_lens_ptr, ws=r["ws2"], n=r["n2"])
+        outputs["wav_predictions"] = wav
+        outputs["z_start_idxs"] = None
+        outputs["segment_size"] = self.segment_size
+        return outputs
+
+    @torch.no_grad()
+    def to_pcm16(self, wav):
+        """The callers' ``wav * 32768 -> int16`` (inference_am_vocoder_joint.py:130-131) on the GPU."""
+        eng = self._engine()
+        wav = _prep(wav, torch.float32, eng.device)
+        pcm = torch.empty(wav.shape, dtype=torch.int16, device=eng.device)
+        _abi.check(eng.lib.ev_wav_to_pcm16(wav.data_ptr(), pcm.data_ptr(), wav.numel(), eng._stream()))
+        return pcm

@@ -1,0 +1,177 @@
+/*
+ * emotivoice_b200.h -- C ABI of libemotivoice_b200.so (sm_100a).
+ *
+ * The reference (netease-youdao/EmotiVoice) has no FFI / plugin registry: its
+ * boundary for this path is the Python torch.nn.Module API of
+ *   JETSGenerator.forward      models/prompt_tts_modified/jets.py:50-71
+ *   PromptTTS.forward          models/prompt_tts_modified/model_open_source.py:102-163
+ *   Generator.forward          models/hifigan/models.py:115-131
+ * The host-side mirror of those classes lives in emotivoice_b200/modules.py and
+ * binds the entry points below with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).  Everything here is plain C: device pointers,
+ * sizes, a CUDA stream handle passed as void*.  No torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative EV_E* code; nothing throws
+ *     or aborts across the ABI; ev_last_error() gives the message (thread local).
+ *   - all work is enqueued asynchronously on the caller's stream; the library never
+ *     synchronises and never allocates device memory: the caller (PyTorch's caching
+ *     allocator) owns weights, workspace, inputs and outputs.
+ *   - activations are fp32, TIME-MAJOR ("channels last"): a tensor of L steps and C
+ *     channels of batch item b lives at base + b*L*C, element (t, c) at t*C + c.
+ *   - `lens` arrays are int32 on the device; NULL means "every item is L long"
+ *     (the reference's literal padded-batch semantics).  With `lens` given, item b
+ *     is treated exactly as the reference treats a B=1 call of that length: rows
+ *     >= lens[b] read as zero padding and are written as zeros.
+ *   - an ev_ctx is immutable after ev_bind_*; concurrent calls are safe as long as
+ *     each call has its own workspace (reference callers are multi-threaded:
+ *     openaiapi.py:162-163).
+ */
+#ifndef EMOTIVOICE_B200_H_
+#define EMOTIVOICE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EV_API __attribute__((visibility("default")))
+#define EV_ABI_VERSION 1
+
+enum {
+  EV_OK = 0,
+  EV_EINVAL = -1,      /* bad argument / unsupported shape */
+  EV_ENOWEIGHT = -2,   /* a required tensor is missing from the bound blob */
+  EV_ECUDA = -3,       /* CUDA runtime error (message has the cudaError string) */
+  EV_EWORKSPACE = -4,  /* workspace too small */
+  EV_EPELEN = -5,      /* positional table shorter than the sequence: rebind a longer one */
+  EV_EARCH = -6        /* device is not sm_100 */
+};
+
+/* activation / epilogue selectors of ev_op_conv1d */
+enum { EV_ACT_NONE = 0, EV_ACT_LRELU = 1, EV_ACT_RELU = 2, EV_ACT_GELU = 3, EV_ACT_TANH = 4 };
+enum { EV_ACC_STORE = 0, EV_ACC_ADD = 1, EV_ACC_ADD_DIV = 2 };
+
+typedef struct ev_ctx ev_ctx;
+
+/* The integers of config/joint/config.yaml:36-94 (+ n_vocab / n_speaker patched in by
+ * every reference caller, inference_am_vocoder_joint.py:57-58). */
+typedef struct ev_config {
+  int32_t n_vocab, n_speaker;
+  int32_t hidden;            /* encoder_n_hidden == decoder_n_hidden == variance_n_hidden (384) */
+  int32_t n_heads;           /* 8 */
+  int32_t enc_layers, dec_layers;
+  int32_t ffn_kernel;        /* *_kernel_size_conv_mod (3) */
+  int32_t bert_dim;          /* bert_embedding (768) */
+  int32_t dur_layers, pitch_layers, energy_layers;
+  int32_t pred_kernel;       /* duration/variance kernel size (3) */
+  int32_t embed_kernel;      /* variance_embed_kernel_size (9) */
+  int32_t n_mels;            /* 80 */
+  int32_t voc_c0;            /* upsample_initial_channel (512) */
+  int32_t n_ups;             /* len(upsample_rates) (4) */
+  int32_t up_rates[8];
+  int32_t up_kernels[8];
+  int32_t n_resk;            /* len(resblock_kernel_sizes) (3) */
+  int32_t res_kernels[4];
+  int32_t n_dil;             /* dilations per ResBlock1 (3) */
+  int32_t res_dils[4][4];
+} ev_config;
+
+/* One tensor of the packed weight blob (built by emotivoice_b200/packing.py). */
+typedef struct ev_weight_entry {
+  char name[56];
+  uint64_t offset;   /* in floats from the blob base */
+  uint64_t numel;
+} ev_weight_entry;
+
+EV_API int ev_abi_version(void);
+EV_API const char* ev_last_error(void);
+
+/* Replaces: JETSGenerator.__init__ (jets.py:27-47). */
+EV_API int ev_create(ev_ctx** out, int device, const ev_config* cfg);
+EV_API void ev_destroy(ev_ctx* ctx);
+
+/* Replaces: module.load_state_dict + the per-forward weight_norm recomputation
+ * (hifigan/models.py:31-46,96-111).  The blob holds folded / re-laid-out fp32 weights;
+ * the engine borrows it (caller keeps it alive). */
+EV_API int ev_bind_weights(ev_ctx* ctx, const float* blob, size_t n_floats,
+                           const ev_weight_entry* index, int n_entries);
+/* Replaces: PositionalEncoding.extend_pe (encoder.py:206-237).  pe is (pe_len, hidden)
+ * fp32 on the device, built by the host with the reference's formula. */
+EV_API int ev_bind_pe(ev_ctx* ctx, const float* pe, int pe_len);
+
+/* Workspace sizes (bytes).  Phase 1 (encoder .. durations) is sized by (B, T); phase 2
+ * (length regulator, decoder, to_mel) and the vocoder share one buffer sized by (B, F) --
+ * F is only known after the host has read mel_lens_out[B] back. */
+EV_API size_t ev_phase1_workspace_bytes(const ev_ctx* ctx, int B, int T);
+EV_API size_t ev_phase2_workspace_bytes(const ev_ctx* ctx, int B, int F);
+
+/* Replaces: PromptTTS.forward up to the duration prediction
+ * (model_open_source.py:102-134; encoder.py:316-324; variance.py:36-56,101-124) plus
+ * the cumsum / length bookkeeping of GaussianUpsampling (alignment.py:183-199).
+ *   ling (B,T) i64; lens (B) i64 true phoneme counts (as the reference passes them); spk (B) i64;
+ *   style, content (B,bert) f32
+ *   dur_out (B,T) i64; pitch_out / energy_out (B,T) f32;
+ *   lens32_out (B) i32: lens clamped to [0,T] (input of the later phases);
+ *   mel_lens_out (B+1) i32: per-item frame counts, and max over items in slot B.
+ *   invariant != 0: batch-invariant contract (each item == the reference's B=1 call);
+ *   invariant == 0: literal padded-batch forward of the reference. */
+EV_API int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens, const int64_t* spk,
+                        const float* style, const float* content, int B, int T, int invariant,
+                        int64_t* dur_out, float* pitch_out, float* energy_out, int32_t* lens32_out,
+                        int32_t* mel_lens_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces: GaussianUpsampling.forward matmul (alignment.py:201-211), the decoder
+ * (model_open_source.py:146) and to_mel (:147).  Must follow ev_am_phase1 on the same stream;
+ * phase1_workspace is the (still live) buffer phase 1 ran on.  F = mel_lens_out[B] read back
+ * by the host (the path's one sync).
+ *   mel_out (B,F,n_mels) f32 time-major == outputs["dec_outputs"]. */
+EV_API int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens32, const int32_t* mel_lens,
+                        int B, int T, int F, int invariant, float* mel_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Replaces: Generator.forward (hifigan/models.py:115-131).
+ *   mel (B,F,n_mels) time-major if mel_time_major else (B,n_mels,F) (the reference layout);
+ *   mel_lens (B) i32 or NULL (literal padded semantics); wav_out (B, F*prod(up_rates)) f32. */
+EV_API int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t* mel_lens, int B, int F,
+                      float* wav_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces the callers' post-processing (inference_am_vocoder_joint.py:130-131):
+ * pcm[i] = (int16) trunc(wav[i] * 32768), n elements. */
+EV_API int ev_wav_to_pcm16(const float* wav, int16_t* pcm, size_t n, void* stream);
+
+/* Number of kernel launches this library has enqueued in this process (bench.py's
+ * `gpu_launches`). */
+EV_API uint64_t ev_launch_count(void);
+
+/* ---- single operators (used by the per-kernel parity tests) ------------------- */
+
+/* Generic time-major 1-D convolution / linear layer (implicit GEMM):
+ *   out[b,t,co] = epi( bias[co] + sum_{j<K} sum_{ci} w[j][ci][co] * act_in(x[b, t+(j-(K-1)/2)*dil, ci]) )
+ * x rows outside [0, len_b) read as zero.  w is (K, Cin, Cout).  bias_bstride: floats between
+ * per-item biases (0 = shared).  res (same layout as out) is added after out_act.
+ * acc: EV_ACC_STORE out=v; EV_ACC_ADD out+=v; EV_ACC_ADD_DIV out=(out+v)/div.
+ * Covers nn.Linear (K=1), the conv-FFN (encoder.py:50-52), predictor convs (variance.py:17-31),
+ * conv_pre / ResBlock1 convs (hifigan/models.py:50-57,116) and, with polyphase-packed
+ * weights, ConvTranspose1d (hifigan/models.py:100-103). */
+EV_API int ev_op_conv1d(const float* x, const float* w, const float* bias, size_t bias_bstride,
+                        const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
+                        const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
+                        int acc, float div, void* stream);
+/* LayerNorm over the last dim, eps 1e-12 (encoder.py:112-127). rows x C. */
+EV_API int ev_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int C, void* stream);
+/* Multi-head self-attention core (encoder.py:84-109) on a packed (B,L,3H) q|k|v buffer. */
+EV_API int ev_op_attention(const float* qkv, const int32_t* key_lens, float* ctx_out, int B, int L, int H,
+                           int n_heads, void* stream);
+/* Gaussian upsampling (alignment.py:180-211) incl. cumsum; out (B,F,H); adds alpha*pe[f] when pe != NULL.
+ * centers_tmp: 2*B*T floats of scratch; mel_lens_tmp: B+1 int32 (frame counts, max in slot B). */
+EV_API int ev_op_gauss_upsample(const float* hs, const int64_t* dur, const int32_t* lens, int B, int T, int H,
+                                int F, int invariant, const float* pe, const float* alpha, float* centers_tmp,
+                                int32_t* mel_lens_tmp, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMOTIVOICE_B200_H_ */
