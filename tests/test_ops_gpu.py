@@ -81,7 +81,8 @@ def test_conv1d_epilogues(lib, dev, out_act):
     # in-place residual (out aliases res), as the engine runs x += f(x)
     xt = x.transpose(1, 2).contiguous().to(dev)
     buf = res.to(dev).clone()
-    _abi.check(lib.ev_op_conv1d(xt.data_ptr(), packing._conv_w(w).to(dev).data_ptr(), b.to(dev).data_ptr(), 0,
+    wd, bd = packing._conv_w(w).to(dev), b.to(dev)
+    _abi.check(lib.ev_op_conv1d(xt.data_ptr(), wd.data_ptr(), bd.data_ptr(), 0,
                                 buf.data_ptr(), buf.data_ptr(), B, L, Cin, Cout, K, 1, None, 1, 0, 0.0, out_act, 0, 1.0,
                                 _stream()))
     torch.cuda.synchronize()
@@ -141,7 +142,8 @@ def test_layernorm(lib, dev, rows, C):
     x = torch.randn(rows, C, generator=g) * 3 + 0.5
     w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
     y = torch.empty(rows, C, device=dev)
-    _abi.check(lib.ev_op_layernorm(x.to(dev).data_ptr(), w.to(dev).data_ptr(), b.to(dev).data_ptr(), y.data_ptr(), rows, C, _stream()))
+    xd, wd, bd = x.to(dev), w.to(dev), b.to(dev)     # keep the device tensors alive across the call
+    _abi.check(lib.ev_op_layernorm(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, C, _stream()))
     torch.cuda.synchronize()
     assert rel_max(y.cpu(), O.layer_norm(x, w, b)) <= TOL
 
@@ -165,7 +167,9 @@ def test_attention(lib, dev, B, L, masked):
         attn = torch.softmax(scores, -1)
     ref = (attn @ v).transpose(1, 2).reshape(B, L, H)
     out = torch.empty(B, L, H, device=dev)
-    _abi.check(lib.ev_op_attention(qkv.to(dev).data_ptr(), _ptr(lens.to(dev)) if masked else None, out.data_ptr(), B, L, H, heads, _stream()))
+    qd = qkv.to(dev)
+    ld = lens.to(dev) if masked else None
+    _abi.check(lib.ev_op_attention(qd.data_ptr(), _ptr(ld), out.data_ptr(), B, L, H, heads, _stream()))
     torch.cuda.synchronize()
     assert rel_max(out.cpu(), ref) <= TOL
 
@@ -195,8 +199,9 @@ def test_gauss_upsample(lib, dev, invariant):
     out = torch.empty(B, F_, H, device=dev)
     tmp = torch.empty(2 * B * T, device=dev)
     mel_lens = torch.empty(B + 1, dtype=torch.int32, device=dev)
-    _abi.check(lib.ev_op_gauss_upsample(hs.to(dev).data_ptr(), dur.to(dev).data_ptr(), lens.to(dev).data_ptr(), B, T, H, F_,
-                                        invariant, pe.to(dev).data_ptr(), alpha.to(dev).data_ptr(), tmp.data_ptr(),
+    hd, dd, ld, pd, ad = hs.to(dev), dur.to(dev), lens.to(dev), pe.to(dev), alpha.to(dev)
+    _abi.check(lib.ev_op_gauss_upsample(hd.data_ptr(), dd.data_ptr(), ld.data_ptr(), B, T, H, F_,
+                                        invariant, pd.data_ptr(), ad.data_ptr(), tmp.data_ptr(),
                                         mel_lens.data_ptr(), out.data_ptr(), _stream()))
     torch.cuda.synchronize()
     assert mel_lens.cpu().tolist() == dur.sum(1).tolist() + [F_]
@@ -214,7 +219,8 @@ def test_gauss_upsample_all_zero_durations(lib, dev):
     out = torch.empty(B, T, H, device=dev)
     tmp = torch.empty(2 * B * T, device=dev)
     mel_lens = torch.empty(B + 1, dtype=torch.int32, device=dev)
-    _abi.check(lib.ev_op_gauss_upsample(hs.to(dev).data_ptr(), dur.to(dev).data_ptr(), lens.to(dev).data_ptr(), B, T, H, T, 0,
+    hd, dd, ld = hs.to(dev), dur.to(dev), lens.to(dev)
+    _abi.check(lib.ev_op_gauss_upsample(hd.data_ptr(), dd.data_ptr(), ld.data_ptr(), B, T, H, T, 0,
                                         None, None, tmp.data_ptr(), mel_lens.data_ptr(), out.data_ptr(), _stream()))
     torch.cuda.synchronize()
     assert mel_lens.cpu().tolist() == [T, T, T]
