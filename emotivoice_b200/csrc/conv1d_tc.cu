@@ -1,0 +1,354 @@
+// Time-major 1-D convolution as an implicit GEMM on the 5th-gen tensor cores (sm_100a):
+// tcgen05.mma (kind::tf32, fp32 accumulate in TMEM), operands staged in shared memory, weights
+// streamed by bulk async copies (cp.async.bulk -> mbarrier complete_tx), accumulator read back
+// with tcgen05.ld for the fused epilogue.  Same contract as conv1d_tm.cu (see ev_common.cuh):
+//
+//   out[b,t,co] = epi( bias[co] + sum_j sum_ci w[j][ci][co] * act_in( x[b, t + (j-(K-1)/2)*dil, ci] ) )
+//
+// GEMM view: M = 128 time steps per CTA, N = C_out tile (<= 256), K = taps x C_in.
+//
+// The trick that makes a dilated k-tap convolution cost ONE activation fetch per tile: the A
+// operand lives in shared memory in the *no-swizzle K-major* UMMA layout with the 8-row-group
+// stride (SBO) set to 128 B, i.e. element (row r, 16-byte K-granule g) sits at
+//        A + (g * rows_pad + r) * 16 bytes
+// so consecutive rows are exactly 16 B apart for the whole tile, and tap j of the convolution is
+// the same tile with the descriptor start address advanced by j*dil rows (16 B granularity).
+// One staged tile of BM + (K-1)*dil rows feeds all K taps.  The producer warps apply the
+// LeakyReLU prologue, the zero padding at the sequence ends and the layout change while staging,
+// so activations stay plain fp32 time-major in HBM and no tensor map is needed.
+//
+// Roles (192 threads): warps 0-3 stage A (then run the epilogue, one TMEM lane = one output row
+// per thread); warp 4 allocates TMEM and its elected lane issues every tcgen05.mma; warp 5's
+// elected lane streams the weight tiles.  Pipelines: A 2 stages (a_full/a_empty), B 3 stages
+// (b_full/b_empty, released by tcgen05.commit), accumulator (acc_full).
+#include "ev_common.cuh"
+
+namespace ev {
+
+namespace tc {
+
+constexpr int BM = 128;         // rows (time steps) per CTA == TMEM lanes
+constexpr int KB = 32;          // input channels per staged block (8 granules of 4 fp32)
+constexpr int A_STAGES = 2;
+constexpr int B_STAGES = 3;
+constexpr int NTHREADS = 192;
+constexpr int NPRODUCER = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate, M=128, N from idesc, K=8
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 (stride between the two 16-B K granules of one MMA)
+// | [32,46) SBO>>4 (stride between 8-row groups) | [46,48) version = 1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct SmemLayout {
+  int rows_pad;        // staged rows per A granule, == 1 (mod 8) -> conflict-free 16 B stores
+  int a_stage_bytes;   // 8 * rows_pad * 16
+  int b_stage_bytes;   // 8 * BN * 16
+  int total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int K, int dil, int BN) {
+  SmemLayout s;
+  const int rows = BM + (K - 1) * dil;
+  s.rows_pad = ((rows + 7) / 8) * 8 + 1;
+  s.a_stage_bytes = (KB / 4) * s.rows_pad * 16;
+  s.b_stage_bytes = (KB / 4) * BN * 16;
+  s.total = 1024 /*barriers + tmem ptr + alignment slack*/ + A_STAGES * s.a_stage_bytes + B_STAGES * s.b_stage_bytes;
+  return s;
+}
+
+__global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int BN, int tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int nt = min(BN, p.Cout - n0);          // this tile's N (multiple of 16)
+  const int len = p.lens ? min(p.L, p.lens[b] * p.lens_mul) : p.L;
+  float* ob = p.out + (size_t)b * p.L * p.Cout;   // may alias p.res (in-place residual)
+
+  if (t0 >= len) {   // whole tile is padding (uniform per CTA): the batch-invariant contract stores zeros
+    for (int i = tid; i < BM * (nt / 4); i += NTHREADS) {
+      const int r = i / (nt / 4), c4 = i % (nt / 4);
+      if (t0 + r < p.L) *reinterpret_cast<float4*>(ob + (size_t)(t0 + r) * p.Cout + n0 + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+
+  const SmemLayout sl = smem_layout(p.K, p.dil, BN);
+  // carve: [0,128) barriers, [128,132) tmem base; tiles from 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 128);
+  uint8_t* a_tiles = smem_raw + 1024;
+  uint8_t* b_tiles = a_tiles + A_STAGES * sl.a_stage_bytes;
+  const uint32_t bar_base = smem_u32(bars);
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (A_STAGES + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * A_STAGES + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * A_STAGES + B_STAGES + s); };
+  const uint32_t acc_full = bar_base + 8u * (2 * A_STAGES + 2 * B_STAGES);
+
+  if (tid == 0) {
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(a_full(s), NPRODUCER); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {   // TMEM allocation by one full warp; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_cb = (p.Cin + KB - 1) / KB;
+  const int halo = ((p.K - 1) / 2) * p.dil;
+  const int rows_a = BM + (p.K - 1) * p.dil;
+
+  if (warp < 4) {
+    // ------------------------------ A producers --------------------------------------------
+    const float* __restrict__ xb = p.x + (size_t)b * p.L * p.Cin;
+    const bool lrelu = (p.in_act == EV_ACT_LRELU);
+    const float slope = p.in_slope;
+    for (int cb = 0; cb < n_cb; ++cb) {
+      const int s = cb % A_STAGES;
+      mbar_wait(a_empty(s), ((cb / A_STAGES) & 1) ^ 1);
+      const int c0 = cb * KB;
+      const int ngran = min(KB, p.Cin - c0) / 4;
+      uint8_t* dst = a_tiles + s * sl.a_stage_bytes;
+      const int total = rows_a * 8;     // (row, granule) pairs; granule fastest -> coalesced 128 B rows
+      for (int base = 0; base < total; base += NPRODUCER * 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * NPRODUCER + tid;
+          const int r = idx >> 3, g = idx & 7;
+          const int row = t0 - halo + r;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < total && g < ngran && row >= 0 && row < len)
+            v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.Cin + c0 + g * 4));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * NPRODUCER + tid;
+          const int r = idx >> 3, g = idx & 7;
+          if (idx < total && g < ngran) {
+            float4 t = v[u];
+            if (lrelu) {
+              t.x = t.x > 0.f ? t.x : t.x * slope;
+              t.y = t.y > 0.f ? t.y : t.y * slope;
+              t.z = t.z > 0.f ? t.z : t.z * slope;
+              t.w = t.w > 0.f ? t.w : t.w * slope;
+            }
+            // round-to-nearest tf32 here (the MMA would otherwise truncate the low 13 mantissa bits)
+            t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
+            *reinterpret_cast<float4*>(dst + ((size_t)g * sl.rows_pad + r) * 16) = t;
+          }
+        }
+      }
+      fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(a_full(s));
+    }
+    // ------------------------------ epilogue ----------------------------------------------
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int row = t0 + warp * 32 + lane;
+    const float* __restrict__ bias = p.bias ? p.bias + (size_t)b * p.bias_bs : nullptr;
+    const float* rb = p.res ? p.res + (size_t)b * p.L * p.Cout : nullptr;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < nt; c += 16) {
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane participates
+      if (row < p.L) {
+        float* orow = ob + (size_t)row * p.Cout + n0 + c;
+        if (row < len) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float t = v[i];
+            if (bias) t += __ldg(bias + n0 + c + i);
+            v[i] = act_apply(t, p.out_act, 0.f);
+          }
+          if (rb) {
+            const float* rrow = rb + (size_t)row * p.Cout + n0 + c;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rrow + q * 4);
+              v[q * 4 + 0] += r4.x; v[q * 4 + 1] += r4.y; v[q * 4 + 2] += r4.z; v[q * 4 + 3] += r4.w;
+            }
+          }
+          if (p.acc != EV_ACC_STORE) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 o4 = *reinterpret_cast<const float4*>(orow + q * 4);
+              v[q * 4 + 0] += o4.x; v[q * 4 + 1] += o4.y; v[q * 4 + 2] += o4.z; v[q * 4 + 3] += o4.w;
+            }
+            if (p.acc == EV_ACC_ADD_DIV) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] /= p.div;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(orow + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------ MMA issuer ---------------------------------------------
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+      // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_lbo = (uint32_t)sl.rows_pad * 16u, b_lbo = (uint32_t)BN * 16u;
+      int it = 0;
+      for (int cb = 0; cb < n_cb; ++cb) {
+        const int sa = cb % A_STAGES;
+        const int nk8 = min(KB, p.Cin - cb * KB) / 8;
+        mbar_wait(a_full(sa), (cb / A_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(a_tiles + sa * sl.a_stage_bytes);
+        for (int j = 0; j < p.K; ++j, ++it) {
+          const int sb = it % B_STAGES;
+          mbar_wait(b_full(sb), (it / B_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(b_tiles + sb * sl.b_stage_bytes);
+          for (int k8 = 0; k8 < nk8; ++k8) {
+            const uint64_t ad = make_desc(a_addr + (uint32_t)((2 * k8) * sl.rows_pad + j * p.dil) * 16u, a_lbo, 128u);
+            const uint64_t bd = make_desc(b_addr + (uint32_t)(2 * k8) * b_lbo, b_lbo, 128u);
+            umma_tf32(tmem_base, ad, bd, idesc, (cb | j | k8) != 0 ? 1u : 0u);
+          }
+          umma_commit(b_empty(sb));     // weight stage free once these MMAs have read it
+        }
+        umma_commit(a_empty(sa));       // activation stage free
+      }
+      umma_commit(acc_full);            // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ weight loader ------------------------------------------
+    if (lane == 0) {
+      // w_tc layout: [tap][Cin/4][Cout][4] fp32  (granule-major; one granule row = 16 B)
+      const int cin4 = p.Cin / 4;
+      int it = 0;
+      for (int cb = 0; cb < n_cb; ++cb) {
+        const int ngran = min(KB, p.Cin - cb * KB) / 4;
+        for (int j = 0; j < p.K; ++j, ++it) {
+          const int sb = it % B_STAGES;
+          mbar_wait(b_empty(sb), ((it / B_STAGES) & 1) ^ 1);
+          mbar_expect_tx(b_full(sb), (uint32_t)(ngran * nt * 16));
+          const uint32_t dst = smem_u32(b_tiles + sb * sl.b_stage_bytes);
+          for (int g = 0; g < ngran; ++g) {
+            const float* src = p.w + (((size_t)j * cin4 + (size_t)cb * (KB / 4) + g) * p.Cout + n0) * 4;
+            bulk_g2s(dst + (uint32_t)(g * BN * 16), src, (uint32_t)(nt * 16), b_full(sb));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+}  // namespace tc
+
+// p.w must be in the tensor-core layout [K][Cin/4][Cout][4] (packing.py: to_tc_layout).
+int launch_conv1d_tc(const ConvParams& p, cudaStream_t st) {
+  EV_CHECK_ARG(p.B > 0 && p.L > 0 && p.B <= 65535, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
+  EV_CHECK_ARG(p.Cin % 8 == 0, "conv1d_tc: Cin=%d must be a multiple of 8", p.Cin);
+  EV_CHECK_ARG(p.Cout % 16 == 0, "conv1d_tc: Cout=%d must be a multiple of 16", p.Cout);
+  EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
+  EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
+  // N tile: a single 256-wide tile when C_out == 256 (A staged once); otherwise <= 128 so two CTAs fit per SM
+  int BN = p.Cout <= 128 ? p.Cout : (p.Cout == 256 ? 256 : 128);
+  int tmem_cols = 32;
+  while (tmem_cols < BN) tmem_cols <<= 1;
+  const tc::SmemLayout sl = tc::smem_layout(p.K, p.dil, BN);
+  EV_CHECK_ARG(sl.total <= 227 * 1024, "conv1d_tc: smem %d too large", sl.total);
+  EV_CHECK_ARG(sl.rows_pad * 16 * 8 < (1 << 18), "conv1d_tc: tile too tall");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((p.L + tc::BM - 1) / tc::BM, (p.Cout + BN - 1) / BN, p.B);
+  tc::conv1d_tc_kernel<<<grid, tc::NTHREADS, sl.total, st>>>(p, BN, tmem_cols);
+  EV_CUDA_LAUNCH_CHECK("conv1d_tc_kernel");
+  return EV_OK;
+}
+
+}  // namespace ev

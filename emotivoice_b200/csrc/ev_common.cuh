@@ -56,6 +56,8 @@ struct ConvParams {
   float div;
 };
 int launch_conv1d(const ConvParams& p, cudaStream_t st);
+// tcgen05 (tf32) variant, conv1d_tc.cu; p.w in the tensor-core layout [K][Cin/4][Cout][4]
+int launch_conv1d_tc(const ConvParams& p, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------
 // acoustic-model kernels (am_kernels.cu)

@@ -64,7 +64,7 @@ def _dirty_post_hook(module, incompatible_keys):
 class _Engine:
     """One ev_ctx + its packed weight blob and positional table on one device."""
 
-    def __init__(self, conf, packed, device):
+    def __init__(self, conf, packed, device, precision="fp32"):
         self.lib = _abi.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -80,9 +80,14 @@ class _Engine:
         self.blob = blob.to(self.device)
         _abi.check(self.lib.ev_bind_weights(self.handle, self.blob.data_ptr(), self.blob.numel(),
                                             ctypes.cast(self.index, ctypes.c_void_p), len(self.index)))
+        self.set_precision(precision)
         self.pe = None
         self.ensure_pe(5000)          # PositionalEncoding max_len=5000 (encoder.py:206)
         self.total_up = int(np.prod([self.cfg.up_rates[i] for i in range(self.cfg.n_ups)]))
+
+    def set_precision(self, precision):
+        _abi.check(self.lib.ev_set_precision(self.handle, _abi.PRECISIONS[precision]))
+        self.precision = precision
 
     def ensure_pe(self, n):
         if self.pe is not None and self.pe.shape[0] >= n:
@@ -154,7 +159,24 @@ class _EngineOwner(nn.Module):
         self._ev_engine = None
         self._ev_dirty = True
         self._ev_lock = threading.Lock()
+        self._ev_precision = "fp32"
         self.register_load_state_dict_post_hook(_dirty_post_hook)
+
+    @property
+    def precision(self):
+        """"fp32": fp32 FFMA everywhere (default; bit-level fp32 parity with the CPU reference).
+        "tf32": decoder + vocoder GEMMs/convolutions on the tcgen05 tensor cores (tf32 operands, fp32
+        accumulation) -- what the reference's eager PyTorch does for convolutions on a GPU.  The
+        duration-critical prefix always stays fp32, so durations are identical in both modes."""
+        return self._ev_precision
+
+    @precision.setter
+    def precision(self, value):
+        if value not in _abi.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_abi.PRECISIONS))
+        self._ev_precision = value
+        if self._ev_engine is not None:
+            self._ev_engine.set_precision(value)
 
     def _mark_dirty(self):
         self._ev_dirty = True
@@ -178,7 +200,7 @@ class _EngineOwner(nn.Module):
             return eng
         with self._ev_lock:
             if self._ev_engine is None or self._ev_dirty or self._ev_engine.device != dev:
-                self._ev_engine = _Engine(self.config, self._pack(), dev)
+                self._ev_engine = _Engine(self.config, packing.add_tc_weights(self._pack()), dev, self._ev_precision)
                 self._ev_dirty = False
             return self._ev_engine
 

@@ -43,6 +43,36 @@ def _lin_w(w):           # (out, in) -> (1, in, out)
     return w.t().contiguous().unsqueeze(0)
 
 
+def to_tc_layout(w_kio):
+    """(K, Cin, Cout) -> (K, Cin/4, Cout, 4): the tensor-core kernel's weight layout -- 16-byte
+    K-granules, C_out rows 16 B apart, so one (tap, 32-channel block) is 8 bulk copies that land in
+    shared memory exactly in the no-swizzle K-major UMMA layout (csrc/conv1d_tc.cu)."""
+    if w_kio.dim() == 2:
+        w_kio = w_kio.unsqueeze(0)
+    K, cin, cout = w_kio.shape
+    assert cin % 4 == 0
+    return round_tf32(w_kio.reshape(K, cin // 4, 4, cout).permute(0, 1, 3, 2).contiguous())
+
+
+def round_tf32(w):
+    """Round fp32 to the nearest tf32 (10 explicit mantissa bits, ties away from zero like
+    cvt.rna.tf32.f32) so the tensor core's operand truncation is exact."""
+    bits = w.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def add_tc_weights(packed):
+    """Adds '<name>.tc' copies for every layer the tf32 precision mode runs on tensor cores: the
+    decoder stack, to_mel and all vocoder GEMM-shaped convs (not the duration-critical prefix)."""
+    extra = {}
+    for k, v in packed.items():
+        if (k.startswith("dec.") and k.rsplit(".", 1)[-1] in ("wqkv", "wo", "w1", "w2")) or k == "to_mel.w" \
+                or (k.startswith("voc.") and k.endswith(".w") and k != "voc.post.w"):
+            extra[k + ".tc"] = to_tc_layout(v)
+    packed.update(extra)
+    return packed
+
+
 def fold_weight_norm(sd, prefix):
     """Folded weight of a weight-normed conv, from either key convention
     (parametrizations.weight.original0/1, legacy weight_g/weight_v, or plain weight)."""

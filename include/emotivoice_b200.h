@@ -102,6 +102,14 @@ EV_API int ev_bind_weights(ev_ctx* ctx, const float* blob, size_t n_floats,
  * fp32 on the device, built by the host with the reference's formula. */
 EV_API int ev_bind_pe(ev_ctx* ctx, const float* pe, int pe_len);
 
+/* Arithmetic of the decoder + vocoder GEMMs/convolutions:
+ *   EV_PREC_FP32 (default): fp32 FFMA everywhere (bit-level fp32 parity with the reference's CPU path);
+ *   EV_PREC_TF32: tcgen05 tensor cores, tf32 operands, fp32 accumulation in TMEM -- the arithmetic the
+ *   reference's eager PyTorch uses for convolutions on a GPU (torch.backends.cudnn.allow_tf32 default).
+ * The duration-critical prefix (encoder, conditioning, predictors) is always fp32 FFMA. */
+enum { EV_PREC_FP32 = 0, EV_PREC_TF32 = 1 };
+EV_API int ev_set_precision(ev_ctx* ctx, int precision);
+
 /* Workspace sizes (bytes).  Phase 1 (encoder .. durations) is sized by (B, T); phase 2
  * (length regulator, decoder, to_mel) and the vocoder share one buffer sized by (B, F) --
  * F is only known after the host has read mel_lens_out[B] back. */
@@ -160,6 +168,12 @@ EV_API int ev_op_conv1d(const float* x, const float* w, const float* bias, size_
                         const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
                         const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
                         int acc, float div, void* stream);
+/* Same contract on the tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM); w is in the
+ * tensor-core layout (K, Cin/4, Cout, 4).  Requires Cin % 8 == 0, Cout % 16 == 0. */
+EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, const float* bias, size_t bias_bstride,
+                           const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
+                           const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
+                           int acc, float div, void* stream);
 /* LayerNorm over the last dim, eps 1e-12 (encoder.py:112-127). rows x C. */
 EV_API int ev_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int C, void* stream);
 /* Multi-head self-attention core (encoder.py:84-109) on a packed (B,L,3H) q|k|v buffer. */
