@@ -185,7 +185,7 @@ def reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def dominant_kernel_roofline(lib, dev, frames, peaks, flush):
+def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
     """conv1d_tm_kernel on the single most expensive layer shape of the step: the k=11
     ResBlock convolutions of HiFi-GAN stage 2 (C=128, L=64*F; 22% of all FLOPs).  Timed live
     with CUDA events on the launching stream, L2 flushed before every launch."""
@@ -193,7 +193,12 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush):
     C, K, L = 128, 11, 64 * frames
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1, L, C, generator=g).to(dev)
-    w = (torch.randn(K, C, C, generator=g) / math.sqrt(C * K)).to(dev)
+    w = torch.randn(K, C, C, generator=g) / math.sqrt(C * K)
+    if precision == "tf32":
+        from emotivoice_b200 import packing
+        w = packing.to_tc_layout(w)
+    w = w.to(dev)
+    fn = lib.ev_op_conv1d_tc if precision == "tf32" else lib.ev_op_conv1d
     b = torch.randn(C, generator=g).to(dev)
     res = torch.randn(1, L, C, generator=g).to(dev)
     out = torch.empty(1, L, C, device=dev)
@@ -203,8 +208,8 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush):
         flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _abi.check(lib.ev_op_conv1d(x.data_ptr(), w.data_ptr(), b.data_ptr(), 0, res.data_ptr(), out.data_ptr(), 1, L, C, C,
-                                    K, 1, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, st))
+        _abi.check(fn(x.data_ptr(), w.data_ptr(), b.data_ptr(), 0, res.data_ptr(), out.data_ptr(), 1, L, C, C,
+                      K, 1, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, st))
         e1.record()
         e1.synchronize()
         if i >= 3:
@@ -214,6 +219,17 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush):
     alg_bytes = 4.0 * (L * C * 3) + 4.0 * K * C * C
     achieved = flops / t / 1e12
     ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    if precision == "tf32":
+        return {
+            "kernel": "conv1d_tc_kernel (tcgen05 kind::tf32; HiFi-GAN stage-2 ResBlock conv, C=128, k=11, L=%d)" % L,
+            "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+            "peak_source": "%s bf16 burst (MEASURED_PEAKS.json); tf32 runs at half the bf16 rate, so frac_of_tf32_peak = 2*frac" % peaks["source"],
+            "frac_of_tf32_peak": 2 * achieved / peaks["bf16_tflops"],
+            "flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
+            "avg_launch_ms": t * 1e3, "hbm_gbs_at_algorithmic_bytes": alg_bytes / t / 1e9,
+            "hbm_frac_at_algorithmic_bytes": alg_bytes / t / 1e9 / peaks["hbm_gbs"],
+        }
     return {
         "kernel": "conv1d_tm_kernel<16,2,8> (HiFi-GAN stage-2 ResBlock conv, C=128, k=11, L=%d)" % L,
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
@@ -234,6 +250,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("EV_PRECISION", "fp32"), choices=["fp32", "tf32"])
     args = ap.parse_args()
     if args.impl == "engine":
         args.warmup = max(args.warmup, 3)
@@ -275,6 +292,7 @@ def main():
     model = JETSGenerator(conf).to(dev)
     model.load_state_dict(sd)
     model.eval()
+    model.precision = args.precision
     lib = _abi.load()
 
     batch_cpu = synth.make_batch([N_PHONEMES], seed=synth.SEED)
@@ -352,12 +370,15 @@ def main():
         value = total_frames * args.steps / dev_s
         e2e_val = total_frames * args.steps / e2e_s
         ms_step = dev_s / args.steps * 1e3
-        roof = dominant_kernel_roofline(lib, dev, frames, peaks, flush)
+        roof = dominant_kernel_roofline(lib, dev, frames, peaks, flush, args.precision)
         line = {
             "metric": "mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": frames, "audio_seconds_per_step_per_gpu": audio_s,
+            "vs_baseline": None,
+            "dtype": "fp32" if args.precision == "fp32" else "tf32 (fp32 storage; decoder+vocoder GEMMs on tcgen05 with tf32 operands "
+                                                            "rounded to nearest, fp32 accumulation; duration prefix fp32)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "precision": args.precision, "frames_per_step_per_gpu": frames, "audio_seconds_per_step_per_gpu": audio_s,
                        "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
                        "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks",
                        "weights": "seeded synthetic, 53.3 M params fp32",
