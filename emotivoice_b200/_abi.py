@@ -13,8 +13,8 @@ EV_OK = 0
 EV_EPELEN = -5
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3, 4
 ACC_STORE, ACC_ADD, ACC_ADD_DIV = 0, 1, 2
-PREC_FP32, PREC_TF32 = 0, 1
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+PREC_FP32, PREC_TF32, PREC_FP32_FFMA = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp32_ffma": PREC_FP32_FFMA}
 
 
 class EvConfig(ctypes.Structure):
@@ -57,7 +57,7 @@ SIGNATURES = {
     "ev_wav_to_pcm16": (_i, [_vp, _vp, _sz, _vp]),
     "ev_launch_count": (_u64, []),
     "ev_op_conv1d": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _i, _i, _f, _vp]),
-    "ev_op_conv1d_tc": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _i, _i, _f, _vp]),
+    "ev_op_conv1d_tc": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _i, _i, _f, _vp]),
     "ev_set_precision": (_i, [_vp, _i]),
     "ev_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ev_op_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -17,9 +17,9 @@
 // LeakyReLU prologue, the zero padding at the sequence ends and the layout change while staging,
 // so activations stay plain fp32 time-major in HBM and no tensor map is needed.
 //
-// Roles (192 threads): warps 0-3 stage A (then run the epilogue, one TMEM lane = one output row
-// per thread); warp 4 allocates TMEM and its elected lane issues every tcgen05.mma; warp 5's
-// elected lane streams the weight tiles.  Pipelines: A 2 stages (a_full/a_empty), B 3 stages
+// Roles (320 threads): warps 0-7 stage A (then run the epilogue, one TMEM lane = one output row
+// per thread, two warps per lane quadrant splitting the columns); warp 8 allocates TMEM and its
+// elected lane issues every tcgen05.mma; warp 9's elected lane streams the weight tiles.  Pipelines: A 2 stages (a_full/a_empty), B 3 stages
 // (b_full/b_empty, released by tcgen05.commit), accumulator (acc_full).
 #include "ev_common.cuh"
 
@@ -31,8 +31,10 @@ constexpr int BM = 128;         // rows (time steps) per CTA == TMEM lanes
 constexpr int KB = 32;          // input channels per staged block (8 granules of 4 fp32)
 constexpr int A_STAGES = 2;
 constexpr int B_STAGES = 3;
-constexpr int NTHREADS = 192;
-constexpr int NPRODUCER = 128;
+constexpr int NPRODUCER = 256;                 // warps 0-7 stage A, then run the epilogue
+constexpr int MMA_WARP = NPRODUCER / 32;       // warp 8: TMEM alloc + MMA issue
+constexpr int NTHREADS = NPRODUCER + 64;       // + warp 9: weight loader
+constexpr int A_LD = 6;                        // float4 loads in flight per producer thread (rows_a <= 192)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -105,21 +107,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 struct SmemLayout {
   int rows_pad;        // staged rows per A granule, == 1 (mod 8) -> conflict-free 16 B stores
-  int a_stage_bytes;   // 8 * rows_pad * 16
-  int b_stage_bytes;   // 8 * BN * 16
+  int a_plane_bytes;   // 8 * rows_pad * 16   (one tf32 plane: hi, or lo in 3xTF32 mode)
+  int b_plane_bytes;   // 8 * BN * 16
+  int a_stage_bytes, b_stage_bytes;
   int total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int K, int dil, int BN) {
+__host__ __device__ inline SmemLayout smem_layout(int K, int dil, int BN, int planes) {
   SmemLayout s;
   const int rows = BM + (K - 1) * dil;
   s.rows_pad = ((rows + 7) / 8) * 8 + 1;
-  s.a_stage_bytes = (KB / 4) * s.rows_pad * 16;
-  s.b_stage_bytes = (KB / 4) * BN * 16;
+  s.a_plane_bytes = (KB / 4) * s.rows_pad * 16;
+  s.b_plane_bytes = (KB / 4) * BN * 16;
+  s.a_stage_bytes = planes * s.a_plane_bytes;
+  s.b_stage_bytes = planes * s.b_plane_bytes;
   s.total = 1024 /*barriers + tmem ptr + alignment slack*/ + A_STAGES * s.a_stage_bytes + B_STAGES * s.b_stage_bytes;
   return s;
 }
 
+// SPLIT3 = false: one tf32 MMA per K step (operands rounded to nearest tf32).
+// SPLIT3 = true : "3xTF32" fp32 emulation: x = hi + lo with hi = tf32(x), lo = tf32(x - hi);
+//                 a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the dropped lo*lo term is 2^-22 relative),
+//                 three MMAs per K step into the same fp32 TMEM accumulator.  Weights arrive pre-split
+//                 (two planes, packing.to_tc_layout); activations are split by the producer warps.
+template <bool SPLIT3>
 __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int BN, int tmem_cols) {
+  constexpr int PLANES = SPLIT3 ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -139,7 +151,7 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
     return;
   }
 
-  const SmemLayout sl = smem_layout(p.K, p.dil, BN);
+  const SmemLayout sl = smem_layout(p.K, p.dil, BN, PLANES);
   // carve: [0,128) barriers, [128,132) tmem base; tiles from 1024
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 128);
@@ -158,7 +170,7 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {   // TMEM allocation by one full warp; the same warp frees it
+  if (warp == MMA_WARP) {   // TMEM allocation by one full warp; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -171,44 +183,49 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
   const int halo = ((p.K - 1) / 2) * p.dil;
   const int rows_a = BM + (p.K - 1) * p.dil;
 
-  if (warp < 4) {
+  if (warp < NPRODUCER / 32) {
     // ------------------------------ A producers --------------------------------------------
     const float* __restrict__ xb = p.x + (size_t)b * p.L * p.Cin;
     const bool lrelu = (p.in_act == EV_ACT_LRELU);
     const float slope = p.in_slope;
+    const int total = rows_a * 8;     // (row, granule) pairs; granule fastest -> coalesced 128 B rows
     for (int cb = 0; cb < n_cb; ++cb) {
       const int s = cb % A_STAGES;
-      mbar_wait(a_empty(s), ((cb / A_STAGES) & 1) ^ 1);
       const int c0 = cb * KB;
       const int ngran = min(KB, p.Cin - c0) / 4;
+      // all global loads of this stage are issued before anything else (memory-level parallelism:
+      // at batch 1 the working set is L2 resident and the kernel is latency bound)
+      float4 v[A_LD];
+#pragma unroll
+      for (int u = 0; u < A_LD; ++u) {
+        const int idx = u * NPRODUCER + tid;
+        const int r = idx >> 3, g = idx & 7;
+        const int row = t0 - halo + r;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < total && g < ngran && row >= 0 && row < len)
+          v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.Cin + c0 + g * 4));
+      }
+      mbar_wait(a_empty(s), ((cb / A_STAGES) & 1) ^ 1);
       uint8_t* dst = a_tiles + s * sl.a_stage_bytes;
-      const int total = rows_a * 8;     // (row, granule) pairs; granule fastest -> coalesced 128 B rows
-      for (int base = 0; base < total; base += NPRODUCER * 4) {
-        float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * NPRODUCER + tid;
-          const int r = idx >> 3, g = idx & 7;
-          const int row = t0 - halo + r;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (idx < total && g < ngran && row >= 0 && row < len)
-            v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.Cin + c0 + g * 4));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * NPRODUCER + tid;
-          const int r = idx >> 3, g = idx & 7;
-          if (idx < total && g < ngran) {
-            float4 t = v[u];
-            if (lrelu) {
-              t.x = t.x > 0.f ? t.x : t.x * slope;
-              t.y = t.y > 0.f ? t.y : t.y * slope;
-              t.z = t.z > 0.f ? t.z : t.z * slope;
-              t.w = t.w > 0.f ? t.w : t.w * slope;
-            }
-            // round-to-nearest tf32 here (the MMA would otherwise truncate the low 13 mantissa bits)
-            t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
-            *reinterpret_cast<float4*>(dst + ((size_t)g * sl.rows_pad + r) * 16) = t;
+      for (int u = 0; u < A_LD; ++u) {
+        const int idx = u * NPRODUCER + tid;
+        const int r = idx >> 3, g = idx & 7;
+        if (idx < total && g < ngran) {
+          float4 t = v[u];
+          if (lrelu) {
+            t.x = t.x > 0.f ? t.x : t.x * slope;
+            t.y = t.y > 0.f ? t.y : t.y * slope;
+            t.z = t.z > 0.f ? t.z : t.z * slope;
+            t.w = t.w > 0.f ? t.w : t.w * slope;
+          }
+          // round-to-nearest tf32 (the MMA would otherwise truncate the low 13 mantissa bits)
+          float4 h = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
+          uint8_t* d = dst + ((size_t)g * sl.rows_pad + r) * 16;
+          *reinterpret_cast<float4*>(d) = h;
+          if (SPLIT3) {
+            const float4 l = make_float4(to_tf32(t.x - h.x), to_tf32(t.y - h.y), to_tf32(t.z - h.z), to_tf32(t.w - h.w));
+            *reinterpret_cast<float4*>(d + sl.a_plane_bytes) = l;
           }
         }
       }
@@ -216,38 +233,49 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
       mbar_arrive(a_full(s));
     }
     // ------------------------------ epilogue ----------------------------------------------
+    // warp w owns TMEM lanes 32*(w%4).. (hardware restriction) and every second 16-column chunk.
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = t0 + quad * 32 + lane;
+    const bool row_ok = row < p.L, row_live = row < len;
+    const float* __restrict__ bias = p.bias ? p.bias + (size_t)b * p.bias_bs : nullptr;
+    const float* rrow = (p.res && row_live) ? p.res + ((size_t)b * p.L + row) * p.Cout + n0 : nullptr;
+    float* orow = ob + (size_t)row * p.Cout + n0;
+    const bool acc_rd = (p.acc != EV_ACC_STORE) && row_live;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float4 rq[4], oq[4];
+    auto prefetch = [&](int c) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (rrow) rq[q] = *reinterpret_cast<const float4*>(rrow + c + q * 4);
+        if (acc_rd) oq[q] = *reinterpret_cast<const float4*>(orow + c + q * 4);
+      }
+    };
+    int c = half * 16;
+    if (c < nt) prefetch(c);               // residual / accumulate operands in flight while the MMAs finish
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int row = t0 + warp * 32 + lane;
-    const float* __restrict__ bias = p.bias ? p.bias + (size_t)b * p.bias_bs : nullptr;
-    const float* rb = p.res ? p.res + (size_t)b * p.L * p.Cout : nullptr;
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int c = 0; c < nt; c += 16) {
+    for (; c < nt; c += 32) {
+      float4 rc[4], oc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { rc[q] = rq[q]; oc[q] = oq[q]; }
+      if (c + 32 < nt) prefetch(c + 32);
       float v[16];
       tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane participates
-      if (row < p.L) {
-        float* orow = ob + (size_t)row * p.Cout + n0 + c;
-        if (row < len) {
+      if (row_ok) {
+        if (row_live) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float t = v[i];
             if (bias) t += __ldg(bias + n0 + c + i);
             v[i] = act_apply(t, p.out_act, 0.f);
           }
-          if (rb) {
-            const float* rrow = rb + (size_t)row * p.Cout + n0 + c;
+          if (rrow) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rrow + q * 4);
-              v[q * 4 + 0] += r4.x; v[q * 4 + 1] += r4.y; v[q * 4 + 2] += r4.z; v[q * 4 + 3] += r4.w;
-            }
+            for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += rc[q].x; v[q * 4 + 1] += rc[q].y; v[q * 4 + 2] += rc[q].z; v[q * 4 + 3] += rc[q].w; }
           }
-          if (p.acc != EV_ACC_STORE) {
+          if (acc_rd) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 o4 = *reinterpret_cast<const float4*>(orow + q * 4);
-              v[q * 4 + 0] += o4.x; v[q * 4 + 1] += o4.y; v[q * 4 + 2] += o4.z; v[q * 4 + 3] += o4.w;
-            }
+            for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += oc[q].x; v[q * 4 + 1] += oc[q].y; v[q * 4 + 2] += oc[q].z; v[q * 4 + 3] += oc[q].w; }
             if (p.acc == EV_ACC_ADD_DIV) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] /= p.div;
@@ -259,10 +287,10 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(orow + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          *reinterpret_cast<float4*>(orow + c + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------ MMA issuer ---------------------------------------------
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
@@ -282,9 +310,20 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
           tc_fence_after();
           const uint32_t b_addr = smem_u32(b_tiles + sb * sl.b_stage_bytes);
           for (int k8 = 0; k8 < nk8; ++k8) {
-            const uint64_t ad = make_desc(a_addr + (uint32_t)((2 * k8) * sl.rows_pad + j * p.dil) * 16u, a_lbo, 128u);
-            const uint64_t bd = make_desc(b_addr + (uint32_t)(2 * k8) * b_lbo, b_lbo, 128u);
-            umma_tf32(tmem_base, ad, bd, idesc, (cb | j | k8) != 0 ? 1u : 0u);
+            const uint32_t a_off = (uint32_t)((2 * k8) * sl.rows_pad + j * p.dil) * 16u;
+            const uint32_t b_off = (uint32_t)(2 * k8) * b_lbo;
+            const uint64_t a_hi = make_desc(a_addr + a_off, a_lbo, 128u);
+            const uint64_t b_hi = make_desc(b_addr + b_off, b_lbo, 128u);
+            const uint32_t first = (cb | j | k8) != 0 ? 1u : 0u;
+            if (SPLIT3) {
+              const uint64_t a_lo = make_desc(a_addr + sl.a_plane_bytes + a_off, a_lbo, 128u);
+              const uint64_t b_lo = make_desc(b_addr + sl.b_plane_bytes + b_off, b_lbo, 128u);
+              umma_tf32(tmem_base, a_lo, b_hi, idesc, first);     // small terms first
+              umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
+              umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma_tf32(tmem_base, a_hi, b_hi, idesc, first);
+            }
           }
           umma_commit(b_empty(sb));     // weight stage free once these MMAs have read it
         }
@@ -296,19 +335,21 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
   } else {
     // ------------------------------ weight loader ------------------------------------------
     if (lane == 0) {
-      // w_tc layout: [tap][Cin/4][Cout][4] fp32  (granule-major; one granule row = 16 B)
+      // w_tc layout: [plane (hi, lo)][tap][Cin/4][Cout][4] fp32  (granule-major; one granule row = 16 B)
       const int cin4 = p.Cin / 4;
+      const size_t plane = (size_t)p.K * p.Cin * p.Cout;
       int it = 0;
       for (int cb = 0; cb < n_cb; ++cb) {
         const int ngran = min(KB, p.Cin - cb * KB) / 4;
         for (int j = 0; j < p.K; ++j, ++it) {
           const int sb = it % B_STAGES;
           mbar_wait(b_empty(sb), ((it / B_STAGES) & 1) ^ 1);
-          mbar_expect_tx(b_full(sb), (uint32_t)(ngran * nt * 16));
+          mbar_expect_tx(b_full(sb), (uint32_t)(PLANES * ngran * nt * 16));
           const uint32_t dst = smem_u32(b_tiles + sb * sl.b_stage_bytes);
           for (int g = 0; g < ngran; ++g) {
             const float* src = p.w + (((size_t)j * cin4 + (size_t)cb * (KB / 4) + g) * p.Cout + n0) * 4;
             bulk_g2s(dst + (uint32_t)(g * BN * 16), src, (uint32_t)(nt * 16), b_full(sb));
+            if (SPLIT3) bulk_g2s(dst + (uint32_t)(sl.b_plane_bytes + g * BN * 16), src + plane, (uint32_t)(nt * 16), b_full(sb));
           }
         }
       }
@@ -318,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
@@ -326,27 +367,30 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
 
 }  // namespace tc
 
-// p.w must be in the tensor-core layout [K][Cin/4][Cout][4] (packing.py: to_tc_layout).
-int launch_conv1d_tc(const ConvParams& p, cudaStream_t st) {
+// p.w must be in the tensor-core layout [plane][K][Cin/4][Cout][4] (packing.py: to_tc_layout);
+// split3 selects the 3xTF32 fp32-emulation variant (reads both planes).
+int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
   EV_CHECK_ARG(p.B > 0 && p.L > 0 && p.B <= 65535, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
   EV_CHECK_ARG(p.Cin % 8 == 0, "conv1d_tc: Cin=%d must be a multiple of 8", p.Cin);
   EV_CHECK_ARG(p.Cout % 16 == 0, "conv1d_tc: Cout=%d must be a multiple of 16", p.Cout);
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
   EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
-  // N tile: a single 256-wide tile when C_out == 256 (A staged once); otherwise <= 128 so two CTAs fit per SM
-  int BN = p.Cout <= 128 ? p.Cout : (p.Cout == 256 ? 256 : 128);
+  EV_CHECK_ARG(tc::BM + (p.K - 1) * p.dil <= tc::A_LD * tc::NPRODUCER / 8, "conv1d_tc: receptive field too wide");
+  // N tile: a single 256-wide tile when C_out == 256 in 1x mode (A staged once); otherwise <= 128
+  int BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
   int tmem_cols = 32;
   while (tmem_cols < BN) tmem_cols <<= 1;
-  const tc::SmemLayout sl = tc::smem_layout(p.K, p.dil, BN);
+  const tc::SmemLayout sl = tc::smem_layout(p.K, p.dil, BN, split3 ? 2 : 1);
   EV_CHECK_ARG(sl.total <= 227 * 1024, "conv1d_tc: smem %d too large", sl.total);
-  EV_CHECK_ARG(sl.rows_pad * 16 * 8 < (1 << 18), "conv1d_tc: tile too tall");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc::conv1d_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc::conv1d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   dim3 grid((p.L + tc::BM - 1) / tc::BM, (p.Cout + BN - 1) / BN, p.B);
-  tc::conv1d_tc_kernel<<<grid, tc::NTHREADS, sl.total, st>>>(p, BN, tmem_cols);
+  if (split3) tc::conv1d_tc_kernel<true><<<grid, tc::NTHREADS, sl.total, st>>>(p, BN, tmem_cols);
+  else tc::conv1d_tc_kernel<false><<<grid, tc::NTHREADS, sl.total, st>>>(p, BN, tmem_cols);
   EV_CUDA_LAUNCH_CHECK("conv1d_tc_kernel");
   return EV_OK;
 }

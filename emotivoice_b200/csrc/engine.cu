@@ -41,7 +41,7 @@ struct StackW {
   const float *lnfw, *lnfb;
 };
 struct PredW {
-  std::vector<const float*> w, b, lnw, lnb;
+  std::vector<const float*> w, b, lnw, lnb, w_tc;
   const float *linw, *linb;
 };
 struct ConvW {
@@ -64,7 +64,8 @@ struct ev_ctx {
   bool has_am = false, has_voc = false;
   bool has_tc = false;      // every '.tc' tensor the tf32 path needs is present
   int precision = EV_PREC_FP32;
-  const float* mel_w_tc = nullptr;   // a blob may carry only one half (PromptTTS / Generator used alone)
+  const float* mel_w_tc = nullptr;
+  const float* cond_wx_tc = nullptr;   // a blob may carry only one half (PromptTTS / Generator used alone)
   std::unordered_map<std::string, ev::Tensor> tensors;
   const float* pe = nullptr;
   int pe_len = 0;
@@ -184,10 +185,10 @@ static int resolve_stack(ev_ctx* c, const char* pre, int n_layers, StackW* s) {
     EV_TRY(find(c, q + ".b1", 4 * H, &l.b1));
     EV_TRY(find(c, q + ".w2", K * 4 * H * H, &l.w2));
     EV_TRY(find(c, q + ".b2", H, &l.b2));
-    l.wqkv_tc = find_opt(c, q + ".wqkv.tc", H * 3 * H);
-    l.wo_tc = find_opt(c, q + ".wo.tc", H * H);
-    l.w1_tc = find_opt(c, q + ".w1.tc", K * H * 4 * H);
-    l.w2_tc = find_opt(c, q + ".w2.tc", K * 4 * H * H);
+    l.wqkv_tc = find_opt(c, q + ".wqkv.tc", 2 * H * 3 * H);
+    l.wo_tc = find_opt(c, q + ".wo.tc", 2 * H * H);
+    l.w1_tc = find_opt(c, q + ".w1.tc", 2 * K * H * 4 * H);
+    l.w2_tc = find_opt(c, q + ".w2.tc", 2 * K * 4 * H * H);
   }
   EV_TRY(find(c, p + ".lnf.w", H, &s->lnfw));
   EV_TRY(find(c, p + ".lnf.b", H, &s->lnfb));
@@ -197,10 +198,11 @@ static int resolve_stack(ev_ctx* c, const char* pre, int n_layers, StackW* s) {
 static int resolve_pred(ev_ctx* c, const char* pre, int n_layers, PredW* s) {
   const uint64_t H = c->cfg.hidden, K = c->cfg.pred_kernel;
   std::string p(pre);
-  s->w.resize(n_layers); s->b.resize(n_layers); s->lnw.resize(n_layers); s->lnb.resize(n_layers);
+  s->w.resize(n_layers); s->b.resize(n_layers); s->lnw.resize(n_layers); s->lnb.resize(n_layers); s->w_tc.resize(n_layers);
   for (int i = 0; i < n_layers; ++i) {
     std::string q = p + "." + std::to_string(i);
     EV_TRY(find(c, q + ".w", K * H * H, &s->w[i]));
+    s->w_tc[i] = find_opt(c, q + ".w.tc", 2 * K * H * H);
     EV_TRY(find(c, q + ".b", H, &s->b[i]));
     EV_TRY(find(c, q + ".ln.w", H, &s->lnw[i]));
     EV_TRY(find(c, q + ".ln.b", H, &s->lnb[i]));
@@ -228,6 +230,7 @@ static int resolve_all(ev_ctx* c) {
   EV_TRY(resolve_stack(c, "enc", g.enc_layers, &c->enc));
   EV_TRY(resolve_stack(c, "dec", g.dec_layers, &c->dec));
   EV_TRY(find(c, "cond.wx", H * H, &c->cond_wx));
+  c->cond_wx_tc = find_opt(c, "cond.wx.tc", 2 * H * H);
   EV_TRY(find(c, "cond.wc", (H + 2 * (uint64_t)g.bert_dim) * H, &c->cond_wc));
   EV_TRY(find(c, "cond.b", H, &c->cond_b));
   EV_TRY(resolve_pred(c, "dur", g.dur_layers, &c->dur));
@@ -239,7 +242,7 @@ static int resolve_all(ev_ctx* c) {
   EV_TRY(find(c, "energy_emb.b", H, &c->eemb_b));
   EV_TRY(find(c, "to_mel.w", H * g.n_mels, &c->mel_w));
   EV_TRY(find(c, "to_mel.b", g.n_mels, &c->mel_b));
-  c->mel_w_tc = find_opt(c, "to_mel.w.tc", H * g.n_mels);
+  c->mel_w_tc = find_opt(c, "to_mel.w.tc", 2 * H * g.n_mels);
   return EV_OK;
 }
 
@@ -248,7 +251,7 @@ static int resolve_voc(ev_ctx* c) {
   c->pre.K = 7; c->pre.dil = 1; c->pre.cin = g.n_mels; c->pre.cout = g.voc_c0;
   EV_TRY(find(c, "voc.pre.w", (uint64_t)7 * g.n_mels * g.voc_c0, &c->pre.w));
   EV_TRY(find(c, "voc.pre.b", g.voc_c0, &c->pre.b));
-  c->pre.w_tc = find_opt(c, "voc.pre.w.tc", (uint64_t)7 * g.n_mels * g.voc_c0);
+  c->pre.w_tc = find_opt(c, "voc.pre.w.tc", (uint64_t)2 * 7 * g.n_mels * g.voc_c0);
   c->ups.resize(g.n_ups);
   c->rb_c1.clear(); c->rb_c2.clear();
   int ch = g.voc_c0, mul = 1;
@@ -267,7 +270,7 @@ static int resolve_voc(ev_ctx* c) {
     }
     u.K = (int)(it->second.numel / per_tap);
     u.w = it->second.p;
-    u.w_tc = find_opt(c, q + ".w.tc", it->second.numel);
+    u.w_tc = find_opt(c, q + ".w.tc", 2 * it->second.numel);
     EV_TRY(find(c, q + ".b", u.cout_packed, &u.b));
     ch = u.cout; mul *= u.rate;
     if (mul * ch > c->max_stage_width) c->max_stage_width = mul * ch;
@@ -282,8 +285,8 @@ static int resolve_voc(ev_ctx* c) {
         EV_TRY(find(c, r + ".c1." + std::to_string(l) + ".b", ch, &c1.b));
         EV_TRY(find(c, r + ".c2." + std::to_string(l) + ".w", (uint64_t)k * ch * ch, &c2.w));
         EV_TRY(find(c, r + ".c2." + std::to_string(l) + ".b", ch, &c2.b));
-        c1.w_tc = find_opt(c, r + ".c1." + std::to_string(l) + ".w.tc", (uint64_t)k * ch * ch);
-        c2.w_tc = find_opt(c, r + ".c2." + std::to_string(l) + ".w.tc", (uint64_t)k * ch * ch);
+        c1.w_tc = find_opt(c, r + ".c1." + std::to_string(l) + ".w.tc", (uint64_t)2 * k * ch * ch);
+        c2.w_tc = find_opt(c, r + ".c2." + std::to_string(l) + ".w.tc", (uint64_t)2 * k * ch * ch);
         c->rb_c1.push_back(c1); c->rb_c2.push_back(c2);
       }
   }
@@ -305,38 +308,44 @@ static int conv(const float* x, const float* w, const float* bias, long long bia
   return launch_conv1d(p, st);
 }
 
-// same, on the tensor cores when w_tc != nullptr (tf32 precision mode), else the fp32 FFMA kernel
-static int conv_x(const float* w_tc, const float* x, const float* w, const float* bias, long long bias_bs, const float* res,
-                  float* out, int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens, int lens_mul,
-                  int in_act, float in_slope, int out_act, int acc, float div, cudaStream_t st) {
-  if (!w_tc) return conv(x, w, bias, bias_bs, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul, in_act, in_slope, out_act, acc, div, st);
+// mode 0: fp32 FFMA kernel; 1: tensor cores, one tf32 MMA per K step; 3: tensor cores, 3xTF32 fp32 emulation.
+// Falls back to the FFMA kernel when the layer has no tensor-core weights or an unsupported shape.
+static int conv_x(int mode, const float* w_tc, const float* x, const float* w, const float* bias, long long bias_bs,
+                  const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens,
+                  int lens_mul, int in_act, float in_slope, int out_act, int acc, float div, cudaStream_t st) {
+  if (mode == 0 || !w_tc || (Cin % 8) || (Cout % 16))
+    return conv(x, w, bias, bias_bs, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul, in_act, in_slope, out_act, acc, div, st);
   ConvParams p;
   p.x = x; p.w = w_tc; p.bias = bias; p.res = res; p.out = out; p.bias_bs = bias_bs;
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil;
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope;
   p.out_act = out_act; p.acc = acc; p.div = div;
-  return launch_conv1d_tc(p, st);
+  return launch_conv1d_tc(p, mode == 3, st);
+}
+
+static inline int body_mode(const ev_ctx* c) {
+  return c->precision == EV_PREC_FP32_FFMA ? 0 : (c->precision == EV_PREC_TF32 ? 1 : 3);
 }
 
 // Encoder.forward (encoder.py:316-324) minus the positional prologue (done by the caller of this
 // function): n x [ x += W_o Attn(LN1 x) ; x += Conv2(GELU(Conv1(LN2 x))) ], then after_norm -> y.
 static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float* qkv, float* ctxb, float* h,
-                     int B, int L, const int32_t* key_lens, const int32_t* conv_lens, bool first_ln_done, bool tc,
+                     int B, int L, const int32_t* key_lens, const int32_t* conv_lens, bool first_ln_done, int mode,
                      cudaStream_t st) {
   const int H = c->cfg.hidden, K = c->cfg.ffn_kernel, heads = c->cfg.n_heads;
   for (size_t i = 0; i < s.layers.size(); ++i) {
     const EncLayerW& l = s.layers[i];
     if (!(i == 0 && first_ln_done))
       EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln1w, l.ln1b, y, B * L, L, H, st));
-    EV_TRY(conv_x(tc ? l.wqkv_tc : nullptr, y, l.wqkv, l.bqkv, 0, nullptr, qkv, B, L, H, 3 * H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
+    EV_TRY(conv_x(mode, l.wqkv_tc, y, l.wqkv, l.bqkv, 0, nullptr, qkv, B, L, H, 3 * H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
                   EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
     EV_TRY(launch_attention(qkv, key_lens, ctxb, B, L, H, heads, st));
-    EV_TRY(conv_x(tc ? l.wo_tc : nullptr, ctxb, l.wo, l.bo, 0, x, x, B, L, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
+    EV_TRY(conv_x(mode, l.wo_tc, ctxb, l.wo, l.bo, 0, x, x, B, L, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
                   EV_ACC_STORE, 1.f, st));
     EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln2w, l.ln2b, y, B * L, L, H, st));
-    EV_TRY(conv_x(tc ? l.w1_tc : nullptr, y, l.w1, l.b1, 0, nullptr, h, B, L, H, 4 * H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_GELU,
+    EV_TRY(conv_x(mode, l.w1_tc, y, l.w1, l.b1, 0, nullptr, h, B, L, H, 4 * H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_GELU,
                   EV_ACC_STORE, 1.f, st));
-    EV_TRY(conv_x(tc ? l.w2_tc : nullptr, h, l.w2, l.b2, 0, x, x, B, L, 4 * H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
+    EV_TRY(conv_x(mode, l.w2_tc, h, l.w2, l.b2, 0, x, x, B, L, 4 * H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
                   EV_ACC_STORE, 1.f, st));
   }
   EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, s.lnfw, s.lnfb, y, B * L, L, H, st));
@@ -346,12 +355,12 @@ static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float
 // [conv k -> ReLU -> channel LN] x n -> Linear(H -> 1) (variance.py:36-56, :101-124)
 static int run_predictor(const ev_ctx* c, const PredW& p, const float* in, float* t1, float* t2, int B, int T,
                          const int32_t* lens, const int32_t* conv_lens, int mode, float* out_f, int64_t* out_i,
-                         cudaStream_t st) {
+                         int cmode, cudaStream_t st) {
   const int H = c->cfg.hidden, K = c->cfg.pred_kernel;
   const float* cur = in;
   for (size_t i = 0; i < p.w.size(); ++i) {
-    EV_TRY(conv(cur, p.w[i], p.b[i], 0, nullptr, t1, B, T, H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_RELU,
-                EV_ACC_STORE, 1.f, st));
+    EV_TRY(conv_x(cmode, p.w_tc[i], cur, p.w[i], p.b[i], 0, nullptr, t1, B, T, H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
+                  EV_ACT_RELU, EV_ACC_STORE, 1.f, st));
     EV_TRY(launch_layernorm(t1, nullptr, nullptr, nullptr, nullptr, nullptr, p.lnw[i], p.lnb[i], t2, B * T, T, H, st));
     cur = t2;
   }
@@ -470,26 +479,28 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   EV_TRY(launch_lens_to_i32(lens64, lens32_out, B, T, st));
   const int32_t* lens = lens32_out;
   const int32_t* conv_lens = invariant ? lens : nullptr;
+  // the duration-critical prefix is fp32-accurate in every mode: 3xTF32 on the tensor cores, or FFMA
+  const int prefix_mode = (ctx->precision == EV_PREC_FP32_FFMA) ? 0 : 3;
 
   // encoder: x = word_emb[ids] + alpha*pe (model_open_source.py:107, encoder.py:257-261), fused with LN1 of layer 0
   EV_TRY(launch_layernorm(nullptr, ling, ctx->emb_word, ctx->pe, ctx->enc.alpha, b.x, ctx->enc.layers[0].ln1w,
                           ctx->enc.layers[0].ln1b, b.y, B * T, T, H, st));
-  EV_TRY(run_stack(ctx, ctx->enc, b.x, b.y, b.qkv, b.ctx, b.h, B, T, lens, conv_lens, true, false, st));
+  EV_TRY(run_stack(ctx, ctx->enc, b.x, b.y, b.qkv, b.ctx, b.h, B, T, lens, conv_lens, true, prefix_mode, st));
   // conditioning (model_open_source.py:109-111): per-utterance bias + W_x x
   EV_TRY(launch_cond_gather(spk, ctx->emb_spk, style, content, b.cond_in, B, H, g.bert_dim, st));
   EV_TRY(conv(b.cond_in, ctx->cond_wc, ctx->cond_b, 0, nullptr, b.cond_bias, 1, B, H + 2 * g.bert_dim, H, 1, 1, nullptr,
               1, EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
-  EV_TRY(conv(b.y, ctx->cond_wx, b.cond_bias, H, nullptr, b.hs, B, T, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
-              EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+  EV_TRY(conv_x(prefix_mode, ctx->cond_wx_tc, b.y, ctx->cond_wx, b.cond_bias, H, nullptr, b.hs, B, T, H, H, 1, 1, conv_lens, 1,
+                EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
   // predictors (model_open_source.py:120-121,130)
   const float* pin = b.hs;
   if (!invariant) {   // literal batch: masked_fill on the input only (variance.py:38-39); pads of hs are live data
     EV_TRY(launch_mask_rows(b.hs, lens, b.pm, B, T, H, st));
     pin = b.pm;
   }
-  EV_TRY(run_predictor(ctx, ctx->pitch, pin, b.p1, b.p2, B, T, lens, conv_lens, 0, pitch_out, nullptr, st));
-  EV_TRY(run_predictor(ctx, ctx->energy, pin, b.p1, b.p2, B, T, lens, conv_lens, 0, energy_out, nullptr, st));
-  EV_TRY(run_predictor(ctx, ctx->dur, pin, b.p1, b.p2, B, T, lens, conv_lens, 1, nullptr, dur_out, st));
+  EV_TRY(run_predictor(ctx, ctx->pitch, pin, b.p1, b.p2, B, T, lens, conv_lens, 0, pitch_out, nullptr, prefix_mode, st));
+  EV_TRY(run_predictor(ctx, ctx->energy, pin, b.p1, b.p2, B, T, lens, conv_lens, 0, energy_out, nullptr, prefix_mode, st));
+  EV_TRY(run_predictor(ctx, ctx->dur, pin, b.p1, b.p2, B, T, lens, conv_lens, 1, nullptr, dur_out, prefix_mode, st));
   // x = x + pitch_embed + energy_embed (model_open_source.py:131-134)
   EV_TRY(launch_var_embed_add(b.hs, pitch_out, energy_out, ctx->pemb_w, ctx->pemb_b, ctx->eemb_w, ctx->eemb_b, B, T, H,
                               g.embed_kernel, st));
@@ -518,10 +529,10 @@ int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens,
   // length regulator + the decoder's positional encoding (alignment.py:198-211, encoder.py:257-261)
   EV_TRY(launch_gauss_upsample(b1.hs, b1.centers, lens, mel_lens, B, T, H, F, invariant, ctx->pe, ctx->dec.alpha, b.x, st));
   // decoder (model_open_source.py:146: mask None in the reference; per-item lengths under the invariant contract)
-  const bool tc = (ctx->precision == EV_PREC_TF32);
-  EV_TRY(run_stack(ctx, ctx->dec, b.x, b.y, b.qkv, b.ctx, b.h, B, F, flens, flens, false, tc, st));
+  const int mode = body_mode(ctx);
+  EV_TRY(run_stack(ctx, ctx->dec, b.x, b.y, b.qkv, b.ctx, b.h, B, F, flens, flens, false, mode, st));
   // to_mel (model_open_source.py:147)
-  EV_TRY(conv_x(tc ? ctx->mel_w_tc : nullptr, b.y, ctx->mel_w, ctx->mel_b, 0, nullptr, mel_out, B, F, H, g.n_mels, 1, 1, flens, 1,
+  EV_TRY(conv_x(mode, ctx->mel_w_tc, b.y, ctx->mel_w, ctx->mel_b, 0, nullptr, mel_out, B, F, H, g.n_mels, 1, 1, flens, 1,
                 EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
   return EV_OK;
 }
@@ -544,15 +555,15 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
     m = v.Tm;
   }
   // conv_pre (hifigan/models.py:116)
-  const bool tc = (ctx->precision == EV_PREC_TF32);
-  EV_TRY(conv_x(tc ? ctx->pre.w_tc : nullptr, m, ctx->pre.w, ctx->pre.b, 0, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1,
+  const int mode = body_mode(ctx);
+  EV_TRY(conv_x(mode, ctx->pre.w_tc, m, ctx->pre.w, ctx->pre.b, 0, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1,
                 mel_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
   int L = F, mul = 1;
   size_t rb = 0;
   for (int s = 0; s < g.n_ups; ++s) {
     const UpW& u = ctx->ups[s];
     // x = ups[i](leaky_relu(x, 0.1)) (:118-119): polyphase-packed transposed conv, output viewed (L, rate*Cout)
-    EV_TRY(conv_x(tc ? u.w_tc : nullptr, v.ACC, u.w, u.b, 0, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, mel_lens, mul,
+    EV_TRY(conv_x(mode, u.w_tc, v.ACC, u.w, u.b, 0, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, mel_lens, mul,
                   EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
     L *= u.rate; mul *= u.rate;
     const int C = u.cout;
@@ -562,7 +573,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
         const ConvW& c1 = ctx->rb_c1[rb];
         const ConvW& c2 = ctx->rb_c2[rb];
         // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
-        EV_TRY(conv_x(tc ? c1.w_tc : nullptr, src, c1.w, c1.b, 0, nullptr, v.Tm, B, L, C, C, c1.K, c1.dil, mel_lens, mul,
+        EV_TRY(conv_x(mode, c1.w_tc, src, c1.w, c1.b, 0, nullptr, v.Tm, B, L, C, C, c1.K, c1.dil, mel_lens, mul,
                       EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
         const bool last = (l == g.n_dil - 1);
         float* dst = last ? v.ACC : ((l & 1) ? v.R2 : v.R1);
@@ -570,7 +581,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
         if (last && j > 0) acc = (j == g.n_resk - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;   // xs += ...; x = xs / n (:120-126)
         const float div = (float)g.n_resk;
         if (last && g.n_resk == 1) acc = EV_ACC_STORE;
-        EV_TRY(conv_x(tc ? c2.w_tc : nullptr, v.Tm, c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+        EV_TRY(conv_x(mode, c2.w_tc, v.Tm, c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
                       EV_ACT_NONE, acc, div, st));
         src = dst;
       }
@@ -596,22 +607,27 @@ int ev_op_conv1d(const float* x, const float* w, const float* bias, size_t bias_
               out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int ev_op_conv1d_tc(const float* x, const float* w_tc, const float* bias, size_t bias_bstride, const float* res, float* out,
-                    int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens, int lens_mul, int in_act,
-                    float in_slope, int out_act, int acc, float div, void* stream) {
+int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* bias, size_t bias_bstride, const float* res,
+                    float* out, int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens, int lens_mul,
+                    int in_act, float in_slope, int out_act, int acc, float div, void* stream) {
   EV_CHECK_ARG(x && w_tc && out, "ev_op_conv1d_tc: null argument");
-  return conv_x(w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul, in_act,
-                in_slope, out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
+  EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0, "ev_op_conv1d_tc: needs Cin %% 8 == 0 and Cout %% 16 == 0 (Cin=%d Cout=%d)", Cin, Cout);
+  return conv_x(split3 ? 3 : 1, w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul,
+                in_act, in_slope, out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ev_set_precision(ev_ctx* ctx, int precision) {
   EV_CHECK_ARG(ctx, "ev_set_precision: null context");
-  EV_CHECK_ARG(precision == EV_PREC_FP32 || precision == EV_PREC_TF32, "ev_set_precision: unknown precision %d", precision);
-  if (precision == EV_PREC_TF32 && ctx->bound) {
+  EV_CHECK_ARG(precision == EV_PREC_FP32 || precision == EV_PREC_TF32 || precision == EV_PREC_FP32_FFMA,
+               "ev_set_precision: unknown precision %d", precision);
+  if (precision != EV_PREC_FP32_FFMA && ctx->bound) {
     bool ok = true;
     if (ctx->has_am) {
-      ok = ok && ctx->mel_w_tc;
-      for (const auto& l : ctx->dec.layers) ok = ok && l.wqkv_tc && l.wo_tc && l.w1_tc && l.w2_tc;
+      ok = ok && ctx->mel_w_tc && ctx->cond_wx_tc;
+      for (const auto* st : {&ctx->enc, &ctx->dec})
+        for (const auto& l : st->layers) ok = ok && l.wqkv_tc && l.wo_tc && l.w1_tc && l.w2_tc;
+      for (const auto* pr : {&ctx->dur, &ctx->pitch, &ctx->energy})
+        for (const float* w : pr->w_tc) ok = ok && w;
     }
     if (ctx->has_voc) {
       ok = ok && ctx->pre.w_tc;

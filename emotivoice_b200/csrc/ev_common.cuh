@@ -56,8 +56,9 @@ struct ConvParams {
   float div;
 };
 int launch_conv1d(const ConvParams& p, cudaStream_t st);
-// tcgen05 (tf32) variant, conv1d_tc.cu; p.w in the tensor-core layout [K][Cin/4][Cout][4]
-int launch_conv1d_tc(const ConvParams& p, cudaStream_t st);
+// tcgen05 variant (conv1d_tc.cu); p.w in the tensor-core layout [plane hi|lo][K][Cin/4][Cout][4];
+// split3 = 3xTF32 fp32 emulation (three MMAs per K step), else one tf32 MMA per K step.
+int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------
 // acoustic-model kernels (am_kernels.cu)

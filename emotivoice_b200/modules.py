@@ -164,10 +164,10 @@ class _EngineOwner(nn.Module):
 
     @property
     def precision(self):
-        """"fp32": fp32 FFMA everywhere (default; bit-level fp32 parity with the CPU reference).
-        "tf32": decoder + vocoder GEMMs/convolutions on the tcgen05 tensor cores (tf32 operands, fp32
-        accumulation) -- what the reference's eager PyTorch does for convolutions on a GPU.  The
-        duration-critical prefix always stays fp32, so durations are identical in both modes."""
+        """"fp32" (default): fp32-accurate 3xTF32 on the tcgen05 tensor cores (~1e-6 relative error).
+        "tf32": decoder + vocoder with one tf32 MMA per K step (what the reference's eager PyTorch does for
+        convolutions on a GPU); the duration-critical prefix stays fp32-accurate, so durations are
+        identical in all modes.  "fp32_ffma": plain fp32 FFMA kernels, no tensor cores."""
         return self._ev_precision
 
     @precision.setter

@@ -43,17 +43,6 @@ def _lin_w(w):           # (out, in) -> (1, in, out)
     return w.t().contiguous().unsqueeze(0)
 
 
-def to_tc_layout(w_kio):
-    """(K, Cin, Cout) -> (K, Cin/4, Cout, 4): the tensor-core kernel's weight layout -- 16-byte
-    K-granules, C_out rows 16 B apart, so one (tap, 32-channel block) is 8 bulk copies that land in
-    shared memory exactly in the no-swizzle K-major UMMA layout (csrc/conv1d_tc.cu)."""
-    if w_kio.dim() == 2:
-        w_kio = w_kio.unsqueeze(0)
-    K, cin, cout = w_kio.shape
-    assert cin % 4 == 0
-    return round_tf32(w_kio.reshape(K, cin // 4, 4, cout).permute(0, 1, 3, 2).contiguous())
-
-
 def round_tf32(w):
     """Round fp32 to the nearest tf32 (10 explicit mantissa bits, ties away from zero like
     cvt.rna.tf32.f32) so the tensor core's operand truncation is exact."""
@@ -61,13 +50,35 @@ def round_tf32(w):
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def to_tc_layout(w_kio):
+    """(K, Cin, Cout) -> (2, K, Cin/4, Cout, 4): the tensor-core kernel's weight layout.
+    Granule-major: 16-byte K-granules with the C_out rows 16 B apart, so one (tap, 32-channel block)
+    is 8 bulk copies that land in shared memory exactly in the no-swizzle K-major UMMA layout
+    (csrc/conv1d_tc.cu).  Plane 0 = tf32(w) ("hi"), plane 1 = tf32(w - hi) ("lo", used by the 3xTF32
+    fp32-emulation mode only)."""
+    if w_kio.dim() == 2:
+        w_kio = w_kio.unsqueeze(0)
+    K, cin, cout = w_kio.shape
+    assert cin % 4 == 0
+    g = w_kio.reshape(K, cin // 4, 4, cout).permute(0, 1, 3, 2).contiguous()
+    hi = round_tf32(g)
+    lo = round_tf32(g - hi)
+    return torch.stack([hi, lo]).contiguous()
+
+
+TC_SUFFIXES = ("wqkv", "wo", "w1", "w2")
+
+
 def add_tc_weights(packed):
-    """Adds '<name>.tc' copies for every layer the tf32 precision mode runs on tensor cores: the
-    decoder stack, to_mel and all vocoder GEMM-shaped convs (not the duration-critical prefix)."""
+    """Adds '<name>.tc' copies for every GEMM-shaped layer that runs on the tensor cores: encoder and
+    decoder stacks, conditioning W_x, predictor convs, to_mel and all vocoder convs but conv_post."""
     extra = {}
     for k, v in packed.items():
-        if (k.startswith("dec.") and k.rsplit(".", 1)[-1] in ("wqkv", "wo", "w1", "w2")) or k == "to_mel.w" \
-                or (k.startswith("voc.") and k.endswith(".w") and k != "voc.post.w"):
+        last = k.rsplit(".", 1)[-1]
+        is_stack = (k.startswith("enc.") or k.startswith("dec.")) and last in TC_SUFFIXES
+        is_pred = k.split(".")[0] in ("dur", "pitch", "energy") and k.endswith(".w") and ".lin." not in k and ".ln." not in k
+        is_voc = k.startswith("voc.") and k.endswith(".w") and k != "voc.post.w"
+        if is_stack or is_pred or is_voc or k in ("to_mel.w", "cond.wx"):
             extra[k + ".tc"] = to_tc_layout(v)
     packed.update(extra)
     return packed

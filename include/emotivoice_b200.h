@@ -102,12 +102,15 @@ EV_API int ev_bind_weights(ev_ctx* ctx, const float* blob, size_t n_floats,
  * fp32 on the device, built by the host with the reference's formula. */
 EV_API int ev_bind_pe(ev_ctx* ctx, const float* pe, int pe_len);
 
-/* Arithmetic of the decoder + vocoder GEMMs/convolutions:
- *   EV_PREC_FP32 (default): fp32 FFMA everywhere (bit-level fp32 parity with the reference's CPU path);
- *   EV_PREC_TF32: tcgen05 tensor cores, tf32 operands, fp32 accumulation in TMEM -- the arithmetic the
- *   reference's eager PyTorch uses for convolutions on a GPU (torch.backends.cudnn.allow_tf32 default).
- * The duration-critical prefix (encoder, conditioning, predictors) is always fp32 FFMA. */
-enum { EV_PREC_FP32 = 0, EV_PREC_TF32 = 1 };
+/* Arithmetic of the GEMM-shaped layers (linear / conv / transposed conv):
+ *   EV_PREC_FP32 (default): fp32-accurate on the tcgen05 tensor cores by 3xTF32 splitting (x = hi + lo,
+ *     three tf32 MMAs per K step, fp32 accumulation in TMEM); error ~1e-6 relative, like an fp32 FFMA chain.
+ *   EV_PREC_TF32: decoder + vocoder with ONE tf32 MMA per K step (operands rounded to nearest tf32) -- the
+ *     arithmetic the reference's eager PyTorch uses for convolutions on a GPU (cudnn.allow_tf32 default);
+ *     the duration-critical prefix (encoder, conditioning, predictors) stays 3xTF32.
+ *   EV_PREC_FP32_FFMA: plain fp32 FFMA kernels everywhere (no tensor cores; the round-1 baseline path).
+ * Attention, LayerNorm, softmax, upsampling and the heads are fp32 in every mode. */
+enum { EV_PREC_FP32 = 0, EV_PREC_TF32 = 1, EV_PREC_FP32_FFMA = 2 };
 EV_API int ev_set_precision(ev_ctx* ctx, int precision);
 
 /* Workspace sizes (bytes).  Phase 1 (encoder .. durations) is sized by (B, T); phase 2
@@ -168,9 +171,10 @@ EV_API int ev_op_conv1d(const float* x, const float* w, const float* bias, size_
                         const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
                         const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
                         int acc, float div, void* stream);
-/* Same contract on the tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM); w is in the
- * tensor-core layout (K, Cin/4, Cout, 4).  Requires Cin % 8 == 0, Cout % 16 == 0. */
-EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, const float* bias, size_t bias_bstride,
+/* Same contract on the tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM); w_tc is in the
+ * tensor-core layout (2 planes hi|lo, K, Cin/4, Cout, 4); split3 != 0 selects 3xTF32 fp32 emulation.
+ * Requires Cin % 8 == 0, Cout % 16 == 0. */
+EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* bias, size_t bias_bstride,
                            const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
                            const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
                            int acc, float div, void* stream);

@@ -2,7 +2,9 @@
 against (a) the committed fixtures generated from the unmodified reference and (b) the
 oracle, plus size-independent properties at larger sizes.
 
-Tolerances (fp32 path; north_star: "within a stated fp32 mel/waveform tolerance"):
+The default precision mode "fp32" is 3xTF32 on the tcgen05 tensor cores (fp32-accurate); the
+plain FFMA path ("fp32_ffma") is held to the same bound.
+Tolerances (north_star: "within a stated fp32 mel/waveform tolerance"):
   durations: identical;  mel: max|err| <= 1e-4 * max|mel|;  wav: rms(err) <= 1e-4 * rms(wav).
 The fp32 reference's own distance from an fp64 run of the same algorithm is ~1e-6 / 3e-7
 (SURVEY.md s4 item 5); the kernels sum in a different order, hence the margin."""
@@ -43,6 +45,20 @@ def test_b1_matches_reference_fixture(model, dev, name):
               "log_p_attn", "bin_loss", "z_start_idxs"):
         assert out[k] is None
     assert out["segment_size"] == 32
+
+
+@pytest.mark.parametrize("name", ["b1_t12", "b1_t100"])
+def test_fp32_ffma_mode_matches_reference_fixture(model, dev, name):
+    """The plain fp32 FFMA kernels (no tensor cores), precision="fp32_ffma"."""
+    g = load_golden(name)
+    model.precision = "fp32_ffma"
+    try:
+        out = _run(model, dev, g)
+    finally:
+        model.precision = "fp32"
+    assert torch.equal(out["log_duration_predictions"].cpu(), g["durations"])
+    assert rel_max(out["dec_outputs"].cpu(), g["mel"]) <= MEL_TOL
+    assert rel_rms(out["wav_predictions"].cpu(), g["wav"]) <= WAV_TOL
 
 
 def test_error_vs_fp64_oracle(model, dev, sd, conf):

@@ -1,9 +1,11 @@
-"""tcgen05 (tf32) implicit-GEMM convolution and the tf32 precision mode of the engine.
+"""tcgen05 implicit-GEMM convolution (conv1d_tc.cu) and the precision modes of the engine.
 
-Tolerance: operands are rounded to tf32 (10-bit mantissa, rel 2^-11 = 4.9e-4 per operand), products
-accumulate in fp32 in TMEM -> |err| <= 3e-3 * max|ref| per operator; end to end (32 tensor-core layers
-deep in the vocoder) mel <= 5e-3 * max|mel|, wav rms <= 2e-2 * rms(wav); durations identical (the
-duration-critical prefix never leaves fp32)."""
+Per-operator tolerances against a torch fp32 CPU reference:
+  1xTF32 (operands rounded to nearest tf32, 10-bit mantissa, fp32 accumulation in TMEM): 3e-3 * max|ref|
+  3xTF32 (fp32 emulation: hi/lo split, three MMAs per K step):                          2e-5 * max|ref|
+    -- the same bound the fp32 FFMA kernel is held to (tests/test_ops_gpu.py).
+End to end in "tf32" mode: mel <= 5e-3 * max|mel|, wav rms <= 2e-2 * rms(wav); durations identical in
+every mode (the duration-critical prefix is always fp32-accurate)."""
 import math
 
 import pytest
@@ -14,7 +16,7 @@ from conftest import load_golden, rel_max, rel_rms
 from emotivoice_b200 import _abi, packing
 
 pytestmark = pytest.mark.gpu
-TOL = 3e-3
+TOL = {0: 3e-3, 1: 2e-5}      # split3 -> tolerance
 KEYS = ("inputs_ling", "input_lengths", "inputs_speaker", "inputs_style_embedding", "inputs_content_embedding")
 
 
@@ -22,12 +24,12 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def run_tc(lib, x_tm, w_kio, bias, res, out_init, K, dil, lens, lens_mul, in_act, in_slope, out_act, acc, div, bias_bs=0):
+def run_tc(lib, split3, x_tm, w_kio, bias, res, out_init, K, dil, lens, lens_mul, in_act, in_slope, out_act, acc, div, bias_bs=0):
     B, L, Cin = x_tm.shape
     Cout = w_kio.shape[2]
     w_tc = packing.to_tc_layout(w_kio.cpu()).to(x_tm.device)
     out = out_init.clone() if out_init is not None else torch.full((B, L, Cout), float("nan"), device=x_tm.device)
-    _abi.check(lib.ev_op_conv1d_tc(_ptr(x_tm), _ptr(w_tc), _ptr(bias), bias_bs, _ptr(res), _ptr(out), B, L, Cin, Cout, K, dil,
+    _abi.check(lib.ev_op_conv1d_tc(_ptr(x_tm), _ptr(w_tc), split3, _ptr(bias), bias_bs, _ptr(res), _ptr(out), B, L, Cin, Cout, K, dil,
                                    _ptr(lens), lens_mul, in_act, in_slope, out_act, acc, div,
                                    torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
@@ -52,21 +54,23 @@ TC_CASES = [
 ]
 
 
+@pytest.mark.parametrize("split3", [0, 1])
 @pytest.mark.parametrize("B,L,Cin,Cout,K,dil", TC_CASES)
-def test_conv1d_tc_matches_torch(lib, dev, B, L, Cin, Cout, K, dil):
+def test_conv1d_tc_matches_torch(lib, dev, B, L, Cin, Cout, K, dil, split3):
     g = torch.Generator().manual_seed(B * 1000 + L + Cin + Cout + K)
     x = torch.randn(B, Cin, L, generator=g)
     w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
     b = torch.randn(Cout, generator=g)
     ref = F.conv1d(F.leaky_relu(x, 0.1), w, b, padding=(K - 1) // 2 * dil, dilation=dil).transpose(1, 2)
-    out = run_tc(lib, x.transpose(1, 2).contiguous().to(dev), packing._conv_w(w), b.to(dev), None, None,
+    out = run_tc(lib, split3, x.transpose(1, 2).contiguous().to(dev), packing._conv_w(w), b.to(dev), None, None,
                  K, dil, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0)
     err = rel_max(out.cpu(), ref)
-    print("tc conv", (B, L, Cin, Cout, K, dil), "rel-max err %.2e" % err)
-    assert err <= TOL
+    print("tc conv", (B, L, Cin, Cout, K, dil), "3xTF32" if split3 else "1xTF32", "rel-max err %.2e" % err)
+    assert err <= TOL[split3]
 
 
-def test_conv1d_tc_epilogue_and_ragged(lib, dev):
+@pytest.mark.parametrize("split3", [0, 1])
+def test_conv1d_tc_epilogue_and_ragged(lib, dev, split3):
     g = torch.Generator().manual_seed(21)
     B, L, C, K, dil, mul = 3, 96 * 4, 64, 7, 3, 4
     lens = torch.tensor([96, 17, 50], dtype=torch.int32)
@@ -75,15 +79,15 @@ def test_conv1d_tc_epilogue_and_ragged(lib, dev):
     b = torch.randn(C, generator=g).to(dev)
     res = torch.randn(B, L, C, generator=g).to(dev)
     prev = torch.randn(B, L, C, generator=g).to(dev)
-    out = run_tc(lib, x, w, b, res, prev, K, dil, lens.to(dev), mul, _abi.ACT_LRELU, 0.1, _abi.ACT_GELU, _abi.ACC_ADD_DIV, 3.0)
+    out = run_tc(lib, split3, x, w, b, res, prev, K, dil, lens.to(dev), mul, _abi.ACT_LRELU, 0.1, _abi.ACT_GELU, _abi.ACC_ADD_DIV, 3.0)
     for i in range(B):
         n = int(lens[i]) * mul
         y = F.conv1d(F.leaky_relu(x[i:i + 1, :n].cpu().transpose(1, 2), 0.1), w.permute(2, 1, 0), b.cpu(),
                      padding=(K - 1) // 2 * dil, dilation=dil).transpose(1, 2)
         ref = (prev[i:i + 1, :n].cpu() + (F.gelu(y) + res[i:i + 1, :n].cpu())) / 3.0
-        assert rel_max(out[i:i + 1, :n].cpu(), ref) <= TOL
+        assert rel_max(out[i:i + 1, :n].cpu(), ref) <= TOL[split3]
         assert torch.count_nonzero(out[i, n:]) == 0
-        single = run_tc(lib, x[i:i + 1, :n].contiguous(), w, b, res[i:i + 1, :n].contiguous(), prev[i:i + 1, :n].contiguous(),
+        single = run_tc(lib, split3, x[i:i + 1, :n].contiguous(), w, b, res[i:i + 1, :n].contiguous(), prev[i:i + 1, :n].contiguous(),
                         K, dil, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_GELU, _abi.ACC_ADD_DIV, 3.0)
         assert torch.equal(single[0], out[i, :n])           # batch-invariant, bitwise
 
