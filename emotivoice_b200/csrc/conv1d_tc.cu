@@ -130,7 +130,7 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int dil, int BN, int pl
 //                 three MMAs per K step into the same fp32 TMEM accumulator.  Weights arrive pre-split
 //                 (two planes, packing.to_tc_layout); activations are split by the producer warps.
 template <bool SPLIT3>
-__global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int BN, int tmem_cols) {
+__global__ void __launch_bounds__(NTHREADS, 2) conv1d_tc_kernel(ConvParams p, int BN, int tmem_cols) {
   constexpr int PLANES = SPLIT3 ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x;
@@ -255,10 +255,6 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
     mbar_wait(acc_full, 0);
     tc_fence_after();
     for (; c < nt; c += 32) {
-      float4 rc[4], oc[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { rc[q] = rq[q]; oc[q] = oq[q]; }
-      if (c + 32 < nt) prefetch(c + 32);
       float v[16];
       tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane participates
       if (row_ok) {
@@ -271,11 +267,11 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
           }
           if (rrow) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += rc[q].x; v[q * 4 + 1] += rc[q].y; v[q * 4 + 2] += rc[q].z; v[q * 4 + 3] += rc[q].w; }
+            for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += rq[q].x; v[q * 4 + 1] += rq[q].y; v[q * 4 + 2] += rq[q].z; v[q * 4 + 3] += rq[q].w; }
           }
           if (acc_rd) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += oc[q].x; v[q * 4 + 1] += oc[q].y; v[q * 4 + 2] += oc[q].z; v[q * 4 + 3] += oc[q].w; }
+            for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += oq[q].x; v[q * 4 + 1] += oq[q].y; v[q * 4 + 2] += oq[q].z; v[q * 4 + 3] += oq[q].w; }
             if (p.acc == EV_ACC_ADD_DIV) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] /= p.div;
@@ -285,6 +281,7 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_tc_kernel(ConvParams p, int B
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0.f;
         }
+        if (c + 32 < nt) prefetch(c + 32);   // next chunk's operands fly during these stores and the next TMEM load
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<float4*>(orow + c + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
