@@ -281,6 +281,50 @@ int launch_cond_gather(const int64_t* spk, const float* spk_emb, const float* st
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-utterance conditioning bias  u[b] = W_c^T c[b] + bias  (the utterance-constant 5/6 of
+// embed_projection1, model_open_source.py:110-111).  A skinny GEMV (M = B rows, K = 1920): one CTA
+// per (8 output columns, batch item); the K axis is split over the CTA's threads and reduced in a
+// fixed order (deterministic).  w is (K, N) row-major.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cond_gemv_kernel(const float* __restrict__ c, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out, int K,
+                                                        int N) {
+  __shared__ float red[8][8][33];
+  const int b = blockIdx.y, n0 = blockIdx.x * 8;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const float* cb = c + (size_t)b * K;
+  for (int k = tid; k < K; k += 256) {
+    const float cv = cb[k];
+    const float4 w0 = *reinterpret_cast<const float4*>(w + (size_t)k * N + n0);
+    const float4 w1 = *reinterpret_cast<const float4*>(w + (size_t)k * N + n0 + 4);
+    acc[0] = fmaf(cv, w0.x, acc[0]); acc[1] = fmaf(cv, w0.y, acc[1]); acc[2] = fmaf(cv, w0.z, acc[2]); acc[3] = fmaf(cv, w0.w, acc[3]);
+    acc[4] = fmaf(cv, w1.x, acc[4]); acc[5] = fmaf(cv, w1.y, acc[5]); acc[6] = fmaf(cv, w1.z, acc[6]); acc[7] = fmaf(cv, w1.w, acc[7]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[wid][j][lane] = acc[j];
+  __syncthreads();
+  if (tid < 64) {
+    const int j = tid >> 3, w8 = tid & 7;      // 8 threads per column, each sums one warp's 32 partials
+    float s = 0.f;
+    for (int l = 0; l < 32; ++l) s += red[w8][j][l];
+    s += __shfl_down_sync(0xffffffffu, s, 4, 8);
+    s += __shfl_down_sync(0xffffffffu, s, 2, 8);
+    s += __shfl_down_sync(0xffffffffu, s, 1, 8);
+    if (w8 == 0) out[(size_t)b * N + n0 + j] = s + bias[n0 + j];
+  }
+}
+int launch_cond_gemv(const float* c, const float* w, const float* bias, float* out, int B, int K, int N, cudaStream_t st) {
+  EV_CHECK_ARG(N % 8 == 0 && B > 0 && B <= 65535, "cond_gemv: N=%d B=%d", N, B);
+  dim3 grid(N / 8, B);
+  cond_gemv_kernel<<<grid, 256, 0, st>>>(c, w, bias, out, K, N);
+  EV_CUDA_LAUNCH_CHECK("cond_gemv_kernel");
+  return EV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Predictor head: Linear(C -> 1) + output mask (variance.py:46-56, :119-124).
 // mode 0: float (pitch / energy);  mode 1: duration = clamp(rint(exp(y) - 1), 0) as int64.
 // ---------------------------------------------------------------------------------------------

@@ -27,8 +27,7 @@ namespace ev {
 
 namespace tc {
 
-constexpr int BM = 128;         // rows (time steps) per CTA == TMEM lanes
-constexpr int KB = 32;          // input channels per staged block (8 granules of 4 fp32)
+constexpr int BM = 128;         // rows (time steps) per accumulator == TMEM lanes; a CTA owns MT of them
 constexpr int A_STAGES = 2;
 constexpr int B_STAGES = 3;
 constexpr int NPRODUCER = 256;                 // warps 0-7 stage A, then run the epilogue
@@ -106,18 +105,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 struct SmemLayout {
-  int rows_pad;        // staged rows per A granule, == 1 (mod 8) -> conflict-free 16 B stores
-  int a_plane_bytes;   // 8 * rows_pad * 16   (one tf32 plane: hi, or lo in 3xTF32 mode)
-  int b_plane_bytes;   // 8 * BN * 16
+  int rows_pad;        // staged rows per A granule; == 8/KBG (mod 8) -> conflict-free 16 B stores
+  int a_plane_bytes;   // KBG * rows_pad * 16   (one tf32 plane: hi, or lo in 3xTF32 mode)
+  int b_plane_bytes;   // KBG * BN * 16
   int a_stage_bytes, b_stage_bytes;
   int total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int K, int dil, int BN, int planes) {
+__host__ __device__ inline SmemLayout smem_layout(int K, int dil, int BN, int planes, int mt, int kbg) {
   SmemLayout s;
-  const int rows = BM + (K - 1) * dil;
-  s.rows_pad = ((rows + 7) / 8) * 8 + 1;
-  s.a_plane_bytes = (KB / 4) * s.rows_pad * 16;
-  s.b_plane_bytes = (KB / 4) * BN * 16;
+  const int rows = BM * mt + (K - 1) * dil;
+  s.rows_pad = ((rows + 7) / 8) * 8 + 8 / kbg;
+  s.a_plane_bytes = kbg * s.rows_pad * 16;
+  s.b_plane_bytes = kbg * BN * 16;
   s.a_stage_bytes = planes * s.a_plane_bytes;
   s.b_stage_bytes = planes * s.b_plane_bytes;
   s.total = 1024 /*barriers + tmem ptr + alignment slack*/ + A_STAGES * s.a_stage_bytes + B_STAGES * s.b_stage_bytes;
@@ -129,29 +128,35 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int dil, int BN, int pl
 //                 a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the dropped lo*lo term is 2^-22 relative),
 //                 three MMAs per K step into the same fp32 TMEM accumulator.  Weights arrive pre-split
 //                 (two planes, packing.to_tc_layout); activations are split by the producer warps.
-template <bool SPLIT3>
-__global__ void __launch_bounds__(NTHREADS, 2) conv1d_tc_kernel(ConvParams p, int BN, int tmem_cols) {
+// MT: 128-row accumulators per CTA (TMEM columns MT*BN).  Every weight tile fetched from L2 is used by
+//     MT MMAs, so the weight stream -- the dominant L2->SM traffic of a k-tap conv at 128 rows per
+//     CTA -- shrinks MT-fold; consecutive accumulators share the halo rows of one staged A tile.
+// KBG: 16-byte K granules (4 fp32 channels) per pipeline stage (8 -> 32 channels, 4 -> 16 channels).
+template <bool SPLIT3, int MT, int KBG>
+__global__ void __launch_bounds__(NTHREADS, (MT == 1 ? 2 : 1)) conv1d_tc_kernel(ConvParams p, int BN, int tmem_cols) {
   constexpr int PLANES = SPLIT3 ? 2 : 1;
+  constexpr int KB = 4 * KBG;
+  constexpr int GSH = (KBG == 8 ? 3 : 2);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int b = blockIdx.z;
-  const int t0 = blockIdx.x * BM;
+  const int t0 = blockIdx.x * (BM * MT);
   const int n0 = blockIdx.y * BN;
   const int nt = min(BN, p.Cout - n0);          // this tile's N (multiple of 16)
   const int len = p.lens ? min(p.L, p.lens[b] * p.lens_mul) : p.L;
   float* ob = p.out + (size_t)b * p.L * p.Cout;   // may alias p.res (in-place residual)
 
   if (t0 >= len) {   // whole tile is padding (uniform per CTA): the batch-invariant contract stores zeros
-    for (int i = tid; i < BM * (nt / 4); i += NTHREADS) {
+    for (int i = tid; i < BM * MT * (nt / 4); i += NTHREADS) {
       const int r = i / (nt / 4), c4 = i % (nt / 4);
       if (t0 + r < p.L) *reinterpret_cast<float4*>(ob + (size_t)(t0 + r) * p.Cout + n0 + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     return;
   }
 
-  const SmemLayout sl = smem_layout(p.K, p.dil, BN, PLANES);
+  const SmemLayout sl = smem_layout(p.K, p.dil, BN, PLANES, MT, KBG);
   // carve: [0,128) barriers, [128,132) tmem base; tiles from 1024
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 128);
@@ -181,51 +186,53 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv1d_tc_kernel(ConvParams p, in
 
   const int n_cb = (p.Cin + KB - 1) / KB;
   const int halo = ((p.K - 1) / 2) * p.dil;
-  const int rows_a = BM + (p.K - 1) * p.dil;
+  const int rows_a = BM * MT + (p.K - 1) * p.dil;
 
   if (warp < NPRODUCER / 32) {
     // ------------------------------ A producers --------------------------------------------
     const float* __restrict__ xb = p.x + (size_t)b * p.L * p.Cin;
     const bool lrelu = (p.in_act == EV_ACT_LRELU);
     const float slope = p.in_slope;
-    const int total = rows_a * 8;     // (row, granule) pairs; granule fastest -> coalesced 128 B rows
+    const int total = rows_a * KBG;   // (row, granule) pairs; granule fastest -> coalesced row segments
     for (int cb = 0; cb < n_cb; ++cb) {
       const int s = cb % A_STAGES;
       const int c0 = cb * KB;
       const int ngran = min(KB, p.Cin - c0) / 4;
-      // all global loads of this stage are issued before anything else (memory-level parallelism:
-      // at batch 1 the working set is L2 resident and the kernel is latency bound)
-      float4 v[A_LD];
-#pragma unroll
-      for (int u = 0; u < A_LD; ++u) {
-        const int idx = u * NPRODUCER + tid;
-        const int r = idx >> 3, g = idx & 7;
-        const int row = t0 - halo + r;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < total && g < ngran && row >= 0 && row < len)
-          v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.Cin + c0 + g * 4));
-      }
-      mbar_wait(a_empty(s), ((cb / A_STAGES) & 1) ^ 1);
       uint8_t* dst = a_tiles + s * sl.a_stage_bytes;
+      for (int base = 0; base < total; base += NPRODUCER * A_LD) {
+        // a batch of global loads is issued before anything else (memory-level parallelism: at
+        // batch 1 the working set is L2 resident and the kernel is latency bound)
+        float4 v[A_LD];
 #pragma unroll
-      for (int u = 0; u < A_LD; ++u) {
-        const int idx = u * NPRODUCER + tid;
-        const int r = idx >> 3, g = idx & 7;
-        if (idx < total && g < ngran) {
-          float4 t = v[u];
-          if (lrelu) {
-            t.x = t.x > 0.f ? t.x : t.x * slope;
-            t.y = t.y > 0.f ? t.y : t.y * slope;
-            t.z = t.z > 0.f ? t.z : t.z * slope;
-            t.w = t.w > 0.f ? t.w : t.w * slope;
-          }
-          // round-to-nearest tf32 (the MMA would otherwise truncate the low 13 mantissa bits)
-          float4 h = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
-          uint8_t* d = dst + ((size_t)g * sl.rows_pad + r) * 16;
-          *reinterpret_cast<float4*>(d) = h;
-          if (SPLIT3) {
-            const float4 l = make_float4(to_tf32(t.x - h.x), to_tf32(t.y - h.y), to_tf32(t.z - h.z), to_tf32(t.w - h.w));
-            *reinterpret_cast<float4*>(d + sl.a_plane_bytes) = l;
+        for (int u = 0; u < A_LD; ++u) {
+          const int idx = base + u * NPRODUCER + tid;
+          const int r = idx >> GSH, g = idx & (KBG - 1);
+          const int row = t0 - halo + r;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < total && g < ngran && row >= 0 && row < len)
+            v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.Cin + c0 + g * 4));
+        }
+        if (base == 0) mbar_wait(a_empty(s), ((cb / A_STAGES) & 1) ^ 1);
+#pragma unroll
+        for (int u = 0; u < A_LD; ++u) {
+          const int idx = base + u * NPRODUCER + tid;
+          const int r = idx >> GSH, g = idx & (KBG - 1);
+          if (idx < total && g < ngran) {
+            float4 t = v[u];
+            if (lrelu) {
+              t.x = t.x > 0.f ? t.x : t.x * slope;
+              t.y = t.y > 0.f ? t.y : t.y * slope;
+              t.z = t.z > 0.f ? t.z : t.z * slope;
+              t.w = t.w > 0.f ? t.w : t.w * slope;
+            }
+            // round-to-nearest tf32 (the MMA would otherwise truncate the low 13 mantissa bits)
+            float4 h = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
+            uint8_t* d = dst + ((size_t)g * sl.rows_pad + r) * 16;
+            *reinterpret_cast<float4*>(d) = h;
+            if (SPLIT3) {
+              const float4 l = make_float4(to_tf32(t.x - h.x), to_tf32(t.y - h.y), to_tf32(t.z - h.z), to_tf32(t.w - h.w));
+              *reinterpret_cast<float4*>(d + sl.a_plane_bytes) = l;
+            }
           }
         }
       }
@@ -235,56 +242,63 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv1d_tc_kernel(ConvParams p, in
     // ------------------------------ epilogue ----------------------------------------------
     // warp w owns TMEM lanes 32*(w%4).. (hardware restriction) and every second 16-column chunk.
     const int quad = warp & 3, half = warp >> 2;
-    const int row = t0 + quad * 32 + lane;
-    const bool row_ok = row < p.L, row_live = row < len;
     const float* __restrict__ bias = p.bias ? p.bias + (size_t)b * p.bias_bs : nullptr;
-    const float* rrow = (p.res && row_live) ? p.res + ((size_t)b * p.L + row) * p.Cout + n0 : nullptr;
-    float* orow = ob + (size_t)row * p.Cout + n0;
-    const bool acc_rd = (p.acc != EV_ACC_STORE) && row_live;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float4 rq[4], oq[4];
-    auto prefetch = [&](int c) {
+    bool waited = false;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row = t0 + mt * BM + quad * 32 + lane;
+      const bool row_ok = row < p.L, row_live = row < len;
+      const float* rrow = (p.res && row_live) ? p.res + ((size_t)b * p.L + row) * p.Cout + n0 : nullptr;
+      float* orow = ob + (size_t)row * p.Cout + n0;
+      const bool acc_rd = (p.acc != EV_ACC_STORE) && row_live;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * BN);
+      float4 rq[4], oq[4];
+      auto prefetch = [&](int c) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (rrow) rq[q] = *reinterpret_cast<const float4*>(rrow + c + q * 4);
-        if (acc_rd) oq[q] = *reinterpret_cast<const float4*>(orow + c + q * 4);
-      }
-    };
-    int c = half * 16;
-    if (c < nt) prefetch(c);               // residual / accumulate operands in flight while the MMAs finish
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    for (; c < nt; c += 32) {
-      float v[16];
-      tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane participates
-      if (row_ok) {
-        if (row_live) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float t = v[i];
-            if (bias) t += __ldg(bias + n0 + c + i);
-            v[i] = act_apply(t, p.out_act, 0.f);
-          }
-          if (rrow) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += rq[q].x; v[q * 4 + 1] += rq[q].y; v[q * 4 + 2] += rq[q].z; v[q * 4 + 3] += rq[q].w; }
-          }
-          if (acc_rd) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += oq[q].x; v[q * 4 + 1] += oq[q].y; v[q * 4 + 2] += oq[q].z; v[q * 4 + 3] += oq[q].w; }
-            if (p.acc == EV_ACC_ADD_DIV) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] /= p.div;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        for (int q = 0; q < 4; ++q) {
+          if (rrow) rq[q] = *reinterpret_cast<const float4*>(rrow + c + q * 4);
+          if (acc_rd) oq[q] = *reinterpret_cast<const float4*>(orow + c + q * 4);
         }
-        if (c + 32 < nt) prefetch(c + 32);   // next chunk's operands fly during these stores and the next TMEM load
+      };
+      int c = half * 16;
+      if (c < nt) prefetch(c);               // residual / accumulate operands in flight while the MMAs finish
+      if (!waited) {
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        waited = true;
+      }
+      for (; c < nt; c += 32) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane participates
+        if (row_ok) {
+          if (row_live) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(orow + c + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            for (int i = 0; i < 16; ++i) {
+              float t = v[i];
+              if (bias) t += __ldg(bias + n0 + c + i);
+              v[i] = act_apply(t, p.out_act, 0.f);
+            }
+            if (rrow) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += rq[q].x; v[q * 4 + 1] += rq[q].y; v[q * 4 + 2] += rq[q].z; v[q * 4 + 3] += rq[q].w; }
+            }
+            if (acc_rd) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += oq[q].x; v[q * 4 + 1] += oq[q].y; v[q * 4 + 2] += oq[q].z; v[q * 4 + 3] += oq[q].w; }
+              if (p.acc == EV_ACC_ADD_DIV) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] /= p.div;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
+          if (c + 32 < nt) prefetch(c + 32);   // next chunk's operands fly during these stores and the next TMEM load
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(orow + c + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -307,19 +321,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv1d_tc_kernel(ConvParams p, in
           tc_fence_after();
           const uint32_t b_addr = smem_u32(b_tiles + sb * sl.b_stage_bytes);
           for (int k8 = 0; k8 < nk8; ++k8) {
-            const uint32_t a_off = (uint32_t)((2 * k8) * sl.rows_pad + j * p.dil) * 16u;
             const uint32_t b_off = (uint32_t)(2 * k8) * b_lbo;
-            const uint64_t a_hi = make_desc(a_addr + a_off, a_lbo, 128u);
             const uint64_t b_hi = make_desc(b_addr + b_off, b_lbo, 128u);
+            const uint64_t b_lo = make_desc(b_addr + sl.b_plane_bytes + b_off, b_lbo, 128u);
             const uint32_t first = (cb | j | k8) != 0 ? 1u : 0u;
-            if (SPLIT3) {
-              const uint64_t a_lo = make_desc(a_addr + sl.a_plane_bytes + a_off, a_lbo, 128u);
-              const uint64_t b_lo = make_desc(b_addr + sl.b_plane_bytes + b_off, b_lbo, 128u);
-              umma_tf32(tmem_base, a_lo, b_hi, idesc, first);     // small terms first
-              umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
-              umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
-            } else {
-              umma_tf32(tmem_base, a_hi, b_hi, idesc, first);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
+              const uint32_t a_off = (uint32_t)((2 * k8) * sl.rows_pad + mt * BM + j * p.dil) * 16u;
+              const uint64_t a_hi = make_desc(a_addr + a_off, a_lbo, 128u);
+              const uint32_t d = tmem_base + (uint32_t)(mt * BN);
+              if (SPLIT3) {
+                const uint64_t a_lo = make_desc(a_addr + sl.a_plane_bytes + a_off, a_lbo, 128u);
+                umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
+                umma_tf32(d, a_hi, b_lo, idesc, 1u);
+                umma_tf32(d, a_hi, b_hi, idesc, 1u);
+              } else {
+                umma_tf32(d, a_hi, b_hi, idesc, first);
+              }
             }
           }
           umma_commit(b_empty(sb));     // weight stage free once these MMAs have read it
@@ -344,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv1d_tc_kernel(ConvParams p, in
           mbar_expect_tx(b_full(sb), (uint32_t)(PLANES * ngran * nt * 16));
           const uint32_t dst = smem_u32(b_tiles + sb * sl.b_stage_bytes);
           for (int g = 0; g < ngran; ++g) {
-            const float* src = p.w + (((size_t)j * cin4 + (size_t)cb * (KB / 4) + g) * p.Cout + n0) * 4;
+            const float* src = p.w + (((size_t)j * cin4 + (size_t)cb * KBG + g) * p.Cout + n0) * 4;
             bulk_g2s(dst + (uint32_t)(g * BN * 16), src, (uint32_t)(nt * 16), b_full(sb));
             if (SPLIT3) bulk_g2s(dst + (uint32_t)(sl.b_plane_bytes + g * BN * 16), src + plane, (uint32_t)(nt * 16), b_full(sb));
           }
@@ -364,6 +382,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv1d_tc_kernel(ConvParams p, in
 
 }  // namespace tc
 
+template <bool SPLIT3, int MT, int KBG>
+static int launch_tc_variant(const ConvParams& p, int BN, cudaStream_t st) {
+  int tmem_cols = 32;
+  while (tmem_cols < MT * BN) tmem_cols <<= 1;
+  const tc::SmemLayout sl = tc::smem_layout(p.K, p.dil, BN, SPLIT3 ? 2 : 1, MT, KBG);
+  EV_CHECK_ARG(sl.total <= 227 * 1024 && tmem_cols <= 512, "conv1d_tc: tile does not fit (smem %d, tmem %d)", sl.total, tmem_cols);
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc::conv1d_tc_kernel<SPLIT3, MT, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((p.L + tc::BM * MT - 1) / (tc::BM * MT), (p.Cout + BN - 1) / BN, p.B);
+  tc::conv1d_tc_kernel<SPLIT3, MT, KBG><<<grid, tc::NTHREADS, sl.total, st>>>(p, BN, tmem_cols);
+  EV_CUDA_LAUNCH_CHECK("conv1d_tc_kernel");
+  return EV_OK;
+}
+
 // p.w must be in the tensor-core layout [plane][K][Cin/4][Cout][4] (packing.py: to_tc_layout);
 // split3 selects the 3xTF32 fp32-emulation variant (reads both planes).
 int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
@@ -372,24 +407,21 @@ int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
   EV_CHECK_ARG(p.Cout % 16 == 0, "conv1d_tc: Cout=%d must be a multiple of 16", p.Cout);
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
   EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
-  EV_CHECK_ARG(tc::BM + (p.K - 1) * p.dil <= tc::A_LD * tc::NPRODUCER / 8, "conv1d_tc: receptive field too wide");
   // N tile: a single 256-wide tile when C_out == 256 in 1x mode (A staged once); otherwise <= 128
-  int BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
-  int tmem_cols = 32;
-  while (tmem_cols < BN) tmem_cols <<= 1;
-  const tc::SmemLayout sl = tc::smem_layout(p.K, p.dil, BN, split3 ? 2 : 1);
-  EV_CHECK_ARG(sl.total <= 227 * 1024, "conv1d_tc: smem %d too large", sl.total);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(tc::conv1d_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc::conv1d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
+  const int BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
+  // rows per CTA: as many 128-row accumulators as keep ~one CTA per SM busy (weight traffic / MT)
+  const long long tiles = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
+  int mt = tiles >= 4 * 120 ? 4 : (tiles >= 2 * 120 ? 2 : 1);
+  const int planes = split3 ? 2 : 1, kbg = split3 ? 4 : 8;
+  while (mt > 1 && (mt * BN > 512 || tc::smem_layout(p.K, p.dil, BN, planes, mt, kbg).total > 227 * 1024)) mt >>= 1;
+  if (split3) {
+    if (mt == 4) return launch_tc_variant<true, 4, 4>(p, BN, st);
+    if (mt == 2) return launch_tc_variant<true, 2, 4>(p, BN, st);
+    return launch_tc_variant<true, 1, 4>(p, BN, st);
   }
-  dim3 grid((p.L + tc::BM - 1) / tc::BM, (p.Cout + BN - 1) / BN, p.B);
-  if (split3) tc::conv1d_tc_kernel<true><<<grid, tc::NTHREADS, sl.total, st>>>(p, BN, tmem_cols);
-  else tc::conv1d_tc_kernel<false><<<grid, tc::NTHREADS, sl.total, st>>>(p, BN, tmem_cols);
-  EV_CUDA_LAUNCH_CHECK("conv1d_tc_kernel");
-  return EV_OK;
+  if (mt == 4) return launch_tc_variant<false, 4, 8>(p, BN, st);
+  if (mt == 2) return launch_tc_variant<false, 2, 8>(p, BN, st);
+  return launch_tc_variant<false, 1, 8>(p, BN, st);
 }
 
 }  // namespace ev

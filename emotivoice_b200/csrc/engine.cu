@@ -488,8 +488,7 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   EV_TRY(run_stack(ctx, ctx->enc, b.x, b.y, b.qkv, b.ctx, b.h, B, T, lens, conv_lens, true, prefix_mode, st));
   // conditioning (model_open_source.py:109-111): per-utterance bias + W_x x
   EV_TRY(launch_cond_gather(spk, ctx->emb_spk, style, content, b.cond_in, B, H, g.bert_dim, st));
-  EV_TRY(conv(b.cond_in, ctx->cond_wc, ctx->cond_b, 0, nullptr, b.cond_bias, 1, B, H + 2 * g.bert_dim, H, 1, 1, nullptr,
-              1, EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+  EV_TRY(launch_cond_gemv(b.cond_in, ctx->cond_wc, ctx->cond_b, b.cond_bias, B, H + 2 * g.bert_dim, H, st));
   EV_TRY(conv_x(prefix_mode, ctx->cond_wx_tc, b.y, ctx->cond_wx, b.cond_bias, H, nullptr, b.hs, B, T, H, H, 1, 1, conv_lens, 1,
                 EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
   // predictors (model_open_source.py:120-121,130)

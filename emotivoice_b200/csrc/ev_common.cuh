@@ -71,6 +71,7 @@ int launch_attention(const float* qkv, const int32_t* key_lens, float* ctx, int 
                      cudaStream_t st);
 int launch_cond_gather(const int64_t* spk, const float* spk_emb, const float* style, const float* content,
                        float* out, int B, int H, int bert, cudaStream_t st);
+int launch_cond_gemv(const float* c, const float* w, const float* bias, float* out, int B, int K, int N, cudaStream_t st);
 // y[row] = dot(x[row,:], w) + b ; masked rows (t >= lens[b]) -> 0.  mode 0: float out; mode 1: duration int64
 int launch_rowdot(const float* x, const float* w, const float* b, const int32_t* lens, int B, int T, int C,
                   int mode, float* out_f, int64_t* out_i, cudaStream_t st);
