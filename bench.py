@@ -185,6 +185,24 @@ def reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def parity_vs_reference_fixture(out):
+    """The bench workload is the committed fixture tests/golden/b1_t100.npz (inputs + outputs of the
+    UNMODIFIED reference, oracle/make_golden.py): report the engine's distance from it."""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "b1_t100.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    mel, wav, dur = torch.from_numpy(z["mel"]), torch.from_numpy(z["wav"]), torch.from_numpy(z["durations"])
+    m, w = out["dec_outputs"].cpu(), out["wav_predictions"].cpu()
+    ok = bool(torch.equal(out["log_duration_predictions"].cpu(), dur))
+    res = {"reference": "tests/golden/b1_t100.npz (unmodified reference, CPU fp32)", "durations_identical": ok}
+    if ok and m.shape == mel.shape:
+        res["mel_max_abs_err_over_max_abs"] = float((m - mel).abs().max() / mel.abs().max())
+        res["wav_rms_err_over_rms"] = float((w - wav).double().pow(2).mean().sqrt() / wav.double().pow(2).mean().sqrt())
+    return res
+
+
 def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
     """conv1d_tm_kernel on the single most expensive layer shape of the step: the k=11
     ResBlock convolutions of HiFi-GAN stage 2 (C=128, L=64*F; 22% of all FLOPs).  Timed live
@@ -324,6 +342,7 @@ def main():
     for _ in range(args.warmup):
         out = model(**batch_dev)
     torch.cuda.synchronize()
+    parity = parity_vs_reference_fixture(out) if rank == 0 else None
     frames = int(out["dec_outputs"].shape[1])
     n_samples = int(out["wav_predictions"].shape[-1])
     wav_pin = torch.empty((1, 1, n_samples), dtype=torch.float32).pin_memory()
@@ -402,6 +421,7 @@ def main():
                     "d2h_bytes_per_step": n_samples * 4, "ms_per_step": e2e_s / args.steps * 1e3,
                     "x_realtime": audio_s / (e2e_s / args.steps)},
             "gpu_launches": int(launches),
+            "parity": parity,
             "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:
