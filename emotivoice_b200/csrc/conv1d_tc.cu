@@ -1,39 +1,44 @@
 // Time-major 1-D convolution as an implicit GEMM on the 5th-gen tensor cores (sm_100a):
 // tcgen05.mma (kind::tf32, fp32 accumulate in TMEM), operands staged in shared memory, weights
-// streamed by bulk async copies (cp.async.bulk -> mbarrier complete_tx), accumulator read back
-// with tcgen05.ld for the fused epilogue.  Same contract as conv1d_tm.cu (see ev_common.cuh):
+// streamed by bulk async copies (cp.async.bulk -> mbarrier complete_tx), accumulators read back
+// with tcgen05.ld by dedicated epilogue warps.  Same contract as conv1d_tm.cu (see ev_common.cuh):
 //
 //   out[b,t,co] = epi( bias[co] + sum_j sum_ci w[j][ci][co] * act_in( x[b, t + (j-(K-1)/2)*dil, ci] ) )
 //
-// GEMM view: M = 128 time steps per CTA, N = C_out tile (<= 256), K = taps x C_in.
+// GEMM view: M = time (128 rows per accumulator, MT accumulators per tile), N = C_out tile (<= 256),
+// K = taps x C_in.
 //
-// The trick that makes a dilated k-tap convolution cost ONE activation fetch per tile: the A
-// operand lives in shared memory in the *no-swizzle K-major* UMMA layout with the 8-row-group
-// stride (SBO) set to 128 B, i.e. element (row r, 16-byte K-granule g) sits at
-//        A + (g * rows_pad + r) * 16 bytes
-// so consecutive rows are exactly 16 B apart for the whole tile, and tap j of the convolution is
-// the same tile with the descriptor start address advanced by j*dil rows (16 B granularity).
-// One staged tile of BM + (K-1)*dil rows feeds all K taps.  The producer warps apply the
-// LeakyReLU prologue, the zero padding at the sequence ends and the layout change while staging,
-// so activations stay plain fp32 time-major in HBM and no tensor map is needed.
+// * ONE activation fetch per tile for all k taps: the A operand lives in shared memory in the
+//   no-swizzle K-major UMMA layout with the 8-row-group stride (SBO) set to 128 B, i.e. element
+//   (row r, 16-byte K-granule g) sits at  A + (g * rows_pad + r) * 16 bytes.  Consecutive rows are
+//   16 B apart for the whole tile, so tap j of a dilated convolution is the same staged tile with the
+//   descriptor start address advanced by j*dil rows, and accumulator mt by 128*mt rows.  The producer
+//   warps apply the LeakyReLU prologue, the zero padding at the sequence ends, the tf32 rounding /
+//   hi-lo split and the layout change while staging, so activations stay plain fp32 time-major in HBM
+//   and no tensor map is needed.
+// * One weight tile from L2 feeds MT accumulators (MT x fewer weight bytes per output row).
+// * Persistent CTAs (one per SM) loop over tiles; the accumulators are double buffered in TMEM so
+//   the epilogue of tile i (TMEM -> registers -> swizzled smem -> fully coalesced 128-byte global
+//   rows, residual/accumulate operands prefetched) overlaps the main loop of tile i+1.
 //
-// Roles (320 threads): warps 0-7 stage A (then run the epilogue, one TMEM lane = one output row
-// per thread, two warps per lane quadrant splitting the columns); warp 8 allocates TMEM and its
-// elected lane issues every tcgen05.mma; warp 9's elected lane streams the weight tiles.  Pipelines: A 2 stages (a_full/a_empty), B 3 stages
-// (b_full/b_empty, released by tcgen05.commit), accumulator (acc_full).
+// Roles (448 threads): warps 0-3 epilogue (warp w <-> TMEM lanes 32w..32w+31), warps 4-11 stage A,
+// warp 12 allocates TMEM and its elected lane issues every tcgen05.mma, warp 13's elected lane
+// streams the weight tiles.  mbarrier pipelines: A ring (a_full/a_empty), B ring (b_full/b_empty,
+// released by tcgen05.commit), accumulators (acc_full/acc_empty).
 #include "ev_common.cuh"
 
 namespace ev {
 
 namespace tc {
 
-constexpr int BM = 128;         // rows (time steps) per accumulator == TMEM lanes; a CTA owns MT of them
-constexpr int A_STAGES = 2;
-constexpr int B_STAGES = 3;
-constexpr int NPRODUCER = 256;                 // warps 0-7 stage A, then run the epilogue
-constexpr int MMA_WARP = NPRODUCER / 32;       // warp 8: TMEM alloc + MMA issue
-constexpr int NTHREADS = NPRODUCER + 64;       // + warp 9: weight loader
-constexpr int A_LD = 6;                        // float4 loads in flight per producer thread (rows_a <= 192)
+constexpr int BM = 128;              // rows (time steps) per accumulator == TMEM lanes
+constexpr int NEPI = 128;            // warps 0-3
+constexpr int NPRODUCER = 256;       // warps 4-11
+constexpr int MMA_WARP = (NEPI + NPRODUCER) / 32;      // warp 12
+constexpr int NTHREADS = NEPI + NPRODUCER + 64;        // + warp 13: weight loader
+constexpr int A_LD = 8;              // float4 loads in flight per producer thread and batch
+constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
+constexpr int STAGING_BYTES = 4 * 32 * 32 * 4;         // per epilogue warp: 32 rows x 32 columns fp32
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -104,23 +109,57 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-struct SmemLayout {
-  int rows_pad;        // staged rows per A granule; == 8/KBG (mod 8) -> conflict-free 16 B stores
-  int a_plane_bytes;   // KBG * rows_pad * 16   (one tf32 plane: hi, or lo in 3xTF32 mode)
-  int b_plane_bytes;   // KBG * BN * 16
-  int a_stage_bytes, b_stage_bytes;
-  int total;
+struct Plan {
+  int BN, mt, kbg, planes;
+  int rows_pad;        // staged rows per A granule; == 8/kbg (mod 8) -> conflict-free 16 B stores
+  int a_plane_bytes, b_plane_bytes, a_stage_bytes, b_stage_bytes;
+  int a_stages, b_stages;
+  int tmem_cols;
+  int tiles_m, tiles_n, total_tiles;
+  int smem_total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int K, int dil, int BN, int planes, int mt, int kbg) {
-  SmemLayout s;
-  const int rows = BM * mt + (K - 1) * dil;
-  s.rows_pad = ((rows + 7) / 8) * 8 + 8 / kbg;
-  s.a_plane_bytes = kbg * s.rows_pad * 16;
-  s.b_plane_bytes = kbg * BN * 16;
-  s.a_stage_bytes = planes * s.a_plane_bytes;
-  s.b_stage_bytes = planes * s.b_plane_bytes;
-  s.total = 1024 /*barriers + tmem ptr + alignment slack*/ + A_STAGES * s.a_stage_bytes + B_STAGES * s.b_stage_bytes;
-  return s;
+
+// smem map: [0,256) barriers | [256,260) tmem base | 1024: epilogue staging | A ring | B ring
+__host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int mt, Plan* o) {
+  Plan q;
+  q.planes = split3 ? 2 : 1;
+  q.kbg = split3 ? 4 : 8;
+  q.mt = mt;
+  q.BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
+  if (2 * mt * q.BN > 512) return false;
+  q.tmem_cols = 32;
+  while (q.tmem_cols < 2 * mt * q.BN) q.tmem_cols <<= 1;
+  const int rows = BM * mt + (p.K - 1) * p.dil;
+  q.rows_pad = ((rows + 7) / 8) * 8 + 8 / q.kbg;
+  q.a_plane_bytes = q.kbg * q.rows_pad * 16;
+  q.b_plane_bytes = q.kbg * q.BN * 16;
+  q.a_stage_bytes = q.planes * q.a_plane_bytes;
+  q.b_stage_bytes = q.planes * q.b_plane_bytes;
+  const int budget = 227 * 1024 - 1024 - STAGING_BYTES;
+  const int n_cb = (p.Cin + 4 * q.kbg - 1) / (4 * q.kbg);
+  // at least 2 + 2 stages; then grow the weight ring first (it turns over K times per A stage)
+  if (2 * q.a_stage_bytes + 2 * q.b_stage_bytes > budget) return false;
+  q.a_stages = 2;
+  q.b_stages = 2;
+  while (q.b_stages < MAX_B_STAGES && q.b_stages < n_cb * p.K &&
+         q.a_stages * q.a_stage_bytes + (q.b_stages + 1) * q.b_stage_bytes <= budget && q.b_stages < 4) ++q.b_stages;
+  while (q.a_stages < MAX_A_STAGES && q.a_stages < n_cb &&
+         (q.a_stages + 1) * q.a_stage_bytes + q.b_stages * q.b_stage_bytes <= budget && q.a_stages < 3) ++q.a_stages;
+  while (q.b_stages < MAX_B_STAGES && q.b_stages < n_cb * p.K &&
+         q.a_stages * q.a_stage_bytes + (q.b_stages + 1) * q.b_stage_bytes <= budget) ++q.b_stages;
+  while (q.a_stages < MAX_A_STAGES && q.a_stages < n_cb &&
+         (q.a_stages + 1) * q.a_stage_bytes + q.b_stages * q.b_stage_bytes <= budget) ++q.a_stages;
+  q.tiles_m = (p.L + BM * mt - 1) / (BM * mt);
+  q.tiles_n = (p.Cout + q.BN - 1) / q.BN;
+  q.total_tiles = p.B * q.tiles_m * q.tiles_n;
+  q.smem_total = 1024 + STAGING_BYTES + q.a_stages * q.a_stage_bytes + q.b_stages * q.b_stage_bytes;
+  *o = q;
+  return true;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int cw, float* v) {
+  tmem_ld16(taddr, v);
+  if (cw > 16) tmem_ld16(taddr + 16u, v + 16);
 }
 
 // SPLIT3 = false: one tf32 MMA per K step (operands rounded to nearest tf32).
@@ -128,55 +167,40 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int dil, int BN, int pl
 //                 a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the dropped lo*lo term is 2^-22 relative),
 //                 three MMAs per K step into the same fp32 TMEM accumulator.  Weights arrive pre-split
 //                 (two planes, packing.to_tc_layout); activations are split by the producer warps.
-// MT: 128-row accumulators per CTA (TMEM columns MT*BN).  Every weight tile fetched from L2 is used by
-//     MT MMAs, so the weight stream -- the dominant L2->SM traffic of a k-tap conv at 128 rows per
-//     CTA -- shrinks MT-fold; consecutive accumulators share the halo rows of one staged A tile.
-// KBG: 16-byte K granules (4 fp32 channels) per pipeline stage (8 -> 32 channels, 4 -> 16 channels).
-template <bool SPLIT3, int MT, int KBG>
-__global__ void __launch_bounds__(NTHREADS, (MT == 1 ? 2 : 1)) conv1d_tc_kernel(ConvParams p, int BN, int tmem_cols) {
+// MT: 128-row accumulators per tile.  KBG = (SPLIT3 ? 4 : 8) 16-byte K granules per pipeline stage.
+template <bool SPLIT3, int MT>
+__global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Plan pl) {
   constexpr int PLANES = SPLIT3 ? 2 : 1;
+  constexpr int KBG = SPLIT3 ? 4 : 8;
   constexpr int KB = 4 * KBG;
   constexpr int GSH = (KBG == 8 ? 3 : 2);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int b = blockIdx.z;
-  const int t0 = blockIdx.x * (BM * MT);
-  const int n0 = blockIdx.y * BN;
-  const int nt = min(BN, p.Cout - n0);          // this tile's N (multiple of 16)
-  const int len = p.lens ? min(p.L, p.lens[b] * p.lens_mul) : p.L;
-  float* ob = p.out + (size_t)b * p.L * p.Cout;   // may alias p.res (in-place residual)
+  const int BN = pl.BN;
 
-  if (t0 >= len) {   // whole tile is padding (uniform per CTA): the batch-invariant contract stores zeros
-    for (int i = tid; i < BM * MT * (nt / 4); i += NTHREADS) {
-      const int r = i / (nt / 4), c4 = i % (nt / 4);
-      if (t0 + r < p.L) *reinterpret_cast<float4*>(ob + (size_t)(t0 + r) * p.Cout + n0 + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    return;
-  }
-
-  const SmemLayout sl = smem_layout(p.K, p.dil, BN, PLANES, MT, KBG);
-  // carve: [0,128) barriers, [128,132) tmem base; tiles from 1024
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 128);
-  uint8_t* a_tiles = smem_raw + 1024;
-  uint8_t* b_tiles = a_tiles + A_STAGES * sl.a_stage_bytes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 256);
+  uint8_t* staging = smem_raw + 1024;
+  uint8_t* a_tiles = staging + STAGING_BYTES;
+  uint8_t* b_tiles = a_tiles + pl.a_stages * pl.a_stage_bytes;
   const uint32_t bar_base = smem_u32(bars);
   auto a_full = [&](int s) { return bar_base + 8u * s; };
-  auto a_empty = [&](int s) { return bar_base + 8u * (A_STAGES + s); };
-  auto b_full = [&](int s) { return bar_base + 8u * (2 * A_STAGES + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (2 * A_STAGES + B_STAGES + s); };
-  const uint32_t acc_full = bar_base + 8u * (2 * A_STAGES + 2 * B_STAGES);
+  auto a_empty = [&](int s) { return bar_base + 8u * (MAX_A_STAGES + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * MAX_A_STAGES + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * MAX_A_STAGES + MAX_B_STAGES + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (2 * MAX_A_STAGES + 2 * MAX_B_STAGES + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 2 + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(a_full(s), NPRODUCER); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < B_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < pl.a_stages; ++s) { mbar_init(a_full(s), NPRODUCER); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < pl.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), NEPI / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {   // TMEM allocation by one full warp; the same warp frees it
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pl.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -187,184 +211,243 @@ __global__ void __launch_bounds__(NTHREADS, (MT == 1 ? 2 : 1)) conv1d_tc_kernel(
   const int n_cb = (p.Cin + KB - 1) / KB;
   const int halo = ((p.K - 1) / 2) * p.dil;
   const int rows_a = BM * MT + (p.K - 1) * p.dil;
+  const int tiles_per_b = pl.tiles_m * pl.tiles_n;
 
-  if (warp < NPRODUCER / 32) {
-    // ------------------------------ A producers --------------------------------------------
-    const float* __restrict__ xb = p.x + (size_t)b * p.L * p.Cin;
+  // tile -> (b, t0, n0, nt, len); every role walks the same sequence
+  auto decode = [&](int tile, int& b, int& t0, int& n0, int& nt, int& len) {
+    b = tile / tiles_per_b;
+    const int r = tile - b * tiles_per_b;
+    const int tm = r / pl.tiles_n, tn = r - tm * pl.tiles_n;
+    t0 = tm * (BM * MT);
+    n0 = tn * BN;
+    nt = min(BN, p.Cout - n0);
+    len = p.lens ? min(p.L, p.lens[b] * p.lens_mul) : p.L;
+  };
+
+  if (warp < NEPI / 32) {
+    // ============================ epilogue warps ==============================================
+    const int quad = warp;
+    float* stg = reinterpret_cast<float*>(staging + quad * (32 * 32 * 4));
+    const int rr = lane >> 3, cq = lane & 7;      // coalesced phase: 4 rows x 8 float4 per instruction
+    int tile_cnt = 0;
+    for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+      int b, t0, n0, nt, len;
+      decode(tile, b, t0, n0, nt, len);
+      float* ob = p.out + (size_t)b * p.L * p.Cout;            // may alias p.res (in-place residual)
+      const float* rb = p.res ? p.res + (size_t)b * p.L * p.Cout : nullptr;
+      if (t0 >= len) {   // padding tile: the batch-invariant contract stores zeros (no MMA work was issued)
+        for (int mt = 0; mt < MT; ++mt)
+          for (int c = 0; c < nt; c += 32)
+            for (int it = 0; it < 8; ++it) {
+              const int row = t0 + mt * BM + quad * 32 + it * 4 + rr;
+              if (row < p.L && c + cq * 4 < nt)
+                *reinterpret_cast<float4*>(ob + (size_t)row * p.Cout + n0 + c + cq * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        continue;
+      }
+      const int buf = tile_cnt & 1;
+      const float* __restrict__ bias = p.bias ? p.bias + (size_t)b * p.bias_bs + n0 : nullptr;
+      bool waited = false;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row_base = t0 + mt * BM + quad * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * MT * BN + mt * BN);
+#pragma unroll 1
+        for (int c = 0; c < nt; c += 32) {
+          const int cw = min(32, nt - c);
+          const bool col_ok = cq * 4 < cw;
+          // residual / accumulate operands: coalesced loads issued before waiting on the accumulator
+          float4 rq[8], oq[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = row_base + it * 4 + rr;
+            const size_t off = (size_t)row * p.Cout + n0 + c + cq * 4;
+            rq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            oq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && row < len) {
+              if (rb) rq[it] = *reinterpret_cast<const float4*>(rb + off);
+              if (p.acc != EV_ACC_STORE) oq[it] = *reinterpret_cast<const float4*>(ob + off);
+            }
+          }
+          if (!waited) {
+            mbar_wait(acc_full(buf), (tile_cnt >> 1) & 1);
+            tc_fence_after();
+            waited = true;
+          }
+          float v[32];
+          tmem_ld32(taddr + (uint32_t)c, cw, v);      // thread = row (TMEM lane), 32 consecutive columns
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = v[i];
+            if (bias && i < cw) t += __ldg(bias + c + i);
+            v[i] = act_apply(t, p.out_act, 0.f);
+          }
+          // registers -> smem, 16-byte chunks XOR-swizzled by the row so both phases are conflict free
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rr;
+            const int row = row_base + r;
+            float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq ^ (r & 7)) << 2));
+            if (row < len) {
+              o.x += rq[it].x; o.y += rq[it].y; o.z += rq[it].z; o.w += rq[it].w;
+              if (p.acc != EV_ACC_STORE) {
+                o.x += oq[it].x; o.y += oq[it].y; o.z += oq[it].z; o.w += oq[it].w;
+                if (p.acc == EV_ACC_ADD_DIV) { o.x /= p.div; o.y /= p.div; o.z /= p.div; o.w /= p.div; }
+              }
+            } else {
+              o = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (col_ok && row < p.L) *reinterpret_cast<float4*>(ob + (size_t)row * p.Cout + n0 + c + cq * 4) = o;
+          }
+          __syncwarp();
+        }
+      }
+      // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld16): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+      ++tile_cnt;
+    }
+  } else if (warp < MMA_WARP) {
+    // ============================ A producers ===================================================
+    const int ptid = tid - NEPI;
     const bool lrelu = (p.in_act == EV_ACT_LRELU);
     const float slope = p.in_slope;
     const int total = rows_a * KBG;   // (row, granule) pairs; granule fastest -> coalesced row segments
-    for (int cb = 0; cb < n_cb; ++cb) {
-      const int s = cb % A_STAGES;
-      const int c0 = cb * KB;
-      const int ngran = min(KB, p.Cin - c0) / 4;
-      uint8_t* dst = a_tiles + s * sl.a_stage_bytes;
-      for (int base = 0; base < total; base += NPRODUCER * A_LD) {
-        // a batch of global loads is issued before anything else (memory-level parallelism: at
-        // batch 1 the working set is L2 resident and the kernel is latency bound)
-        float4 v[A_LD];
+    int a_cnt = 0;
+    for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+      int b, t0, n0, nt, len;
+      decode(tile, b, t0, n0, nt, len);
+      if (t0 >= len) continue;
+      const float* __restrict__ xb = p.x + (size_t)b * p.L * p.Cin;
+      for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
+        const int s = a_cnt % pl.a_stages;
+        const int c0 = cb * KB;
+        const int ngran = min(KB, p.Cin - c0) / 4;
+        uint8_t* dst = a_tiles + s * pl.a_stage_bytes;
+        for (int base = 0; base < total; base += NPRODUCER * A_LD) {
+          // a batch of global loads is issued before anything else (memory-level parallelism)
+          float4 v[A_LD];
 #pragma unroll
-        for (int u = 0; u < A_LD; ++u) {
-          const int idx = base + u * NPRODUCER + tid;
-          const int r = idx >> GSH, g = idx & (KBG - 1);
-          const int row = t0 - halo + r;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (idx < total && g < ngran && row >= 0 && row < len)
-            v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.Cin + c0 + g * 4));
-        }
-        if (base == 0) mbar_wait(a_empty(s), ((cb / A_STAGES) & 1) ^ 1);
-#pragma unroll
-        for (int u = 0; u < A_LD; ++u) {
-          const int idx = base + u * NPRODUCER + tid;
-          const int r = idx >> GSH, g = idx & (KBG - 1);
-          if (idx < total && g < ngran) {
-            float4 t = v[u];
-            if (lrelu) {
-              t.x = t.x > 0.f ? t.x : t.x * slope;
-              t.y = t.y > 0.f ? t.y : t.y * slope;
-              t.z = t.z > 0.f ? t.z : t.z * slope;
-              t.w = t.w > 0.f ? t.w : t.w * slope;
-            }
-            // round-to-nearest tf32 (the MMA would otherwise truncate the low 13 mantissa bits)
-            float4 h = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
-            uint8_t* d = dst + ((size_t)g * sl.rows_pad + r) * 16;
-            *reinterpret_cast<float4*>(d) = h;
-            if (SPLIT3) {
-              const float4 l = make_float4(to_tf32(t.x - h.x), to_tf32(t.y - h.y), to_tf32(t.z - h.z), to_tf32(t.w - h.w));
-              *reinterpret_cast<float4*>(d + sl.a_plane_bytes) = l;
-            }
+          for (int u = 0; u < A_LD; ++u) {
+            const int idx = base + u * NPRODUCER + ptid;
+            const int r = idx >> GSH, g = idx & (KBG - 1);
+            const int row = t0 - halo + r;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < total && g < ngran && row >= 0 && row < len)
+              v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.Cin + c0 + g * 4));
           }
-        }
-      }
-      fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(a_full(s));
-    }
-    // ------------------------------ epilogue ----------------------------------------------
-    // warp w owns TMEM lanes 32*(w%4).. (hardware restriction) and every second 16-column chunk.
-    const int quad = warp & 3, half = warp >> 2;
-    const float* __restrict__ bias = p.bias ? p.bias + (size_t)b * p.bias_bs : nullptr;
-    bool waited = false;
-#pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      const int row = t0 + mt * BM + quad * 32 + lane;
-      const bool row_ok = row < p.L, row_live = row < len;
-      const float* rrow = (p.res && row_live) ? p.res + ((size_t)b * p.L + row) * p.Cout + n0 : nullptr;
-      float* orow = ob + (size_t)row * p.Cout + n0;
-      const bool acc_rd = (p.acc != EV_ACC_STORE) && row_live;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * BN);
-      float4 rq[4], oq[4];
-      auto prefetch = [&](int c) {
+          if (base == 0) mbar_wait(a_empty(s), ((a_cnt / pl.a_stages) & 1) ^ 1);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (rrow) rq[q] = *reinterpret_cast<const float4*>(rrow + c + q * 4);
-          if (acc_rd) oq[q] = *reinterpret_cast<const float4*>(orow + c + q * 4);
-        }
-      };
-      int c = half * 16;
-      if (c < nt) prefetch(c);               // residual / accumulate operands in flight while the MMAs finish
-      if (!waited) {
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        waited = true;
-      }
-      for (; c < nt; c += 32) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c, v);     // warp-collective: every lane participates
-        if (row_ok) {
-          if (row_live) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float t = v[i];
-              if (bias) t += __ldg(bias + n0 + c + i);
-              v[i] = act_apply(t, p.out_act, 0.f);
-            }
-            if (rrow) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += rq[q].x; v[q * 4 + 1] += rq[q].y; v[q * 4 + 2] += rq[q].z; v[q * 4 + 3] += rq[q].w; }
-            }
-            if (acc_rd) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { v[q * 4 + 0] += oq[q].x; v[q * 4 + 1] += oq[q].y; v[q * 4 + 2] += oq[q].z; v[q * 4 + 3] += oq[q].w; }
-              if (p.acc == EV_ACC_ADD_DIV) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] /= p.div;
+          for (int u = 0; u < A_LD; ++u) {
+            const int idx = base + u * NPRODUCER + ptid;
+            const int r = idx >> GSH, g = idx & (KBG - 1);
+            if (idx < total && g < ngran) {
+              float4 t = v[u];
+              if (lrelu) {
+                t.x = t.x > 0.f ? t.x : t.x * slope;
+                t.y = t.y > 0.f ? t.y : t.y * slope;
+                t.z = t.z > 0.f ? t.z : t.z * slope;
+                t.w = t.w > 0.f ? t.w : t.w * slope;
+              }
+              // round-to-nearest tf32 (the MMA would otherwise truncate the low 13 mantissa bits)
+              const float4 h = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
+              uint8_t* d = dst + ((size_t)g * pl.rows_pad + r) * 16;
+              *reinterpret_cast<float4*>(d) = h;
+              if (SPLIT3) {
+                const float4 l = make_float4(to_tf32(t.x - h.x), to_tf32(t.y - h.y), to_tf32(t.z - h.z), to_tf32(t.w - h.w));
+                *reinterpret_cast<float4*>(d + pl.a_plane_bytes) = l;
               }
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
           }
-          if (c + 32 < nt) prefetch(c + 32);   // next chunk's operands fly during these stores and the next TMEM load
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(orow + c + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
+        fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(a_full(s));
       }
     }
   } else if (warp == MMA_WARP) {
-    // ------------------------------ MMA issuer ---------------------------------------------
+    // ============================ MMA issuer =====================================================
     if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
-      // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t a_lbo = (uint32_t)sl.rows_pad * 16u, b_lbo = (uint32_t)BN * 16u;
-      int it = 0;
-      for (int cb = 0; cb < n_cb; ++cb) {
-        const int sa = cb % A_STAGES;
-        const int nk8 = min(KB, p.Cin - cb * KB) / 8;
-        mbar_wait(a_full(sa), (cb / A_STAGES) & 1);
+      const uint32_t a_lbo = (uint32_t)pl.rows_pad * 16u, b_lbo = (uint32_t)BN * 16u;
+      int a_cnt = 0, b_cnt = 0, tile_cnt = 0;
+      for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+        int b, t0, n0, nt, len;
+        decode(tile, b, t0, n0, nt, len);
+        if (t0 >= len) continue;
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+        // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const int buf = tile_cnt & 1;
+        mbar_wait(acc_empty(buf), ((tile_cnt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(a_tiles + sa * sl.a_stage_bytes);
-        for (int j = 0; j < p.K; ++j, ++it) {
-          const int sb = it % B_STAGES;
-          mbar_wait(b_full(sb), (it / B_STAGES) & 1);
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * MT * BN);
+        for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
+          const int sa = a_cnt % pl.a_stages;
+          const int nk8 = min(KB, p.Cin - cb * KB) / 8;
+          mbar_wait(a_full(sa), (a_cnt / pl.a_stages) & 1);
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(b_tiles + sb * sl.b_stage_bytes);
-          for (int k8 = 0; k8 < nk8; ++k8) {
-            const uint32_t b_off = (uint32_t)(2 * k8) * b_lbo;
-            const uint64_t b_hi = make_desc(b_addr + b_off, b_lbo, 128u);
-            const uint64_t b_lo = make_desc(b_addr + sl.b_plane_bytes + b_off, b_lbo, 128u);
-            const uint32_t first = (cb | j | k8) != 0 ? 1u : 0u;
+          const uint32_t a_addr = smem_u32(a_tiles + sa * pl.a_stage_bytes);
+          for (int j = 0; j < p.K; ++j, ++b_cnt) {
+            const int sb = b_cnt % pl.b_stages;
+            mbar_wait(b_full(sb), (b_cnt / pl.b_stages) & 1);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(b_tiles + sb * pl.b_stage_bytes);
+            for (int k8 = 0; k8 < nk8; ++k8) {
+              const uint32_t b_off = (uint32_t)(2 * k8) * b_lbo;
+              const uint64_t b_hi = make_desc(b_addr + b_off, b_lbo, 128u);
+              const uint64_t b_lo = make_desc(b_addr + pl.b_plane_bytes + b_off, b_lbo, 128u);
+              const uint32_t first = (cb | j | k8) != 0 ? 1u : 0u;
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
-              const uint32_t a_off = (uint32_t)((2 * k8) * sl.rows_pad + mt * BM + j * p.dil) * 16u;
-              const uint64_t a_hi = make_desc(a_addr + a_off, a_lbo, 128u);
-              const uint32_t d = tmem_base + (uint32_t)(mt * BN);
-              if (SPLIT3) {
-                const uint64_t a_lo = make_desc(a_addr + sl.a_plane_bytes + a_off, a_lbo, 128u);
-                umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
-                umma_tf32(d, a_hi, b_lo, idesc, 1u);
-                umma_tf32(d, a_hi, b_hi, idesc, 1u);
-              } else {
-                umma_tf32(d, a_hi, b_hi, idesc, first);
+              for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
+                const uint32_t a_off = (uint32_t)((2 * k8) * pl.rows_pad + mt * BM + j * p.dil) * 16u;
+                const uint64_t a_hi = make_desc(a_addr + a_off, a_lbo, 128u);
+                const uint32_t d = d_base + (uint32_t)(mt * BN);
+                if (SPLIT3) {
+                  const uint64_t a_lo = make_desc(a_addr + pl.a_plane_bytes + a_off, a_lbo, 128u);
+                  umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
+                  umma_tf32(d, a_hi, b_lo, idesc, 1u);
+                  umma_tf32(d, a_hi, b_hi, idesc, 1u);
+                } else {
+                  umma_tf32(d, a_hi, b_hi, idesc, first);
+                }
               }
             }
+            umma_commit(b_empty(sb));     // weight stage free once these MMAs have read it
           }
-          umma_commit(b_empty(sb));     // weight stage free once these MMAs have read it
+          umma_commit(a_empty(sa));       // activation stage free
         }
-        umma_commit(a_empty(sa));       // activation stage free
+        umma_commit(acc_full(buf));       // accumulators of this tile complete -> epilogue
+        ++tile_cnt;
       }
-      umma_commit(acc_full);            // accumulator complete -> epilogue
     }
     __syncwarp();
   } else {
-    // ------------------------------ weight loader ------------------------------------------
+    // ============================ weight loader ==================================================
     if (lane == 0) {
       // w_tc layout: [plane (hi, lo)][tap][Cin/4][Cout][4] fp32  (granule-major; one granule row = 16 B)
       const int cin4 = p.Cin / 4;
       const size_t plane = (size_t)p.K * p.Cin * p.Cout;
-      int it = 0;
-      for (int cb = 0; cb < n_cb; ++cb) {
-        const int ngran = min(KB, p.Cin - cb * KB) / 4;
-        for (int j = 0; j < p.K; ++j, ++it) {
-          const int sb = it % B_STAGES;
-          mbar_wait(b_empty(sb), ((it / B_STAGES) & 1) ^ 1);
-          mbar_expect_tx(b_full(sb), (uint32_t)(PLANES * ngran * nt * 16));
-          const uint32_t dst = smem_u32(b_tiles + sb * sl.b_stage_bytes);
-          for (int g = 0; g < ngran; ++g) {
-            const float* src = p.w + (((size_t)j * cin4 + (size_t)cb * KBG + g) * p.Cout + n0) * 4;
-            bulk_g2s(dst + (uint32_t)(g * BN * 16), src, (uint32_t)(nt * 16), b_full(sb));
-            if (SPLIT3) bulk_g2s(dst + (uint32_t)(sl.b_plane_bytes + g * BN * 16), src + plane, (uint32_t)(nt * 16), b_full(sb));
+      int b_cnt = 0;
+      for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+        int b, t0, n0, nt, len;
+        decode(tile, b, t0, n0, nt, len);
+        if (t0 >= len) continue;
+        for (int cb = 0; cb < n_cb; ++cb) {
+          const int ngran = min(KB, p.Cin - cb * KB) / 4;
+          for (int j = 0; j < p.K; ++j, ++b_cnt) {
+            const int sb = b_cnt % pl.b_stages;
+            mbar_wait(b_empty(sb), ((b_cnt / pl.b_stages) & 1) ^ 1);
+            mbar_expect_tx(b_full(sb), (uint32_t)(PLANES * ngran * nt * 16));
+            const uint32_t dst = smem_u32(b_tiles + sb * pl.b_stage_bytes);
+            for (int g = 0; g < ngran; ++g) {
+              const float* src = p.w + (((size_t)j * cin4 + (size_t)cb * KBG + g) * p.Cout + n0) * 4;
+              bulk_g2s(dst + (uint32_t)(g * BN * 16), src, (uint32_t)(nt * 16), b_full(sb));
+              if (SPLIT3) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane, (uint32_t)(nt * 16), b_full(sb));
+            }
           }
         }
       }
@@ -376,25 +459,32 @@ __global__ void __launch_bounds__(NTHREADS, (MT == 1 ? 2 : 1)) conv1d_tc_kernel(
   __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols));
   }
 }
 
 }  // namespace tc
 
-template <bool SPLIT3, int MT, int KBG>
-static int launch_tc_variant(const ConvParams& p, int BN, cudaStream_t st) {
-  int tmem_cols = 32;
-  while (tmem_cols < MT * BN) tmem_cols <<= 1;
-  const tc::SmemLayout sl = tc::smem_layout(p.K, p.dil, BN, SPLIT3 ? 2 : 1, MT, KBG);
-  EV_CHECK_ARG(sl.total <= 227 * 1024 && tmem_cols <= 512, "conv1d_tc: tile does not fit (smem %d, tmem %d)", sl.total, tmem_cols);
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool SPLIT3, int MT>
+static int launch_tc_variant(const ConvParams& p, const tc::Plan& pl, cudaStream_t st) {
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(tc::conv1d_tc_kernel<SPLIT3, MT, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc::conv1d_tc_kernel<SPLIT3, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  dim3 grid((p.L + tc::BM * MT - 1) / (tc::BM * MT), (p.Cout + BN - 1) / BN, p.B);
-  tc::conv1d_tc_kernel<SPLIT3, MT, KBG><<<grid, tc::NTHREADS, sl.total, st>>>(p, BN, tmem_cols);
+  const int grid = pl.total_tiles < sm_count() ? pl.total_tiles : sm_count();
+  tc::conv1d_tc_kernel<SPLIT3, MT><<<grid, tc::NTHREADS, pl.smem_total, st>>>(p, pl);
   EV_CUDA_LAUNCH_CHECK("conv1d_tc_kernel");
   return EV_OK;
 }
@@ -402,26 +492,28 @@ static int launch_tc_variant(const ConvParams& p, int BN, cudaStream_t st) {
 // p.w must be in the tensor-core layout [plane][K][Cin/4][Cout][4] (packing.py: to_tc_layout);
 // split3 selects the 3xTF32 fp32-emulation variant (reads both planes).
 int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
-  EV_CHECK_ARG(p.B > 0 && p.L > 0 && p.B <= 65535, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
+  EV_CHECK_ARG(p.B > 0 && p.L > 0, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
   EV_CHECK_ARG(p.Cin % 8 == 0, "conv1d_tc: Cin=%d must be a multiple of 8", p.Cin);
   EV_CHECK_ARG(p.Cout % 16 == 0, "conv1d_tc: Cout=%d must be a multiple of 16", p.Cout);
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
   EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
-  // N tile: a single 256-wide tile when C_out == 256 in 1x mode (A staged once); otherwise <= 128
-  const int BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
-  // rows per CTA: as many 128-row accumulators as keep ~one CTA per SM busy (weight traffic / MT)
-  const long long tiles = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
-  int mt = tiles >= 4 * 120 ? 4 : (tiles >= 2 * 120 ? 2 : 1);
-  const int planes = split3 ? 2 : 1, kbg = split3 ? 4 : 8;
-  while (mt > 1 && (mt * BN > 512 || tc::smem_layout(p.K, p.dil, BN, planes, mt, kbg).total > 227 * 1024)) mt >>= 1;
-  if (split3) {
-    if (mt == 4) return launch_tc_variant<true, 4, 4>(p, BN, st);
-    if (mt == 2) return launch_tc_variant<true, 2, 4>(p, BN, st);
-    return launch_tc_variant<true, 1, 4>(p, BN, st);
+  // rows per tile: as many 128-row accumulators as still leave about one tile per SM (each weight
+  // tile fetched from L2 then feeds MT MMAs), limited by TMEM (2 x MT x BN <= 512 columns) and smem
+  const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
+  int mt = tiles128 >= 4 * 120 ? 4 : (tiles128 >= 2 * 120 ? 2 : 1);
+  tc::Plan pl;
+  while (!tc::make_plan(p, split3, mt, &pl)) {
+    if (mt == 1) { set_error("conv1d_tc: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
+    mt >>= 1;
   }
-  if (mt == 4) return launch_tc_variant<false, 4, 8>(p, BN, st);
-  if (mt == 2) return launch_tc_variant<false, 2, 8>(p, BN, st);
-  return launch_tc_variant<false, 1, 8>(p, BN, st);
+  if (split3) {
+    if (mt == 4) return launch_tc_variant<true, 4>(p, pl, st);
+    if (mt == 2) return launch_tc_variant<true, 2>(p, pl, st);
+    return launch_tc_variant<true, 1>(p, pl, st);
+  }
+  if (mt == 4) return launch_tc_variant<false, 4>(p, pl, st);
+  if (mt == 2) return launch_tc_variant<false, 2>(p, pl, st);
+  return launch_tc_variant<false, 1>(p, pl, st);
 }
 
 }  // namespace ev
