@@ -38,7 +38,8 @@ constexpr int MMA_WARP = (NEPI + NPRODUCER) / 32;      // warp 12
 constexpr int NTHREADS = NEPI + NPRODUCER + 64;        // + warp 13: weight loader
 constexpr int A_LD = 8;              // float4 loads in flight per producer thread and batch
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
-constexpr int STAGING_BYTES = 4 * 32 * 32 * 4;         // per epilogue warp: 32 rows x 32 columns fp32
+constexpr int RES_DEPTH = 3;        // residual chunks prefetched ahead per epilogue warp (cp.async ring)
+constexpr int STAGING_BYTES = 4 * 32 * 32 * 4 * (1 + RES_DEPTH);   // per epilogue warp: 32x32 fp32 transpose tile + residual ring
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -119,7 +120,7 @@ struct Plan {
   int smem_total;
 };
 
-// smem map: [0,256) barriers | [256,260) tmem base | 1024: epilogue staging | A ring | B ring
+// smem map: [0,256) barriers | [256,260) tmem base | 1024: epilogue staging (4 warps x (transpose tile + residual ring)) | A ring | B ring
 __host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int mt, Plan* o) {
   Plan q;
   q.planes = split3 ? 2 : 1;
@@ -227,14 +228,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   if (warp < NEPI / 32) {
     // ============================ epilogue warps ==============================================
     const int quad = warp;
-    float* stg = reinterpret_cast<float*>(staging + quad * (32 * 32 * 4));
-    const int rr = lane >> 3, cq = lane & 7;      // coalesced phase: 4 rows x 8 float4 per instruction
-    int tile_cnt = 0;
+    float* stg = reinterpret_cast<float*>(staging + quad * (32 * 32 * 4 * (1 + RES_DEPTH)));
+    float* res_ring = stg + 32 * 32;                 // RES_DEPTH slots of [8 it][32 lanes] float4
+    const int rr = lane >> 3, cq = lane & 7;         // coalesced phase: 4 rows x 8 float4 per instruction
+    const bool has_res = p.res != nullptr;
+
+    // Residual prefetcher: walks the same (tile, mt, chunk) sequence RES_DEPTH chunks ahead of the
+    // consumer and pulls each lane's own (row, 16 B) pieces into shared memory with cp.async, so
+    // the residual read never sits on the epilogue's critical path and costs no registers.
+    int pf_tile = blockIdx.x, pf_mt = 0, pf_c = 0, pf_slot = 0;
+    auto pf_issue = [&]() {
+      while (pf_tile < pl.total_tiles) {
+        int b, t0, n0, nt, len;
+        decode(pf_tile, b, t0, n0, nt, len);
+        if (t0 >= len) { pf_tile += gridDim.x; pf_mt = 0; pf_c = 0; continue; }
+        const float* rb = p.res + (size_t)b * p.L * p.Cout;
+        const int cw = min(32, nt - pf_c);
+        const uint32_t dst = smem_u32(res_ring + pf_slot * (32 * 32)) + (uint32_t)lane * 16u;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = t0 + pf_mt * BM + quad * 32 + it * 4 + rr;
+          if (cq * 4 < cw && row < len)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(it * 512)),
+                         "l"(rb + (size_t)row * p.Cout + n0 + pf_c + cq * 4)
+                         : "memory");
+        }
+        pf_c += 32;
+        if (pf_c >= nt) { pf_c = 0; if (++pf_mt == MT) { pf_mt = 0; pf_tile += gridDim.x; } }
+        break;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");     // (possibly empty) group: uniform accounting
+      pf_slot = (pf_slot + 1) % RES_DEPTH;
+    };
+    if (has_res)
+      for (int i = 0; i < RES_DEPTH; ++i) pf_issue();
+
+    int tile_cnt = 0, rd_slot = 0;
     for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
       int b, t0, n0, nt, len;
       decode(tile, b, t0, n0, nt, len);
       float* ob = p.out + (size_t)b * p.L * p.Cout;            // may alias p.res (in-place residual)
-      const float* rb = p.res ? p.res + (size_t)b * p.L * p.Cout : nullptr;
       if (t0 >= len) {   // padding tile: the batch-invariant contract stores zeros (no MMA work was issued)
         for (int mt = 0; mt < MT; ++mt)
           for (int c = 0; c < nt; c += 32)
@@ -256,17 +289,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
         for (int c = 0; c < nt; c += 32) {
           const int cw = min(32, nt - c);
           const bool col_ok = cq * 4 < cw;
-          // residual / accumulate operands: coalesced loads issued before waiting on the accumulator
-          float4 rq[8], oq[8];
+          // accumulate operands (rare: last conv of a ResBlock): plain coalesced loads issued up front
+          float4 oq[8];
+          if (p.acc != EV_ACC_STORE) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int row = row_base + it * 4 + rr;
-            const size_t off = (size_t)row * p.Cout + n0 + c + cq * 4;
-            rq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            oq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col_ok && row < len) {
-              if (rb) rq[it] = *reinterpret_cast<const float4*>(rb + off);
-              if (p.acc != EV_ACC_STORE) oq[it] = *reinterpret_cast<const float4*>(ob + off);
+            for (int it = 0; it < 8; ++it) {
+              const int row = row_base + it * 4 + rr;
+              oq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col_ok && row < len) oq[it] = *reinterpret_cast<const float4*>(ob + (size_t)row * p.Cout + n0 + c + cq * 4);
             }
           }
           if (!waited) {
@@ -286,14 +316,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (has_res) asm volatile("cp.async.wait_group %0;" ::"n"(RES_DEPTH - 1) : "memory");   // this chunk's residual has landed
           __syncwarp();
+          const float* rs = res_ring + rd_slot * (32 * 32) + lane * 4;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rr;
             const int row = row_base + r;
             float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq ^ (r & 7)) << 2));
             if (row < len) {
-              o.x += rq[it].x; o.y += rq[it].y; o.z += rq[it].z; o.w += rq[it].w;
+              if (has_res && col_ok) {
+                const float4 q4 = *reinterpret_cast<const float4*>(rs + it * 128);
+                o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
+              }
               if (p.acc != EV_ACC_STORE) {
                 o.x += oq[it].x; o.y += oq[it].y; o.z += oq[it].z; o.w += oq[it].w;
                 if (p.acc == EV_ACC_ADD_DIV) { o.x /= p.div; o.y /= p.div; o.z /= p.div; o.w /= p.div; }
@@ -304,6 +339,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
             if (col_ok && row < p.L) *reinterpret_cast<float4*>(ob + (size_t)row * p.Cout + n0 + c + cq * 4) = o;
           }
           __syncwarp();
+          if (has_res) {           // the slot just consumed is free: prefetch RES_DEPTH chunks ahead
+            rd_slot = (rd_slot + 1) % RES_DEPTH;
+            pf_issue();
+          }
         }
       }
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld16): hand it back
@@ -312,6 +351,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
       if (lane == 0) mbar_arrive(acc_empty(buf));
       ++tile_cnt;
     }
+    if (has_res) asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp < MMA_WARP) {
     // ============================ A producers ===================================================
     const int ptid = tid - NEPI;
