@@ -38,7 +38,7 @@ constexpr int MMA_WARP = (NEPI + NPRODUCER) / 32;      // warp 12
 constexpr int NTHREADS = NEPI + NPRODUCER + 64;        // + warp 13: weight loader
 constexpr int A_LD = 8;              // float4 loads in flight per producer thread and batch
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
-constexpr int RES_DEPTH = 3;        // residual chunks prefetched ahead per epilogue warp (cp.async ring)
+constexpr int RES_DEPTH = 2;        // residual chunks prefetched ahead per epilogue warp (cp.async ring)
 constexpr int STAGING_BYTES = 4 * 32 * 32 * 4 * (1 + RES_DEPTH);   // per epilogue warp: 32x32 fp32 transpose tile + residual ring
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,10 +121,10 @@ struct Plan {
 };
 
 // smem map: [0,256) barriers | [256,260) tmem base | 1024: epilogue staging (4 warps x (transpose tile + residual ring)) | A ring | B ring
-__host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int mt, Plan* o) {
+__host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int mt, int kbg, int min_b_stages, Plan* o) {
   Plan q;
   q.planes = split3 ? 2 : 1;
-  q.kbg = split3 ? 4 : 8;
+  q.kbg = kbg;
   q.mt = mt;
   q.BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
   if (2 * mt * q.BN > 512) return false;
@@ -139,7 +139,9 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int 
   const int budget = 227 * 1024 - 1024 - STAGING_BYTES;
   const int n_cb = (p.Cin + 4 * q.kbg - 1) / (4 * q.kbg);
   // at least 2 + 2 stages; then grow the weight ring first (it turns over K times per A stage)
-  if (2 * q.a_stage_bytes + 2 * q.b_stage_bytes > budget) return false;
+  if (min_b_stages > n_cb * p.K) min_b_stages = n_cb * p.K;
+  if (min_b_stages < 2) min_b_stages = 2;
+  if (2 * q.a_stage_bytes + min_b_stages * q.b_stage_bytes > budget) return false;
   q.a_stages = 2;
   q.b_stages = 2;
   while (q.b_stages < MAX_B_STAGES && q.b_stages < n_cb * p.K &&
@@ -168,11 +170,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int cw, float* v) {
 //                 a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the dropped lo*lo term is 2^-22 relative),
 //                 three MMAs per K step into the same fp32 TMEM accumulator.  Weights arrive pre-split
 //                 (two planes, packing.to_tc_layout); activations are split by the producer warps.
-// MT: 128-row accumulators per tile.  KBG = (SPLIT3 ? 4 : 8) 16-byte K granules per pipeline stage.
-template <bool SPLIT3, int MT>
+// MT: 128-row accumulators per tile.  KBG: 16-byte K granules (4 channels each) per pipeline stage.
+template <bool SPLIT3, int MT, int KBG>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Plan pl) {
   constexpr int PLANES = SPLIT3 ? 2 : 1;
-  constexpr int KBG = SPLIT3 ? 4 : 8;
   constexpr int KB = 4 * KBG;
   constexpr int GSH = (KBG == 8 ? 3 : 2);
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -483,10 +484,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
             mbar_wait(b_empty(sb), ((b_cnt / pl.b_stages) & 1) ^ 1);
             mbar_expect_tx(b_full(sb), (uint32_t)(PLANES * ngran * nt * 16));
             const uint32_t dst = smem_u32(b_tiles + sb * pl.b_stage_bytes);
-            for (int g = 0; g < ngran; ++g) {
-              const float* src = p.w + (((size_t)j * cin4 + (size_t)cb * KBG + g) * p.Cout + n0) * 4;
-              bulk_g2s(dst + (uint32_t)(g * BN * 16), src, (uint32_t)(nt * 16), b_full(sb));
-              if (SPLIT3) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane, (uint32_t)(nt * 16), b_full(sb));
+            if (nt == p.Cout) {
+              // the tile spans every output channel: the stage's granules are adjacent in memory -> ONE bulk copy per plane
+              const float* src = p.w + ((size_t)j * cin4 + (size_t)cb * KBG) * p.Cout * 4;
+              bulk_g2s(dst, src, (uint32_t)(ngran * nt * 16), b_full(sb));
+              if (SPLIT3) bulk_g2s(dst + (uint32_t)pl.b_plane_bytes, src + plane, (uint32_t)(ngran * nt * 16), b_full(sb));
+            } else {
+              for (int g = 0; g < ngran; ++g) {
+                const float* src = p.w + (((size_t)j * cin4 + (size_t)cb * KBG + g) * p.Cout + n0) * 4;
+                bulk_g2s(dst + (uint32_t)(g * BN * 16), src, (uint32_t)(nt * 16), b_full(sb));
+                if (SPLIT3) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane, (uint32_t)(nt * 16), b_full(sb));
+              }
             }
           }
         }
@@ -516,17 +524,24 @@ static int sm_count() {
   return n;
 }
 
-template <bool SPLIT3, int MT>
+template <bool SPLIT3, int MT, int KBG>
 static int launch_tc_variant(const ConvParams& p, const tc::Plan& pl, cudaStream_t st) {
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(tc::conv1d_tc_kernel<SPLIT3, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc::conv1d_tc_kernel<SPLIT3, MT, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const int grid = pl.total_tiles < sm_count() ? pl.total_tiles : sm_count();
-  tc::conv1d_tc_kernel<SPLIT3, MT><<<grid, tc::NTHREADS, pl.smem_total, st>>>(p, pl);
+  tc::conv1d_tc_kernel<SPLIT3, MT, KBG><<<grid, tc::NTHREADS, pl.smem_total, st>>>(p, pl);
   EV_CUDA_LAUNCH_CHECK("conv1d_tc_kernel");
   return EV_OK;
+}
+
+template <bool SPLIT3, int KBG>
+static int launch_tc_mt(const ConvParams& p, const tc::Plan& pl, cudaStream_t st) {
+  if (pl.mt == 4) return launch_tc_variant<SPLIT3, 4, KBG>(p, pl, st);
+  if (pl.mt == 2) return launch_tc_variant<SPLIT3, 2, KBG>(p, pl, st);
+  return launch_tc_variant<SPLIT3, 1, KBG>(p, pl, st);
 }
 
 // p.w must be in the tensor-core layout [plane][K][Cin/4][Cout][4] (packing.py: to_tc_layout);
@@ -538,22 +553,20 @@ int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
   EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
   // rows per tile: as many 128-row accumulators as still leave about one tile per SM (each weight
-  // tile fetched from L2 then feeds MT MMAs), limited by TMEM (2 x MT x BN <= 512 columns) and smem
+  // tile fetched from L2 then feeds MT MMAs), limited by TMEM (2 x MT x BN <= 512 columns) and smem.
+  // K granules per stage: 8 (32 channels) if the rings still get >= 2 A stages and >= 4 weight stages, else 4.
   const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
   int mt = tiles128 >= 4 * 120 ? 4 : (tiles128 >= 2 * 120 ? 2 : 1);
   tc::Plan pl;
-  while (!tc::make_plan(p, split3, mt, &pl)) {
+  for (;; mt >>= 1) {
+    if (!split3 && tc::make_plan(p, split3, mt, 8, 4, &pl)) break;
+    if (tc::make_plan(p, split3, mt, 4, 4, &pl)) break;
+    if (tc::make_plan(p, split3, mt, 4, 2, &pl)) break;
     if (mt == 1) { set_error("conv1d_tc: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
-    mt >>= 1;
   }
-  if (split3) {
-    if (mt == 4) return launch_tc_variant<true, 4>(p, pl, st);
-    if (mt == 2) return launch_tc_variant<true, 2>(p, pl, st);
-    return launch_tc_variant<true, 1>(p, pl, st);
-  }
-  if (mt == 4) return launch_tc_variant<false, 4>(p, pl, st);
-  if (mt == 2) return launch_tc_variant<false, 2>(p, pl, st);
-  return launch_tc_variant<false, 1>(p, pl, st);
+  if (split3) return launch_tc_mt<true, 4>(p, pl, st);
+  if (pl.kbg == 8) return launch_tc_mt<false, 8>(p, pl, st);
+  return launch_tc_mt<false, 4>(p, pl, st);
 }
 
 }  // namespace ev
