@@ -161,8 +161,24 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int 
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int cw, float* v) {
-  tmem_ld16(taddr, v);
-  if (cw > 16) tmem_ld16(taddr + 16u, v + 16);
+  if (cw > 16) {      // one 32-column load (32 lanes x 32 columns), one wait
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  } else {
+    tmem_ld16(taddr, v);
+#pragma unroll
+    for (int i = 16; i < 32; ++i) v[i] = 0.f;
+  }
 }
 
 // SPLIT3 = false: one tf32 MMA per K step (operands rounded to nearest tf32).
@@ -307,25 +323,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
           }
           float v[32];
           tmem_ld32(taddr + (uint32_t)c, cw, v);      // thread = row (TMEM lane), 32 consecutive columns
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float t = v[i];
-            if (bias && i < cw) t += __ldg(bias + c + i);
-            v[i] = act_apply(t, p.out_act, 0.f);
-          }
           // registers -> smem, 16-byte chunks XOR-swizzled by the row so both phases are conflict free
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          // in the coalesced phase a lane owns 4 fixed columns: its bias is one float4 per chunk
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(bias + c + cq * 4));
           if (has_res) asm volatile("cp.async.wait_group %0;" ::"n"(RES_DEPTH - 1) : "memory");   // this chunk's residual has landed
           __syncwarp();
           const float* rs = res_ring + rd_slot * (32 * 32) + lane * 4;
+          const int oact = p.out_act;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rr;
             const int row = row_base + r;
             float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq ^ (r & 7)) << 2));
             if (row < len) {
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              if (oact != EV_ACT_NONE) {
+                o.x = act_apply(o.x, oact, 0.f); o.y = act_apply(o.y, oact, 0.f);
+                o.z = act_apply(o.z, oact, 0.f); o.w = act_apply(o.w, oact, 0.f);
+              }
               if (has_res && col_ok) {
                 const float4 q4 = *reinterpret_cast<const float4*>(rs + it * 128);
                 o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
