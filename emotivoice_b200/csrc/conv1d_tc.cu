@@ -21,9 +21,9 @@
 //   the epilogue of tile i (TMEM -> registers -> swizzled smem -> fully coalesced 128-byte global
 //   rows, residual/accumulate operands prefetched) overlaps the main loop of tile i+1.
 //
-// Roles (448 threads): warps 0-3 epilogue (warp w <-> TMEM lanes 32w..32w+31), warps 4-11 stage A,
-// warp 12 allocates TMEM and its elected lane issues every tcgen05.mma, warp 13's elected lane
-// streams the weight tiles.  mbarrier pipelines: A ring (a_full/a_empty), B ring (b_full/b_empty,
+// Roles (512 threads): warps 0-7 epilogue (warp e <-> TMEM lanes 32(e%4).., alternate 32-column
+// chunks), warps 8-13 stage A, warp 14 allocates TMEM and its elected lane issues every tcgen05.mma,
+// warp 15's elected lane streams the weight tiles.  mbarrier pipelines: A ring (a_full/a_empty), B ring (b_full/b_empty,
 // released by tcgen05.commit), accumulators (acc_full/acc_empty).
 #include "ev_common.cuh"
 
@@ -32,14 +32,13 @@ namespace ev {
 namespace tc {
 
 constexpr int BM = 128;              // rows (time steps) per accumulator == TMEM lanes
-constexpr int NEPI = 128;            // warps 0-3
-constexpr int NPRODUCER = 256;       // warps 4-11
-constexpr int MMA_WARP = (NEPI + NPRODUCER) / 32;      // warp 12
-constexpr int NTHREADS = NEPI + NPRODUCER + 64;        // + warp 13: weight loader
+constexpr int NEPI = 256;            // warps 0-7: epilogue (warp e <-> TMEM lane quadrant e%4, every second 32-column chunk)
+constexpr int NPRODUCER = 192;       // warps 8-13: stage A
+constexpr int MMA_WARP = (NEPI + NPRODUCER) / 32;      // warp 14
+constexpr int NTHREADS = NEPI + NPRODUCER + 64;        // + warp 15: weight loader
 constexpr int A_LD = 8;              // float4 loads in flight per producer thread and batch
 constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
-constexpr int RES_DEPTH = 2;        // residual chunks prefetched ahead per epilogue warp (cp.async ring)
-constexpr int STAGING_BYTES = 4 * 32 * 32 * 4 * (1 + RES_DEPTH);   // per epilogue warp: 32x32 fp32 transpose tile + residual ring
+constexpr int STAGING_BYTES = (NEPI / 32) * 32 * 32 * 4;   // per epilogue warp: one 32x32 fp32 transpose tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -120,7 +119,7 @@ struct Plan {
   int smem_total;
 };
 
-// smem map: [0,256) barriers | [256,260) tmem base | 1024: epilogue staging (4 warps x (transpose tile + residual ring)) | A ring | B ring
+// smem map: [0,256) barriers | [256,260) tmem base | 1024: epilogue staging (8 warps x 4 KB) | A ring | B ring
 __host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int mt, int kbg, int min_b_stages, Plan* o) {
   Plan q;
   q.planes = split3 ? 2 : 1;
@@ -244,50 +243,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
 
   if (warp < NEPI / 32) {
     // ============================ epilogue warps ==============================================
-    const int quad = warp;
-    float* stg = reinterpret_cast<float*>(staging + quad * (32 * 32 * 4 * (1 + RES_DEPTH)));
-    float* res_ring = stg + 32 * 32;                 // RES_DEPTH slots of [8 it][32 lanes] float4
+    const int quad = warp & 3, chalf = warp >> 2;
+    float* stg = reinterpret_cast<float*>(staging + warp * (32 * 32 * 4));
     const int rr = lane >> 3, cq = lane & 7;         // coalesced phase: 4 rows x 8 float4 per instruction
     const bool has_res = p.res != nullptr;
-
-    // Residual prefetcher: walks the same (tile, mt, chunk) sequence RES_DEPTH chunks ahead of the
-    // consumer and pulls each lane's own (row, 16 B) pieces into shared memory with cp.async, so
-    // the residual read never sits on the epilogue's critical path and costs no registers.
-    int pf_tile = blockIdx.x, pf_mt = 0, pf_c = 0, pf_slot = 0;
-    auto pf_issue = [&]() {
-      while (pf_tile < pl.total_tiles) {
-        int b, t0, n0, nt, len;
-        decode(pf_tile, b, t0, n0, nt, len);
-        if (t0 >= len) { pf_tile += gridDim.x; pf_mt = 0; pf_c = 0; continue; }
-        const float* rb = p.res + (size_t)b * p.L * p.Cout;
-        const int cw = min(32, nt - pf_c);
-        const uint32_t dst = smem_u32(res_ring + pf_slot * (32 * 32)) + (uint32_t)lane * 16u;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = t0 + pf_mt * BM + quad * 32 + it * 4 + rr;
-          if (cq * 4 < cw && row < len)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(it * 512)),
-                         "l"(rb + (size_t)row * p.Cout + n0 + pf_c + cq * 4)
-                         : "memory");
-        }
-        pf_c += 32;
-        if (pf_c >= nt) { pf_c = 0; if (++pf_mt == MT) { pf_mt = 0; pf_tile += gridDim.x; } }
-        break;
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");     // (possibly empty) group: uniform accounting
-      pf_slot = (pf_slot + 1) % RES_DEPTH;
-    };
-    if (has_res)
-      for (int i = 0; i < RES_DEPTH; ++i) pf_issue();
-
-    int tile_cnt = 0, rd_slot = 0;
+    const int oact = p.out_act, accm = p.acc;
+    int tile_cnt = 0;
     for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
       int b, t0, n0, nt, len;
       decode(tile, b, t0, n0, nt, len);
       float* ob = p.out + (size_t)b * p.L * p.Cout;            // may alias p.res (in-place residual)
+      const float* rb = has_res ? p.res + (size_t)b * p.L * p.Cout : nullptr;
       if (t0 >= len) {   // padding tile: the batch-invariant contract stores zeros (no MMA work was issued)
         for (int mt = 0; mt < MT; ++mt)
-          for (int c = 0; c < nt; c += 32)
+          for (int c = chalf * 32; c < nt; c += 64)
             for (int it = 0; it < 8; ++it) {
               const int row = t0 + mt * BM + quad * 32 + it * 4 + rr;
               if (row < p.L && c + cq * 4 < nt)
@@ -303,19 +272,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
         const int row_base = t0 + mt * BM + quad * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * MT * BN + mt * BN);
 #pragma unroll 1
-        for (int c = 0; c < nt; c += 32) {
+        for (int c = chalf * 32; c < nt; c += 64) {
           const int cw = min(32, nt - c);
           const bool col_ok = cq * 4 < cw;
-          // accumulate operands (rare: last conv of a ResBlock): plain coalesced loads issued up front
-          float4 oq[8];
-          if (p.acc != EV_ACC_STORE) {
+          // residual / accumulate operands and the bias: coalesced loads issued before the accumulator is needed
+          float4 rq[8], oq[8];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = row_base + it * 4 + rr;
+          for (int it = 0; it < 8; ++it) {
+            const int row = row_base + it * 4 + rr;
+            const size_t off = (size_t)row * p.Cout + n0 + c + cq * 4;
+            rq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res && col_ok && row < len) rq[it] = *reinterpret_cast<const float4*>(rb + off);
+            if (accm != EV_ACC_STORE) {
               oq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (col_ok && row < len) oq[it] = *reinterpret_cast<const float4*>(ob + (size_t)row * p.Cout + n0 + c + cq * 4);
+              if (col_ok && row < len) oq[it] = *reinterpret_cast<const float4*>(ob + off);
             }
           }
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(bias + c + cq * 4));
           if (!waited) {
             mbar_wait(acc_full(buf), (tile_cnt >> 1) & 1);
             tc_fence_after();
@@ -327,13 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          // in the coalesced phase a lane owns 4 fixed columns: its bias is one float4 per chunk
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(bias + c + cq * 4));
-          if (has_res) asm volatile("cp.async.wait_group %0;" ::"n"(RES_DEPTH - 1) : "memory");   // this chunk's residual has landed
           __syncwarp();
-          const float* rs = res_ring + rd_slot * (32 * 32) + lane * 4;
-          const int oact = p.out_act;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rr;
@@ -345,13 +313,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
                 o.x = act_apply(o.x, oact, 0.f); o.y = act_apply(o.y, oact, 0.f);
                 o.z = act_apply(o.z, oact, 0.f); o.w = act_apply(o.w, oact, 0.f);
               }
-              if (has_res && col_ok) {
-                const float4 q4 = *reinterpret_cast<const float4*>(rs + it * 128);
-                o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
-              }
-              if (p.acc != EV_ACC_STORE) {
+              o.x += rq[it].x; o.y += rq[it].y; o.z += rq[it].z; o.w += rq[it].w;
+              if (accm != EV_ACC_STORE) {
                 o.x += oq[it].x; o.y += oq[it].y; o.z += oq[it].z; o.w += oq[it].w;
-                if (p.acc == EV_ACC_ADD_DIV) { o.x /= p.div; o.y /= p.div; o.z /= p.div; o.w /= p.div; }
+                if (accm == EV_ACC_ADD_DIV) { o.x /= p.div; o.y /= p.div; o.z /= p.div; o.w /= p.div; }
               }
             } else {
               o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -359,19 +324,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
             if (col_ok && row < p.L) *reinterpret_cast<float4*>(ob + (size_t)row * p.Cout + n0 + c + cq * 4) = o;
           }
           __syncwarp();
-          if (has_res) {           // the slot just consumed is free: prefetch RES_DEPTH chunks ahead
-            rd_slot = (rd_slot + 1) % RES_DEPTH;
-            pf_issue();
-          }
         }
       }
-      // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld16): hand it back
+      // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
       ++tile_cnt;
     }
-    if (has_res) asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp < MMA_WARP) {
     // ============================ A producers ===================================================
     const int ptid = tid - NEPI;
