@@ -326,6 +326,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
           __syncwarp();
         }
       }
+      if (!waited) {     // a warp without columns in this tile (N <= 32) still follows the accumulator phases
+        mbar_wait(acc_full(buf), (tile_cnt >> 1) & 1);
+        tc_fence_after();
+      }
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
       tc_fence_before();
       __syncwarp();

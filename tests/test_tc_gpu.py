@@ -51,6 +51,8 @@ TC_CASES = [
     (2, 900, 256, 256, 11, 1),    # N = 256 single tile
     (1, 537, 384, 80, 1, 1),      # to_mel: N = 80
     (1, 5000, 32, 32, 3, 3),
+    (3, 70000, 32, 32, 11, 5),    # persistent: many tiles per CTA, N = 32 (half of the epilogue warps idle)
+    (2, 40000, 64, 64, 3, 1),     # persistent, MT = 4
 ]
 
 
