@@ -36,8 +36,10 @@ constexpr int NEPI = 256;            // warps 0-7: epilogue (warp e <-> TMEM lan
 constexpr int NPRODUCER = 192;       // warps 8-13: stage A
 constexpr int MMA_WARP = (NEPI + NPRODUCER) / 32;      // warp 14
 constexpr int NTHREADS = NEPI + NPRODUCER + 64;        // + warp 15: weight loader
-constexpr int A_LD = 8;              // float4 loads in flight per producer thread and batch
-constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
+constexpr int A_LD = 12;             // float4 loads in flight per producer thread and batch
+constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 8;
+constexpr int NGROUPS = NPRODUCER / 32;   // every producer warp stages whole A stages on its own (stage a_cnt -> warp a_cnt % NGROUPS):
+                                          // NGROUPS stages are in flight at once instead of one stop-and-go stage
 constexpr int STAGING_BYTES = (NEPI / 32) * 32 * 32 * 4;   // per epilogue warp: one 32x32 fp32 transpose tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,7 +121,7 @@ struct Plan {
   int smem_total;
 };
 
-// smem map: [0,256) barriers | [256,260) tmem base | 1024: epilogue staging (8 warps x 4 KB) | A ring | B ring
+// smem map: [0,288) barriers | [512,516) tmem base | 1024: epilogue staging (8 warps x 4 KB) | A ring | B ring
 __host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int mt, int kbg, int min_b_stages, Plan* o) {
   Plan q;
   q.planes = split3 ? 2 : 1;
@@ -146,7 +148,7 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int 
   while (q.b_stages < MAX_B_STAGES && q.b_stages < n_cb * p.K &&
          q.a_stages * q.a_stage_bytes + (q.b_stages + 1) * q.b_stage_bytes <= budget && q.b_stages < 4) ++q.b_stages;
   while (q.a_stages < MAX_A_STAGES && q.a_stages < n_cb &&
-         (q.a_stages + 1) * q.a_stage_bytes + q.b_stages * q.b_stage_bytes <= budget && q.a_stages < 3) ++q.a_stages;
+         (q.a_stages + 1) * q.a_stage_bytes + q.b_stages * q.b_stage_bytes <= budget && q.a_stages < 6) ++q.a_stages;
   while (q.b_stages < MAX_B_STAGES && q.b_stages < n_cb * p.K &&
          q.a_stages * q.a_stage_bytes + (q.b_stages + 1) * q.b_stage_bytes <= budget) ++q.b_stages;
   while (q.a_stages < MAX_A_STAGES && q.a_stages < n_cb &&
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   const int BN = pl.BN;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 512);   // barriers occupy [0, 8*(2*MAX_A+2*MAX_B+4)) = 288 B
   uint8_t* staging = smem_raw + 1024;
   uint8_t* a_tiles = staging + STAGING_BYTES;
   uint8_t* b_tiles = a_tiles + pl.a_stages * pl.a_stage_bytes;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   auto acc_empty = [&](int s) { return bar_base + 8u * (2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 2 + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < pl.a_stages; ++s) { mbar_init(a_full(s), NPRODUCER); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < pl.a_stages; ++s) { mbar_init(a_full(s), 32); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < pl.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), NEPI / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
     }
   } else if (warp < MMA_WARP) {
     // ============================ A producers ===================================================
-    const int ptid = tid - NEPI;
+    const int grp = warp - NEPI / 32;
     const bool lrelu = (p.in_act == EV_ACT_LRELU);
     const float slope = p.in_slope;
     const int total = rows_a * KBG;   // (row, granule) pairs; granule fastest -> coalesced row segments
@@ -349,16 +351,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
       if (t0 >= len) continue;
       const float* __restrict__ xb = p.x + (size_t)b * p.L * p.Cin;
       for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
+        if (a_cnt % NGROUPS != grp) continue;          // this stage belongs to another producer warp
         const int s = a_cnt % pl.a_stages;
         const int c0 = cb * KB;
         const int ngran = min(KB, p.Cin - c0) / 4;
         uint8_t* dst = a_tiles + s * pl.a_stage_bytes;
-        for (int base = 0; base < total; base += NPRODUCER * A_LD) {
+        for (int base = 0; base < total; base += 32 * A_LD) {
           // a batch of global loads is issued before anything else (memory-level parallelism)
           float4 v[A_LD];
 #pragma unroll
           for (int u = 0; u < A_LD; ++u) {
-            const int idx = base + u * NPRODUCER + ptid;
+            const int idx = base + u * 32 + lane;
             const int r = idx >> GSH, g = idx & (KBG - 1);
             const int row = t0 - halo + r;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
           if (base == 0) mbar_wait(a_empty(s), ((a_cnt / pl.a_stages) & 1) ^ 1);
 #pragma unroll
           for (int u = 0; u < A_LD; ++u) {
-            const int idx = base + u * NPRODUCER + ptid;
+            const int idx = base + u * 32 + lane;
             const int r = idx >> GSH, g = idx & (KBG - 1);
             if (idx < total && g < ngran) {
               float4 t = v[u];
