@@ -36,10 +36,13 @@ constexpr int NEPI = 256;            // warps 0-7: epilogue (warp e <-> TMEM lan
 constexpr int NPRODUCER = 192;       // warps 8-13: stage A
 constexpr int MMA_WARP = (NEPI + NPRODUCER) / 32;      // warp 14
 constexpr int NTHREADS = NEPI + NPRODUCER + 64;        // + warp 15: weight loader
-constexpr int A_LD = 12;             // float4 loads in flight per producer thread and batch
+constexpr int A_LD = 8;              // float4 loads in flight per producer thread and batch
 constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 8;
-constexpr int NGROUPS = NPRODUCER / 32;   // every producer warp stages whole A stages on its own (stage a_cnt -> warp a_cnt % NGROUPS):
-                                          // NGROUPS stages are in flight at once instead of one stop-and-go stage
+constexpr int NPWARPS = NPRODUCER / 32;   // producer warps are split into `ngroups` groups; group g stages A stage a_cnt when
+                                          // a_cnt % ngroups == g, so `ngroups` stages are being filled concurrently instead of one
+                                          // stop-and-go stage.  SAFETY: the parity wait on a_empty can only tell consecutive
+                                          // phases apart, so a group must never run two uses of a ring slot ahead of the
+                                          // consumer; that holds iff ngroups <= a_stages (see make_plan).
 constexpr int STAGING_BYTES = (NEPI / 32) * 32 * 32 * 4;   // per epilogue warp: one 32x32 fp32 transpose tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,6 +119,7 @@ struct Plan {
   int rows_pad;        // staged rows per A granule; == 8/kbg (mod 8) -> conflict-free 16 B stores
   int a_plane_bytes, b_plane_bytes, a_stage_bytes, b_stage_bytes;
   int a_stages, b_stages;
+  int ngroups;         // producer groups: largest of {6,3,2,1} that is <= a_stages
   int tmem_cols;
   int tiles_m, tiles_n, total_tiles;
   int smem_total;
@@ -153,6 +157,7 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int 
          q.a_stages * q.a_stage_bytes + (q.b_stages + 1) * q.b_stage_bytes <= budget) ++q.b_stages;
   while (q.a_stages < MAX_A_STAGES && q.a_stages < n_cb &&
          (q.a_stages + 1) * q.a_stage_bytes + q.b_stages * q.b_stage_bytes <= budget) ++q.a_stages;
+  q.ngroups = q.a_stages >= 6 ? 6 : (q.a_stages >= 3 ? 3 : (q.a_stages >= 2 ? 2 : 1));
   q.tiles_m = (p.L + BM * mt - 1) / (BM * mt);
   q.tiles_n = (p.Cout + q.BN - 1) / q.BN;
   q.total_tiles = p.B * q.tiles_m * q.tiles_n;
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   auto acc_empty = [&](int s) { return bar_base + 8u * (2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 2 + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < pl.a_stages; ++s) { mbar_init(a_full(s), 32); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < pl.a_stages; ++s) { mbar_init(a_full(s), (NPWARPS / pl.ngroups) * 32); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < pl.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), NEPI / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -340,7 +345,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
     }
   } else if (warp < MMA_WARP) {
     // ============================ A producers ===================================================
-    const int grp = warp - NEPI / 32;
+    const int pwarp = warp - NEPI / 32;
+    const int wpg = NPWARPS / pl.ngroups;          // warps per group
+    const int grp = pwarp / wpg;
+    const int gt = (pwarp - grp * wpg) * 32 + lane;  // thread index inside the group
+    const int GT = wpg * 32;
     const bool lrelu = (p.in_act == EV_ACT_LRELU);
     const float slope = p.in_slope;
     const int total = rows_a * KBG;   // (row, granule) pairs; granule fastest -> coalesced row segments
@@ -351,17 +360,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
       if (t0 >= len) continue;
       const float* __restrict__ xb = p.x + (size_t)b * p.L * p.Cin;
       for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
-        if (a_cnt % NGROUPS != grp) continue;          // this stage belongs to another producer warp
+        if (a_cnt % pl.ngroups != grp) continue;       // this stage belongs to another producer group
         const int s = a_cnt % pl.a_stages;
         const int c0 = cb * KB;
         const int ngran = min(KB, p.Cin - c0) / 4;
         uint8_t* dst = a_tiles + s * pl.a_stage_bytes;
-        for (int base = 0; base < total; base += 32 * A_LD) {
+        for (int base = 0; base < total; base += GT * A_LD) {
           // a batch of global loads is issued before anything else (memory-level parallelism)
           float4 v[A_LD];
 #pragma unroll
           for (int u = 0; u < A_LD; ++u) {
-            const int idx = base + u * 32 + lane;
+            const int idx = base + u * GT + gt;
             const int r = idx >> GSH, g = idx & (KBG - 1);
             const int row = t0 - halo + r;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
           if (base == 0) mbar_wait(a_empty(s), ((a_cnt / pl.a_stages) & 1) ^ 1);
 #pragma unroll
           for (int u = 0; u < A_LD; ++u) {
-            const int idx = base + u * 32 + lane;
+            const int idx = base + u * GT + gt;
             const int r = idx >> GSH, g = idx & (KBG - 1);
             if (idx < total && g < ngran) {
               float4 t = v[u];
