@@ -229,7 +229,7 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
         e0.record()
         if use_tc:
             _abi.check(lib.ev_op_conv1d_tc(x.data_ptr(), w.data_ptr(), split3, b.data_ptr(), 0, res.data_ptr(), out.data_ptr(), 1, L, C, C,
-                                           K, 1, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, st))
+                                           K, 1, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, None, 0, st))
         else:
             _abi.check(lib.ev_op_conv1d(x.data_ptr(), w.data_ptr(), b.data_ptr(), 0, res.data_ptr(), out.data_ptr(), 1, L, C, C,
                                         K, 1, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, st))

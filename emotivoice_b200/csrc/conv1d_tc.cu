@@ -120,6 +120,8 @@ struct Plan {
   int a_plane_bytes, b_plane_bytes, a_stage_bytes, b_stage_bytes;
   int a_stages, b_stages;
   int ngroups;         // producer groups: largest of {6,3,2,1} that is <= a_stages
+  int ksplit;          // K-split factor S: S CTAs share one output tile, each reducing a slice of the C_in blocks
+                       // into a private partial buffer; splitk_reduce_kernel sums them in a fixed order
   int tmem_cols;
   int tiles_m, tiles_n, total_tiles;
   int smem_total;
@@ -160,6 +162,7 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int 
   q.ngroups = q.a_stages >= 6 ? 6 : (q.a_stages >= 3 ? 3 : (q.a_stages >= 2 ? 2 : 1));
   q.tiles_m = (p.L + BM * mt - 1) / (BM * mt);
   q.tiles_n = (p.Cout + q.BN - 1) / q.BN;
+  q.ksplit = 1;
   q.total_tiles = p.B * q.tiles_m * q.tiles_n;
   q.smem_total = 1024 + STAGING_BYTES + q.a_stages * q.a_stage_bytes + q.b_stages * q.b_stage_bytes;
   *o = q;
@@ -238,7 +241,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   const int tiles_per_b = pl.tiles_m * pl.tiles_n;
 
   // tile -> (b, t0, n0, nt, len); every role walks the same sequence
+  int z_cur = 0;     // K-split slice of the tile most recently decoded by this thread
   auto decode = [&](int tile, int& b, int& t0, int& n0, int& nt, int& len) {
+    z_cur = tile % pl.ksplit;
+    tile /= pl.ksplit;
     b = tile / tiles_per_b;
     const int r = tile - b * tiles_per_b;
     const int tm = r / pl.tiles_n, tn = r - tm * pl.tiles_n;
@@ -253,13 +259,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
     const int quad = warp & 3, chalf = warp >> 2;
     float* stg = reinterpret_cast<float*>(staging + warp * (32 * 32 * 4));
     const int rr = lane >> 3, cq = lane & 7;         // coalesced phase: 4 rows x 8 float4 per instruction
-    const bool has_res = p.res != nullptr;
-    const int oact = p.out_act, accm = p.acc;
+    const bool split = pl.ksplit > 1;           // K-split: raw partial sums, the fused epilogue runs in the reduce kernel
+    const bool has_res = p.res != nullptr && !split;
+    const int oact = split ? EV_ACT_NONE : p.out_act, accm = split ? EV_ACC_STORE : p.acc;
     int tile_cnt = 0;
     for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
       int b, t0, n0, nt, len;
       decode(tile, b, t0, n0, nt, len);
-      float* ob = p.out + (size_t)b * p.L * p.Cout;            // may alias p.res (in-place residual)
+      float* ob = (split ? p.splitk_ws + (size_t)z_cur * p.B * p.L * p.Cout : p.out) + (size_t)b * p.L * p.Cout;   // may alias p.res
       const float* rb = has_res ? p.res + (size_t)b * p.L * p.Cout : nullptr;
       if (t0 >= len) {   // padding tile: the batch-invariant contract stores zeros (no MMA work was issued)
         for (int mt = 0; mt < MT; ++mt)
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
         continue;
       }
       const int buf = tile_cnt & 1;
-      const float* __restrict__ bias = p.bias ? p.bias + (size_t)b * p.bias_bs + n0 : nullptr;
+      const float* __restrict__ bias = (p.bias && !split) ? p.bias + (size_t)b * p.bias_bs + n0 : nullptr;
       bool waited = false;
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
@@ -359,7 +366,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
       decode(tile, b, t0, n0, nt, len);
       if (t0 >= len) continue;
       const float* __restrict__ xb = p.x + (size_t)b * p.L * p.Cin;
-      for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
+      const int cb_lo = (z_cur * n_cb) / pl.ksplit, cb_hi = ((z_cur + 1) * n_cb) / pl.ksplit;
+      for (int cb = cb_lo; cb < cb_hi; ++cb, ++a_cnt) {
         if (a_cnt % pl.ngroups != grp) continue;       // this stage belongs to another producer group
         const int s = a_cnt % pl.a_stages;
         const int c0 = cb * KB;
@@ -421,7 +429,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
         mbar_wait(acc_empty(buf), ((tile_cnt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(buf * MT * BN);
-        for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
+        const int cb_lo = (z_cur * n_cb) / pl.ksplit, cb_hi = ((z_cur + 1) * n_cb) / pl.ksplit;
+        for (int cb = cb_lo; cb < cb_hi; ++cb, ++a_cnt) {
           const int sa = a_cnt % pl.a_stages;
           const int nk8 = min(KB, p.Cin - cb * KB) / 8;
           mbar_wait(a_full(sa), (a_cnt / pl.a_stages) & 1);
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
               const uint32_t b_off = (uint32_t)(2 * k8) * b_lbo;
               const uint64_t b_hi = make_desc(b_addr + b_off, b_lbo, 128u);
               const uint64_t b_lo = make_desc(b_addr + pl.b_plane_bytes + b_off, b_lbo, 128u);
-              const uint32_t first = (cb | j | k8) != 0 ? 1u : 0u;
+              const uint32_t first = ((cb - cb_lo) | j | k8) != 0 ? 1u : 0u;
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
                 const uint32_t a_off = (uint32_t)((2 * k8) * pl.rows_pad + mt * BM + j * p.dil) * 16u;
@@ -472,7 +481,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
         int b, t0, n0, nt, len;
         decode(tile, b, t0, n0, nt, len);
         if (t0 >= len) continue;
-        for (int cb = 0; cb < n_cb; ++cb) {
+        const int cb_lo = (z_cur * n_cb) / pl.ksplit, cb_hi = ((z_cur + 1) * n_cb) / pl.ksplit;
+        for (int cb = cb_lo; cb < cb_hi; ++cb) {
           const int ngran = min(KB, p.Cin - cb * KB) / 4;
           for (int j = 0; j < p.K; ++j, ++b_cnt) {
             const int sb = b_cnt % pl.b_stages;
@@ -504,6 +514,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols));
   }
+}
+
+// Second half of a K-split convolution: out = epi( sum_z partial[z] ) with the slices added in the
+// fixed order z = 0..S-1 (deterministic, batch invariant), then bias / activation / residual /
+// accumulate exactly like the fused epilogue.  One float4 per thread.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(ConvParams p, int S) {
+  const size_t per = (size_t)p.B * p.L * p.Cout;
+  const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= per) return;
+  const size_t e = i4 * 4;
+  const int col = (int)(e % p.Cout);
+  const size_t rowg = e / p.Cout;
+  const int b = (int)(rowg / p.L), row = (int)(rowg % p.L);
+  const int len = p.lens ? min(p.L, p.lens[b] * p.lens_mul) : p.L;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < len) {
+    for (int z = 0; z < S; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(p.splitk_ws + (size_t)z * per + e);
+      o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+    }
+    if (p.bias) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)b * p.bias_bs + col));
+      o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+    }
+    if (p.out_act != EV_ACT_NONE) {
+      o.x = act_apply(o.x, p.out_act, 0.f); o.y = act_apply(o.y, p.out_act, 0.f);
+      o.z = act_apply(o.z, p.out_act, 0.f); o.w = act_apply(o.w, p.out_act, 0.f);
+    }
+    if (p.res) {
+      const float4 r4 = *reinterpret_cast<const float4*>(p.res + e);
+      o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+    }
+    if (p.acc != EV_ACC_STORE) {
+      const float4 q4 = *reinterpret_cast<const float4*>(p.out + e);
+      o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
+      if (p.acc == EV_ACC_ADD_DIV) { o.x /= p.div; o.y /= p.div; o.z /= p.div; o.w /= p.div; }
+    }
+  }
+  *reinterpret_cast<float4*>(p.out + e) = o;
 }
 
 }  // namespace tc
@@ -559,9 +608,30 @@ int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
     if (tc::make_plan(p, split3, mt, 4, 2, &pl)) break;
     if (mt == 1) { set_error("conv1d_tc: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
   }
-  if (split3) return launch_tc_mt<true, 4>(p, pl, st);
-  if (pl.kbg == 8) return launch_tc_mt<false, 8>(p, pl, st);
-  return launch_tc_mt<false, 4>(p, pl, st);
+  // K-split: few output tiles but a long reduction (the conv-FFN's second conv at batch 1: 15 tiles, K = 3*1536;
+  // HiFi-GAN stage 1) leaves most SMs idle and makes the launch one long serial chain -> share each tile among
+  // S CTAs.  Deterministic: private partial buffers + a fixed-order reduce kernel.
+  const int n_cb = (p.Cin + 4 * pl.kbg - 1) / (4 * pl.kbg);
+  const size_t per = (size_t)p.B * p.L * p.Cout;
+  if (p.splitk_ws && pl.total_tiles * 2 <= sm_count() && n_cb >= 8) {
+    int S = sm_count() / pl.total_tiles;
+    if (S > 8) S = 8;
+    if (S > n_cb / 4) S = n_cb / 4;
+    while (S > 1 && (size_t)S * per > p.splitk_cap) --S;
+    if (S > 1) {
+      pl.ksplit = S;
+      pl.total_tiles *= S;
+    }
+  }
+  int rc;
+  if (split3) rc = launch_tc_mt<true, 4>(p, pl, st);
+  else if (pl.kbg == 8) rc = launch_tc_mt<false, 8>(p, pl, st);
+  else rc = launch_tc_mt<false, 4>(p, pl, st);
+  if (rc != EV_OK || pl.ksplit == 1) return rc;
+  const size_t n4 = per / 4;
+  tc::splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(p, pl.ksplit);
+  EV_CUDA_LAUNCH_CHECK("splitk_reduce_kernel");
+  return EV_OK;
 }
 
 }  // namespace ev

@@ -102,13 +102,16 @@ struct Carver {
 };
 
 struct Phase1Bufs {
-  float *x, *y, *qkv, *ctx, *h, *cond_in, *cond_bias, *hs, *pm, *p1, *p2, *centers, *ds_f;
+  float *x, *y, *qkv, *ctx, *h, *cond_in, *cond_bias, *hs, *pm, *p1, *p2, *centers, *ds_f, *part;
+  size_t part_cap;
 };
 struct Phase2Bufs {
-  float *x, *y, *qkv, *ctx, *h;
+  float *x, *y, *qkv, *ctx, *h, *part;
+  size_t part_cap;
 };
 struct VocBufs {
-  float *X, *Tm, *R1, *R2, *ACC;
+  float *X, *Tm, *R1, *R2, *ACC, *part;
+  size_t part_cap;
 };
 
 static void carve_phase1(const ev_ctx* c, Carver& cv, int B, int T, Phase1Bufs* o) {
@@ -126,6 +129,8 @@ static void carve_phase1(const ev_ctx* c, Carver& cv, int B, int T, Phase1Bufs* 
   o->p2 = cv.take(n * H);
   o->centers = cv.take(n);
   o->ds_f = cv.take(n);
+  o->part_cap = 8 * n * 4 * H;          // split-K partials: up to 8 slices of the widest GEMM output (4H)
+  o->part = cv.take(o->part_cap);
 }
 static void carve_phase2(const ev_ctx* c, Carver& cv, int B, int F, Phase2Bufs* o) {
   const size_t H = c->cfg.hidden, n = (size_t)B * F;
@@ -134,6 +139,8 @@ static void carve_phase2(const ev_ctx* c, Carver& cv, int B, int F, Phase2Bufs* 
   o->qkv = cv.take(n * 3 * H);
   o->ctx = cv.take(n * H);
   o->h = cv.take(n * 4 * H);
+  o->part_cap = 8 * n * 4 * H;
+  o->part = cv.take(o->part_cap);
 }
 static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
   const size_t n = (size_t)B * F * (size_t)c->max_stage_width;
@@ -142,6 +149,8 @@ static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
   o->R1 = cv.take(n);
   o->R2 = cv.take(n);
   o->ACC = cv.take(n);
+  o->part_cap = n;                      // split-K partials (stage-1 convs: 4 slices of B*8F*256)
+  o->part = cv.take(n);
 }
 
 static int find(ev_ctx* c, const std::string& name, uint64_t expect, const float** out) {
@@ -310,6 +319,12 @@ static int conv(const float* x, const float* w, const float* bias, long long bia
 
 // mode 0: fp32 FFMA kernel; 1: tensor cores, one tf32 MMA per K step; 3: tensor cores, 3xTF32 fp32 emulation.
 // Falls back to the FFMA kernel when the layer has no tensor-core weights or an unsupported shape.
+struct SplitWs {
+  float* p = nullptr;
+  size_t cap = 0;
+};
+static thread_local SplitWs g_split_ws;   // set by the phase entry points for the convs they launch
+
 static int conv_x(int mode, const float* w_tc, const float* x, const float* w, const float* bias, long long bias_bs,
                   const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens,
                   int lens_mul, int in_act, float in_slope, int out_act, int acc, float div, cudaStream_t st) {
@@ -320,6 +335,7 @@ static int conv_x(int mode, const float* w_tc, const float* x, const float* w, c
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil;
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope;
   p.out_act = out_act; p.acc = acc; p.div = div;
+  p.splitk_ws = g_split_ws.p; p.splitk_cap = g_split_ws.cap;
   return launch_conv1d_tc(p, mode == 3, st);
 }
 
@@ -476,6 +492,7 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   carve_phase1(ctx, cv, B, T, &b);
   if (cv.off > workspace_bytes) { set_error("ev_am_phase1: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
   EV_TRY(use_device(ctx));
+  g_split_ws.p = b.part; g_split_ws.cap = b.part_cap;
   EV_TRY(launch_lens_to_i32(lens64, lens32_out, B, T, st));
   const int32_t* lens = lens32_out;
   const int32_t* conv_lens = invariant ? lens : nullptr;
@@ -525,6 +542,7 @@ int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens,
   carve_phase2(ctx, cv, B, F, &b);
   if (cv.off > workspace_bytes) { set_error("ev_am_phase2: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
   const int32_t* flens = invariant ? mel_lens : nullptr;
+  g_split_ws.p = b.part; g_split_ws.cap = b.part_cap;
   // length regulator + the decoder's positional encoding (alignment.py:198-211, encoder.py:257-261)
   EV_TRY(launch_gauss_upsample(b1.hs, b1.centers, lens, mel_lens, B, T, H, F, invariant, ctx->pe, ctx->dec.alpha, b.x, st));
   // decoder (model_open_source.py:146: mask None in the reference; per-item lengths under the invariant contract)
@@ -548,6 +566,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   VocBufs v;
   carve_voc(ctx, cv, B, F, &v);
   if (cv.off > workspace_bytes) { set_error("ev_vocoder: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
+  g_split_ws.p = v.part; g_split_ws.cap = v.part_cap;
   const float* m = mel;
   if (!mel_time_major) {
     EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm, B, g.n_mels, F, st));
@@ -608,7 +627,9 @@ int ev_op_conv1d(const float* x, const float* w, const float* bias, size_t bias_
 
 int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* bias, size_t bias_bstride, const float* res,
                     float* out, int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens, int lens_mul,
-                    int in_act, float in_slope, int out_act, int acc, float div, void* stream) {
+                    int in_act, float in_slope, int out_act, int acc, float div, float* splitk_ws, size_t splitk_floats,
+                    void* stream) {
+  g_split_ws.p = splitk_ws; g_split_ws.cap = splitk_ws ? splitk_floats : 0;
   EV_CHECK_ARG(x && w_tc && out, "ev_op_conv1d_tc: null argument");
   EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0, "ev_op_conv1d_tc: needs Cin %% 8 == 0 and Cout %% 16 == 0 (Cin=%d Cout=%d)", Cin, Cout);
   return conv_x(split3 ? 3 : 1, w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul,

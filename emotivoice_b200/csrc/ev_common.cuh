@@ -54,6 +54,9 @@ struct ConvParams {
   int out_act;         // EV_ACT_*
   int acc;             // EV_ACC_*
   float div;
+  // optional scratch for deterministic split-K on the tensor-core path (conv1d_tc.cu); floats
+  float* splitk_ws = nullptr;
+  size_t splitk_cap = 0;
 };
 int launch_conv1d(const ConvParams& p, cudaStream_t st);
 // tcgen05 variant (conv1d_tc.cu); p.w in the tensor-core layout [plane hi|lo][K][Cin/4][Cout][4];

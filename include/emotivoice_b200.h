@@ -173,11 +173,12 @@ EV_API int ev_op_conv1d(const float* x, const float* w, const float* bias, size_
                         int acc, float div, void* stream);
 /* Same contract on the tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM); w_tc is in the
  * tensor-core layout (2 planes hi|lo, K, Cin/4, Cout, 4); split3 != 0 selects 3xTF32 fp32 emulation.
- * Requires Cin % 8 == 0, Cout % 16 == 0. */
+ * Requires Cin % 8 == 0, Cout % 16 == 0.  splitk_ws (optional, splitk_floats floats of scratch) lets a
+ * launch with few output tiles and a long reduction be split along K (deterministic two-pass). */
 EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* bias, size_t bias_bstride,
                            const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
                            const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
-                           int acc, float div, void* stream);
+                           int acc, float div, float* splitk_ws, size_t splitk_floats, void* stream);
 /* LayerNorm over the last dim, eps 1e-12 (encoder.py:112-127). rows x C. */
 EV_API int ev_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int C, void* stream);
 /* Multi-head self-attention core (encoder.py:84-109) on a packed (B,L,3H) q|k|v buffer. */

@@ -24,13 +24,13 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def run_tc(lib, split3, x_tm, w_kio, bias, res, out_init, K, dil, lens, lens_mul, in_act, in_slope, out_act, acc, div, bias_bs=0):
+def run_tc(lib, split3, x_tm, w_kio, bias, res, out_init, K, dil, lens, lens_mul, in_act, in_slope, out_act, acc, div, bias_bs=0, ws=None):
     B, L, Cin = x_tm.shape
     Cout = w_kio.shape[2]
     w_tc = packing.to_tc_layout(w_kio.cpu()).to(x_tm.device)
     out = out_init.clone() if out_init is not None else torch.full((B, L, Cout), float("nan"), device=x_tm.device)
     _abi.check(lib.ev_op_conv1d_tc(_ptr(x_tm), _ptr(w_tc), split3, _ptr(bias), bias_bs, _ptr(res), _ptr(out), B, L, Cin, Cout, K, dil,
-                                   _ptr(lens), lens_mul, in_act, in_slope, out_act, acc, div,
+                                   _ptr(lens), lens_mul, in_act, in_slope, out_act, acc, div, _ptr(ws), 0 if ws is None else ws.numel(),
                                    torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return out
@@ -92,6 +92,28 @@ def test_conv1d_tc_epilogue_and_ragged(lib, dev, split3):
         single = run_tc(lib, split3, x[i:i + 1, :n].contiguous(), w, b, res[i:i + 1, :n].contiguous(), prev[i:i + 1, :n].contiguous(),
                         K, dil, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_GELU, _abi.ACC_ADD_DIV, 3.0)
         assert torch.equal(single[0], out[i, :n])           # batch-invariant, bitwise
+
+
+@pytest.mark.parametrize("split3", [0, 1])
+def test_conv1d_tc_split_k_is_deterministic_and_matches(lib, dev, split3):
+    """Few output tiles + long reduction (the conv-FFN's second conv): K-split over CTAs with private
+    partial buffers and a fixed-order reduce.  Same tolerance; bitwise reproducible; epilogue fused in
+    the reduce kernel (bias, GELU, residual, accumulate)."""
+    g = torch.Generator().manual_seed(31)
+    B, L, Cin, Cout, K = 1, 300, 1536, 384, 3
+    x = torch.randn(B, L, Cin, generator=g).to(dev)
+    w = torch.randn(K, Cin, Cout, generator=g) / math.sqrt(Cin * K)
+    b = torch.randn(Cout, generator=g).to(dev)
+    res = torch.randn(B, L, Cout, generator=g).to(dev)
+    prev = torch.randn(B, L, Cout, generator=g).to(dev)
+    ws = torch.empty(8 * B * L * Cout, device=dev)
+    y = F.conv1d(x.cpu().transpose(1, 2), w.permute(2, 1, 0), b.cpu(), padding=1).transpose(1, 2)
+    ref = (prev.cpu() + (F.gelu(y) + res.cpu())) / 3.0
+    o1 = run_tc(lib, split3, x, w, b, res, prev, K, 1, None, 1, 0, 0.0, _abi.ACT_GELU, _abi.ACC_ADD_DIV, 3.0, ws=ws)
+    o2 = run_tc(lib, split3, x, w, b, res, prev, K, 1, None, 1, 0, 0.0, _abi.ACT_GELU, _abi.ACC_ADD_DIV, 3.0, ws=ws)
+    o0 = run_tc(lib, split3, x, w, b, res, prev, K, 1, None, 1, 0, 0.0, _abi.ACT_GELU, _abi.ACC_ADD_DIV, 3.0, ws=None)
+    assert torch.equal(o1, o2)
+    assert rel_max(o1.cpu(), ref) <= TOL[split3] and rel_max(o0.cpu(), ref) <= TOL[split3]
 
 
 @pytest.mark.parametrize("name", ["b1_t12", "b1_t100"])

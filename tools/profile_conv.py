@@ -33,7 +33,7 @@ for i in range(reps):
                                     None, 1, 1, 0.1, 0, 0, 1.0, st))
     else:
         _abi.check(lib.ev_op_conv1d_tc(x.data_ptr(), wd.data_ptr(), 1 if mode == "fp32" else 0, b.data_ptr(), 0, res.data_ptr(),
-                                       out.data_ptr(), B, L, C, C, K, dil, None, 1, 1, 0.1, 0, 0, 1.0, st))
+                                       out.data_ptr(), B, L, C, C, K, dil, None, 1, 1, 0.1, 0, 0, 1.0, None, 0, st))
     e1.record()
     e1.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
