@@ -102,16 +102,18 @@ int launch_layernorm(const float* x, const int64_t* ids, const float* emb, const
 // [h*DK, (h+1)*DK) of each third (encoder.py:72-82).  Query rows >= key_len are computed like
 // the reference computes them (they attend to the valid keys).
 // ---------------------------------------------------------------------------------------------
-template <int DK>
+template <int DK, int BQ>
 __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ key_lens,
                                                         float* __restrict__ ctx, int L, int H) {
-  constexpr int BQ = 64, BK = 64, LDT = BQ + 1;
-  constexpr int OC = DK / 8;  // output columns per thread
+  constexpr int BK = 64, LDQ = BQ + 1, LDT = BK + 1;
+  constexpr int RQ = BQ / 16;   // query rows per thread
+  constexpr int OC = DK / 8;    // output columns per thread
+  constexpr int D4 = DK / 4;    // float4 per head row
   extern __shared__ __align__(16) float att_smem[];
-  float (*Qt)[LDT] = reinterpret_cast<float (*)[LDT]>(att_smem);                 // [DK][LDT] transposed: [d][query]
-  float (*Kt)[LDT] = reinterpret_cast<float (*)[LDT]>(att_smem + DK * LDT);      // [DK][LDT] transposed: [d][key]
-  float (*Vs)[DK] = reinterpret_cast<float (*)[DK]>(att_smem + 2 * DK * LDT);    // [BK][DK]
-  float (*Ps)[LDT] = reinterpret_cast<float (*)[LDT]>(att_smem + 2 * DK * LDT + BK * DK);   // [BQ][LDT]
+  float (*Qt)[LDQ] = reinterpret_cast<float (*)[LDQ]>(att_smem);                        // [DK][LDQ] transposed: [d][query]
+  float (*Kt)[LDT] = reinterpret_cast<float (*)[LDT]>(att_smem + DK * LDQ);             // [DK][LDT] transposed: [d][key]
+  float (*Vs)[DK] = reinterpret_cast<float (*)[DK]>(att_smem + DK * LDQ + DK * LDT);    // [BK][DK]
+  float (*Ps)[LDT] = reinterpret_cast<float (*)[LDT]>(att_smem + DK * LDQ + DK * LDT + BK * DK);   // [BQ][LDT]
 
   const int tid = threadIdx.x;
   const int tx = tid & 7, ty = tid >> 3;   // 8 x 16
@@ -121,16 +123,18 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   const float* base = qkv + (size_t)b * L * ld;
   const float sqrt_dk = sqrtf((float)DK);
 
-  // load the Q tile (transposed)
-  for (int idx = tid; idx < BQ * DK; idx += 128) {
-    const int r = idx / DK, d = idx % DK;
+  // load the Q tile (transposed), 16-byte global loads
+  for (int idx = tid; idx < BQ * D4; idx += 128) {
+    const int r = idx / D4, d4 = idx % D4;
     const int row = q0 + r;
-    Qt[d][r] = row < L ? base[(size_t)row * ld + h * DK + d] : 0.f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < L) v = *reinterpret_cast<const float4*>(base + (size_t)row * ld + h * DK + d4 * 4);
+    Qt[d4 * 4 + 0][r] = v.x; Qt[d4 * 4 + 1][r] = v.y; Qt[d4 * 4 + 2][r] = v.z; Qt[d4 * 4 + 3][r] = v.w;
   }
 
-  float m_i[4], l_i[4], o[4][OC];
+  float m_i[RQ], l_i[RQ], o[RQ][OC];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < RQ; ++i) {
     m_i[i] = -INFINITY;
     l_i[i] = 0.f;
 #pragma unroll
@@ -139,40 +143,40 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 
   for (int k0 = 0; k0 < klen; k0 += BK) {
     __syncthreads();   // previous tile fully consumed (also orders the Q tile on the first pass)
-    for (int idx = tid; idx < BK * DK; idx += 128) {
-      const int r = idx / DK, d = idx % DK;
+    for (int idx = tid; idx < BK * D4; idx += 128) {
+      const int r = idx / D4, d4 = idx % D4;
       const int row = k0 + r;
-      float kv = 0.f, vv = 0.f;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
       if (row < klen) {
-        kv = base[(size_t)row * ld + H + h * DK + d];
-        vv = base[(size_t)row * ld + 2 * H + h * DK + d];
+        kv = *reinterpret_cast<const float4*>(base + (size_t)row * ld + H + h * DK + d4 * 4);
+        vv = *reinterpret_cast<const float4*>(base + (size_t)row * ld + 2 * H + h * DK + d4 * 4);
       }
-      Kt[d][r] = kv;
-      Vs[r][d] = vv;
+      Kt[d4 * 4 + 0][r] = kv.x; Kt[d4 * 4 + 1][r] = kv.y; Kt[d4 * 4 + 2][r] = kv.z; Kt[d4 * 4 + 3][r] = kv.w;
+      *reinterpret_cast<float4*>(&Vs[r][d4 * 4]) = vv;
     }
     __syncthreads();
 
-    // S = Q K^T : thread owns rows ty*4..+3, cols tx + 8j
-    float s[4][8];
+    // S = Q K^T : thread owns rows ty*RQ..+RQ-1, cols tx + 8j
+    float s[RQ][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RQ; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[i][j] = 0.f;
 #pragma unroll 4
     for (int d = 0; d < DK; ++d) {
-      float qv[4], kv[8];
+      float qv[RQ], kv[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qv[i] = Qt[d][ty * 4 + i];
+      for (int i = 0; i < RQ; ++i) qv[i] = Qt[d][ty * RQ + i];
 #pragma unroll
       for (int j = 0; j < 8; ++j) kv[j] = Kt[d][tx + 8 * j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RQ; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[i][j] = fmaf(qv[i], kv[j], s[i][j]);
     }
     // scale, mask, online softmax
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RQ; ++i) {
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
       for (int j = 0; j < 8; ++j) {
         const float pv = expf(s[i][j] - m_new);
         rs += pv;
-        Ps[ty * 4 + i][tx + 8 * j] = pv;
+        Ps[ty * RQ + i][tx + 8 * j] = pv;
       }
       rs += __shfl_xor_sync(0xffffffffu, rs, 1);
       rs += __shfl_xor_sync(0xffffffffu, rs, 2);
@@ -200,17 +204,17 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 #pragma unroll
       for (int c = 0; c < OC; ++c) o[i][c] *= scale;
     }
-    __syncwarp();   // Ps rows ty*4..+3 are written and read by the same 8 lanes (one warp)
-    // O += P V : thread owns rows ty*4..+3, cols tx + 8c
+    __syncwarp();   // Ps rows ty*RQ.. are written and read by the same 8 lanes (one warp)
+    // O += P V : thread owns rows ty*RQ..+RQ-1, cols tx + 8c
 #pragma unroll 4
     for (int k = 0; k < BK; ++k) {
-      float pv[4], vv[OC];
+      float pv[RQ], vv[OC];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pv[i] = Ps[ty * 4 + i][k];
+      for (int i = 0; i < RQ; ++i) pv[i] = Ps[ty * RQ + i][k];
 #pragma unroll
       for (int c = 0; c < OC; ++c) vv[c] = Vs[k][tx + 8 * c];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RQ; ++i)
 #pragma unroll
         for (int c = 0; c < OC; ++c) o[i][c] = fmaf(pv[i], vv[c], o[i][c]);
     }
@@ -218,8 +222,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 
   float* ob = ctx + (size_t)b * L * H;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = q0 + ty * 4 + i;
+  for (int i = 0; i < RQ; ++i) {
+    const int row = q0 + ty * RQ + i;
     if (row >= L) continue;
     const float inv = 1.0f / l_i[i];
 #pragma unroll
@@ -227,18 +231,17 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   }
 }
 
-template <int DK>
+template <int DK, int BQ>
 static int launch_attention_dk(const float* qkv, const int32_t* key_lens, float* ctx, int B, int L, int H, int heads,
                                cudaStream_t st) {
-  constexpr int LDT = 65;
-  const size_t smem = (size_t)(2 * DK * LDT + 64 * DK + 64 * LDT) * sizeof(float);
+  const size_t smem = (size_t)(DK * (BQ + 1) + DK * 65 + 64 * DK + BQ * 65) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attention_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(attention_kernel<DK, BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  dim3 grid((L + 63) / 64, heads, B);
-  attention_kernel<DK><<<grid, 128, smem, st>>>(qkv, key_lens, ctx, L, H);
+  dim3 grid((L + BQ - 1) / BQ, heads, B);
+  attention_kernel<DK, BQ><<<grid, 128, smem, st>>>(qkv, key_lens, ctx, L, H);
   EV_CUDA_LAUNCH_CHECK("attention_kernel");
   return EV_OK;
 }
@@ -248,9 +251,14 @@ int launch_attention(const float* qkv, const int32_t* key_lens, float* ctx, int 
   EV_CHECK_ARG(B > 0 && L > 0 && heads > 0 && H % heads == 0, "attention: bad shape B=%d L=%d H=%d heads=%d", B, L, H, heads);
   EV_CHECK_ARG(B <= 65535 && heads <= 65535, "attention: grid too large");
   const int dk = H / heads;
-  if (dk == 48) return launch_attention_dk<48>(qkv, key_lens, ctx, B, L, H, heads, st);
-  if (dk == 64) return launch_attention_dk<64>(qkv, key_lens, ctx, B, L, H, heads, st);
-  if (dk == 32) return launch_attention_dk<32>(qkv, key_lens, ctx, B, L, H, heads, st);
+  // 32-query tiles while 64-query tiles would leave SMs idle (batch 1), 64-query tiles otherwise
+  const bool small = (long long)((L + 63) / 64) * heads * B < 2 * 148;
+  if (dk == 48) return small ? launch_attention_dk<48, 32>(qkv, key_lens, ctx, B, L, H, heads, st)
+                             : launch_attention_dk<48, 64>(qkv, key_lens, ctx, B, L, H, heads, st);
+  if (dk == 64) return small ? launch_attention_dk<64, 32>(qkv, key_lens, ctx, B, L, H, heads, st)
+                             : launch_attention_dk<64, 64>(qkv, key_lens, ctx, B, L, H, heads, st);
+  if (dk == 32) return small ? launch_attention_dk<32, 32>(qkv, key_lens, ctx, B, L, H, heads, st)
+                             : launch_attention_dk<32, 64>(qkv, key_lens, ctx, B, L, H, heads, st);
   set_error("attention: unsupported head dim %d (32/48/64)", dk);
   return EV_EINVAL;
 }
