@@ -128,12 +128,12 @@ struct Plan {
 };
 
 // smem map: [0,288) barriers | [512,516) tmem base | 1024: epilogue staging (8 warps x 4 KB) | A ring | B ring
-__host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int mt, int kbg, int min_b_stages, Plan* o) {
+__host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int BN, int mt, int kbg, int min_b_stages, Plan* o) {
   Plan q;
   q.planes = split3 ? 2 : 1;
   q.kbg = kbg;
   q.mt = mt;
-  q.BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
+  q.BN = BN;
   if (2 * mt * q.BN > 512) return false;
   q.tmem_cols = 32;
   while (q.tmem_cols < 2 * mt * q.BN) q.tmem_cols <<= 1;
@@ -596,28 +596,35 @@ int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
   EV_CHECK_ARG(p.Cout % 16 == 0, "conv1d_tc: Cout=%d must be a multiple of 16", p.Cout);
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
   EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
-  // rows per tile: as many 128-row accumulators as still leave about one tile per SM (each weight
-  // tile fetched from L2 then feeds MT MMAs), limited by TMEM (2 x MT x BN <= 512 columns) and smem.
-  // K granules per stage: 8 (32 channels) if the rings still get >= 2 A stages and >= 4 weight stages, else 4.
+  // Tile shape.  None of these choices changes the order in which any output element's K reduction is
+  // summed, so results are bitwise independent of batch size / sequence length (batch-invariant contract).
+  //  * N tile: a single 256-wide tile when C_out == 256 in 1x mode, else <= 128; halved (down to 32) while
+  //    the launch would leave most SMs without a tile (batch 1: HiFi-GAN stage 1, the AM GEMMs) -- each
+  //    CTA then streams 1/2..1/4 of the weights.
+  //  * rows per tile: as many 128-row accumulators as still leave about one tile per SM (every weight tile
+  //    fetched from L2 then feeds MT MMAs), limited by TMEM (2 x MT x BN <= 512 columns) and smem.
   const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
+  int BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
+  while (BN >= 64 && (BN / 2) % 16 == 0 && tiles128 * ((p.Cout + BN - 1) / BN) < 96) BN /= 2;
   int mt = tiles128 >= 4 * 120 ? 4 : (tiles128 >= 2 * 120 ? 2 : 1);
   tc::Plan pl;
+  // K granules per stage decide how the (channel block, tap) reduction is ordered, so they must be a function
+  // of the layer shape alone: 8 if a (widest-N, one-accumulator) tile fits with them in 1x mode, else 4.
+  const int bn_max = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
+  const int kbg = (!split3 && tc::make_plan(p, split3, bn_max, 1, 8, 4, &pl)) ? 8 : 4;
   for (;; mt >>= 1) {
-    if (!split3 && tc::make_plan(p, split3, mt, 8, 4, &pl)) break;
-    if (tc::make_plan(p, split3, mt, 4, 4, &pl)) break;
-    if (tc::make_plan(p, split3, mt, 4, 2, &pl)) break;
+    if (tc::make_plan(p, split3, BN, mt, kbg, 4, &pl)) break;
+    if (tc::make_plan(p, split3, BN, mt, kbg, 2, &pl)) break;
     if (mt == 1) { set_error("conv1d_tc: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
   }
-  // K-split: few output tiles but a long reduction (the conv-FFN's second conv at batch 1: 15 tiles, K = 3*1536;
-  // HiFi-GAN stage 1) leaves most SMs idle and makes the launch one long serial chain -> share each tile among
-  // S CTAs.  Deterministic: private partial buffers + a fixed-order reduce kernel.
-  const int n_cb = (p.Cin + 4 * pl.kbg - 1) / (4 * pl.kbg);
+  // K-split: a long reduction into a narrow output (the conv-FFN's second conv: K = 3*1536 -> 384) is one long
+  // serial chain per tile; share it among S CTAs with private partial buffers + a fixed-order reduce kernel.
+  // S depends on the LAYER SHAPE only (never on batch or length), so the summation order -- and therefore
+  // every output bit -- is the same for a B=1 call and for the same utterance inside any batch.
   const size_t per = (size_t)p.B * p.L * p.Cout;
-  if (p.splitk_ws && pl.total_tiles * 2 <= sm_count() && n_cb >= 8) {
-    int S = sm_count() / pl.total_tiles;
-    if (S > 8) S = 8;
-    if (S > n_cb / 4) S = n_cb / 4;
-    while (S > 1 && (size_t)S * per > p.splitk_cap) --S;
+  if (p.splitk_ws && p.Cin >= 1024 && p.Cout <= 512) {
+    int S = 4;
+    while (S > 1 && (size_t)S * per > p.splitk_cap) S >>= 1;
     if (S > 1) {
       pl.ksplit = S;
       pl.total_tiles *= S;
