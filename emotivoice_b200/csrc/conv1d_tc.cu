@@ -617,14 +617,17 @@ int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
     if (tc::make_plan(p, split3, BN, mt, kbg, 2, &pl)) break;
     if (mt == 1) { set_error("conv1d_tc: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
   }
-  // K-split: a long reduction into a narrow output (the conv-FFN's second conv: K = 3*1536 -> 384) is one long
-  // serial chain per tile; share it among S CTAs with private partial buffers + a fixed-order reduce kernel.
-  // S depends on the LAYER SHAPE only (never on batch or length), so the summation order -- and therefore
-  // every output bit -- is the same for a B=1 call and for the same utterance inside any batch.
+  // K-split: a long reduction at few output tiles (the acoustic model's GEMMs at batch 1; the conv-FFN's second
+  // conv has K = 3*1536) is one long serial chain per tile; share it among S CTAs with private partial buffers
+  // + a fixed-order reduce kernel.  S is requested per LAYER by the engine (never derived from batch or
+  // length), so the summation order -- and therefore every output bit -- is the same for a B=1 call and for
+  // the same utterance inside any batch.
   const size_t per = (size_t)p.B * p.L * p.Cout;
-  if (p.splitk_ws && p.Cin >= 1024 && p.Cout <= 512) {
-    int S = 4;
-    while (S > 1 && (size_t)S * per > p.splitk_cap) S >>= 1;
+  if (p.splitk_ws && p.ksplit > 1) {
+    int S = p.ksplit;
+    const int n_cb = (p.Cin + 4 * pl.kbg - 1) / (4 * pl.kbg);
+    if (S > n_cb) S = n_cb;
+    if ((size_t)S * per > p.splitk_cap) { set_error("conv1d_tc: split-K scratch too small (%zu < %zu floats)", p.splitk_cap, (size_t)S * per); return EV_EWORKSPACE; }
     if (S > 1) {
       pl.ksplit = S;
       pl.total_tiles *= S;

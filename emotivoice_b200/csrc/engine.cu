@@ -322,6 +322,7 @@ static int conv(const float* x, const float* w, const float* bias, long long bia
 struct SplitWs {
   float* p = nullptr;
   size_t cap = 0;
+  int ksplit = 0;     // K-split factor for the convs launched next (set per layer, see conv1d_tc.cu)
 };
 static thread_local SplitWs g_split_ws;   // set by the phase entry points for the convs they launch
 
@@ -335,7 +336,7 @@ static int conv_x(int mode, const float* w_tc, const float* x, const float* w, c
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil;
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope;
   p.out_act = out_act; p.acc = acc; p.div = div;
-  p.splitk_ws = g_split_ws.p; p.splitk_cap = g_split_ws.cap;
+  p.splitk_ws = g_split_ws.p; p.splitk_cap = g_split_ws.cap; p.ksplit = g_split_ws.ksplit;
   return launch_conv1d_tc(p, mode == 3, st);
 }
 
@@ -353,17 +354,21 @@ static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float
     const EncLayerW& l = s.layers[i];
     if (!(i == 0 && first_ln_done))
       EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln1w, l.ln1b, y, B * L, L, H, st));
+    g_split_ws.ksplit = 2;   // K = H: two slices
     EV_TRY(conv_x(mode, l.wqkv_tc, y, l.wqkv, l.bqkv, 0, nullptr, qkv, B, L, H, 3 * H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
                   EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
     EV_TRY(launch_attention(qkv, key_lens, ctxb, B, L, H, heads, st));
     EV_TRY(conv_x(mode, l.wo_tc, ctxb, l.wo, l.bo, 0, x, x, B, L, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
                   EV_ACC_STORE, 1.f, st));
     EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln2w, l.ln2b, y, B * L, L, H, st));
+    g_split_ws.ksplit = 2;
     EV_TRY(conv_x(mode, l.w1_tc, y, l.w1, l.b1, 0, nullptr, h, B, L, H, 4 * H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_GELU,
                   EV_ACC_STORE, 1.f, st));
+    g_split_ws.ksplit = 4;   // K = 3 * 4H: four slices
     EV_TRY(conv_x(mode, l.w2_tc, h, l.w2, l.b2, 0, x, x, B, L, 4 * H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
                   EV_ACC_STORE, 1.f, st));
   }
+  g_split_ws.ksplit = 2;
   EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, s.lnfw, s.lnfb, y, B * L, L, H, st));
   return EV_OK;
 }
@@ -492,7 +497,7 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   carve_phase1(ctx, cv, B, T, &b);
   if (cv.off > workspace_bytes) { set_error("ev_am_phase1: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
   EV_TRY(use_device(ctx));
-  g_split_ws.p = b.part; g_split_ws.cap = b.part_cap;
+  g_split_ws.p = b.part; g_split_ws.cap = b.part_cap; g_split_ws.ksplit = 2;
   EV_TRY(launch_lens_to_i32(lens64, lens32_out, B, T, st));
   const int32_t* lens = lens32_out;
   const int32_t* conv_lens = invariant ? lens : nullptr;
@@ -542,7 +547,7 @@ int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens,
   carve_phase2(ctx, cv, B, F, &b);
   if (cv.off > workspace_bytes) { set_error("ev_am_phase2: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
   const int32_t* flens = invariant ? mel_lens : nullptr;
-  g_split_ws.p = b.part; g_split_ws.cap = b.part_cap;
+  g_split_ws.p = b.part; g_split_ws.cap = b.part_cap; g_split_ws.ksplit = 2;
   // length regulator + the decoder's positional encoding (alignment.py:198-211, encoder.py:257-261)
   EV_TRY(launch_gauss_upsample(b1.hs, b1.centers, lens, mel_lens, B, T, H, F, invariant, ctx->pe, ctx->dec.alpha, b.x, st));
   // decoder (model_open_source.py:146: mask None in the reference; per-item lengths under the invariant contract)
@@ -566,7 +571,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   VocBufs v;
   carve_voc(ctx, cv, B, F, &v);
   if (cv.off > workspace_bytes) { set_error("ev_vocoder: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
-  g_split_ws.p = v.part; g_split_ws.cap = v.part_cap;
+  g_split_ws.p = v.part; g_split_ws.cap = v.part_cap; g_split_ws.ksplit = 0;   // vocoder: outputs too large to split (traffic)
   const float* m = mel;
   if (!mel_time_major) {
     EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm, B, g.n_mels, F, st));
@@ -629,7 +634,7 @@ int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* 
                     float* out, int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens, int lens_mul,
                     int in_act, float in_slope, int out_act, int acc, float div, float* splitk_ws, size_t splitk_floats,
                     void* stream) {
-  g_split_ws.p = splitk_ws; g_split_ws.cap = splitk_ws ? splitk_floats : 0;
+  g_split_ws.p = splitk_ws; g_split_ws.cap = splitk_ws ? splitk_floats : 0; g_split_ws.ksplit = splitk_ws ? 4 : 0;
   EV_CHECK_ARG(x && w_tc && out, "ev_op_conv1d_tc: null argument");
   EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0, "ev_op_conv1d_tc: needs Cin %% 8 == 0 and Cout %% 16 == 0 (Cin=%d Cout=%d)", Cin, Cout);
   return conv_x(split3 ? 3 : 1, w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul,

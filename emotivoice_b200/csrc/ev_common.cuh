@@ -57,6 +57,8 @@ struct ConvParams {
   // optional scratch for deterministic split-K on the tensor-core path (conv1d_tc.cu); floats
   float* splitk_ws = nullptr;
   size_t splitk_cap = 0;
+  int ksplit = 0;      // requested K-split factor (fixed per LAYER by the engine, never by batch size: keeps the
+                       // summation order, hence every output bit, independent of how utterances are batched)
 };
 int launch_conv1d(const ConvParams& p, cudaStream_t st);
 // tcgen05 variant (conv1d_tc.cu); p.w in the tensor-core layout [plane hi|lo][K][Cin/4][Cout][4];

@@ -177,6 +177,9 @@ class _EngineOwner(nn.Module):
         self._ev_precision = value
         if self._ev_engine is not None:
             self._ev_engine.set_precision(value)
+        for m in self.children():            # JETSGenerator.precision also governs .am / .generator used stand-alone
+            if isinstance(m, _EngineOwner):
+                m.precision = value
 
     def _mark_dirty(self):
         self._ev_dirty = True
