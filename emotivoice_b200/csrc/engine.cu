@@ -83,6 +83,9 @@ struct ev_ctx {
   int post_k = 7;
   int total_up = 1;
   int max_stage_width = 0;   // max over stages of prod(rates so far) * channels
+  // two auxiliary streams: at small batch the three ResBlocks of a stage (and the three predictors) are
+  // independent chains of small launches; running them side by side fills the SMs the single chain leaves idle
+  cudaStream_t aux[2] = {nullptr, nullptr};
 };
 
 namespace ev {
@@ -102,7 +105,7 @@ struct Carver {
 };
 
 struct Phase1Bufs {
-  float *x, *y, *qkv, *ctx, *h, *cond_in, *cond_bias, *hs, *pm, *p1, *p2, *centers, *ds_f, *part;
+  float *x, *y, *qkv, *ctx, *h, *cond_in, *cond_bias, *hs, *pm, *p1[3], *p2[3], *centers, *ds_f, *part;
   size_t part_cap;
 };
 struct Phase2Bufs {
@@ -110,8 +113,9 @@ struct Phase2Bufs {
   size_t part_cap;
 };
 struct VocBufs {
-  float *X, *Tm, *R1, *R2, *ACC, *part;
-  size_t part_cap;
+  float *X, *ACC;
+  float *Tm[3], *R1[3], *R2[3];   // per-ResBlock chain scratch (chains 1,2 alias chain 0 when run sequentially)
+  bool concurrent;
 };
 
 static void carve_phase1(const ev_ctx* c, Carver& cv, int B, int T, Phase1Bufs* o) {
@@ -125,8 +129,7 @@ static void carve_phase1(const ev_ctx* c, Carver& cv, int B, int T, Phase1Bufs* 
   o->cond_bias = cv.take((size_t)B * H);
   o->hs = cv.take(n * H);
   o->pm = cv.take(n * H);
-  o->p1 = cv.take(n * H);
-  o->p2 = cv.take(n * H);
+  for (int i = 0; i < 3; ++i) { o->p1[i] = cv.take(n * H); o->p2[i] = cv.take(n * H); }
   o->centers = cv.take(n);
   o->ds_f = cv.take(n);
   o->part_cap = 8 * n * 4 * H;          // split-K partials: up to 8 slices of the widest GEMM output (4H)
@@ -142,15 +145,45 @@ static void carve_phase2(const ev_ctx* c, Carver& cv, int B, int F, Phase2Bufs* 
   o->part_cap = 8 * n * 4 * H;
   o->part = cv.take(o->part_cap);
 }
+// ResBlock chains run concurrently (3x the chain scratch) only while the whole call is small: that is where a
+// single chain cannot fill the GPU, and where the extra scratch is cheap.
+static inline bool voc_concurrent(int B, int F) { return (long long)B * F <= 4096; }
+
 static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
   const size_t n = (size_t)B * F * (size_t)c->max_stage_width;
+  o->concurrent = voc_concurrent(B, F);
   o->X = cv.take(n);
-  o->Tm = cv.take(n);
-  o->R1 = cv.take(n);
-  o->R2 = cv.take(n);
   o->ACC = cv.take(n);
-  o->part_cap = n;                      // split-K partials (stage-1 convs: 4 slices of B*8F*256)
-  o->part = cv.take(n);
+  for (int i = 0; i < 3; ++i) {
+    if (i == 0 || o->concurrent) {
+      o->Tm[i] = cv.take(n);
+      o->R1[i] = cv.take(n);
+      o->R2[i] = cv.take(n);
+    } else {
+      o->Tm[i] = o->Tm[0]; o->R1[i] = o->R1[0]; o->R2[i] = o->R2[0];
+    }
+  }
+}
+
+// fork/join helpers: events are created per call (cheap, timing disabled) so concurrent callers never share one
+struct EventPool {
+  std::vector<cudaEvent_t> evs;
+  cudaEvent_t get() {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    evs.push_back(e);
+    return e;
+  }
+  ~EventPool() { for (auto e : evs) cudaEventDestroy(e); }   // deferred by the runtime until the event completes
+};
+static int edge(EventPool& pool, cudaStream_t from, cudaStream_t to) {   // work queued on `to` after this waits for `from`
+  if (from == to) return EV_OK;
+  cudaEvent_t e = pool.get();
+  if (!e || cudaEventRecord(e, from) != cudaSuccess || cudaStreamWaitEvent(to, e, 0) != cudaSuccess) {
+    set_error("stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return EV_ECUDA;
+  }
+  return EV_OK;
 }
 
 static int find(ev_ctx* c, const std::string& name, uint64_t expect, const float** out) {
@@ -378,6 +411,7 @@ static int run_predictor(const ev_ctx* c, const PredW& p, const float* in, float
                          const int32_t* lens, const int32_t* conv_lens, int mode, float* out_f, int64_t* out_i,
                          int cmode, cudaStream_t st) {
   const int H = c->cfg.hidden, K = c->cfg.pred_kernel;
+  g_split_ws.ksplit = 0;   // the three predictor chains run concurrently and would share the split-K scratch
   const float* cur = in;
   for (size_t i = 0; i < p.w.size(); ++i) {
     EV_TRY(conv_x(cmode, p.w_tc[i], cur, p.w[i], p.b[i], 0, nullptr, t1, B, T, H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
@@ -418,11 +452,18 @@ int ev_create(ev_ctx** out, int device, const ev_config* cfg) {
   ev_ctx* c = new ev_ctx();
   c->cfg = *cfg;
   c->device = device;
+  for (int i = 0; i < 2; ++i)
+    if (cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking) != cudaSuccess) c->aux[i] = nullptr;
   *out = c;
   return EV_OK;
 }
 
-void ev_destroy(ev_ctx* ctx) { delete ctx; }
+void ev_destroy(ev_ctx* ctx) {
+  if (!ctx) return;
+  for (int i = 0; i < 2; ++i)
+    if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+  delete ctx;
+}
 
 int ev_bind_weights(ev_ctx* ctx, const float* blob, size_t n_floats, const ev_weight_entry* index, int n_entries) {
   EV_CHECK_ARG(ctx && blob && index && n_entries > 0, "ev_bind_weights: null argument");
@@ -519,9 +560,18 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
     EV_TRY(launch_mask_rows(b.hs, lens, b.pm, B, T, H, st));
     pin = b.pm;
   }
-  EV_TRY(run_predictor(ctx, ctx->pitch, pin, b.p1, b.p2, B, T, lens, conv_lens, 0, pitch_out, nullptr, prefix_mode, st));
-  EV_TRY(run_predictor(ctx, ctx->energy, pin, b.p1, b.p2, B, T, lens, conv_lens, 0, energy_out, nullptr, prefix_mode, st));
-  EV_TRY(run_predictor(ctx, ctx->dur, pin, b.p1, b.p2, B, T, lens, conv_lens, 1, nullptr, dur_out, prefix_mode, st));
+  {
+    // three independent predictor chains: pitch on the caller's stream, energy / duration on the auxiliary ones
+    EventPool pool;
+    cudaStream_t s1 = ctx->aux[0] ? ctx->aux[0] : st, s2 = ctx->aux[1] ? ctx->aux[1] : st;
+    EV_TRY(edge(pool, st, s1));
+    EV_TRY(edge(pool, st, s2));
+    EV_TRY(run_predictor(ctx, ctx->pitch, pin, b.p1[0], b.p2[0], B, T, lens, conv_lens, 0, pitch_out, nullptr, prefix_mode, st));
+    EV_TRY(run_predictor(ctx, ctx->energy, pin, b.p1[1], b.p2[1], B, T, lens, conv_lens, 0, energy_out, nullptr, prefix_mode, s1));
+    EV_TRY(run_predictor(ctx, ctx->dur, pin, b.p1[2], b.p2[2], B, T, lens, conv_lens, 1, nullptr, dur_out, prefix_mode, s2));
+    EV_TRY(edge(pool, s1, st));
+    EV_TRY(edge(pool, s2, st));
+  }
   // x = x + pitch_embed + energy_embed (model_open_source.py:131-134)
   EV_TRY(launch_var_embed_add(b.hs, pitch_out, energy_out, ctx->pemb_w, ctx->pemb_b, ctx->eemb_w, ctx->eemb_b, B, T, H,
                               g.embed_kernel, st));
@@ -571,16 +621,21 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   VocBufs v;
   carve_voc(ctx, cv, B, F, &v);
   if (cv.off > workspace_bytes) { set_error("ev_vocoder: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
-  g_split_ws.p = v.part; g_split_ws.cap = v.part_cap; g_split_ws.ksplit = 0;   // vocoder: outputs too large to split (traffic)
+  g_split_ws.p = nullptr; g_split_ws.cap = 0; g_split_ws.ksplit = 0;   // vocoder outputs are too large to K-split (traffic)
   const float* m = mel;
   if (!mel_time_major) {
-    EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm, B, g.n_mels, F, st));
-    m = v.Tm;
+    EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm[0], B, g.n_mels, F, st));
+    m = v.Tm[0];
   }
   // conv_pre (hifigan/models.py:116)
   const int mode = body_mode(ctx);
   EV_TRY(conv_x(mode, ctx->pre.w_tc, m, ctx->pre.w, ctx->pre.b, 0, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1,
                 mel_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+  // chain j of a stage (ResBlock j) runs on its own stream when the call is small; the xs accumulation
+  // (xs = r0; xs += r1; xs += r2; x = xs / 3, :120-126) keeps its order through events
+  const bool par = v.concurrent && g.n_resk <= 3 && ctx->aux[0] && ctx->aux[1];
+  cudaStream_t chain_st[3] = {st, par ? ctx->aux[0] : st, par ? ctx->aux[1] : st};
+  EventPool pool;
   int L = F, mul = 1;
   size_t rb = 0;
   for (int s = 0; s < g.n_ups; ++s) {
@@ -591,24 +646,29 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
     L *= u.rate; mul *= u.rate;
     const int C = u.cout;
     for (int j = 0; j < g.n_resk; ++j) {
+      cudaStream_t cs = chain_st[j % 3];
+      const int cj = par ? j % 3 : 0;
+      EV_TRY(edge(pool, st, cs));                       // X (and the previous stage) is ready
       const float* src = v.X;
       for (int l = 0; l < g.n_dil; ++l, ++rb) {
         const ConvW& c1 = ctx->rb_c1[rb];
         const ConvW& c2 = ctx->rb_c2[rb];
         // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
-        EV_TRY(conv_x(mode, c1.w_tc, src, c1.w, c1.b, 0, nullptr, v.Tm, B, L, C, C, c1.K, c1.dil, mel_lens, mul,
-                      EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+        EV_TRY(conv_x(mode, c1.w_tc, src, c1.w, c1.b, 0, nullptr, v.Tm[cj], B, L, C, C, c1.K, c1.dil, mel_lens, mul,
+                      EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, cs));
         const bool last = (l == g.n_dil - 1);
-        float* dst = last ? v.ACC : ((l & 1) ? v.R2 : v.R1);
+        float* dst = last ? v.ACC : ((l & 1) ? v.R2[cj] : v.R1[cj]);
         int acc = EV_ACC_STORE;
         if (last && j > 0) acc = (j == g.n_resk - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;   // xs += ...; x = xs / n (:120-126)
         const float div = (float)g.n_resk;
         if (last && g.n_resk == 1) acc = EV_ACC_STORE;
-        EV_TRY(conv_x(mode, c2.w_tc, v.Tm, c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
-                      EV_ACT_NONE, acc, div, st));
+        if (last && j > 0) EV_TRY(edge(pool, chain_st[(j - 1) % 3], cs));   // xs accumulation in ResBlock order
+        EV_TRY(conv_x(mode, c2.w_tc, v.Tm[cj], c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+                      EV_ACT_NONE, acc, div, cs));
         src = dst;
       }
     }
+    EV_TRY(edge(pool, chain_st[(g.n_resk - 1) % 3], st));   // the stage output (ACC) is complete
   }
   // x = leaky_relu(x) [slope 0.01]; conv_post; tanh (:127-129)
   EV_CHECK_ARG(mul == ctx->total_up, "ev_vocoder: internal rate mismatch");
