@@ -4,6 +4,7 @@
 // caller's stream and carves the caller-provided workspace.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -147,7 +148,14 @@ static void carve_phase2(const ev_ctx* c, Carver& cv, int B, int F, Phase2Bufs* 
 }
 // ResBlock chains run concurrently (3x the chain scratch) only while the whole call is small: that is where a
 // single chain cannot fill the GPU, and where the extra scratch is cheap.
-static inline bool voc_concurrent(int B, int F) { return (long long)B * F <= 4096; }
+// EXPERIMENTAL (off by default, EV_STREAMS=1 enables): the first on-device trial of the multi-stream path hung,
+// so until that is understood every chain runs on the caller's stream.
+static inline bool streams_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EV_STREAMS"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+static inline bool voc_concurrent(int B, int F) { return streams_enabled() && (long long)B * F <= 4096; }
 
 static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
   const size_t n = (size_t)B * F * (size_t)c->max_stage_width;
@@ -563,7 +571,8 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   {
     // three independent predictor chains: pitch on the caller's stream, energy / duration on the auxiliary ones
     EventPool pool;
-    cudaStream_t s1 = ctx->aux[0] ? ctx->aux[0] : st, s2 = ctx->aux[1] ? ctx->aux[1] : st;
+    const bool fork = streams_enabled() && ctx->aux[0] && ctx->aux[1];
+    cudaStream_t s1 = fork ? ctx->aux[0] : st, s2 = fork ? ctx->aux[1] : st;
     EV_TRY(edge(pool, st, s1));
     EV_TRY(edge(pool, st, s2));
     EV_TRY(run_predictor(ctx, ctx->pitch, pin, b.p1[0], b.p2[0], B, T, lens, conv_lens, 0, pitch_out, nullptr, prefix_mode, st));
@@ -645,10 +654,10 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
                   EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
     L *= u.rate; mul *= u.rate;
     const int C = u.cout;
+    for (int j = 1; j < 3; ++j) EV_TRY(edge(pool, st, chain_st[j]));   // fork: X (and the previous stage) is ready
     for (int j = 0; j < g.n_resk; ++j) {
       cudaStream_t cs = chain_st[j % 3];
       const int cj = par ? j % 3 : 0;
-      EV_TRY(edge(pool, st, cs));                       // X (and the previous stage) is ready
       const float* src = v.X;
       for (int l = 0; l < g.n_dil; ++l, ++rb) {
         const ConvW& c1 = ctx->rb_c1[rb];
