@@ -150,12 +150,12 @@ static void carve_phase2(const ev_ctx* c, Carver& cv, int B, int F, Phase2Bufs* 
 // single chain cannot fill the GPU, and where the extra scratch is cheap.
 // EXPERIMENTAL (off by default, EV_STREAMS=1 enables): the first on-device trial of the multi-stream path hung,
 // so until that is understood every chain runs on the caller's stream.
-static inline bool streams_enabled() {
+static inline int streams_mask() {     // bit 0: predictor chains, bit 1: ResBlock chains
   static int v = -1;
-  if (v < 0) { const char* e = getenv("EV_STREAMS"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
+  if (v < 0) { const char* e = getenv("EV_STREAMS"); v = e ? atoi(e) : 0; }
+  return v;
 }
-static inline bool voc_concurrent(int B, int F) { return streams_enabled() && (long long)B * F <= 4096; }
+static inline bool voc_concurrent(int B, int F) { return (streams_mask() & 2) && (long long)B * F <= 4096; }
 
 static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
   const size_t n = (size_t)B * F * (size_t)c->max_stage_width;
@@ -419,7 +419,7 @@ static int run_predictor(const ev_ctx* c, const PredW& p, const float* in, float
                          const int32_t* lens, const int32_t* conv_lens, int mode, float* out_f, int64_t* out_i,
                          int cmode, cudaStream_t st) {
   const int H = c->cfg.hidden, K = c->cfg.pred_kernel;
-  g_split_ws.ksplit = 0;   // the three predictor chains run concurrently and would share the split-K scratch
+  g_split_ws.ksplit = (streams_mask() & 1) ? 0 : 2;   // concurrent predictor chains would share the split-K scratch
   const float* cur = in;
   for (size_t i = 0; i < p.w.size(); ++i) {
     EV_TRY(conv_x(cmode, p.w_tc[i], cur, p.w[i], p.b[i], 0, nullptr, t1, B, T, H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
@@ -571,7 +571,7 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   {
     // three independent predictor chains: pitch on the caller's stream, energy / duration on the auxiliary ones
     EventPool pool;
-    const bool fork = streams_enabled() && ctx->aux[0] && ctx->aux[1];
+    const bool fork = (streams_mask() & 1) && ctx->aux[0] && ctx->aux[1];
     cudaStream_t s1 = fork ? ctx->aux[0] : st, s2 = fork ? ctx->aux[1] : st;
     EV_TRY(edge(pool, st, s1));
     EV_TRY(edge(pool, st, s2));
