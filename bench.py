@@ -244,11 +244,18 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
     ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     if use_tc:
         mma_mult = 3 if split3 else 1
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes/launch from the committed ncu --set full capture
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(precision, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
         return {
             "kernel": "conv1d_tc_kernel<%s> (tcgen05 kind::tf32, %s; HiFi-GAN stage-2 ResBlock conv, C=128, k=11, L=%d)"
                       % ("true" if split3 else "false", "3xTF32 fp32 emulation" if split3 else "1xTF32", L),
             "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+            "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
             "peak_source": "%s bf16 burst (MEASURED_PEAKS.json). `achieved` counts ALGORITHMIC flops (2*L*Cin*Cout*k); the tensor "
                            "pipe executes %dx that in tf32 MMAs at half the bf16 rate, so tensor-pipe occupancy ~ %d*frac"
                            % (peaks["source"], mma_mult, 2 * mma_mult),
