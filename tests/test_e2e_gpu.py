@@ -181,3 +181,45 @@ def test_engine_reports_its_kernel_launches(model, dev):
     n0 = _abi.launch_count()
     _run(model, dev, g)
     assert _abi.launch_count() - n0 > 100
+
+
+def test_corpus_runner_is_independent_of_batching(model, dev):
+    """utterances are independent, so how they are batched / sharded over ranks must not
+    change a single PCM sample: synthesize_corpus with batch 1, batch 5 and a 2-rank LPT shard plan."""
+    import numpy as np
+    from emotivoice_b200 import runner
+    rng = np.random.default_rng(5)
+    utts = [synth.make_utterance(rng, int(n)) for n in rng.integers(8, 60, size=9)]
+    lens = [len(u["ids"]) for u in utts]
+    one = runner.synthesize_corpus(model, utts, dev, batch_size=1)
+    five = runner.synthesize_corpus(model, utts, dev, batch_size=5)
+    shards = runner.plan_shards(lens, 2)
+    sharded = {}
+    for r in range(2):
+        sharded.update(runner.synthesize_corpus(model, utts, dev, batch_size=3, indices=shards[r]))
+    assert sorted(one) == sorted(five) == sorted(sharded) == list(range(9))
+    for i in range(9):
+        assert one[i][1] == five[i][1] == sharded[i][1] and one[i][0].shape == (one[i][1] * 256,)
+        assert np.array_equal(one[i][0], five[i][0]) and np.array_equal(one[i][0], sharded[i][0])
+        assert one[i][0].dtype == np.int16
+
+
+def test_minimal_and_long_sequences(conf, sd, dev, lib):
+    """Edge sizes: a 2-phoneme utterance, and an utterance whose frame count exceeds the 5000-row positional
+    table the reference starts with (extend_pe, encoder.py:206-237) -- acoustic model only, against the oracle."""
+    from emotivoice_b200.modules import PromptTTS
+    am = PromptTTS(conf).to(dev)
+    am.load_state_dict({k[3:]: v for k, v in sd.items() if k.startswith("am.")})
+    tiny = synth.make_batch([2], seed=9)
+    out = am(**{k: tiny[k].to(dev) for k in KEYS})
+    ref = O.acoustic_model(sd, conf, tiny["inputs_ling"], tiny["input_lengths"], tiny["inputs_speaker"],
+                           tiny["inputs_style_embedding"], tiny["inputs_content_embedding"])
+    assert torch.equal(out["log_duration_predictions"].cpu(), ref["log_duration_predictions"])
+    assert rel_max(out["dec_outputs"].cpu(), ref["dec_outputs"]) <= MEL_TOL
+    big = synth.make_batch([900], seed=15)
+    out = am(**{k: big[k].to(dev) for k in KEYS})
+    ref = O.acoustic_model(sd, conf, big["inputs_ling"], big["input_lengths"], big["inputs_speaker"],
+                           big["inputs_style_embedding"], big["inputs_content_embedding"])
+    assert out["dec_outputs"].shape[1] > 5000                       # the table had to grow
+    assert torch.equal(out["log_duration_predictions"].cpu(), ref["log_duration_predictions"])
+    assert rel_max(out["dec_outputs"].cpu(), ref["dec_outputs"]) <= MEL_TOL
