@@ -25,6 +25,8 @@
 // chunks), warps 8-13 stage A, warp 14 allocates TMEM and its elected lane issues every tcgen05.mma,
 // warp 15's elected lane streams the weight tiles.  mbarrier pipelines: A ring (a_full/a_empty), B ring (b_full/b_empty,
 // released by tcgen05.commit), accumulators (acc_full/acc_empty).
+#include <cstdlib>
+
 #include "ev_common.cuh"
 
 namespace ev {
@@ -557,6 +559,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(ConvParams p, int S)
 
 }  // namespace tc
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -603,10 +610,12 @@ int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
   //    CTA then streams 1/2..1/4 of the weights.
   //  * rows per tile: as many 128-row accumulators as still leave about one tile per SM (every weight tile
   //    fetched from L2 then feeds MT MMAs), limited by TMEM (2 x MT x BN <= 512 columns) and smem.
+  static const int bn_thresh = env_int("EV_TC_BN_TILES", 96);     // tuning knobs (tile shape only: results are unaffected)
+  static const int mt_thresh = env_int("EV_TC_MT_TILES", 120);
   const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
   int BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
-  while (BN >= 64 && (BN / 2) % 16 == 0 && tiles128 * ((p.Cout + BN - 1) / BN) < 96) BN /= 2;
-  int mt = tiles128 >= 4 * 120 ? 4 : (tiles128 >= 2 * 120 ? 2 : 1);
+  while (BN >= 64 && (BN / 2) % 16 == 0 && tiles128 * ((p.Cout + BN - 1) / BN) < bn_thresh) BN /= 2;
+  int mt = tiles128 >= 4 * mt_thresh ? 4 : (tiles128 >= 2 * mt_thresh ? 2 : 1);
   tc::Plan pl;
   // K granules per stage decide how the (channel block, tap) reduction is ordered, so they must be a function
   // of the layer shape alone: 8 if a (widest-N, one-accumulator) tile fits with them in 1x mode, else 4.
