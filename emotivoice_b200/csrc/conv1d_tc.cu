@@ -475,14 +475,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   } else {
     // ============================ weight loader ==================================================
     if (lane == 0) {
-      // w_tc layout: [plane (hi, lo)][tap][Cin/4][Cout][4] fp32  (granule-major; one granule row = 16 B)
+      // w_tc layout: [plane (hi, lo)][N tile of BNp = min(Cout,128)][tap][Cin/4][BNp][4] fp32 (granule-major inside a tile)
       const int cin4 = p.Cin / 4;
+      const int bnp = p.Cout < 128 ? p.Cout : 128;
       const size_t plane = (size_t)p.K * p.Cin * p.Cout;
+      const size_t tile_stride = (size_t)p.K * cin4 * bnp * 4;      // floats per packed N tile
       int b_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
         int b, t0, n0, nt, len;
         decode(tile, b, t0, n0, nt, len);
         if (t0 >= len) continue;
+        const float* wt = p.w + (size_t)(n0 / bnp) * tile_stride + (size_t)(n0 % bnp) * 4;
         const int cb_lo = (z_cur * n_cb) / pl.ksplit, cb_hi = ((z_cur + 1) * n_cb) / pl.ksplit;
         for (int cb = cb_lo; cb < cb_hi; ++cb) {
           const int ngran = min(KB, p.Cin - cb * KB) / 4;
@@ -491,16 +494,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
             mbar_wait(b_empty(sb), ((b_cnt / pl.b_stages) & 1) ^ 1);
             mbar_expect_tx(b_full(sb), (uint32_t)(PLANES * ngran * nt * 16));
             const uint32_t dst = smem_u32(b_tiles + sb * pl.b_stage_bytes);
-            if (nt == p.Cout) {
-              // the tile spans every output channel: the stage's granules are adjacent in memory -> ONE bulk copy per plane
-              const float* src = p.w + ((size_t)j * cin4 + (size_t)cb * KBG) * p.Cout * 4;
+            const float* src = wt + ((size_t)j * cin4 + (size_t)cb * KBG) * bnp * 4;
+            if (nt == bnp) {
+              // the CTA's N tile is a whole packed tile: the stage's granules are adjacent in memory -> ONE bulk copy per plane
               bulk_g2s(dst, src, (uint32_t)(ngran * nt * 16), b_full(sb));
               if (SPLIT3) bulk_g2s(dst + (uint32_t)pl.b_plane_bytes, src + plane, (uint32_t)(ngran * nt * 16), b_full(sb));
             } else {
               for (int g = 0; g < ngran; ++g) {
-                const float* src = p.w + (((size_t)j * cin4 + (size_t)cb * KBG + g) * p.Cout + n0) * 4;
-                bulk_g2s(dst + (uint32_t)(g * BN * 16), src, (uint32_t)(nt * 16), b_full(sb));
-                if (SPLIT3) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane, (uint32_t)(nt * 16), b_full(sb));
+                bulk_g2s(dst + (uint32_t)(g * BN * 16), src + (size_t)g * bnp * 4, (uint32_t)(nt * 16), b_full(sb));
+                if (SPLIT3) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane + (size_t)g * bnp * 4, (uint32_t)(nt * 16), b_full(sb));
               }
             }
           }
@@ -595,31 +597,31 @@ static int launch_tc_mt(const ConvParams& p, const tc::Plan& pl, cudaStream_t st
   return launch_tc_variant<SPLIT3, 1, KBG>(p, pl, st);
 }
 
-// p.w must be in the tensor-core layout [plane][K][Cin/4][Cout][4] (packing.py: to_tc_layout);
+// p.w must be in the tensor-core layout [plane][Cout/BNp][K][Cin/4][BNp][4] (packing.py: to_tc_layout);
 // split3 selects the 3xTF32 fp32-emulation variant (reads both planes).
 int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
   EV_CHECK_ARG(p.B > 0 && p.L > 0, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
   EV_CHECK_ARG(p.Cin % 8 == 0, "conv1d_tc: Cin=%d must be a multiple of 8", p.Cin);
-  EV_CHECK_ARG(p.Cout % 16 == 0, "conv1d_tc: Cout=%d must be a multiple of 16", p.Cout);
+  EV_CHECK_ARG(p.Cout % 16 == 0 && (p.Cout <= 128 || p.Cout % 128 == 0), "conv1d_tc: Cout=%d must be a multiple of 16, and of 128 above 128", p.Cout);
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
   EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
   // Tile shape.  None of these choices changes the order in which any output element's K reduction is
   // summed, so results are bitwise independent of batch size / sequence length (batch-invariant contract).
-  //  * N tile: a single 256-wide tile when C_out == 256 in 1x mode, else <= 128; halved (down to 32) while
-  //    the launch would leave most SMs without a tile (batch 1: HiFi-GAN stage 1, the AM GEMMs) -- each
-  //    CTA then streams 1/2..1/4 of the weights.
+  //  * N tile: min(C_out, 128) (the weight packing tile: one bulk copy per stage); halved (down to 32) only for
+  //    launches with a handful of tiles (measured: finer N splitting costs more in per-granule copies and
+  //    replicated A staging than it gains in parallelism).
   //  * rows per tile: as many 128-row accumulators as still leave about one tile per SM (every weight tile
   //    fetched from L2 then feeds MT MMAs), limited by TMEM (2 x MT x BN <= 512 columns) and smem.
-  static const int bn_thresh = env_int("EV_TC_BN_TILES", 96);     // tuning knobs (tile shape only: results are unaffected)
+  static const int bn_thresh = env_int("EV_TC_BN_TILES", 24);     // tuning knobs (tile shape only: results are unaffected)
   static const int mt_thresh = env_int("EV_TC_MT_TILES", 120);
   const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
-  int BN = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
+  int BN = p.Cout <= 128 ? p.Cout : 128;          // == the packing tile of packing.to_tc_layout
   while (BN >= 64 && (BN / 2) % 16 == 0 && tiles128 * ((p.Cout + BN - 1) / BN) < bn_thresh) BN /= 2;
   int mt = tiles128 >= 4 * mt_thresh ? 4 : (tiles128 >= 2 * mt_thresh ? 2 : 1);
   tc::Plan pl;
   // K granules per stage decide how the (channel block, tap) reduction is ordered, so they must be a function
   // of the layer shape alone: 8 if a (widest-N, one-accumulator) tile fits with them in 1x mode, else 4.
-  const int bn_max = p.Cout <= 128 ? p.Cout : ((p.Cout == 256 && !split3) ? 256 : 128);
+  const int bn_max = p.Cout <= 128 ? p.Cout : 128;
   const int kbg = (!split3 && tc::make_plan(p, split3, bn_max, 1, 8, 4, &pl)) ? 8 : 4;
   for (;; mt >>= 1) {
     if (tc::make_plan(p, split3, BN, mt, kbg, 4, &pl)) break;

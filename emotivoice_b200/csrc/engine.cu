@@ -370,7 +370,7 @@ static thread_local SplitWs g_split_ws;   // set by the phase entry points for t
 static int conv_x(int mode, const float* w_tc, const float* x, const float* w, const float* bias, long long bias_bs,
                   const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens,
                   int lens_mul, int in_act, float in_slope, int out_act, int acc, float div, cudaStream_t st) {
-  if (mode == 0 || !w_tc || (Cin % 8) || (Cout % 16))
+  if (mode == 0 || !w_tc || (Cin % 8) || (Cout % 16) || (Cout > 128 && Cout % 128))
     return conv(x, w, bias, bias_bs, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul, in_act, in_slope, out_act, acc, div, st);
   ConvParams p;
   p.x = x; p.w = w_tc; p.bias = bias; p.res = res; p.out = out; p.bias_bs = bias_bs;
@@ -705,7 +705,8 @@ int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* 
                     void* stream) {
   g_split_ws.p = splitk_ws; g_split_ws.cap = splitk_ws ? splitk_floats : 0; g_split_ws.ksplit = splitk_ws ? 4 : 0;
   EV_CHECK_ARG(x && w_tc && out, "ev_op_conv1d_tc: null argument");
-  EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0, "ev_op_conv1d_tc: needs Cin %% 8 == 0 and Cout %% 16 == 0 (Cin=%d Cout=%d)", Cin, Cout);
+  EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0 && (Cout <= 128 || Cout % 128 == 0),
+               "ev_op_conv1d_tc: needs Cin %% 8 == 0, Cout %% 16 == 0 and Cout <= 128 or a multiple of 128 (Cin=%d Cout=%d)", Cin, Cout);
   return conv_x(split3 ? 3 : 1, w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul,
                 in_act, in_slope, out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
 }

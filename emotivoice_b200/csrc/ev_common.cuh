@@ -61,7 +61,7 @@ struct ConvParams {
                        // summation order, hence every output bit, independent of how utterances are batched)
 };
 int launch_conv1d(const ConvParams& p, cudaStream_t st);
-// tcgen05 variant (conv1d_tc.cu); p.w in the tensor-core layout [plane hi|lo][K][Cin/4][Cout][4];
+// tcgen05 variant (conv1d_tc.cu); p.w in the tensor-core layout [plane hi|lo][Cout/BNp][K][Cin/4][BNp][4], BNp = min(Cout,128);
 // split3 = 3xTF32 fp32 emulation (three MMAs per K step), else one tf32 MMA per K step.
 int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st);
 

@@ -50,17 +50,22 @@ def round_tf32(w):
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+TC_BN = 128     # widest N tile of the tensor-core kernel (csrc/conv1d_tc.cu); weights are blocked by it
+
+
 def to_tc_layout(w_kio):
-    """(K, Cin, Cout) -> (2, K, Cin/4, Cout, 4): the tensor-core kernel's weight layout.
-    Granule-major: 16-byte K-granules with the C_out rows 16 B apart, so one (tap, 32-channel block)
-    is 8 bulk copies that land in shared memory exactly in the no-swizzle K-major UMMA layout
-    (csrc/conv1d_tc.cu).  Plane 0 = tf32(w) ("hi"), plane 1 = tf32(w - hi) ("lo", used by the 3xTF32
-    fp32-emulation mode only)."""
+    """(K, Cin, Cout) -> (2, Cout/BNp, K, Cin/4, BNp, 4) with BNp = min(Cout, 128): the tensor-core
+    kernel's weight layout.  Blocked by N tile, then granule-major: 16-byte K-granules with the tile's
+    C_out rows 16 B apart, so one pipeline stage (tap, channel block) of one N tile is ONE contiguous run
+    that a single bulk copy lands in shared memory exactly in the no-swizzle K-major UMMA layout.
+    Plane 0 = tf32(w) ("hi"), plane 1 = tf32(w - hi) ("lo", used by the 3xTF32 fp32-emulation mode only)."""
     if w_kio.dim() == 2:
         w_kio = w_kio.unsqueeze(0)
     K, cin, cout = w_kio.shape
     assert cin % 4 == 0
-    g = w_kio.reshape(K, cin // 4, 4, cout).permute(0, 1, 3, 2).contiguous()
+    bnp = min(cout, TC_BN)
+    assert cout % bnp == 0, "C_out must be <= 128 or a multiple of 128"
+    g = w_kio.reshape(K, cin // 4, 4, cout // bnp, bnp).permute(3, 0, 1, 4, 2).contiguous()   # (NT, K, Cin/4, BNp, 4)
     hi = round_tf32(g)
     lo = round_tf32(g - hi)
     return torch.stack([hi, lo]).contiguous()

@@ -172,8 +172,8 @@ EV_API int ev_op_conv1d(const float* x, const float* w, const float* bias, size_
                         const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
                         int acc, float div, void* stream);
 /* Same contract on the tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM); w_tc is in the
- * tensor-core layout (2 planes hi|lo, K, Cin/4, Cout, 4); split3 != 0 selects 3xTF32 fp32 emulation.
- * Requires Cin % 8 == 0, Cout % 16 == 0.  splitk_ws (optional, splitk_floats floats of scratch) lets a
+ * tensor-core layout (2 planes hi|lo, Cout/BNp N tiles, K, Cin/4, BNp = min(Cout,128), 4; packing.to_tc_layout);
+ * split3 != 0 selects 3xTF32 fp32 emulation.  Requires Cin % 8 == 0, Cout % 16 == 0 and Cout <= 128 or Cout % 128 == 0.  splitk_ws (optional, splitk_floats floats of scratch) lets a
  * launch with few output tiles and a long reduction be split along K (deterministic two-pass). */
 EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* bias, size_t bias_bstride,
                            const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
