@@ -114,7 +114,8 @@ struct Phase2Bufs {
   size_t part_cap;
 };
 struct VocBufs {
-  float *X, *ACC;
+  float *X, *ACC, *part;
+  size_t part_cap;
   float *Tm[3], *R1[3], *R2[3];   // per-ResBlock chain scratch (chains 1,2 alias chain 0 when run sequentially)
   bool concurrent;
 };
@@ -162,6 +163,8 @@ static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
   o->concurrent = voc_concurrent(B, F);
   o->X = cv.take(n);
   o->ACC = cv.take(n);
+  o->part_cap = n / 2;                  // split-K partials of the first (widest-channel) stage: 2 slices of B*r0*F*C1
+  o->part = cv.take(o->part_cap);
   for (int i = 0; i < 3; ++i) {
     if (i == 0 || o->concurrent) {
       o->Tm[i] = cv.take(n);
@@ -630,7 +633,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   VocBufs v;
   carve_voc(ctx, cv, B, F, &v);
   if (cv.off > workspace_bytes) { set_error("ev_vocoder: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
-  g_split_ws.p = nullptr; g_split_ws.cap = 0; g_split_ws.ksplit = 0;   // vocoder outputs are too large to K-split (traffic)
+  g_split_ws.p = v.part; g_split_ws.cap = v.part_cap; g_split_ws.ksplit = 0;
   const float* m = mel;
   if (!mel_time_major) {
     EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm[0], B, g.n_mels, F, st));
@@ -654,6 +657,9 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
                   EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
     L *= u.rate; mul *= u.rate;
     const int C = u.cout;
+    // K-split (2 slices, fixed per layer) only for the first stage: its 256-channel convs are the longest serial
+    // reductions over the fewest tiles; later stages have outputs too large for the extra partial traffic to pay
+    g_split_ws.ksplit = (s == 0 && !par) ? 2 : 0;
     for (int j = 1; j < 3; ++j) EV_TRY(edge(pool, st, chain_st[j]));   // fork: X (and the previous stage) is ready
     for (int j = 0; j < g.n_resk; ++j) {
       cudaStream_t cs = chain_st[j % 3];
