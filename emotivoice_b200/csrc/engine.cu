@@ -652,6 +652,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   size_t rb = 0;
   for (int s = 0; s < g.n_ups; ++s) {
     const UpW& u = ctx->ups[s];
+    g_split_ws.ksplit = 0;
     // x = ups[i](leaky_relu(x, 0.1)) (:118-119): polyphase-packed transposed conv, output viewed (L, rate*Cout)
     EV_TRY(conv_x(mode, u.w_tc, v.ACC, u.w, u.b, 0, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, mel_lens, mul,
                   EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
