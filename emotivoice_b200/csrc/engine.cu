@@ -658,9 +658,8 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
                   EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
     L *= u.rate; mul *= u.rate;
     const int C = u.cout;
-    // K-split (2 slices, fixed per layer) only for the first stage: its 256-channel convs are the longest serial
-    // reductions over the fewest tiles; later stages have outputs too large for the extra partial traffic to pay
-    g_split_ws.ksplit = (s == 0 && !par) ? 2 : 0;
+    // no K-split in the vocoder: outputs are large, the partial-sum traffic costs more than the shorter reduction gains
+    g_split_ws.ksplit = 0;   // measured: 2-slice K-split of stage 1 gains 4.6 % at batch 1 and costs 6 % at batch 32 -> off
     for (int j = 1; j < 3; ++j) EV_TRY(edge(pool, st, chain_st[j]));   // fork: X (and the previous stage) is ready
     for (int j = 0; j < g.n_resk; ++j) {
       cudaStream_t cs = chain_st[j % 3];
