@@ -597,9 +597,9 @@ static int launch_tc_mt(const ConvParams& p, const tc::Plan& pl, cudaStream_t st
   return launch_tc_variant<SPLIT3, 1, KBG>(p, pl, st);
 }
 
-// p.w must be in the tensor-core layout [plane][Cout/BNp][K][Cin/4][BNp][4] (packing.py: to_tc_layout);
-// split3 selects the 3xTF32 fp32-emulation variant (reads both planes).
-int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
+// Tile / pipeline plan of one launch (pure host arithmetic; also exported as ev_debug_tc_plan so the CPU tests
+// can check the invariants the kernel's barrier protocol and the batch-invariance contract rely on).
+static int plan_conv1d_tc(const ConvParams& p, bool split3, tc::Plan* out) {
   EV_CHECK_ARG(p.B > 0 && p.L > 0, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
   EV_CHECK_ARG(p.Cin % 8 == 0, "conv1d_tc: Cin=%d must be a multiple of 8", p.Cin);
   EV_CHECK_ARG(p.Cout % 16 == 0 && (p.Cout <= 128 || p.Cout % 128 == 0), "conv1d_tc: Cout=%d must be a multiple of 16, and of 128 above 128", p.Cout);
@@ -634,7 +634,7 @@ int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
   // length), so the summation order -- and therefore every output bit -- is the same for a B=1 call and for
   // the same utterance inside any batch.
   const size_t per = (size_t)p.B * p.L * p.Cout;
-  if (p.splitk_ws && p.ksplit > 1) {
+  if (p.ksplit > 1 && (p.splitk_ws || p.splitk_cap == (size_t)-1)) {
     int S = p.ksplit;
     const int n_cb = (p.Cin + 4 * pl.kbg - 1) / (4 * pl.kbg);
     if (S > n_cb) S = n_cb;
@@ -644,6 +644,25 @@ int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
       pl.total_tiles *= S;
     }
   }
+  *out = pl;
+  return EV_OK;
+}
+
+int debug_tc_plan(const ConvParams& p, bool split3, int* v) {
+  tc::Plan pl;
+  const int rc = plan_conv1d_tc(p, split3, &pl);
+  if (rc != EV_OK) return rc;
+  v[0] = pl.BN; v[1] = pl.mt; v[2] = pl.kbg; v[3] = pl.a_stages; v[4] = pl.b_stages; v[5] = pl.ngroups;
+  v[6] = pl.ksplit; v[7] = pl.tmem_cols; v[8] = pl.smem_total; v[9] = pl.total_tiles; v[10] = pl.rows_pad;
+  return EV_OK;
+}
+
+// p.w must be in the tensor-core layout [plane][Cout/BNp][K][Cin/4][BNp][4] (packing.py: to_tc_layout);
+// split3 selects the 3xTF32 fp32-emulation variant (reads both planes).
+int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
+  tc::Plan pl;
+  EV_TRY(plan_conv1d_tc(p, split3, &pl));
+  const size_t per = (size_t)p.B * p.L * p.Cout;
   int rc;
   if (split3) rc = launch_tc_mt<true, 4>(p, pl, st);
   else if (pl.kbg == 8) rc = launch_tc_mt<false, 8>(p, pl, st);

@@ -717,6 +717,14 @@ int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* 
                 in_act, in_slope, out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int split3, int ksplit, int* out11) {
+  EV_CHECK_ARG(out11, "ev_debug_tc_plan: null output");
+  ConvParams p{};
+  p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.in_act = EV_ACT_NONE;
+  p.ksplit = ksplit; p.splitk_ws = nullptr; p.splitk_cap = (size_t)-1;   // "scratch of any size is available"
+  return debug_tc_plan(p, split3 != 0, out11);
+}
+
 int ev_set_precision(ev_ctx* ctx, int precision) {
   EV_CHECK_ARG(ctx, "ev_set_precision: null context");
   EV_CHECK_ARG(precision == EV_PREC_FP32 || precision == EV_PREC_TF32 || precision == EV_PREC_FP32_FFMA,

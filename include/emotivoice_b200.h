@@ -179,6 +179,11 @@ EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const 
                            const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
                            const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
                            int acc, float div, float* splitk_ws, size_t splitk_floats, void* stream);
+/* Host-only introspection (no GPU needed): the tile / pipeline plan ev_op_conv1d_tc would use for a shape.
+ * out11 = {BN, MT, KBG, a_stages, b_stages, producer groups, ksplit, tmem columns, smem bytes, tiles, rows_pad}.
+ * The CPU tests check the invariants the kernel relies on (ring depth >= producer groups, TMEM/smem limits,
+ * summation-order parameters independent of batch and length). */
+EV_API int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int split3, int ksplit, int* out11);
 /* LayerNorm over the last dim, eps 1e-12 (encoder.py:112-127). rows x C. */
 EV_API int ev_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int C, void* stream);
 /* Multi-head self-attention core (encoder.py:84-109) on a packed (B,L,3H) q|k|v buffer. */

@@ -154,3 +154,51 @@ def test_synthetic_inputs_follow_the_input_contract():
 def test_oracle_int16_truncates_toward_zero():
     w = torch.tensor([[0.99999, -0.99999, 0.5 / 32768, -0.5 / 32768, 1.5 / 32768, -1.5 / 32768]])
     assert O.to_int16(w).tolist() == [32767, -32767, 0, 0, 1, -1]
+
+
+# ---- tensor-core convolution: launch plan invariants (host arithmetic, no GPU needed) -----------------------
+_SHAPES = [  # (Cin, Cout, K, dil): every GEMM-shaped layer of the model
+    (384, 1152, 1, 1), (384, 384, 1, 1), (384, 1536, 3, 1), (1536, 384, 3, 1), (384, 80, 1, 1), (384, 384, 3, 1),
+    (80, 512, 7, 1), (512, 2048, 3, 1), (256, 1024, 3, 1), (128, 128, 3, 1), (64, 64, 3, 1),
+] + [(c, c, k, d) for c in (256, 128, 64, 32) for k in (3, 7, 11) for d in (1, 3, 5)]
+
+
+def _plan(lib, B, L, Cin, Cout, K, dil, split3, ksplit=0):
+    import ctypes
+    out = (ctypes.c_int * 11)()
+    _abi.check(lib.ev_debug_tc_plan(B, L, Cin, Cout, K, dil, split3, ksplit, out))
+    keys = ("BN", "MT", "KBG", "a_stages", "b_stages", "ngroups", "ksplit", "tmem_cols", "smem", "tiles", "rows_pad")
+    return dict(zip(keys, list(out)))
+
+
+@pytest.mark.parametrize("split3", [0, 1])
+def test_tc_plan_respects_hardware_limits_and_barrier_protocol(lib, split3):
+    for Cin, Cout, K, dil in _SHAPES:
+        for B, L in ((1, 100), (1, 537), (1, 4296), (1, 137472), (3, 300), (32, 1600), (128, 65536)):
+            p = _plan(lib, B, L, Cin, Cout, K, dil, split3, ksplit=2)
+            assert p["smem"] <= 227 * 1024 and p["tmem_cols"] <= 512 and 2 * p["MT"] * p["BN"] <= p["tmem_cols"]
+            assert p["BN"] % 16 == 0 and p["BN"] <= 128 and p["MT"] in (1, 2, 4) and p["KBG"] in (4, 8)
+            assert 2 <= p["a_stages"] <= 8 and 2 <= p["b_stages"] <= 8
+            # a producer group may never run two uses of a ring slot ahead of the consumer: the parity wait on
+            # a_empty cannot tell them apart (this was a real deadlock) -> groups <= ring depth
+            assert p["ngroups"] in (1, 2, 3, 6) and p["ngroups"] <= p["a_stages"]
+            assert p["rows_pad"] % 8 == 8 // p["KBG"]            # conflict-free 16-byte producer stores
+            assert p["rows_pad"] >= 128 * p["MT"] + (K - 1) * dil
+
+
+@pytest.mark.parametrize("split3", [0, 1])
+def test_tc_plan_summation_order_is_a_function_of_the_layer_only(lib, split3):
+    """KBG (how the (channel block, tap) reduction is ordered) and the K-split factor must not depend on batch or
+    length: that is what makes a batched run bitwise equal to the B=1 runs."""
+    for Cin, Cout, K, dil in _SHAPES:
+        seen = {(_plan(lib, B, L, Cin, Cout, K, dil, split3, ksplit=4)["KBG"], _plan(lib, B, L, Cin, Cout, K, dil, split3, ksplit=4)["ksplit"])
+                for B, L in ((1, 64), (1, 537), (1, 34368), (2, 900), (32, 1600), (64, 40000))}
+        assert len(seen) == 1, (Cin, Cout, K, dil, seen)
+
+
+def test_tc_plan_rejects_unsupported_shapes(lib):
+    import ctypes
+    out = (ctypes.c_int * 11)()
+    assert lib.ev_debug_tc_plan(1, 100, 30, 32, 3, 1, 0, 0, out) == -1       # Cin % 8
+    assert lib.ev_debug_tc_plan(1, 100, 32, 200, 3, 1, 0, 0, out) == -1      # Cout > 128 and not a multiple of 128
+    assert lib.ev_debug_tc_plan(1, 100, 32, 32, 4, 1, 0, 0, out) == -1       # even kernel size
