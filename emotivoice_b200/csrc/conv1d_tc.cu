@@ -5,7 +5,7 @@
 //
 //   out[b,t,co] = epi( bias[co] + sum_j sum_ci w[j][ci][co] * act_in( x[b, t + (j-(K-1)/2)*dil, ci] ) )
 //
-// GEMM view: M = time (128 rows per accumulator, MT accumulators per tile), N = C_out tile (<= 256),
+// GEMM view: M = time (128 rows per accumulator, MT accumulators per tile), N = C_out tile (<= 128),
 // K = taps x C_in.
 //
 // * ONE activation fetch per tile for all k taps: the A operand lives in shared memory in the
