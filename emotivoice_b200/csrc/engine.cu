@@ -463,8 +463,15 @@ int ev_create(ev_ctx** out, int device, const ev_config* cfg) {
   ev_ctx* c = new ev_ctx();
   c->cfg = *cfg;
   c->device = device;
-  for (int i = 0; i < 2; ++i)
-    if (cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking) != cudaSuccess) c->aux[i] = nullptr;
+  {   // auxiliary streams live on the engine's device, whatever device is current for the caller
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device);
+    for (int i = 0; i < 2; ++i)
+      if (cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking) != cudaSuccess) c->aux[i] = nullptr;
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    cudaGetLastError();
+  }
   *out = c;
   return EV_OK;
 }
