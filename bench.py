@@ -212,12 +212,12 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1, L, C, generator=g).to(dev)
     w = torch.randn(K, C, C, generator=g) / math.sqrt(C * K)
-    use_tc = precision in ("fp32", "tf32")
+    use_tc = precision in ("fp32", "tf32", "bf16")
     if use_tc:
         from emotivoice_b200 import packing
-        w = packing.to_tc_layout(w)
+        w = packing.to_tc16_layout(w) if precision == "bf16" else packing.to_tc_layout(w)
     w = w.to(dev)
-    split3 = 1 if precision == "fp32" else 0
+    split3 = {"fp32": 1, "tf32": 0, "bf16": 2}.get(precision, 0)
     b = torch.randn(C, generator=g).to(dev)
     res = torch.randn(1, L, C, generator=g).to(dev)
     out = torch.empty(1, L, C, device=dev)
@@ -243,7 +243,7 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
     achieved = flops / t / 1e12
     ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     if use_tc:
-        mma_mult = 3 if split3 else 1
+        mma_mult = 3 if split3 == 1 else 1
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes/launch from the committed ncu --set full capture
         if os.path.exists(tpath):
@@ -253,13 +253,13 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
                 traffic = None
         return {
             "kernel": "conv1d_tc_kernel<%s> (tcgen05 kind::tf32, %s; HiFi-GAN stage-2 ResBlock conv, C=128, k=11, L=%d)"
-                      % ("true" if split3 else "false", "3xTF32 fp32 emulation" if split3 else "1xTF32", L),
+                      % (split3, ("1xTF32", "3xTF32 fp32 emulation", "bf16 operands")[split3], L),
             "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
             "peak_source": "%s bf16 burst (MEASURED_PEAKS.json). `achieved` counts ALGORITHMIC flops (2*L*Cin*Cout*k); the tensor "
                            "pipe executes %dx that in tf32 MMAs at half the bf16 rate, so tensor-pipe occupancy ~ %d*frac"
                            % (peaks["source"], mma_mult, 2 * mma_mult),
-            "tensor_pipe_frac_est": 2 * mma_mult * achieved / peaks["bf16_tflops"],
+            "tensor_pipe_frac_est": (1 if split3 == 2 else 2 * mma_mult) * achieved / peaks["bf16_tflops"],
             "flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
             "avg_launch_ms": t * 1e3, "hbm_gbs_at_algorithmic_bytes": alg_bytes / t / 1e9,
             "hbm_frac_at_algorithmic_bytes": alg_bytes / t / 1e9 / peaks["hbm_gbs"],
@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("EV_PRECISION", "fp32"), choices=["fp32", "tf32", "fp32_ffma"])
+    ap.add_argument("--precision", default=os.environ.get("EV_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16", "fp32_ffma"])
     args = ap.parse_args()
     if args.impl == "engine":
         args.warmup = max(args.warmup, 3)
@@ -416,6 +416,8 @@ def main():
                               "everything else fp32 FFMA)",
                       "tf32": "tf32 (fp32 storage; decoder+vocoder GEMMs on tcgen05 with tf32 operands rounded to nearest, fp32 "
                               "accumulation; duration prefix 3xTF32)",
+                      "bf16": "bf16 (fp32 storage; decoder+vocoder GEMMs on tcgen05 kind::f16 with bf16 operands, fp32 accumulation; "
+                              "duration prefix 3xTF32)",
                       "fp32_ffma": "fp32 (FFMA kernels, no tensor cores)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "precision": args.precision, "frames_per_step_per_gpu": frames, "audio_seconds_per_step_per_gpu": audio_s,

@@ -13,8 +13,8 @@ EV_OK = 0
 EV_EPELEN = -5
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3, 4
 ACC_STORE, ACC_ADD, ACC_ADD_DIV = 0, 1, 2
-PREC_FP32, PREC_TF32, PREC_FP32_FFMA = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp32_ffma": PREC_FP32_FFMA}
+PREC_FP32, PREC_TF32, PREC_FP32_FFMA, PREC_BF16 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp32_ffma": PREC_FP32_FFMA, "bf16": PREC_BF16}
 
 
 class EvConfig(ctypes.Structure):

@@ -92,6 +92,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, M=128, N from idesc, K=16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// two fp32 -> packed bf16x2 (round to nearest even); `lo` lands in the low half = lower address
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4 | [16,30) LBO>>4 (stride between the two 16-B K granules of one MMA)
 // | [32,46) SBO>>4 (stride between 8-row groups) | [46,48) version = 1 | [61,64) layout = 0
@@ -130,9 +147,10 @@ struct Plan {
 };
 
 // smem map: [0,288) barriers | [512,516) tmem base | 1024: epilogue staging (8 warps x 4 KB) | A ring | B ring
-__host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int BN, int mt, int kbg, int min_b_stages, Plan* o) {
+__host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN, int mt, int kbg, int min_b_stages, Plan* o) {
   Plan q;
-  q.planes = split3 ? 2 : 1;
+  q.planes = mode == 1 ? 2 : 1;
+  const int cpg = mode == 2 ? 8 : 4;      // channels per 16-byte granule (bf16 : tf32)
   q.kbg = kbg;
   q.mt = mt;
   q.BN = BN;
@@ -146,7 +164,7 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, bool split3, int 
   q.a_stage_bytes = q.planes * q.a_plane_bytes;
   q.b_stage_bytes = q.planes * q.b_plane_bytes;
   const int budget = 227 * 1024 - 1024 - STAGING_BYTES;
-  const int n_cb = (p.Cin + 4 * q.kbg - 1) / (4 * q.kbg);
+  const int n_cb = (p.Cin + cpg * q.kbg - 1) / (cpg * q.kbg);
   // at least 2 + 2 stages; then grow the weight ring first (it turns over K times per A stage)
   if (min_b_stages > n_cb * p.K) min_b_stages = n_cb * p.K;
   if (min_b_stages < 2) min_b_stages = 2;
@@ -192,16 +210,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int cw, float* v) {
   }
 }
 
-// SPLIT3 = false: one tf32 MMA per K step (operands rounded to nearest tf32).
-// SPLIT3 = true : "3xTF32" fp32 emulation: x = hi + lo with hi = tf32(x), lo = tf32(x - hi);
+// MODE 0: one tf32 MMA per K step (operands rounded to nearest tf32).
+// MODE 2: bf16 operands (rounded to nearest even by the producers / the host), kind::f16, 8 channels per granule.
+// MODE 1: "3xTF32" fp32 emulation: x = hi + lo with hi = tf32(x), lo = tf32(x - hi);
 //                 a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the dropped lo*lo term is 2^-22 relative),
 //                 three MMAs per K step into the same fp32 TMEM accumulator.  Weights arrive pre-split
 //                 (two planes, packing.to_tc_layout); activations are split by the producer warps.
-// MT: 128-row accumulators per tile.  KBG: 16-byte K granules (4 channels each) per pipeline stage.
-template <bool SPLIT3, int MT, int KBG>
+// MT: 128-row accumulators per tile.  KBG: 16-byte K granules (4 tf32 or 8 bf16 channels each) per pipeline stage.
+template <int MODE, int MT, int KBG>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Plan pl) {
+  constexpr bool SPLIT3 = (MODE == 1);
+  constexpr bool BF16 = (MODE == 2);
   constexpr int PLANES = SPLIT3 ? 2 : 1;
-  constexpr int KB = 4 * KBG;
+  constexpr int CPG = BF16 ? 8 : 4;       // channels per 16-byte granule
+  constexpr int KB = CPG * KBG;
   constexpr int GSH = (KBG == 8 ? 3 : 2);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x;
@@ -373,40 +395,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
         if (a_cnt % pl.ngroups != grp) continue;       // this stage belongs to another producer group
         const int s = a_cnt % pl.a_stages;
         const int c0 = cb * KB;
-        const int ngran = min(KB, p.Cin - c0) / 4;
+        const int ngran = min(KB, p.Cin - c0) / CPG;
         uint8_t* dst = a_tiles + s * pl.a_stage_bytes;
-        for (int base = 0; base < total; base += GT * A_LD) {
+        constexpr int ALD = BF16 ? A_LD / 2 : A_LD;     // (row, granule) pairs per thread and batch
+        constexpr int NW = BF16 ? 2 : 1;                // float4 loads per pair (8 : 4 channels)
+        for (int base = 0; base < total; base += GT * ALD) {
           // a batch of global loads is issued before anything else (memory-level parallelism)
-          float4 v[A_LD];
+          float4 v[ALD * NW];
 #pragma unroll
-          for (int u = 0; u < A_LD; ++u) {
+          for (int u = 0; u < ALD; ++u) {
             const int idx = base + u * GT + gt;
             const int r = idx >> GSH, g = idx & (KBG - 1);
             const int row = t0 - halo + r;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < total && g < ngran && row >= 0 && row < len)
-              v[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)row * p.Cin + c0 + g * 4));
+            const bool ok = idx < total && g < ngran && row >= 0 && row < len;
+            const float* src = xb + (size_t)row * p.Cin + c0 + g * CPG;
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+              v[u * NW + w] = ok ? __ldg(reinterpret_cast<const float4*>(src + 4 * w)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           if (base == 0) mbar_wait(a_empty(s), ((a_cnt / pl.a_stages) & 1) ^ 1);
 #pragma unroll
-          for (int u = 0; u < A_LD; ++u) {
+          for (int u = 0; u < ALD; ++u) {
             const int idx = base + u * GT + gt;
             const int r = idx >> GSH, g = idx & (KBG - 1);
             if (idx < total && g < ngran) {
-              float4 t = v[u];
-              if (lrelu) {
-                t.x = t.x > 0.f ? t.x : t.x * slope;
-                t.y = t.y > 0.f ? t.y : t.y * slope;
-                t.z = t.z > 0.f ? t.z : t.z * slope;
-                t.w = t.w > 0.f ? t.w : t.w * slope;
+#pragma unroll
+              for (int w = 0; w < NW; ++w) {
+                float4& t = v[u * NW + w];
+                if (lrelu) {
+                  t.x = t.x > 0.f ? t.x : t.x * slope;
+                  t.y = t.y > 0.f ? t.y : t.y * slope;
+                  t.z = t.z > 0.f ? t.z : t.z * slope;
+                  t.w = t.w > 0.f ? t.w : t.w * slope;
+                }
               }
-              // round-to-nearest tf32 (the MMA would otherwise truncate the low 13 mantissa bits)
-              const float4 h = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
               uint8_t* d = dst + ((size_t)g * pl.rows_pad + r) * 16;
-              *reinterpret_cast<float4*>(d) = h;
-              if (SPLIT3) {
-                const float4 l = make_float4(to_tf32(t.x - h.x), to_tf32(t.y - h.y), to_tf32(t.z - h.z), to_tf32(t.w - h.w));
-                *reinterpret_cast<float4*>(d + pl.a_plane_bytes) = l;
+              if (BF16) {
+                const float4 t0 = v[u * NW], t1 = v[u * NW + NW - 1];
+                uint4 q;
+                q.x = pack_bf16(t0.x, t0.y); q.y = pack_bf16(t0.z, t0.w);
+                q.z = pack_bf16(t1.x, t1.y); q.w = pack_bf16(t1.z, t1.w);
+                *reinterpret_cast<uint4*>(d) = q;
+              } else {
+                const float4 t = v[u * NW];
+                // round-to-nearest tf32 (the MMA would otherwise truncate the low 13 mantissa bits)
+                const float4 h = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
+                *reinterpret_cast<float4*>(d) = h;
+                if (SPLIT3) {
+                  const float4 l = make_float4(to_tf32(t.x - h.x), to_tf32(t.y - h.y), to_tf32(t.z - h.z), to_tf32(t.w - h.w));
+                  *reinterpret_cast<float4*>(d + pl.a_plane_bytes) = l;
+                }
               }
             }
           }
@@ -426,7 +464,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
         if (t0 >= len) continue;
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
         // A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // (bf16 mode: A = B = BF16, format code 1)
+        const uint32_t fmt = BF16 ? 1u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         const int buf = tile_cnt & 1;
         mbar_wait(acc_empty(buf), ((tile_cnt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
@@ -434,7 +474,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
         const int cb_lo = (z_cur * n_cb) / pl.ksplit, cb_hi = ((z_cur + 1) * n_cb) / pl.ksplit;
         for (int cb = cb_lo; cb < cb_hi; ++cb, ++a_cnt) {
           const int sa = a_cnt % pl.a_stages;
-          const int nk8 = min(KB, p.Cin - cb * KB) / 8;
+          const int nk8 = min(KB, p.Cin - cb * KB) / (2 * CPG);   // MMA K steps: two 16-byte granules each
           mbar_wait(a_full(sa), (a_cnt / pl.a_stages) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_tiles + sa * pl.a_stage_bytes);
@@ -458,6 +498,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
                   umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
                   umma_tf32(d, a_hi, b_lo, idesc, 1u);
                   umma_tf32(d, a_hi, b_hi, idesc, 1u);
+                } else if (BF16) {
+                  umma_bf16(d, a_hi, b_hi, idesc, first);
                 } else {
                   umma_tf32(d, a_hi, b_hi, idesc, first);
                 }
@@ -475,8 +517,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   } else {
     // ============================ weight loader ==================================================
     if (lane == 0) {
-      // w_tc layout: [plane (hi, lo)][N tile of BNp = min(Cout,128)][tap][Cin/4][BNp][4] fp32 (granule-major inside a tile)
-      const int cin4 = p.Cin / 4;
+      // w_tc layout: [plane (hi, lo)][N tile of BNp = min(Cout,128)][tap][Cin/CPG granules][BNp][16 bytes]
+      // (4 fp32 or 8 bf16 per granule; granule-major inside a tile)
+      const int cin4 = p.Cin / CPG;
       const int bnp = p.Cout < 128 ? p.Cout : 128;
       const size_t plane = (size_t)p.K * p.Cin * p.Cout;
       const size_t tile_stride = (size_t)p.K * cin4 * bnp * 4;      // floats per packed N tile
@@ -488,7 +531,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
         const float* wt = p.w + (size_t)(n0 / bnp) * tile_stride + (size_t)(n0 % bnp) * 4;
         const int cb_lo = (z_cur * n_cb) / pl.ksplit, cb_hi = ((z_cur + 1) * n_cb) / pl.ksplit;
         for (int cb = cb_lo; cb < cb_hi; ++cb) {
-          const int ngran = min(KB, p.Cin - cb * KB) / 4;
+          const int ngran = min(KB, p.Cin - cb * KB) / CPG;
           for (int j = 0; j < p.K; ++j, ++b_cnt) {
             const int sb = b_cnt % pl.b_stages;
             mbar_wait(b_empty(sb), ((b_cnt / pl.b_stages) & 1) ^ 1);
@@ -577,31 +620,32 @@ static int sm_count() {
   return n;
 }
 
-template <bool SPLIT3, int MT, int KBG>
+template <int MODE, int MT, int KBG>
 static int launch_tc_variant(const ConvParams& p, const tc::Plan& pl, cudaStream_t st) {
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(tc::conv1d_tc_kernel<SPLIT3, MT, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc::conv1d_tc_kernel<MODE, MT, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const int grid = pl.total_tiles < sm_count() ? pl.total_tiles : sm_count();
-  tc::conv1d_tc_kernel<SPLIT3, MT, KBG><<<grid, tc::NTHREADS, pl.smem_total, st>>>(p, pl);
+  tc::conv1d_tc_kernel<MODE, MT, KBG><<<grid, tc::NTHREADS, pl.smem_total, st>>>(p, pl);
   EV_CUDA_LAUNCH_CHECK("conv1d_tc_kernel");
   return EV_OK;
 }
 
-template <bool SPLIT3, int KBG>
+template <int MODE, int KBG>
 static int launch_tc_mt(const ConvParams& p, const tc::Plan& pl, cudaStream_t st) {
-  if (pl.mt == 4) return launch_tc_variant<SPLIT3, 4, KBG>(p, pl, st);
-  if (pl.mt == 2) return launch_tc_variant<SPLIT3, 2, KBG>(p, pl, st);
-  return launch_tc_variant<SPLIT3, 1, KBG>(p, pl, st);
+  if (pl.mt == 4) return launch_tc_variant<MODE, 4, KBG>(p, pl, st);
+  if (pl.mt == 2) return launch_tc_variant<MODE, 2, KBG>(p, pl, st);
+  return launch_tc_variant<MODE, 1, KBG>(p, pl, st);
 }
 
 // Tile / pipeline plan of one launch (pure host arithmetic; also exported as ev_debug_tc_plan so the CPU tests
 // can check the invariants the kernel's barrier protocol and the batch-invariance contract rely on).
-static int plan_conv1d_tc(const ConvParams& p, bool split3, tc::Plan* out) {
+static int plan_conv1d_tc(const ConvParams& p, int mode, tc::Plan* out) {
+  const bool split3 = (mode == 1);
   EV_CHECK_ARG(p.B > 0 && p.L > 0, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
-  EV_CHECK_ARG(p.Cin % 8 == 0, "conv1d_tc: Cin=%d must be a multiple of 8", p.Cin);
+  EV_CHECK_ARG(p.Cin % (mode == 2 ? 16 : 8) == 0, "conv1d_tc: Cin=%d must be a multiple of %d", p.Cin, mode == 2 ? 16 : 8);
   EV_CHECK_ARG(p.Cout % 16 == 0 && (p.Cout <= 128 || p.Cout % 128 == 0), "conv1d_tc: Cout=%d must be a multiple of 16, and of 128 above 128", p.Cout);
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
   EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
@@ -622,10 +666,10 @@ static int plan_conv1d_tc(const ConvParams& p, bool split3, tc::Plan* out) {
   // K granules per stage decide how the (channel block, tap) reduction is ordered, so they must be a function
   // of the layer shape alone: 8 if a (widest-N, one-accumulator) tile fits with them in 1x mode, else 4.
   const int bn_max = p.Cout <= 128 ? p.Cout : 128;
-  const int kbg = (!split3 && tc::make_plan(p, split3, bn_max, 1, 8, 4, &pl)) ? 8 : 4;
+  const int kbg = (!split3 && tc::make_plan(p, mode, bn_max, 1, 8, 4, &pl)) ? 8 : 4;
   for (;; mt >>= 1) {
-    if (tc::make_plan(p, split3, BN, mt, kbg, 4, &pl)) break;
-    if (tc::make_plan(p, split3, BN, mt, kbg, 2, &pl)) break;
+    if (tc::make_plan(p, mode, BN, mt, kbg, 4, &pl)) break;
+    if (tc::make_plan(p, mode, BN, mt, kbg, 2, &pl)) break;
     if (mt == 1) { set_error("conv1d_tc: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
   }
   // K-split: a long reduction at few output tiles (the acoustic model's GEMMs at batch 1; the conv-FFN's second
@@ -636,7 +680,8 @@ static int plan_conv1d_tc(const ConvParams& p, bool split3, tc::Plan* out) {
   const size_t per = (size_t)p.B * p.L * p.Cout;
   if (p.ksplit > 1 && (p.splitk_ws || p.splitk_cap == (size_t)-1)) {
     int S = p.ksplit;
-    const int n_cb = (p.Cin + 4 * pl.kbg - 1) / (4 * pl.kbg);
+    const int cpg = mode == 2 ? 8 : 4;
+    const int n_cb = (p.Cin + cpg * pl.kbg - 1) / (cpg * pl.kbg);
     if (S > n_cb) S = n_cb;
     if ((size_t)S * per > p.splitk_cap) { set_error("conv1d_tc: split-K scratch too small (%zu < %zu floats)", p.splitk_cap, (size_t)S * per); return EV_EWORKSPACE; }
     if (S > 1) {
@@ -648,9 +693,9 @@ static int plan_conv1d_tc(const ConvParams& p, bool split3, tc::Plan* out) {
   return EV_OK;
 }
 
-int debug_tc_plan(const ConvParams& p, bool split3, int* v) {
+int debug_tc_plan(const ConvParams& p, int mode, int* v) {
   tc::Plan pl;
-  const int rc = plan_conv1d_tc(p, split3, &pl);
+  const int rc = plan_conv1d_tc(p, mode, &pl);
   if (rc != EV_OK) return rc;
   v[0] = pl.BN; v[1] = pl.mt; v[2] = pl.kbg; v[3] = pl.a_stages; v[4] = pl.b_stages; v[5] = pl.ngroups;
   v[6] = pl.ksplit; v[7] = pl.tmem_cols; v[8] = pl.smem_total; v[9] = pl.total_tiles; v[10] = pl.rows_pad;
@@ -658,15 +703,16 @@ int debug_tc_plan(const ConvParams& p, bool split3, int* v) {
 }
 
 // p.w must be in the tensor-core layout [plane][Cout/BNp][K][Cin/4][BNp][4] (packing.py: to_tc_layout);
-// split3 selects the 3xTF32 fp32-emulation variant (reads both planes).
-int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st) {
+// mode 0: 1xTF32, 1: 3xTF32 fp32 emulation (reads both planes), 2: bf16 operands (p.w in the bf16 tc layout).
+int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st) {
   tc::Plan pl;
-  EV_TRY(plan_conv1d_tc(p, split3, &pl));
+  EV_TRY(plan_conv1d_tc(p, mode, &pl));
   const size_t per = (size_t)p.B * p.L * p.Cout;
   int rc;
-  if (split3) rc = launch_tc_mt<true, 4>(p, pl, st);
-  else if (pl.kbg == 8) rc = launch_tc_mt<false, 8>(p, pl, st);
-  else rc = launch_tc_mt<false, 4>(p, pl, st);
+  if (mode == 1) rc = launch_tc_mt<1, 4>(p, pl, st);
+  else if (mode == 2) rc = pl.kbg == 8 ? launch_tc_mt<2, 8>(p, pl, st) : launch_tc_mt<2, 4>(p, pl, st);
+  else if (pl.kbg == 8) rc = launch_tc_mt<0, 8>(p, pl, st);
+  else rc = launch_tc_mt<0, 4>(p, pl, st);
   if (rc != EV_OK || pl.ksplit == 1) return rc;
   const size_t n4 = per / 4;
   tc::splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(p, pl.ksplit);

@@ -35,6 +35,7 @@ struct Tensor {
 struct EncLayerW {
   const float *ln1w, *ln1b, *wqkv, *bqkv, *wo, *bo, *ln2w, *ln2b, *w1, *b1, *w2, *b2;
   const float *wqkv_tc = nullptr, *wo_tc = nullptr, *w1_tc = nullptr, *w2_tc = nullptr;   // tensor-core layout (optional)
+  const float *wqkv_h = nullptr, *wo_h = nullptr, *w1_h = nullptr, *w2_h = nullptr;       // bf16 tensor-core layout (optional)
 };
 struct StackW {
   const float* alpha;
@@ -48,11 +49,13 @@ struct PredW {
 struct ConvW {
   const float *w, *b;
   const float* w_tc = nullptr;
+  const float* w_h = nullptr;
   int K, dil, cin, cout;
 };
 struct UpW {
   const float *w, *b;
   const float* w_tc = nullptr;
+  const float* w_h = nullptr;
   int K, cin, cout_packed, rate, cout;
 };
 
@@ -66,6 +69,7 @@ struct ev_ctx {
   bool has_tc = false;      // every '.tc' tensor the tf32 path needs is present
   int precision = EV_PREC_FP32;
   const float* mel_w_tc = nullptr;
+  const float* mel_w_h = nullptr;
   const float* cond_wx_tc = nullptr;   // a blob may carry only one half (PromptTTS / Generator used alone)
   std::unordered_map<std::string, ev::Tensor> tensors;
   const float* pe = nullptr;
@@ -242,6 +246,10 @@ static int resolve_stack(ev_ctx* c, const char* pre, int n_layers, StackW* s) {
     l.wo_tc = find_opt(c, q + ".wo.tc", 2 * H * H);
     l.w1_tc = find_opt(c, q + ".w1.tc", 2 * K * H * 4 * H);
     l.w2_tc = find_opt(c, q + ".w2.tc", 2 * K * 4 * H * H);
+    l.wqkv_h = find_opt(c, q + ".wqkv.tc16", H * 3 * H / 2);
+    l.wo_h = find_opt(c, q + ".wo.tc16", H * H / 2);
+    l.w1_h = find_opt(c, q + ".w1.tc16", K * H * 4 * H / 2);
+    l.w2_h = find_opt(c, q + ".w2.tc16", K * 4 * H * H / 2);
   }
   EV_TRY(find(c, p + ".lnf.w", H, &s->lnfw));
   EV_TRY(find(c, p + ".lnf.b", H, &s->lnfb));
@@ -296,6 +304,7 @@ static int resolve_all(ev_ctx* c) {
   EV_TRY(find(c, "to_mel.w", H * g.n_mels, &c->mel_w));
   EV_TRY(find(c, "to_mel.b", g.n_mels, &c->mel_b));
   c->mel_w_tc = find_opt(c, "to_mel.w.tc", 2 * H * g.n_mels);
+  c->mel_w_h = find_opt(c, "to_mel.w.tc16", H * g.n_mels / 2);
   return EV_OK;
 }
 
@@ -305,6 +314,7 @@ static int resolve_voc(ev_ctx* c) {
   EV_TRY(find(c, "voc.pre.w", (uint64_t)7 * g.n_mels * g.voc_c0, &c->pre.w));
   EV_TRY(find(c, "voc.pre.b", g.voc_c0, &c->pre.b));
   c->pre.w_tc = find_opt(c, "voc.pre.w.tc", (uint64_t)2 * 7 * g.n_mels * g.voc_c0);
+  c->pre.w_h = find_opt(c, "voc.pre.w.tc16", (uint64_t)7 * g.n_mels * g.voc_c0 / 2);
   c->ups.resize(g.n_ups);
   c->rb_c1.clear(); c->rb_c2.clear();
   int ch = g.voc_c0, mul = 1;
@@ -324,6 +334,7 @@ static int resolve_voc(ev_ctx* c) {
     u.K = (int)(it->second.numel / per_tap);
     u.w = it->second.p;
     u.w_tc = find_opt(c, q + ".w.tc", 2 * it->second.numel);
+    u.w_h = find_opt(c, q + ".w.tc16", it->second.numel / 2);
     EV_TRY(find(c, q + ".b", u.cout_packed, &u.b));
     ch = u.cout; mul *= u.rate;
     if (mul * ch > c->max_stage_width) c->max_stage_width = mul * ch;
@@ -340,6 +351,8 @@ static int resolve_voc(ev_ctx* c) {
         EV_TRY(find(c, r + ".c2." + std::to_string(l) + ".b", ch, &c2.b));
         c1.w_tc = find_opt(c, r + ".c1." + std::to_string(l) + ".w.tc", (uint64_t)2 * k * ch * ch);
         c2.w_tc = find_opt(c, r + ".c2." + std::to_string(l) + ".w.tc", (uint64_t)2 * k * ch * ch);
+        c1.w_h = find_opt(c, r + ".c1." + std::to_string(l) + ".w.tc16", (uint64_t)k * ch * ch / 2);
+        c2.w_h = find_opt(c, r + ".c2." + std::to_string(l) + ".w.tc16", (uint64_t)k * ch * ch / 2);
         c->rb_c1.push_back(c1); c->rb_c2.push_back(c2);
       }
   }
@@ -361,7 +374,8 @@ static int conv(const float* x, const float* w, const float* bias, long long bia
   return launch_conv1d(p, st);
 }
 
-// mode 0: fp32 FFMA kernel; 1: tensor cores, one tf32 MMA per K step; 3: tensor cores, 3xTF32 fp32 emulation.
+// mode 0: fp32 FFMA kernel; 1: tensor cores, one tf32 MMA per K step; 3: tensor cores, 3xTF32 fp32 emulation;
+// 2: tensor cores, bf16 operands (needs w_h; layers without bf16 weights run 3xTF32).
 // Falls back to the FFMA kernel when the layer has no tensor-core weights or an unsupported shape.
 struct SplitWs {
   float* p = nullptr;
@@ -370,22 +384,24 @@ struct SplitWs {
 };
 static thread_local SplitWs g_split_ws;   // set by the phase entry points for the convs they launch
 
-static int conv_x(int mode, const float* w_tc, const float* x, const float* w, const float* bias, long long bias_bs,
-                  const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens,
-                  int lens_mul, int in_act, float in_slope, int out_act, int acc, float div, cudaStream_t st) {
-  if (mode == 0 || !w_tc || (Cin % 8) || (Cout % 16) || (Cout > 128 && Cout % 128))
+static int conv_x(int mode, const float* w_tc, const float* w_h, const float* x, const float* w, const float* bias,
+                  long long bias_bs, const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
+                  const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act, int acc, float div,
+                  cudaStream_t st) {
+  if (mode == 2 && (!w_h || (Cin % 16))) mode = 3;
+  if (mode == 0 || (mode != 2 && !w_tc) || (Cin % 8) || (Cout % 16) || (Cout > 128 && Cout % 128))
     return conv(x, w, bias, bias_bs, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul, in_act, in_slope, out_act, acc, div, st);
   ConvParams p;
-  p.x = x; p.w = w_tc; p.bias = bias; p.res = res; p.out = out; p.bias_bs = bias_bs;
+  p.x = x; p.w = (mode == 2) ? w_h : w_tc; p.bias = bias; p.res = res; p.out = out; p.bias_bs = bias_bs;
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil;
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope;
   p.out_act = out_act; p.acc = acc; p.div = div;
   p.splitk_ws = g_split_ws.p; p.splitk_cap = g_split_ws.cap; p.ksplit = g_split_ws.ksplit;
-  return launch_conv1d_tc(p, mode == 3, st);
+  return launch_conv1d_tc(p, mode == 3 ? 1 : (mode == 2 ? 2 : 0), st);
 }
 
 static inline int body_mode(const ev_ctx* c) {
-  return c->precision == EV_PREC_FP32_FFMA ? 0 : (c->precision == EV_PREC_TF32 ? 1 : 3);
+  return c->precision == EV_PREC_FP32_FFMA ? 0 : (c->precision == EV_PREC_TF32 ? 1 : (c->precision == EV_PREC_BF16 ? 2 : 3));
 }
 
 // Encoder.forward (encoder.py:316-324) minus the positional prologue (done by the caller of this
@@ -399,17 +415,17 @@ static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float
     if (!(i == 0 && first_ln_done))
       EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln1w, l.ln1b, y, B * L, L, H, st));
     g_split_ws.ksplit = 2;   // K = H: two slices
-    EV_TRY(conv_x(mode, l.wqkv_tc, y, l.wqkv, l.bqkv, 0, nullptr, qkv, B, L, H, 3 * H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
+    EV_TRY(conv_x(mode, l.wqkv_tc, l.wqkv_h, y, l.wqkv, l.bqkv, 0, nullptr, qkv, B, L, H, 3 * H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
                   EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
     EV_TRY(launch_attention(qkv, key_lens, ctxb, B, L, H, heads, st));
-    EV_TRY(conv_x(mode, l.wo_tc, ctxb, l.wo, l.bo, 0, x, x, B, L, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
+    EV_TRY(conv_x(mode, l.wo_tc, l.wo_h, ctxb, l.wo, l.bo, 0, x, x, B, L, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
                   EV_ACC_STORE, 1.f, st));
     EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln2w, l.ln2b, y, B * L, L, H, st));
     g_split_ws.ksplit = 2;
-    EV_TRY(conv_x(mode, l.w1_tc, y, l.w1, l.b1, 0, nullptr, h, B, L, H, 4 * H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_GELU,
+    EV_TRY(conv_x(mode, l.w1_tc, l.w1_h, y, l.w1, l.b1, 0, nullptr, h, B, L, H, 4 * H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_GELU,
                   EV_ACC_STORE, 1.f, st));
     g_split_ws.ksplit = 4;   // K = 3 * 4H: four slices
-    EV_TRY(conv_x(mode, l.w2_tc, h, l.w2, l.b2, 0, x, x, B, L, 4 * H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
+    EV_TRY(conv_x(mode, l.w2_tc, l.w2_h, h, l.w2, l.b2, 0, x, x, B, L, 4 * H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
                   EV_ACC_STORE, 1.f, st));
   }
   g_split_ws.ksplit = 2;
@@ -425,7 +441,7 @@ static int run_predictor(const ev_ctx* c, const PredW& p, const float* in, float
   g_split_ws.ksplit = (streams_mask() & 1) ? 0 : 2;   // concurrent predictor chains would share the split-K scratch
   const float* cur = in;
   for (size_t i = 0; i < p.w.size(); ++i) {
-    EV_TRY(conv_x(cmode, p.w_tc[i], cur, p.w[i], p.b[i], 0, nullptr, t1, B, T, H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
+    EV_TRY(conv_x(cmode, p.w_tc[i], nullptr, cur, p.w[i], p.b[i], 0, nullptr, t1, B, T, H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
                   EV_ACT_RELU, EV_ACC_STORE, 1.f, st));
     EV_TRY(launch_layernorm(t1, nullptr, nullptr, nullptr, nullptr, nullptr, p.lnw[i], p.lnb[i], t2, B * T, T, H, st));
     cur = t2;
@@ -570,7 +586,7 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   // conditioning (model_open_source.py:109-111): per-utterance bias + W_x x
   EV_TRY(launch_cond_gather(spk, ctx->emb_spk, style, content, b.cond_in, B, H, g.bert_dim, st));
   EV_TRY(launch_cond_gemv(b.cond_in, ctx->cond_wc, ctx->cond_b, b.cond_bias, B, H + 2 * g.bert_dim, H, st));
-  EV_TRY(conv_x(prefix_mode, ctx->cond_wx_tc, b.y, ctx->cond_wx, b.cond_bias, H, nullptr, b.hs, B, T, H, H, 1, 1, conv_lens, 1,
+  EV_TRY(conv_x(prefix_mode, ctx->cond_wx_tc, nullptr, b.y, ctx->cond_wx, b.cond_bias, H, nullptr, b.hs, B, T, H, H, 1, 1, conv_lens, 1,
                 EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
   // predictors (model_open_source.py:120-121,130)
   const float* pin = b.hs;
@@ -623,7 +639,7 @@ int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens,
   const int mode = body_mode(ctx);
   EV_TRY(run_stack(ctx, ctx->dec, b.x, b.y, b.qkv, b.ctx, b.h, B, F, flens, flens, false, mode, st));
   // to_mel (model_open_source.py:147)
-  EV_TRY(conv_x(mode, ctx->mel_w_tc, b.y, ctx->mel_w, ctx->mel_b, 0, nullptr, mel_out, B, F, H, g.n_mels, 1, 1, flens, 1,
+  EV_TRY(conv_x(mode, ctx->mel_w_tc, ctx->mel_w_h, b.y, ctx->mel_w, ctx->mel_b, 0, nullptr, mel_out, B, F, H, g.n_mels, 1, 1, flens, 1,
                 EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
   return EV_OK;
 }
@@ -648,7 +664,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   }
   // conv_pre (hifigan/models.py:116)
   const int mode = body_mode(ctx);
-  EV_TRY(conv_x(mode, ctx->pre.w_tc, m, ctx->pre.w, ctx->pre.b, 0, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1,
+  EV_TRY(conv_x(mode, ctx->pre.w_tc, ctx->pre.w_h, m, ctx->pre.w, ctx->pre.b, 0, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1,
                 mel_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
   // chain j of a stage (ResBlock j) runs on its own stream when the call is small; the xs accumulation
   // (xs = r0; xs += r1; xs += r2; x = xs / 3, :120-126) keeps its order through events
@@ -661,7 +677,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
     const UpW& u = ctx->ups[s];
     g_split_ws.ksplit = 0;
     // x = ups[i](leaky_relu(x, 0.1)) (:118-119): polyphase-packed transposed conv, output viewed (L, rate*Cout)
-    EV_TRY(conv_x(mode, u.w_tc, v.ACC, u.w, u.b, 0, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, mel_lens, mul,
+    EV_TRY(conv_x(mode, u.w_tc, u.w_h, v.ACC, u.w, u.b, 0, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, mel_lens, mul,
                   EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
     L *= u.rate; mul *= u.rate;
     const int C = u.cout;
@@ -676,7 +692,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
         const ConvW& c1 = ctx->rb_c1[rb];
         const ConvW& c2 = ctx->rb_c2[rb];
         // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
-        EV_TRY(conv_x(mode, c1.w_tc, src, c1.w, c1.b, 0, nullptr, v.Tm[cj], B, L, C, C, c1.K, c1.dil, mel_lens, mul,
+        EV_TRY(conv_x(mode, c1.w_tc, c1.w_h, src, c1.w, c1.b, 0, nullptr, v.Tm[cj], B, L, C, C, c1.K, c1.dil, mel_lens, mul,
                       EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, cs));
         const bool last = (l == g.n_dil - 1);
         float* dst = last ? v.ACC : ((l & 1) ? v.R2[cj] : v.R1[cj]);
@@ -685,7 +701,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
         const float div = (float)g.n_resk;
         if (last && g.n_resk == 1) acc = EV_ACC_STORE;
         if (last && j > 0) EV_TRY(edge(pool, chain_st[(j - 1) % 3], cs));   // xs accumulation in ResBlock order
-        EV_TRY(conv_x(mode, c2.w_tc, v.Tm[cj], c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+        EV_TRY(conv_x(mode, c2.w_tc, c2.w_h, v.Tm[cj], c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
                       EV_ACT_NONE, acc, div, cs));
         src = dst;
       }
@@ -720,7 +736,7 @@ int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* 
   EV_CHECK_ARG(x && w_tc && out, "ev_op_conv1d_tc: null argument");
   EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0 && (Cout <= 128 || Cout % 128 == 0),
                "ev_op_conv1d_tc: needs Cin %% 8 == 0, Cout %% 16 == 0 and Cout <= 128 or a multiple of 128 (Cin=%d Cout=%d)", Cin, Cout);
-  return conv_x(split3 ? 3 : 1, w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul,
+  return conv_x(split3 == 2 ? 2 : (split3 ? 3 : 1), w_tc, w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul,
                 in_act, in_slope, out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -729,12 +745,12 @@ int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int split3
   ConvParams p{};
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.in_act = EV_ACT_NONE;
   p.ksplit = ksplit; p.splitk_ws = nullptr; p.splitk_cap = (size_t)-1;   // "scratch of any size is available"
-  return debug_tc_plan(p, split3 != 0, out11);
+  return debug_tc_plan(p, split3, out11);
 }
 
 int ev_set_precision(ev_ctx* ctx, int precision) {
   EV_CHECK_ARG(ctx, "ev_set_precision: null context");
-  EV_CHECK_ARG(precision == EV_PREC_FP32 || precision == EV_PREC_TF32 || precision == EV_PREC_FP32_FFMA,
+  EV_CHECK_ARG(precision == EV_PREC_FP32 || precision == EV_PREC_TF32 || precision == EV_PREC_FP32_FFMA || precision == EV_PREC_BF16,
                "ev_set_precision: unknown precision %d", precision);
   if (precision != EV_PREC_FP32_FFMA && ctx->bound) {
     bool ok = true;
@@ -751,7 +767,19 @@ int ev_set_precision(ev_ctx* ctx, int precision) {
       for (const auto& c1 : ctx->rb_c1) ok = ok && c1.w_tc;
       for (const auto& c2 : ctx->rb_c2) ok = ok && c2.w_tc;
     }
-    if (!ok) { set_error("ev_set_precision: the bound blob lacks the '.tc' (tensor-core layout) weights"); return EV_ENOWEIGHT; }
+    if (precision == EV_PREC_BF16) {
+      if (ctx->has_am) {
+        ok = ok && ctx->mel_w_h;
+        for (const auto& l : ctx->dec.layers) ok = ok && l.wqkv_h && l.wo_h && l.w1_h && l.w2_h;
+      }
+      if (ctx->has_voc) {
+        ok = ok && ctx->pre.w_h;
+        for (const auto& u : ctx->ups) ok = ok && u.w_h;
+        for (const auto& c1 : ctx->rb_c1) ok = ok && c1.w_h;
+        for (const auto& c2 : ctx->rb_c2) ok = ok && c2.w_h;
+      }
+    }
+    if (!ok) { set_error("ev_set_precision: the bound blob lacks the '.tc' / '.tc16' (tensor-core layout) weights"); return EV_ENOWEIGHT; }
   }
   ctx->precision = precision;
   return EV_OK;

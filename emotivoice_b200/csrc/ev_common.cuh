@@ -62,9 +62,10 @@ struct ConvParams {
 };
 int launch_conv1d(const ConvParams& p, cudaStream_t st);
 // tcgen05 variant (conv1d_tc.cu); p.w in the tensor-core layout [plane hi|lo][Cout/BNp][K][Cin/4][BNp][4], BNp = min(Cout,128);
-// split3 = 3xTF32 fp32 emulation (three MMAs per K step), else one tf32 MMA per K step.
-int launch_conv1d_tc(const ConvParams& p, bool split3, cudaStream_t st);
-int debug_tc_plan(const ConvParams& p, bool split3, int* v11);   // host-only: the plan launch_conv1d_tc would use
+// mode 0: one tf32 MMA per K step; 1: 3xTF32 fp32 emulation (three MMAs per K step); 2: bf16 operands
+// (p.w then in the bf16 layout [Cout/BNp][K][Cin/8][BNp][8 bf16]).
+int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st);
+int debug_tc_plan(const ConvParams& p, int mode, int* v11);   // host-only: the plan launch_conv1d_tc would use
 
 // ---------------------------------------------------------------------------------
 // acoustic-model kernels (am_kernels.cu)

@@ -71,6 +71,19 @@ def to_tc_layout(w_kio):
     return torch.stack([hi, lo]).contiguous()
 
 
+def to_tc16_layout(w_kio):
+    """(K, Cin, Cout) -> bf16 (Cout/BNp, K, Cin/8, BNp, 8) viewed as fp32 words (..., 4): the bf16 variant of the
+    tensor-core weight layout (8 channels per 16-byte granule, round to nearest even)."""
+    if w_kio.dim() == 2:
+        w_kio = w_kio.unsqueeze(0)
+    K, cin, cout = w_kio.shape
+    assert cin % 16 == 0, "bf16 tensor-core path needs C_in % 16 == 0"
+    bnp = min(cout, TC_BN)
+    assert cout % bnp == 0
+    g = w_kio.reshape(K, cin // 8, 8, cout // bnp, bnp).permute(3, 0, 1, 4, 2).contiguous()   # (NT, K, Cin/8, BNp, 8)
+    return g.to(torch.bfloat16).view(torch.float32)
+
+
 TC_SUFFIXES = ("wqkv", "wo", "w1", "w2")
 
 
@@ -85,6 +98,8 @@ def add_tc_weights(packed):
         is_voc = k.startswith("voc.") and k.endswith(".w") and k != "voc.post.w"
         if is_stack or is_pred or is_voc or k in ("to_mel.w", "cond.wx"):
             extra[k + ".tc"] = to_tc_layout(v)
+        if (is_stack and k.startswith("dec.")) or is_voc or k == "to_mel.w":      # layers the bf16 mode runs in bf16
+            extra[k + ".tc16"] = to_tc16_layout(v)
     packed.update(extra)
     return packed
 

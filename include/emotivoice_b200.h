@@ -108,9 +108,11 @@ EV_API int ev_bind_pe(ev_ctx* ctx, const float* pe, int pe_len);
  *   EV_PREC_TF32: decoder + vocoder with ONE tf32 MMA per K step (operands rounded to nearest tf32) -- the
  *     arithmetic the reference's eager PyTorch uses for convolutions on a GPU (cudnn.allow_tf32 default);
  *     the duration-critical prefix (encoder, conditioning, predictors) stays 3xTF32.
+ *   EV_PREC_BF16: decoder + vocoder with bf16 operands (tcgen05 kind::f16, fp32 accumulation; activations stay fp32
+ *     in HBM and are rounded by the staging warps); prefix 3xTF32 like EV_PREC_TF32.  BASELINE.json configs[2].
  *   EV_PREC_FP32_FFMA: plain fp32 FFMA kernels everywhere (no tensor cores; the round-1 baseline path).
  * Attention, LayerNorm, softmax, upsampling and the heads are fp32 in every mode. */
-enum { EV_PREC_FP32 = 0, EV_PREC_TF32 = 1, EV_PREC_FP32_FFMA = 2 };
+enum { EV_PREC_FP32 = 0, EV_PREC_TF32 = 1, EV_PREC_FP32_FFMA = 2, EV_PREC_BF16 = 3 };
 EV_API int ev_set_precision(ev_ctx* ctx, int precision);
 
 /* Workspace sizes (bytes).  Phase 1 (encoder .. durations) is sized by (B, T); phase 2
@@ -173,7 +175,8 @@ EV_API int ev_op_conv1d(const float* x, const float* w, const float* bias, size_
                         int acc, float div, void* stream);
 /* Same contract on the tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM); w_tc is in the
  * tensor-core layout (2 planes hi|lo, Cout/BNp N tiles, K, Cin/4, BNp = min(Cout,128), 4; packing.to_tc_layout);
- * split3 != 0 selects 3xTF32 fp32 emulation.  Requires Cin % 8 == 0, Cout % 16 == 0 and Cout <= 128 or Cout % 128 == 0.  splitk_ws (optional, splitk_floats floats of scratch) lets a
+ * split3 = 0: 1xTF32, 1: 3xTF32 fp32 emulation, 2: bf16 operands (w_tc then in the bf16 layout of
+ * packing.to_tc16_layout; Cin % 16 == 0).  Requires Cin % 8 == 0, Cout % 16 == 0 and Cout <= 128 or Cout % 128 == 0.  splitk_ws (optional, splitk_floats floats of scratch) lets a
  * launch with few output tiles and a long reduction be split along K (deterministic two-pass). */
 EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* bias, size_t bias_bstride,
                            const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,

@@ -1,5 +1,5 @@
 """Launch one conv shape through the C ABI a few times (for ncu / timing).
-usage: python tools/profile_conv.py MODE C K DIL L [B] [reps]   MODE in {ffma, tf32, fp32};  C may be "Cin:Cout"."""
+usage: python tools/profile_conv.py MODE C K DIL L [B] [reps]   MODE in {ffma, tf32, fp32, bf16};  C may be "Cin:Cout"."""
 import math
 import sys
 import os
@@ -19,7 +19,7 @@ dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 x = torch.randn(B, L, Cin, generator=g).to(dev)
 w = torch.randn(K, Cin, Cout, generator=g) / math.sqrt(Cin * K)
-wd = (packing.to_tc_layout(w) if mode != "ffma" else w).to(dev)
+wd = (packing.to_tc16_layout(w) if mode == "bf16" else (packing.to_tc_layout(w) if mode != "ffma" else w)).to(dev)
 b = torch.randn(C, generator=g).to(dev)
 res = torch.randn(B, L, C, generator=g).to(dev)
 out = torch.empty(B, L, C, device=dev)
@@ -34,7 +34,7 @@ for i in range(reps):
         _abi.check(lib.ev_op_conv1d(x.data_ptr(), wd.data_ptr(), b.data_ptr(), 0, res.data_ptr(), out.data_ptr(), B, L, Cin, Cout, K, dil,
                                     None, 1, 1, 0.1, 0, 0, 1.0, st))
     else:
-        _abi.check(lib.ev_op_conv1d_tc(x.data_ptr(), wd.data_ptr(), 1 if mode == "fp32" else 0, b.data_ptr(), 0, res.data_ptr(),
+        _abi.check(lib.ev_op_conv1d_tc(x.data_ptr(), wd.data_ptr(), {"fp32": 1, "tf32": 0, "bf16": 2}[mode], b.data_ptr(), 0, res.data_ptr(),
                                        out.data_ptr(), B, L, Cin, Cout, K, dil, None, 1, 1, 0.1, 0, 0, 1.0, None, 0, st))
     e1.record()
     e1.synchronize()
