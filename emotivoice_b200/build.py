@@ -29,7 +29,7 @@ def _digest():
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     files.append(os.path.join(INCLUDE, "emotivoice_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # names, not absolute paths: the tree is relocated on the GPU box
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
