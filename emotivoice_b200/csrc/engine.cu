@@ -736,6 +736,7 @@ int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* 
   EV_CHECK_ARG(x && w_tc && out, "ev_op_conv1d_tc: null argument");
   EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0 && (Cout <= 128 || Cout % 128 == 0),
                "ev_op_conv1d_tc: needs Cin %% 8 == 0, Cout %% 16 == 0 and Cout <= 128 or a multiple of 128 (Cin=%d Cout=%d)", Cin, Cout);
+  EV_CHECK_ARG(split3 != 2 || Cin % 16 == 0, "ev_op_conv1d_tc: the bf16 mode needs Cin %% 16 == 0 (Cin=%d)", Cin);
   return conv_x(split3 == 2 ? 2 : (split3 ? 3 : 1), w_tc, w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul,
                 in_act, in_slope, out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -171,9 +171,11 @@ def _plan(lib, B, L, Cin, Cout, K, dil, split3, ksplit=0):
     return dict(zip(keys, list(out)))
 
 
-@pytest.mark.parametrize("split3", [0, 1])
+@pytest.mark.parametrize("split3", [0, 1, 2])
 def test_tc_plan_respects_hardware_limits_and_barrier_protocol(lib, split3):
     for Cin, Cout, K, dil in _SHAPES:
+        if split3 == 2 and Cin % 16:
+            continue
         for B, L in ((1, 100), (1, 537), (1, 4296), (1, 137472), (3, 300), (32, 1600), (128, 65536)):
             p = _plan(lib, B, L, Cin, Cout, K, dil, split3, ksplit=2)
             assert p["smem"] <= 227 * 1024 and p["tmem_cols"] <= 512 and 2 * p["MT"] * p["BN"] <= p["tmem_cols"]
@@ -186,11 +188,13 @@ def test_tc_plan_respects_hardware_limits_and_barrier_protocol(lib, split3):
             assert p["rows_pad"] >= 128 * p["MT"] + (K - 1) * dil
 
 
-@pytest.mark.parametrize("split3", [0, 1])
+@pytest.mark.parametrize("split3", [0, 1, 2])
 def test_tc_plan_summation_order_is_a_function_of_the_layer_only(lib, split3):
     """KBG (how the (channel block, tap) reduction is ordered) and the K-split factor must not depend on batch or
     length: that is what makes a batched run bitwise equal to the B=1 runs."""
     for Cin, Cout, K, dil in _SHAPES:
+        if split3 == 2 and Cin % 16:
+            continue
         seen = {(_plan(lib, B, L, Cin, Cout, K, dil, split3, ksplit=4)["KBG"], _plan(lib, B, L, Cin, Cout, K, dil, split3, ksplit=4)["ksplit"])
                 for B, L in ((1, 64), (1, 537), (1, 34368), (2, 900), (32, 1600), (64, 40000))}
         assert len(seen) == 1, (Cin, Cout, K, dil, seen)
