@@ -299,8 +299,7 @@ def main():
 
     import __graft_entry__  # noqa: F401  (sys.path)
     from emotivoice_b200 import build as _build
-    if rank == 0 or world == 1:
-        _build.build(verbose=False)      # no-op when the in-tree .so is current
+    _build.build(verbose=False)          # no-op when the in-tree .so is current; file-locked, so every rank may call it
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

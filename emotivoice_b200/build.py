@@ -44,7 +44,19 @@ def nvcc_path():
 
 
 def build(force=False, verbose=True):
+    """Idempotent and safe to call from several processes at once (torchrun ranks): the check-and-compile
+    section runs under an exclusive file lock, so one process compiles and the others then find the stamp."""
+    import fcntl
     os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     stamp = os.path.join(LIB_DIR, "build.stamp")
     dig = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
