@@ -206,3 +206,30 @@ def test_tc_plan_rejects_unsupported_shapes(lib):
     assert lib.ev_debug_tc_plan(1, 100, 30, 32, 3, 1, 0, 0, out) == -1       # Cin % 8
     assert lib.ev_debug_tc_plan(1, 100, 32, 200, 3, 1, 0, 0, out) == -1      # Cout > 128 and not a multiple of 128
     assert lib.ev_debug_tc_plan(1, 100, 32, 32, 4, 1, 0, 0, out) == -1       # even kernel size
+
+
+def test_3xtf32_split_is_fp32_accurate_in_emulation():
+    """The arithmetic behind the default "fp32" mode, emulated on the CPU: x = hi + lo with hi = tf32(x),
+    lo = tf32(x - hi); a.b ~= sum(a_lo*b_hi + a_hi*b_lo + a_hi*b_hi) accumulated in fp32.  Its error against an
+    fp64 dot product must be at the fp32 level (the dropped lo*lo term is 2^-22 relative), far below one tf32
+    product (2^-11)."""
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(256, 1152, generator=g), torch.randn(1152, 64, generator=g)
+
+    def split(x):
+        hi = packing.round_tf32(x)
+        return hi, packing.round_tf32(x - hi)
+
+    a_hi, a_lo = split(a)
+    b_hi, b_lo = split(b)
+    exact = a.double() @ b.double()
+    one = (a_hi.double() @ b_hi.double())
+    three = (a_lo.double() @ b_hi.double() + a_hi.double() @ b_lo.double() + a_hi.double() @ b_hi.double()).float().double()
+    fp32 = (a @ b).double()
+    scale = exact.abs().max()
+    e1, e3, ef = ((one - exact).abs().max() / scale).item(), ((three - exact).abs().max() / scale).item(), ((fp32 - exact).abs().max() / scale).item()
+    assert e1 > 1e-5           # one tf32 product is visibly worse than fp32
+    assert e3 < 3e-7           # the split is at the fp32 level ...
+    assert e3 < 5 * max(ef, 1e-8) + 1e-7    # ... comparable to a plain fp32 matmul
+    # hi + lo reconstructs x to ~2^-22
+    assert ((a_hi + a_lo) - a).abs().max() <= a.abs().max() * 2.0 ** -21
