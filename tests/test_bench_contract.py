@@ -1,0 +1,50 @@
+"""bench.py's JSON contract: the committed round-1 lines (measured on the B200) and a live run of the
+CPU reference arm carry every key the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def _check_common(d):
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "mel_frames_per_sec" and d["unit"] == "mel-frames/s" and d["higher_is_better"] is True
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+
+
+def test_committed_engine_lines_have_the_contract_keys():
+    for name, n in (("r01_bench_final_fp32.json", 1), ("r01_bench_final_tf32.json", 1), ("r01_bench_final_2gpu_fp32.json", 2)):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        _check_common(d)
+        assert d["n_gpus"] == n and d["warmup"] >= 3 and d["gpu_launches"] > 0
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] in ("hbm", "tensor")
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert d["parity"]["durations_identical"] is True
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_final_fp32.json")))
+    cb = d["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] in ("port", "reference")
+    assert d["parity"]["wav_rms_err_over_rms"] < 1e-4 and d["parity"]["mel_max_abs_err_over_max_abs"] < 1e-4
+
+
+def test_reference_arm_runs_on_cpu_and_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    _check_common(d)
+    assert d["impl"] == "reference" and d["steps"] == 1 and d["warmup"] == 1 and d["gpu_launches"] == 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
