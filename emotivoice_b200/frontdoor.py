@@ -1,0 +1,143 @@
+"""The caller-side plumbing either side of the hot path: the
+``<speaker>|<prompt>|<phoneme>|<content>`` input contract and a micro-batching queue.
+
+Every reference front-end (inference_am_vocoder_joint.py:76-131, demo_page.py:119-150,
+openaiapi.py:110-142) does the same four things around ``generator(...)``: read the symbol tables,
+split the 4-field line, map phonemes / speaker to ids, and run B=1.  This module restates that
+plumbing for hosts that want it without the reference scripts, and adds what turns batch throughput
+into served throughput: a queue that groups concurrent requests into one padded forward.  Because the
+engine's batches are bitwise equal to B=1 runs, micro-batching is invisible to callers.
+
+Pure host code: no CUDA, no torch ops beyond tensor construction.  The style / content vectors come
+from the caller (the simbert encoder is out of scope).
+"""
+import threading
+import time
+from collections import namedtuple
+from concurrent.futures import Future
+
+import numpy as np
+import torch
+
+Request = namedtuple("Request", "speaker prompt phonemes content")
+
+
+def load_symbol_table(path):
+    """line -> index, exactly like inference_am_vocoder_joint.py:76-80 (tokenlist, speaker2)."""
+    with open(path, encoding="utf-8") as f:
+        return {t.strip(): idx for idx, t in enumerate(f.readlines())}
+
+
+def parse_line(line):
+    """``speaker|prompt|phonemes|content`` (inference_am_vocoder_joint.py:96-102).  Phonemes are
+    whitespace separated; extra fields are ignored like the reference ignores them."""
+    parts = line.strip().split("|")
+    if len(parts) < 4:
+        raise ValueError("expected <speaker>|<prompt>|<phoneme>|<content>, got %d field(s)" % len(parts))
+    return Request(parts[0], parts[1], parts[2].split(), parts[3])
+
+
+def encode(req, token2id, speaker2id):
+    """-> (int64 ids, speaker id) or None for an unknown speaker (the reference skips such lines,
+    inference_am_vocoder_joint.py:109-110).  An unknown phoneme raises KeyError like the reference (:113)."""
+    if req.speaker not in speaker2id:
+        return None
+    ids = np.asarray([token2id[ph] for ph in req.phonemes], dtype=np.int64)
+    if ids.size == 0:
+        raise ValueError("empty phoneme sequence")
+    return ids, int(speaker2id[req.speaker])
+
+
+def collate(items, device="cpu", pad_id=0):
+    """items: list of (ids, speaker_id, style_vec, content_vec) -> the keyword arguments of
+    ``JETSGenerator.forward`` (inference_am_vocoder_joint.py:113-128), padded with id 0 (the collate
+    convention of the reference's dataset, prompt_dataset.py:183)."""
+    B, T = len(items), max(len(it[0]) for it in items)
+    ling = np.full((B, T), pad_id, dtype=np.int64)
+    for b, it in enumerate(items):
+        ling[b, :len(it[0])] = it[0]
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    return dict(
+        inputs_ling=to(ling),
+        input_lengths=to(np.asarray([len(it[0]) for it in items], dtype=np.int64)),
+        inputs_speaker=to(np.asarray([it[1] for it in items], dtype=np.int64)),
+        inputs_style_embedding=to(np.stack([np.asarray(it[2], dtype=np.float32) for it in items])),
+        inputs_content_embedding=to(np.stack([np.asarray(it[3], dtype=np.float32) for it in items])),
+    )
+
+
+class MicroBatcher:
+    """Groups concurrent synthesis requests into padded batches.
+
+    ``forward(**kwargs) -> dict`` is the model (``emotivoice_b200.modules.JETSGenerator``); requests are
+    ``(ids, speaker_id, style_vec, content_vec)``.  ``submit`` returns a Future whose result is the item's
+    float32 waveform trimmed to its own length (``mel_lengths[b] * hop``).  A worker thread collects up to
+    ``max_batch`` requests, waiting at most ``max_wait_s`` after the first one, and runs ONE forward.
+    Errors of a batch are delivered to every future of that batch.
+    """
+
+    def __init__(self, forward, device="cpu", max_batch=32, max_wait_s=0.005, hop=256):
+        self._forward, self._device, self._hop = forward, device, hop
+        self._max_batch, self._max_wait = int(max_batch), float(max_wait_s)
+        self._lock = threading.Condition()
+        self._queue = []
+        self._closed = False
+        self.batches_run = 0
+        self._thread = threading.Thread(target=self._loop, name="ev-microbatcher", daemon=True)
+        self._thread.start()
+
+    def submit(self, ids, speaker_id, style_vec, content_vec):
+        fut = Future()
+        with self._lock:
+            if self._closed:
+                raise RuntimeError("MicroBatcher is closed")
+            self._queue.append(((np.asarray(ids, dtype=np.int64), int(speaker_id), style_vec, content_vec), fut))
+            self._lock.notify()
+        return fut
+
+    def close(self):
+        with self._lock:
+            self._closed = True
+            self._lock.notify()
+        self._thread.join()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _take(self):
+        with self._lock:
+            while not self._queue and not self._closed:
+                self._lock.wait()
+            if not self._queue:
+                return None
+            deadline = time.monotonic() + self._max_wait
+            while len(self._queue) < self._max_batch and not self._closed:
+                left = deadline - time.monotonic()
+                if left <= 0:
+                    break
+                self._lock.wait(left)
+            batch, self._queue = self._queue[:self._max_batch], self._queue[self._max_batch:]
+            return batch
+
+    def _loop(self):
+        while True:
+            batch = self._take()
+            if batch is None:
+                return
+            futs = [f for _, f in batch]
+            try:
+                out = self._forward(**collate([it for it, _ in batch], self._device))
+                wav = out["wav_predictions"]
+                lens = out.get("mel_lengths")
+                lens = [int(wav.shape[-1]) // self._hop] * len(batch) if lens is None else [int(v) for v in lens.tolist()]
+                wav = wav.detach().cpu()
+                self.batches_run += 1
+                for b, f in enumerate(futs):
+                    f.set_result(wav[b, 0, :lens[b] * self._hop].clone())
+            except BaseException as e:       # deliver, keep serving
+                for f in futs:
+                    if not f.done():
+                        f.set_exception(e)
