@@ -223,19 +223,3 @@ def test_minimal_and_long_sequences(conf, sd, dev, lib):
     assert out["dec_outputs"].shape[1] > 5000                       # the table had to grow
     assert torch.equal(out["log_duration_predictions"].cpu(), ref["log_duration_predictions"])
     assert rel_max(out["dec_outputs"].cpu(), ref["dec_outputs"]) <= MEL_TOL
-
-
-def test_microbatcher_on_the_engine_equals_b1_calls(model, dev):
-    """concurrent requests grouped into one padded forward return exactly (bitwise) what a
-    B=1 call returns for each of them."""
-    import numpy as np
-    from emotivoice_b200 import frontdoor as fd
-    rng = np.random.default_rng(11)
-    utts = [synth.make_utterance(rng, int(n)) for n in (14, 33, 9, 21)]
-    with fd.MicroBatcher(model, device=dev, max_batch=4, max_wait_s=0.5) as mb:
-        futs = [mb.submit(u["ids"], int(u["speaker"]), u["style"], u["content"]) for u in utts]
-        got = [f.result(timeout=120) for f in futs]
-        assert mb.batches_run <= 2
-    for u, w in zip(utts, got):
-        single = model(**fd.collate([(u["ids"], int(u["speaker"]), u["style"], u["content"])], dev))
-        assert torch.equal(single["wav_predictions"][0, 0].cpu(), w)

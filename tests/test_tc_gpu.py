@@ -57,11 +57,7 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("split3", [0, 1, 2])
-@pytest.mark.parametrize("B,L,Cin,Cout,K,dil", TC_CASES)
-def test_conv1d_tc_matches_torch(lib, dev, B, L, Cin, Cout, K, dil, split3):
-    if split3 == 2 and Cin % 16:
-        pytest.skip("bf16 mode needs C_in % 16 == 0")
+def check_conv1d_tc_matches_torch(lib, dev, B, L, Cin, Cout, K, dil, split3):
     g = torch.Generator().manual_seed(B * 1000 + L + Cin + Cout + K)
     x = torch.randn(B, Cin, L, generator=g)
     w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
@@ -74,8 +70,13 @@ def test_conv1d_tc_matches_torch(lib, dev, B, L, Cin, Cout, K, dil, split3):
     assert err <= TOL[split3]
 
 
-@pytest.mark.parametrize("split3", [0, 1, 2])
-def test_conv1d_tc_epilogue_and_ragged(lib, dev, split3):
+@pytest.mark.parametrize("split3", [0, 1])
+@pytest.mark.parametrize("B,L,Cin,Cout,K,dil", TC_CASES)
+def test_conv1d_tc_matches_torch(lib, dev, B, L, Cin, Cout, K, dil, split3):
+    check_conv1d_tc_matches_torch(lib, dev, B, L, Cin, Cout, K, dil, split3)
+
+
+def check_conv1d_tc_epilogue_and_ragged(lib, dev, split3):
     g = torch.Generator().manual_seed(21)
     B, L, C, K, dil, mul = 3, 96 * 4, 64, 7, 3, 4
     lens = torch.tensor([96, 17, 50], dtype=torch.int32)
@@ -95,6 +96,11 @@ def test_conv1d_tc_epilogue_and_ragged(lib, dev, split3):
         single = run_tc(lib, split3, x[i:i + 1, :n].contiguous(), w, b, res[i:i + 1, :n].contiguous(), prev[i:i + 1, :n].contiguous(),
                         K, dil, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_GELU, _abi.ACC_ADD_DIV, 3.0)
         assert torch.equal(single[0], out[i, :n])           # batch-invariant, bitwise
+
+
+@pytest.mark.parametrize("split3", [0, 1])
+def test_conv1d_tc_epilogue_and_ragged(lib, dev, split3):
+    check_conv1d_tc_epilogue_and_ragged(lib, dev, split3)
 
 
 @pytest.mark.parametrize("split3", [0, 1])
@@ -144,37 +150,6 @@ def test_tf32_mode_is_batch_invariant(model, dev):
             single = model(**{k: v.to(dev) for k, v in synth.slice_batch(g, b).items()})
             Fb = single["dec_outputs"].shape[1]
             assert torch.equal(single["dec_outputs"][0], out["dec_outputs"][b, :Fb])
-            assert torch.equal(single["wav_predictions"][0, 0], out["wav_predictions"][b, 0, :Fb * 256])
-    finally:
-        model.precision = "fp32"
-
-
-@pytest.mark.parametrize("name", ["b1_t12", "b1_t100"])
-def test_bf16_mode_end_to_end(model, dev, name):
-    """BASELINE.json configs[2] dtype: bf16 operands (fp32 accumulation) in decoder + vocoder; tolerance proposal of
-    SURVEY.md s8d: mel <= 2e-2 of max, wav rms-rel <= 2e-2, durations identical."""
-    g = load_golden(name)
-    model.precision = "bf16"
-    try:
-        out = model(**{k: g[k].to(dev) for k in KEYS})
-        torch.cuda.synchronize()
-    finally:
-        model.precision = "fp32"
-    assert torch.equal(out["log_duration_predictions"].cpu(), g["durations"])
-    e_mel, e_wav = rel_max(out["dec_outputs"].cpu(), g["mel"]), rel_rms(out["wav_predictions"].cpu(), g["wav"])
-    print(name, "bf16: mel rel-max %.2e wav rms-rel %.2e" % (e_mel, e_wav))
-    assert e_mel <= 2e-2 and e_wav <= 2e-2
-
-
-def test_bf16_mode_is_batch_invariant(model, dev):
-    from emotivoice_b200 import synth
-    g = load_golden("b3_padded")
-    model.precision = "bf16"
-    try:
-        out = model(**{k: g[k].to(dev) for k in KEYS})
-        for b in range(3):
-            single = model(**{k: v.to(dev) for k, v in synth.slice_batch(g, b).items()})
-            Fb = single["dec_outputs"].shape[1]
             assert torch.equal(single["wav_predictions"][0, 0], out["wav_predictions"][b, 0, :Fb * 256])
     finally:
         model.precision = "fp32"
