@@ -10,7 +10,11 @@ engine's batches are bitwise equal to B=1 runs, micro-batching is
 
 Pure host code: no CUDA, no torch ops beyond tensor construction.  The style / content vectors come
 from the caller (the simbert encoder is out of scope).
+
+Output side (s8f rank 2): ``fetch_pcm16`` (GPU int16 conversion + one pinned device->host copy + per-item trim) and
+``pcm16_to_wav_bytes`` (the 16 kHz mono PCM16 RIFF image the front-ends emit).
 """
+import struct
 import threading
 import time
 from collections import namedtuple
@@ -141,3 +145,37 @@ class MicroBatcher:
                 for f in futs:
                     if not f.done():
                         f.set_exception(e)
+
+
+# ---- output side: the on-wire format every front-end emits -----------------------------------
+
+def pcm16_to_wav_bytes(pcm, sample_rate=16000):
+    """int16 mono samples -> a complete RIFF/WAVE file image (PCM, 16 bit, mono), i.e. what the reference writes with
+    ``sf.write(path, int16_audio, samplerate=config.sampling_rate)`` (inference_am_vocoder_joint.py:132-134) and what
+    openaiapi.py:139-140,172-174 sends for ``response_format="wav"``.  44-byte canonical header, little endian."""
+    pcm = np.ascontiguousarray(np.asarray(pcm))
+    if pcm.dtype != np.int16 or pcm.ndim != 1:
+        raise ValueError("expected a 1-D int16 array, got %s %s" % (pcm.dtype, pcm.shape))
+    data = pcm.astype("<i2", copy=False).tobytes()
+    if len(data) > 0xFFFFFFFF - 36:
+        raise ValueError("waveform too long for a RIFF container")
+    header = struct.pack("<4sI4s4sIHHIIHH4sI", b"RIFF", 36 + len(data), b"WAVE", b"fmt ", 16,
+                         1, 1, int(sample_rate), int(sample_rate) * 2, 2, 16, b"data", len(data))
+    return header + data
+
+
+def fetch_pcm16(model, out, hop=256):
+    """Finish one forward the way the callers do (inference_am_vocoder_joint.py:130-131), without the fp32 waveform
+    ever crossing PCIe: ``wav * 32768 -> int16`` on the GPU (``model.to_pcm16``), ONE device->host copy of the int16
+    batch into pinned memory, then per-item trimming to ``mel_lengths[b] * hop`` on the host.
+    ``out`` is the dict ``model(...)`` returned.  Returns a list of 1-D int16 numpy arrays (one per batch item)."""
+    wav = out["wav_predictions"]
+    pcm = model.to_pcm16(wav)                                              # (B, 1, 256 F) int16, device
+    host = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)
+    host.copy_(pcm, non_blocking=True)
+    lens = out.get("mel_lengths")
+    lens = None if lens is None else [int(v) for v in lens.tolist()]      # tiny D2H; also orders after the copy above
+    torch.cuda.current_stream(pcm.device).synchronize()
+    B, n = pcm.shape[0], int(pcm.shape[-1])
+    arr = host.numpy().reshape(B, n)
+    return [arr[b, :(n if lens is None else min(n, lens[b] * hop))].copy() for b in range(B)]

@@ -105,3 +105,25 @@ def test_microbatcher_delivers_errors_and_keeps_serving():
         assert f2.result(timeout=10).shape == (3 * 2 * 256,)
     with pytest.raises(RuntimeError):
         mb.submit(np.array([1]), 0, np.zeros(768, np.float32), np.zeros(768, np.float32))
+
+
+def test_wav_container_is_the_canonical_pcm16_file():
+    """16 kHz mono PCM16 RIFF, readable by the stdlib and byte-identical to scipy's writer."""
+    import io
+    import wave
+    from scipy.io import wavfile
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 12345):
+        pcm = rng.integers(-32768, 32768, size=n).astype(np.int16)
+        img = fd.pcm16_to_wav_bytes(pcm, 16000)
+        assert len(img) == 44 + 2 * n
+        with wave.open(io.BytesIO(img)) as w:
+            assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 16000, n)
+            assert np.array_equal(np.frombuffer(w.readframes(n), "<i2"), pcm)
+        ref = io.BytesIO()
+        wavfile.write(ref, 16000, pcm)
+        assert ref.getvalue() == img
+    with pytest.raises(ValueError):
+        fd.pcm16_to_wav_bytes(np.zeros(4, np.float32))
+    with pytest.raises(ValueError):
+        fd.pcm16_to_wav_bytes(np.zeros((2, 4), np.int16))

@@ -68,3 +68,18 @@ def test_microbatcher_on_the_engine_equals_b1_calls(model, dev):
     for u, w in zip(utts, got):
         single = model(**fd.collate([(u["ids"], int(u["speaker"]), u["style"], u["content"])], dev))
         assert torch.equal(single["wav_predictions"][0, 0].cpu(), w)
+
+
+def test_fetch_pcm16_trims_and_matches_the_callers_cast(model, dev):
+    """GPU int16 conversion + one pinned D2H + per-item trim == what the reference callers compute
+    from the fp32 waveform on the host (inference_am_vocoder_joint.py:130-131: `wav * 32768` -> `.astype('int16')`)."""
+    import numpy as np
+    from emotivoice_b200 import frontdoor as fd
+    g = load_golden("b3_padded")
+    out = model(**{k: g[k].to(dev) for k in KEYS})
+    got = fd.fetch_pcm16(model, out)
+    wav, lens = out["wav_predictions"].cpu().numpy(), out["mel_lengths"].cpu().tolist()
+    assert len(got) == 3
+    for b in range(3):
+        want = (wav[b, 0, :lens[b] * 256] * 32768.0).astype("int16")
+        assert got[b].dtype == np.int16 and np.array_equal(got[b], want)
