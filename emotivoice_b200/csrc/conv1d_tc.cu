@@ -144,6 +144,7 @@ struct Plan {
   int tmem_cols;
   int tiles_m, tiles_n, total_tiles;
   int smem_total;
+  int pdl;             // launched with programmatic stream serialization (EV_PDL=1): see the note in the kernel
 };
 
 // smem map: [0,288) barriers | [512,516) tmem base | 1024: epilogue staging (8 warps x 4 KB) | A ring | B ring
@@ -185,6 +186,7 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN,
   q.ksplit = 1;
   q.total_tiles = p.B * q.tiles_m * q.tiles_n;
   q.smem_total = 1024 + STAGING_BYTES + q.a_stages * q.a_stage_bytes + q.b_stages * q.b_stage_bytes;
+  q.pdl = 0;
   *o = q;
   return true;
 }
@@ -259,6 +261,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Programmatic dependent launch (opt-in, EV_PDL=1).  The grid is persistent (<= one CTA per SM, all resident), so it
+  // lets the NEXT launch in the stream start as soon as SMs free up: that kernel's CTAs run their set-up (barriers, TMEM)
+  // and its loader warp prefetches the first weight stages -- none of which depends on this grid -- while this grid's tail
+  // is still running.  Everything that touches activations (producers: x; epilogue: res / out / split-K partials) first
+  // executes griddepcontrol.wait, which returns once the preceding grid has completed and its writes are visible.
+  // The loader and the MMA issuer read only weights and p.lens; p.lens must therefore not be written by the launch
+  // immediately before a convolution (the engine writes it at the start of a phase, kernels earlier).
+  if (pl.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   const int n_cb = (p.Cin + KB - 1) / KB;
   const int halo = ((p.K - 1) / 2) * p.dil;
   const int rows_a = BM * MT + (p.K - 1) * p.dil;
@@ -280,6 +291,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
 
   if (warp < NEPI / 32) {
     // ============================ epilogue warps ==============================================
+    if (pl.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int quad = warp & 3, chalf = warp >> 2;
     float* stg = reinterpret_cast<float*>(staging + warp * (32 * 32 * 4));
     const int rr = lane >> 3, cq = lane & 7;         // coalesced phase: 4 rows x 8 float4 per instruction
@@ -376,6 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
     }
   } else if (warp < MMA_WARP) {
     // ============================ A producers ===================================================
+    if (pl.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int pwarp = warp - NEPI / 32;
     const int wpg = NPWARPS / pl.ngroups;          // warps per group
     const int grp = pwarp / wpg;
@@ -628,6 +641,22 @@ static int launch_tc_variant(const ConvParams& p, const tc::Plan& pl, cudaStream
     attr_set = true;
   }
   const int grid = pl.total_tiles < sm_count() ? pl.total_tiles : sm_count();
+  if (pl.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(tc::NTHREADS);
+    cfg.dynamicSmemBytes = (size_t)pl.smem_total;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, tc::conv1d_tc_kernel<MODE, MT, KBG>, p, pl);
+    if (e != cudaSuccess) { set_error("conv1d_tc_kernel (PDL launch): %s", cudaGetErrorString(e)); return EV_ECUDA; }
+    count_launch();
+    return EV_OK;
+  }
   tc::conv1d_tc_kernel<MODE, MT, KBG><<<grid, tc::NTHREADS, pl.smem_total, st>>>(p, pl);
   EV_CUDA_LAUNCH_CHECK("conv1d_tc_kernel");
   return EV_OK;
@@ -707,6 +736,8 @@ int debug_tc_plan(const ConvParams& p, int mode, int* v) {
 int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st) {
   tc::Plan pl;
   EV_TRY(plan_conv1d_tc(p, mode, &pl));
+  static const int pdl = env_int("EV_PDL", 0);      // opt-in until it has been measured on hardware
+  pl.pdl = pdl ? 1 : 0;
   const size_t per = (size_t)p.B * p.L * p.Cout;
   int rc;
   if (mode == 1) rc = launch_tc_mt<1, 4>(p, pl, st);

@@ -83,3 +83,48 @@ def test_fetch_pcm16_trims_and_matches_the_callers_cast(model, dev):
     for b in range(3):
         want = (wav[b, 0, :lens[b] * 256] * 32768.0).astype("int16")
         assert got[b].dtype == np.int16 and np.array_equal(got[b], want)
+
+
+_PDL_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from emotivoice_b200 import synth
+from emotivoice_b200.config import default_config
+from emotivoice_b200.modules import JETSGenerator
+conf = default_config()
+m = JETSGenerator(conf).to("cuda:0"); m.load_state_dict(synth.make_state_dict(conf)); m.eval()
+z = np.load(sys.argv[2])
+keys = ("inputs_ling", "input_lengths", "inputs_speaker", "inputs_style_embedding", "inputs_content_embedding")
+res = {}
+for prec in ("fp32", "tf32"):
+    m.precision = prec
+    for rep in range(3):                      # back-to-back forwards: launches of one forward overlap the tail of the previous one
+        out = m(**{k: torch.from_numpy(z[k]).cuda() for k in keys})
+    torch.cuda.synchronize()
+    res[prec + "_mel"] = out["dec_outputs"].cpu().numpy(); res[prec + "_wav"] = out["wav_predictions"].cpu().numpy()
+np.savez(sys.argv[3], **res)
+"""
+
+
+def test_programmatic_dependent_launch_is_bitwise_identical(model, dev, tmp_path):
+    """EV_PDL=1 launches the tensor-core convolutions with programmatic stream serialization (set-up and weight prefetch
+    of launch n+1 overlap the tail of launch n).  It reorders nothing inside a kernel, so every output bit must equal
+    the default launch mode's; a missing griddepcontrol.wait would show up here as a mismatch."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    from conftest import GOLDEN, ROOT
+    src, dst = os.path.join(GOLDEN, "b3_padded.npz"), str(tmp_path / "pdl.npz")
+    env = dict(os.environ, EV_PDL="1")
+    subprocess.run([sys.executable, "-c", _PDL_CHILD, ROOT, src, dst], env=env, check=True, timeout=600)
+    got = np.load(dst)
+    g = load_golden("b3_padded")
+    try:
+        for prec in ("fp32", "tf32"):
+            model.precision = prec
+            out = model(**{k: g[k].to(dev) for k in KEYS})
+            assert np.array_equal(out["dec_outputs"].cpu().numpy(), got[prec + "_mel"])
+            assert np.array_equal(out["wav_predictions"].cpu().numpy(), got[prec + "_wav"])
+    finally:
+        model.precision = "fp32"
