@@ -25,7 +25,11 @@
 // chunks), warps 8-13 stage A, warp 14 allocates TMEM and its elected lane issues every tcgen05.mma,
 // warp 15's elected lane streams the weight tiles.  mbarrier pipelines: A ring (a_full/a_empty), B ring (b_full/b_empty,
 // released by tcgen05.commit), accumulators (acc_full/acc_empty).
+#include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "ev_common.cuh"
 
@@ -669,15 +673,58 @@ static int launch_tc_mt(const ConvParams& p, const tc::Plan& pl, cudaStream_t st
   return launch_tc_variant<MODE, 1, KBG>(p, pl, st);
 }
 
-// Tile / pipeline plan of one launch (pure host arithmetic; also exported as ev_debug_tc_plan so the CPU tests
-// can check the invariants the kernel's barrier protocol and the batch-invariance contract rely on).
-static int plan_conv1d_tc(const ConvParams& p, int mode, tc::Plan* out) {
-  const bool split3 = (mode == 1);
+static int validate_conv1d_tc(const ConvParams& p, int mode) {
   EV_CHECK_ARG(p.B > 0 && p.L > 0, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
   EV_CHECK_ARG(p.Cin % (mode == 2 ? 16 : 8) == 0, "conv1d_tc: Cin=%d must be a multiple of %d", p.Cin, mode == 2 ? 16 : 8);
   EV_CHECK_ARG(p.Cout % 16 == 0 && (p.Cout <= 128 || p.Cout % 128 == 0), "conv1d_tc: Cout=%d must be a multiple of 16, and of 128 above 128", p.Cout);
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
   EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
+  return EV_OK;
+}
+
+// K granules per stage decide how the (channel block, tap) reduction is ordered, so they must be a function
+// of the layer shape alone: 8 if a (widest-N, one-accumulator) tile fits with them in 1x mode, else 4.
+static int shape_kbg(const ConvParams& p, int mode) {
+  tc::Plan pl;
+  const int bn_max = p.Cout <= 128 ? p.Cout : 128;
+  return (mode != 1 && tc::make_plan(p, mode, bn_max, 1, 8, 4, &pl)) ? 8 : 4;
+}
+
+// K-split: a long reduction at few output tiles (the acoustic model's GEMMs at batch 1; the conv-FFN's second
+// conv has K = 3*1536) is one long serial chain per tile; share it among S CTAs with private partial buffers
+// + a fixed-order reduce kernel.  S is requested per LAYER by the engine (never derived from batch or
+// length), so the summation order -- and therefore every output bit -- is the same for a B=1 call and for
+// the same utterance inside any batch.
+static int apply_ksplit(const ConvParams& p, int mode, tc::Plan* pl) {
+  const size_t per = (size_t)p.B * p.L * p.Cout;
+  if (p.ksplit > 1 && (p.splitk_ws || p.splitk_cap == (size_t)-1)) {
+    int S = p.ksplit;
+    const int cpg = mode == 2 ? 8 : 4;
+    const int n_cb = (p.Cin + cpg * pl->kbg - 1) / (cpg * pl->kbg);
+    if (S > n_cb) S = n_cb;
+    if ((size_t)S * per > p.splitk_cap) { set_error("conv1d_tc: split-K scratch too small (%zu < %zu floats)", p.splitk_cap, (size_t)S * per); return EV_EWORKSPACE; }
+    if (S > 1) {
+      pl->ksplit = S;
+      pl->total_tiles *= S;
+    }
+  }
+  return EV_OK;
+}
+
+// Plan with a prescribed tile shape (the autotuner's candidates): false if it does not fit.
+static bool plan_with_shape(const ConvParams& p, int mode, int BN, int mt, tc::Plan* out) {
+  const int kbg = shape_kbg(p, mode);
+  tc::Plan pl;
+  if (!tc::make_plan(p, mode, BN, mt, kbg, 4, &pl) && !tc::make_plan(p, mode, BN, mt, kbg, 2, &pl)) return false;
+  if (apply_ksplit(p, mode, &pl) != EV_OK) return false;
+  *out = pl;
+  return true;
+}
+
+// Tile / pipeline plan of one launch (pure host arithmetic; also exported as ev_debug_tc_plan so the CPU tests
+// can check the invariants the kernel's barrier protocol and the batch-invariance contract rely on).
+static int plan_conv1d_tc(const ConvParams& p, int mode, tc::Plan* out) {
+  EV_TRY(validate_conv1d_tc(p, mode));
   // Tile shape.  None of these choices changes the order in which any output element's K reduction is
   // summed, so results are bitwise independent of batch size / sequence length (batch-invariant contract).
   //  * N tile: min(C_out, 128) (the weight packing tile: one bulk copy per stage); halved (down to 32) only for
@@ -692,32 +739,13 @@ static int plan_conv1d_tc(const ConvParams& p, int mode, tc::Plan* out) {
   while (BN >= 64 && (BN / 2) % 16 == 0 && tiles128 * ((p.Cout + BN - 1) / BN) < bn_thresh) BN /= 2;
   int mt = tiles128 >= 4 * mt_thresh ? 4 : (tiles128 >= 2 * mt_thresh ? 2 : 1);
   tc::Plan pl;
-  // K granules per stage decide how the (channel block, tap) reduction is ordered, so they must be a function
-  // of the layer shape alone: 8 if a (widest-N, one-accumulator) tile fits with them in 1x mode, else 4.
-  const int bn_max = p.Cout <= 128 ? p.Cout : 128;
-  const int kbg = (!split3 && tc::make_plan(p, mode, bn_max, 1, 8, 4, &pl)) ? 8 : 4;
+  const int kbg = shape_kbg(p, mode);
   for (;; mt >>= 1) {
     if (tc::make_plan(p, mode, BN, mt, kbg, 4, &pl)) break;
     if (tc::make_plan(p, mode, BN, mt, kbg, 2, &pl)) break;
     if (mt == 1) { set_error("conv1d_tc: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
   }
-  // K-split: a long reduction at few output tiles (the acoustic model's GEMMs at batch 1; the conv-FFN's second
-  // conv has K = 3*1536) is one long serial chain per tile; share it among S CTAs with private partial buffers
-  // + a fixed-order reduce kernel.  S is requested per LAYER by the engine (never derived from batch or
-  // length), so the summation order -- and therefore every output bit -- is the same for a B=1 call and for
-  // the same utterance inside any batch.
-  const size_t per = (size_t)p.B * p.L * p.Cout;
-  if (p.ksplit > 1 && (p.splitk_ws || p.splitk_cap == (size_t)-1)) {
-    int S = p.ksplit;
-    const int cpg = mode == 2 ? 8 : 4;
-    const int n_cb = (p.Cin + cpg * pl.kbg - 1) / (cpg * pl.kbg);
-    if (S > n_cb) S = n_cb;
-    if ((size_t)S * per > p.splitk_cap) { set_error("conv1d_tc: split-K scratch too small (%zu < %zu floats)", p.splitk_cap, (size_t)S * per); return EV_EWORKSPACE; }
-    if (S > 1) {
-      pl.ksplit = S;
-      pl.total_tiles *= S;
-    }
-  }
+  EV_TRY(apply_ksplit(p, mode, &pl));
   *out = pl;
   return EV_OK;
 }
@@ -731,19 +759,103 @@ int debug_tc_plan(const ConvParams& p, int mode, int* v) {
   return EV_OK;
 }
 
+static int dispatch_tc(const ConvParams& p, int mode, const tc::Plan& pl, cudaStream_t st) {
+  if (mode == 1) return launch_tc_mt<1, 4>(p, pl, st);
+  if (mode == 2) return pl.kbg == 8 ? launch_tc_mt<2, 8>(p, pl, st) : launch_tc_mt<2, 4>(p, pl, st);
+  return pl.kbg == 8 ? launch_tc_mt<0, 8>(p, pl, st) : launch_tc_mt<0, 4>(p, pl, st);
+}
+
+// ---- opt-in online tile-shape tuner (EV_AUTOTUNE=1; =2 also logs its choices to stderr) -------------------------------
+// The N-tile width and the accumulators per tile change how a layer is cut into CTAs (SM fill, weight bytes streamed per
+// output row, A staging replicated per N tile) but never the order of any output element's reduction, so every
+// candidate is bitwise equivalent and the fastest one can be picked by measurement.  The first launch of a
+// (mode, layer shape, K-split, half-octave bucket of the tile count) times each candidate that fits (one warm-up + 3 timed
+// launches into a scratch output, CUDA events on the caller's stream, synchronising: this is a one-off per key) and the
+// choice is cached for the life of the process.  Default off until it has been validated on hardware.
+namespace {
+typedef std::tuple<int, int, int, int, int, int, int, int> TuneKey;     // mode, Cin, Cout, K, dil, ksplit, has_lens, bucket
+std::mutex g_tune_mu;
+std::map<TuneKey, std::pair<int, int>> g_tuned;                          // -> (BN, mt); (0, 0) = keep the default plan
+
+int tile_bucket(long long tiles128) {      // half-octave buckets: 1,2,3,4,6,8,12,16,24,...
+  int b = 0;
+  long long lo = 1;
+  while (lo * 2 <= tiles128) { lo *= 2; b += 2; }
+  return b + (tiles128 * 2 >= lo * 3 ? 1 : 0);
+}
+
+float time_plan(const ConvParams& q, int mode, const tc::Plan& pl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+  if (dispatch_tc(q, mode, pl, st) != EV_OK) return -1.f;     // warm-up (also faults in the kernel image / smem attribute)
+  if (cudaEventRecord(e0, st) != cudaSuccess) return -1.f;
+  for (int r = 0; r < 3; ++r)
+    if (dispatch_tc(q, mode, pl, st) != EV_OK) return -1.f;
+  if (cudaEventRecord(e1, st) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+std::pair<int, int> tune(const ConvParams& p, int mode, const tc::Plan& dflt, cudaStream_t st, int verbose) {
+  std::pair<int, int> best(0, 0);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  float* scratch = nullptr;
+  ConvParams q = p;
+  const size_t per = (size_t)p.B * p.L * p.Cout;
+  // the timed launches must not touch the caller's output (it may be an accumulate target or alias the residual)
+  if (dflt.ksplit == 1) {
+    if (cudaMalloc(&scratch, per * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return best; }
+    q.out = scratch;
+  }   // K-split launches only write the partial buffers, which are scratch by contract
+  if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+    float best_ms = time_plan(q, mode, dflt, st, e0, e1);
+    if (verbose) fprintf(stderr, "[ev autotune] mode %d Cin %d Cout %d K %d dil %d B %d L %d S %d: default BN %d MT %d %.1f us", mode, p.Cin,
+                         p.Cout, p.K, p.dil, p.B, p.L, dflt.ksplit, dflt.BN, dflt.mt, best_ms * 1000.f / 3.f);
+    if (best_ms > 0.f) {
+      const int bn_max = p.Cout <= 128 ? p.Cout : 128;
+      for (int BN = bn_max; BN >= 32 && BN % 16 == 0; BN /= 2)
+        for (int mt = 1; mt <= 4; mt *= 2) {
+          if (BN == dflt.BN && mt == dflt.mt) continue;
+          if ((long long)tc::BM * (mt / 2) >= p.L && mt > 1) continue;          // more accumulators than rows
+          tc::Plan pl;
+          if (!plan_with_shape(p, mode, BN, mt, &pl)) continue;
+          const float ms = time_plan(q, mode, pl, st, e0, e1);
+          if (verbose) fprintf(stderr, " | BN %d MT %d %.1f", BN, mt, ms * 1000.f / 3.f);
+          if (ms > 0.f && ms < best_ms * 0.97f) { best_ms = ms; best = std::make_pair(BN, mt); }   // 3 % hysteresis for the default
+        }
+    }
+    if (verbose) fprintf(stderr, " -> BN %d MT %d\n", best.first ? best.first : dflt.BN, best.first ? best.second : dflt.mt);
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (scratch) { cudaStreamSynchronize(st); cudaFree(scratch); }
+  cudaGetLastError();
+  return best;
+}
+}  // namespace
+
 // p.w must be in the tensor-core layout [plane][Cout/BNp][K][Cin/4][BNp][4] (packing.py: to_tc_layout);
 // mode 0: 1xTF32, 1: 3xTF32 fp32 emulation (reads both planes), 2: bf16 operands (p.w in the bf16 tc layout).
 int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st) {
   tc::Plan pl;
   EV_TRY(plan_conv1d_tc(p, mode, &pl));
+  static const int autotune = env_int("EV_AUTOTUNE", 0);
+  if (autotune) {
+    const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
+    const TuneKey key(mode, p.Cin, p.Cout, p.K, p.dil, pl.ksplit, p.lens ? 1 : 0, tile_bucket(tiles128));
+    std::pair<int, int> choice;
+    {
+      std::lock_guard<std::mutex> lock(g_tune_mu);
+      auto it = g_tuned.find(key);
+      if (it == g_tuned.end()) it = g_tuned.emplace(key, tune(p, mode, pl, st, autotune > 1)).first;
+      choice = it->second;
+    }
+    tc::Plan tuned;
+    if (choice.first && plan_with_shape(p, mode, choice.first, choice.second, &tuned)) pl = tuned;
+  }
   static const int pdl = env_int("EV_PDL", 0);      // opt-in until it has been measured on hardware
   pl.pdl = pdl ? 1 : 0;
   const size_t per = (size_t)p.B * p.L * p.Cout;
-  int rc;
-  if (mode == 1) rc = launch_tc_mt<1, 4>(p, pl, st);
-  else if (mode == 2) rc = pl.kbg == 8 ? launch_tc_mt<2, 8>(p, pl, st) : launch_tc_mt<2, 4>(p, pl, st);
-  else if (pl.kbg == 8) rc = launch_tc_mt<0, 8>(p, pl, st);
-  else rc = launch_tc_mt<0, 4>(p, pl, st);
+  const int rc = dispatch_tc(p, mode, pl, st);
   if (rc != EV_OK || pl.ksplit == 1) return rc;
   const size_t n4 = per / 4;
   tc::splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(p, pl.ksplit);

@@ -85,7 +85,7 @@ def test_fetch_pcm16_trims_and_matches_the_callers_cast(model, dev):
         assert got[b].dtype == np.int16 and np.array_equal(got[b], want)
 
 
-_PDL_CHILD = r"""
+_KNOB_CHILD = r"""
 import sys, numpy as np, torch
 sys.path.insert(0, sys.argv[1])
 from emotivoice_b200 import synth
@@ -106,18 +106,21 @@ np.savez(sys.argv[3], **res)
 """
 
 
-def test_programmatic_dependent_launch_is_bitwise_identical(model, dev, tmp_path):
+@pytest.mark.parametrize("knobs", [{"EV_PDL": "1"}, {"EV_AUTOTUNE": "2"}, {"EV_PDL": "1", "EV_AUTOTUNE": "1"}],
+                         ids=["pdl", "autotune", "pdl+autotune"])
+def test_opt_in_launch_modes_are_bitwise_identical(model, dev, tmp_path, knobs):
     """EV_PDL=1 launches the tensor-core convolutions with programmatic stream serialization (set-up and weight prefetch
-    of launch n+1 overlap the tail of launch n).  It reorders nothing inside a kernel, so every output bit must equal
-    the default launch mode's; a missing griddepcontrol.wait would show up here as a mismatch."""
+    of launch n+1 overlap the tail of launch n); EV_AUTOTUNE=1 picks each layer's N-tile width / accumulators per tile by
+    measurement.  Neither reorders any output element's reduction, so every output bit must equal the default mode's;
+    a missing griddepcontrol.wait or a tile-shape-dependent result would show up here as a mismatch."""
     import os
     import subprocess
     import sys
     import numpy as np
     from conftest import GOLDEN, ROOT
-    src, dst = os.path.join(GOLDEN, "b3_padded.npz"), str(tmp_path / "pdl.npz")
-    env = dict(os.environ, EV_PDL="1")
-    subprocess.run([sys.executable, "-c", _PDL_CHILD, ROOT, src, dst], env=env, check=True, timeout=600)
+    src, dst = os.path.join(GOLDEN, "b3_padded.npz"), str(tmp_path / "knobs.npz")
+    env = dict(os.environ, **knobs)
+    subprocess.run([sys.executable, "-c", _KNOB_CHILD, ROOT, src, dst], env=env, check=True, timeout=600)
     got = np.load(dst)
     g = load_golden("b3_padded")
     try:
