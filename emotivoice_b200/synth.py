@@ -209,3 +209,83 @@ def make_mel(batch, frames, seed=SEED, n_mels=80):
     """cfg4 vocoder-only input: N(0,1)*1.2, shape (B, 80, F)."""
     rng = np.random.default_rng(seed)
     return torch.from_numpy((rng.normal(size=(batch, n_mels, frames)) * 1.2).astype(np.float32))
+
+
+# ---- style encoder (SURVEY.md s8f rank 1): seeded BERT weights with the reference's state-dict names ----------------
+
+STYLE_SEED = 4321
+
+
+def style_config(small=False):
+    """Architecture integers of the style encoder.  Full size = ``WangZeJun/simbert-base-chinese`` (config/joint/config.py:44:
+    BERT-base, 12 x 768, 12 heads, FFN 3072, vocab 13685, 512 positions, 2 token types) + the four classification heads of
+    simbert.py:39-42 with the label counts of data/youdao/text/{pitch,speed,energy,emotion}.  ``small`` is a 2-layer,
+    256-wide model of the same structure for fast tests."""
+    from .config import AttrDict
+    if small:
+        return AttrDict(vocab_size=1000, hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=1024,
+                        max_position_embeddings=128, type_vocab_size=2, pitch_n_labels=3, speed_n_labels=3,
+                        energy_n_labels=3, emotion_n_labels=7, style_dim=128)
+    return AttrDict(vocab_size=13685, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                    max_position_embeddings=512, type_vocab_size=2, pitch_n_labels=3, speed_n_labels=3,
+                    energy_n_labels=3, emotion_n_labels=7, style_dim=128)
+
+
+def style_param_shapes(sc):
+    """(name, shape, kind) of every tensor of the reference StyleEncoder's state dict (simbert.py:33-44: ``bert.*`` is
+    transformers' BertModel, then the heads)."""
+    H, I = sc.hidden_size, sc.intermediate_size
+    out = [("bert.embeddings.word_embeddings.weight", (sc.vocab_size, H), "emb"),
+           ("bert.embeddings.position_embeddings.weight", (sc.max_position_embeddings, H), "emb"),
+           ("bert.embeddings.token_type_embeddings.weight", (sc.type_vocab_size, H), "emb"),
+           ("bert.embeddings.LayerNorm.weight", (H,), "ln_w"), ("bert.embeddings.LayerNorm.bias", (H,), "ln_b")]
+    for i in range(sc.num_hidden_layers):
+        p = "bert.encoder.layer.%d." % i
+        for n in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense"):
+            out += [(p + n + ".weight", (H, H), "w"), (p + n + ".bias", (H,), "b")]
+        out += [(p + "attention.output.LayerNorm.weight", (H,), "ln_w"), (p + "attention.output.LayerNorm.bias", (H,), "ln_b"),
+                (p + "intermediate.dense.weight", (I, H), "w"), (p + "intermediate.dense.bias", (I,), "b"),
+                (p + "output.dense.weight", (H, I), "w"), (p + "output.dense.bias", (H,), "b"),
+                (p + "output.LayerNorm.weight", (H,), "ln_w"), (p + "output.LayerNorm.bias", (H,), "ln_b")]
+    out += [("bert.pooler.dense.weight", (H, H), "w"), ("bert.pooler.dense.bias", (H,), "b")]
+    for n, k in (("pitch_clf", sc.pitch_n_labels), ("speed_clf", sc.speed_n_labels), ("energy_clf", sc.energy_n_labels),
+                 ("emotion_clf", sc.emotion_n_labels)):
+        out += [(n + ".classifier.weight", (k, H), "w"), (n + ".classifier.bias", (k,), "b")]
+    out += [("style_embed_proj.weight", (sc.style_dim, H), "w"), ("style_embed_proj.bias", (sc.style_dim,), "b")]
+    return out
+
+
+def make_style_state_dict(sc, seed=STYLE_SEED):
+    """Seeded weights in the range of a trained BERT (matrices N(0, 0.04) -- twice the HF init so attention is not
+    uniform --, embeddings N(0, 0.05), non-trivial LayerNorm affine and biases so every term is exercised)."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name, shape, kind in style_param_shapes(sc):
+        if kind == "w":
+            a = rng.normal(0.0, 0.04, size=shape)
+        elif kind == "b":
+            a = rng.normal(0.0, 0.02, size=shape)
+        elif kind == "ln_w":
+            a = rng.uniform(0.8, 1.2, size=shape)
+        elif kind == "ln_b":
+            a = rng.normal(0.0, 0.05, size=shape)
+        else:
+            a = rng.normal(0.0, 0.05, size=shape)
+        sd[name] = torch.from_numpy(a.astype(np.float32))
+    return sd
+
+
+def make_style_batch(sc, lengths, seed=STYLE_SEED + 1):
+    """Tokenizer-shaped inputs (inference_am_vocoder_joint.py:25-29): ids with [CLS]=101 ... [SEP]=102 when the vocabulary
+    has them, right-padded with 0; token_type_ids all zero; attention_mask = 1 on the valid prefix."""
+    rng = np.random.default_rng(seed)
+    B, N = len(lengths), int(max(lengths))
+    ids = np.zeros((B, N), np.int64)
+    mask = np.zeros((B, N), np.int64)
+    for b, n in enumerate(lengths):
+        row = rng.integers(min(200, sc.vocab_size // 2), sc.vocab_size, size=n)
+        if sc.vocab_size > 102 and n >= 2:
+            row[0], row[-1] = 101, 102
+        ids[b, :n], mask[b, :n] = row, 1
+    return dict(input_ids=torch.from_numpy(ids), token_type_ids=torch.zeros((B, N), dtype=torch.int64),
+                attention_mask=torch.from_numpy(mask))
