@@ -33,6 +33,12 @@ class EvConfig(ctypes.Structure):
     ]
 
 
+class EvStyleConfig(ctypes.Structure):
+    """ev_style_config (include/emotivoice_b200.h)."""
+    _fields_ = [(n, ctypes.c_int32) for n in ("vocab_size", "max_position", "type_vocab", "hidden", "n_heads", "n_layers",
+                                              "intermediate", "n_head_out")]
+
+
 class EvError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libemotivoice_b200 error %d: %s" % (code, msg))
@@ -63,6 +69,12 @@ SIGNATURES = {
     "ev_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ev_op_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ev_op_gauss_upsample": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ev_style_create": (_i, [ctypes.POINTER(_vp), _i, _vp]),
+    "ev_style_destroy": (None, [_vp]),
+    "ev_style_bind_weights": (_i, [_vp, _vp, _sz, _vp, _i]),
+    "ev_style_set_precision": (_i, [_vp, _i]),
+    "ev_style_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "ev_style_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -18,7 +18,7 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over the last dim, eps = 1e-12, biased variance (encoder.py:112-127).  One warp per
-// row, the row lives in registers (C <= 512, C % 128 == 0).  Optional prologue for the first
+// row, the row lives in registers (C <= 768, C % 128 == 0; 768 = the style encoder's BERT width).  Optional prologue for the first
 // layer of the encoder: x = word_emb[id] + alpha * pe[t]  (model_open_source.py:107,
 // encoder.py:257-261), which is also written back as the residual stream.
 // ---------------------------------------------------------------------------------------------
@@ -81,14 +81,16 @@ int launch_layernorm(const float* x, const int64_t* ids, const float* emb, const
                      float* x_out, const float* w, const float* b, float* y, int rows, int L, int C,
                      cudaStream_t st) {
   EV_CHECK_ARG(rows > 0, "layernorm: rows=%d", rows);
-  EV_CHECK_ARG(C % 128 == 0 && C <= 512, "layernorm: C=%d must be a multiple of 128 and <= 512", C);
+  EV_CHECK_ARG(C % 128 == 0 && C <= 768, "layernorm: C=%d must be a multiple of 128 and <= 768", C);
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb);
   switch (C / 128) {
     case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
     case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
     case 3: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    default: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    case 4: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    case 5: layernorm_kernel<5><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    default: layernorm_kernel<6><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
   }
   EV_CUDA_LAUNCH_CHECK("layernorm_kernel");
   return EV_OK;

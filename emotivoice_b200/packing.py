@@ -228,3 +228,49 @@ def make_blob(packed, align=64):
         index[i].offset = offs[k]
         index[i].numel = v.numel()
     return blob, index
+
+
+# ---- style encoder (simbert.py:33-72; transformers BertModel names under ``bert.``) ---------------------------------
+
+STYLE_HEADS = ("pitch", "speed", "energy", "emotion")      # order of the packed classifier columns (simbert.py:58-61)
+
+
+def style_head_slices(sc):
+    """name -> (first column, n_labels) inside the packed ``sty.heads`` output; total padded to a multiple of 8."""
+    out, c = {}, 0
+    for n in STYLE_HEADS:
+        k = int(getattr(sc, n + "_n_labels"))
+        out[n] = (c, k)
+        c += k
+    return out, (c + 7) // 8 * 8
+
+
+def pack_style_state_dict(sd, sc, prefix=""):
+    """Reference StyleEncoder state dict -> engine layout ("sty.*").  Linear weights go straight to the tensor-core layout
+    (two tf32 planes; no plain fp32 copy: the style encoder has no FFMA mode), q|k|v are fused into one (H, 3H) GEMM, the
+    pooler / classifier matrices are stored (K, N) row-major for the GEMV kernel, the four heads side by side."""
+    g = lambda k: sd[prefix + k].detach().float().cpu()
+    H = sc.hidden_size
+    out = {}
+    e = "bert.embeddings."
+    out["sty.emb.word"], out["sty.emb.pos"] = g(e + "word_embeddings.weight"), g(e + "position_embeddings.weight")
+    out["sty.emb.type"] = g(e + "token_type_embeddings.weight")
+    out["sty.emb.ln.w"], out["sty.emb.ln.b"] = g(e + "LayerNorm.weight"), g(e + "LayerNorm.bias")
+    for i in range(sc.num_hidden_layers):
+        r, o = "bert.encoder.layer.%d." % i, "sty.%d" % i
+        wqkv = torch.cat([g(r + "attention.self.%s.weight" % n).t() for n in ("query", "key", "value")], dim=1).contiguous()
+        out[o + ".wqkv.tc"] = to_tc_layout(wqkv.unsqueeze(0))
+        out[o + ".bqkv"] = torch.cat([g(r + "attention.self.%s.bias" % n) for n in ("query", "key", "value")])
+        out[o + ".wo.tc"], out[o + ".bo"] = to_tc_layout(_lin_w(g(r + "attention.output.dense.weight"))), g(r + "attention.output.dense.bias")
+        out[o + ".ln1.w"], out[o + ".ln1.b"] = g(r + "attention.output.LayerNorm.weight"), g(r + "attention.output.LayerNorm.bias")
+        out[o + ".w1.tc"], out[o + ".b1"] = to_tc_layout(_lin_w(g(r + "intermediate.dense.weight"))), g(r + "intermediate.dense.bias")
+        out[o + ".w2.tc"], out[o + ".b2"] = to_tc_layout(_lin_w(g(r + "output.dense.weight"))), g(r + "output.dense.bias")
+        out[o + ".ln2.w"], out[o + ".ln2.b"] = g(r + "output.LayerNorm.weight"), g(r + "output.LayerNorm.bias")
+    out["sty.pool.w"], out["sty.pool.b"] = g("bert.pooler.dense.weight").t().contiguous(), g("bert.pooler.dense.bias")
+    slices, width = style_head_slices(sc)
+    hw, hb = torch.zeros(H, width), torch.zeros(width)
+    for n, (c0, k) in slices.items():
+        hw[:, c0:c0 + k] = g(n + "_clf.classifier.weight").t()
+        hb[c0:c0 + k] = g(n + "_clf.classifier.bias")
+    out["sty.heads.w"], out["sty.heads.b"] = hw.contiguous(), hb
+    return out

@@ -198,6 +198,37 @@ EV_API int ev_op_gauss_upsample(const float* hs, const int64_t* dur, const int32
                                 int F, int invariant, const float* pe, const float* alpha, float* centers_tmp,
                                 int32_t* mel_lens_tmp, float* out, void* stream);
 
+/* ---- style encoder (the callers' prompt / content embedding: simbert.py:33-72 -> transformers BertModel) ---------------
+ * Next-row widening: the reference runs this BERT-base on the CPU twice per utterance
+ * (inference_am_vocoder_joint.py:25-38,106-107).  Separate context: it is a separate model with its own checkpoint. */
+typedef struct ev_style_ctx ev_style_ctx;
+
+/* The integers of the checkpoint's BertConfig + the width of the packed classification heads. */
+typedef struct ev_style_config {
+  int32_t vocab_size, max_position, type_vocab;
+  int32_t hidden;            /* 768; multiple of 128, <= 768 */
+  int32_t n_heads;           /* 12; hidden / n_heads in {32, 48, 64} */
+  int32_t n_layers;          /* 12 */
+  int32_t intermediate;      /* 3072; multiple of 128 */
+  int32_t n_head_out;        /* columns of the packed [pitch|speed|energy|emotion] classifier (multiple of 8), 0 = none */
+} ev_style_config;
+
+/* StyleEncoder.__init__ (simbert.py:34-44). */
+EV_API int ev_style_create(ev_style_ctx** out, int device, const ev_style_config* cfg);
+EV_API void ev_style_destroy(ev_style_ctx* ctx);
+/* load_state_dict (inference_am_vocoder_joint.py:60-65): same blob + index convention as ev_bind_weights; names are
+ * the ones emotivoice_b200.packing.pack_style_state_dict emits ("sty.*"). */
+EV_API int ev_style_bind_weights(ev_style_ctx* ctx, const float* blob, size_t blob_floats, const ev_weight_entry* index,
+                                 int n_entries);
+/* EV_PREC_FP32 (3xTF32 on tcgen05, default) or EV_PREC_TF32. */
+EV_API int ev_style_set_precision(ev_style_ctx* ctx, int precision);
+EV_API size_t ev_style_workspace_bytes(const ev_style_ctx* ctx, int B, int N);
+/* StyleEncoder.forward (simbert.py:48-72): ids / type_ids (B,N) int64, lens (B,) int64 = number of leading tokens with
+ * attention_mask == 1 (tokenizer padding is a suffix).  pooled (B, hidden) = BertModel's pooler_output;
+ * heads (B, n_head_out) = the four classification heads side by side, or NULL to skip them. */
+EV_API int ev_style_forward(ev_style_ctx* ctx, const int64_t* ids, const int64_t* type_ids, const int64_t* lens, int B, int N,
+                            float* pooled, float* heads, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,8 @@ def main():
             assert not unexpected and all("position_ids" in m for m in missing), (missing, unexpected)
             models[small] = (sd, ref)
             meta["state_dict_digest_" + ("small" if small else "base")] = synth.state_dict_digest(sd)
+            if small:      # the reference module's own state-dict contract (names + shapes) for the host-mirror test
+                meta["reference_state_dict_small"] = {k: list(v.shape) for k, v in ref.state_dict().items()}
         sd, ref = models[small]
         batch = synth.make_style_batch(sc, lens, seed)
         with torch.no_grad():

@@ -131,3 +131,69 @@ def test_opt_in_launch_modes_are_bitwise_identical(model, dev, tmp_path, knobs):
             assert np.array_equal(out["wav_predictions"].cpu().numpy(), got[prec + "_wav"])
     finally:
         model.precision = "fp32"
+
+
+# ---- style encoder: BERT forward on the engine's kernels ------------------------------------------
+
+STYLE_KEYS = ("input_ids", "token_type_ids", "attention_mask")
+STYLE_OUTS = ("pooled_output", "pitch_outputs", "speed_outputs", "energy_outputs", "emotion_outputs")
+_style_models = {}
+
+
+def _style_model(small, dev):
+    """One StyleEncoder per size for the whole session (BERT-base: 110 M seeded weights, packed once)."""
+    if small not in _style_models:
+        from types import SimpleNamespace
+        from emotivoice_b200.style import StyleEncoder
+        sc = synth.style_config(small)
+        conf = SimpleNamespace(bert_path="(offline)", bert_hidden_size=sc.hidden_size, style_dim=sc.style_dim,
+                               pitch_n_labels=sc.pitch_n_labels, speed_n_labels=sc.speed_n_labels,
+                               energy_n_labels=sc.energy_n_labels, emotion_n_labels=sc.emotion_n_labels)
+        m = StyleEncoder(conf, bert_config=dict(sc), _init=synth.make_style_state_dict(sc)).to(dev).eval()
+        _style_models[small] = m
+    return _style_models[small]
+
+
+@pytest.mark.parametrize("name,small", [("style_small_b3", True), ("style_small_b1_n40", True), ("style_base_b2", False)])
+def test_style_encoder_matches_reference_fixture(lib, dev, name, small):
+    """Fixtures come from the reference's StyleEncoder class driving transformers' BertModel (oracle/make_golden_style.py).
+    Default mode is 3xTF32 (fp32-accurate): 1e-4 of max|ref| through 12 post-LN layers (the two fp32 CPU evaluation orders
+    already differ by 4e-6); tf32 mode: 2e-2."""
+    m = _style_model(small, dev)
+    g = load_golden(name)
+    out = m(**{k: g[k].to(dev) for k in STYLE_KEYS})
+    torch.cuda.synchronize()
+    assert list(out.keys()) == list(STYLE_OUTS)
+    for k in STYLE_OUTS:
+        err = rel_max(out[k].cpu(), g[k])
+        print(name, k, "rel-max %.2e" % err)
+        assert out[k].shape == g[k].shape and err <= 1e-4
+    m.precision = "tf32"
+    try:
+        out = m(**{k: g[k].to(dev) for k in STYLE_KEYS})
+        assert rel_max(out["pooled_output"].cpu(), g["pooled_output"]) <= 2e-2
+    finally:
+        m.precision = "fp32"
+
+
+def test_style_encoder_padding_is_invisible_and_errors_are_loud(lib, dev):
+    """A right-padded item equals the same item alone, bitwise (key mask + batch-invariant GEMM plans); malformed masks and
+    out-of-range ids raise like the library the reference uses would (IndexError from the embedding lookup)."""
+    m = _style_model(True, dev)
+    g = load_golden("style_small_b3")
+    full = m(**{k: g[k].to(dev) for k in STYLE_KEYS})
+    for b in range(3):
+        n = int(g["attention_mask"][b].sum())
+        alone = m(**{k: g[k][b:b + 1, :n].to(dev) for k in STYLE_KEYS})
+        assert torch.equal(alone["pooled_output"][0], full["pooled_output"][b])
+        assert torch.equal(alone["emotion_outputs"][0], full["emotion_outputs"][b])
+    bad = {k: g[k].clone().to(dev) for k in STYLE_KEYS}
+    bad["attention_mask"][0, 0] = 0
+    with pytest.raises(RuntimeError, match="prefix"):
+        m(**bad)
+    bad = {k: g[k].clone().to(dev) for k in STYLE_KEYS}
+    bad["input_ids"][1, 2] = 10 ** 6
+    with pytest.raises(IndexError):
+        m(**bad)
+    with pytest.raises(RuntimeError):
+        m(**{k: g[k] for k in STYLE_KEYS})           # CPU tensors: no CPU path
