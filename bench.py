@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- mel-frames/s and RTF of JETSGenerator.forward (PromptTTS AM + HiFi-GAN).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp32|tf32|bf16|fp32_ffma]
+                    [--no-experiments]
 
 Workload (BASELINE.json configs[1], the configuration `metric` is quoted on): batch = 1,
 one 100-phoneme utterance (seed 1234 -> 537 mel frames = 8.6 s of 16 kHz audio), fp32,
@@ -14,6 +15,8 @@ A "step" is one forward() over that batch.
 * --impl reference: the reference's algorithm on the host CPU (oracle/jets_oracle.py, the
   torch-CPU restatement pinned bit-exactly to the unmodified reference; the reference tree
   itself is Python and does not travel to the GPU box), all host threads.
+At N=1, after the headline numbers are final, an "experiments" block re-measures the workload in the other precision modes
+and the opt-in launch modes (EV_PDL, EV_AUTOTUNE) plus the style encoder, each in a separate process under a timeout.
 Under torchrun every rank runs the same per-GPU workload (weak scaling) after a one-time
 NCCL weight broadcast from rank 0; time = max over ranks (CUDA events).
 """
@@ -203,6 +206,69 @@ def parity_vs_reference_fixture(out):
     return res
 
 
+def probe(args):
+    """Child mode of `experiments()`: a short B=1 measurement of the same workload (3 warm-up + 10 timed forwards, L2
+    flushed, CUDA events) in whatever mode the environment / --precision select; prints one small JSON object."""
+    import __graft_entry__  # noqa: F401
+    from emotivoice_b200.config import default_config
+    from emotivoice_b200 import synth, _abi
+    from emotivoice_b200.modules import JETSGenerator
+    dev = torch.device("cuda", 0)
+    conf = default_config()
+    model = JETSGenerator(conf).to(dev)
+    model.load_state_dict(synth.make_state_dict(conf))
+    model.eval()
+    model.precision = args.precision
+    batch = {k: v.to(dev) for k, v in synth.make_batch([N_PHONEMES], seed=synth.SEED).items()}
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    for _ in range(3):
+        out = model(**batch)
+    torch.cuda.synchronize()
+    l0 = _abi.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a, b in ev:
+        flush_buf.zero_()
+        a.record()
+        out = model(**batch)
+        b.record()
+    torch.cuda.synchronize()
+    print(json.dumps({"ms_per_step": sum(a.elapsed_time(b) for a, b in ev) / len(ev),
+                      "gpu_launches_per_step": (_abi.launch_count() - l0) / len(ev), "parity": parity_vs_reference_fixture(out)}))
+
+
+def experiments(budget_s=240.0):
+    """Opt-in modes measured AFTER the headline numbers are final, each in its own process under a timeout, so a failure
+    or a hang in an experimental path cannot touch `value` / `e2e`.  Reported under "experiments"; never part of them."""
+    runs = [("tf32", ["--precision", "tf32"], {}), ("bf16", ["--precision", "bf16"], {}),
+            ("fp32+pdl", ["--precision", "fp32"], {"EV_PDL": "1"}),
+            ("fp32+autotune", ["--precision", "fp32"], {"EV_AUTOTUNE": "2"}),
+            ("fp32+pdl+autotune", ["--precision", "fp32"], {"EV_PDL": "1", "EV_AUTOTUNE": "1"})]
+    res = {"note": "opt-in / secondary modes of the same B=1 workload, 10 timed steps each, separate processes; not part of value or e2e"}
+    t_end = time.time() + budget_s
+
+    def child(cmd, env_extra, timeout):
+        left = t_end - time.time()
+        if left < 20:
+            return {"skipped": "time budget of the experiments block spent"}
+        try:
+            r = subprocess.run(cmd, env=dict(os.environ, **env_extra), capture_output=True, text=True, timeout=min(timeout, left))
+        except subprocess.TimeoutExpired:
+            return {"error": "timeout"}
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-300:])}
+        d = json.loads(lines[-1])
+        tune = [ln[len("[ev autotune] "):] for ln in r.stderr.splitlines() if ln.startswith("[ev autotune]")]
+        if tune:
+            d["autotune_log"] = tune
+        return d
+
+    for name, flags, env in runs:
+        res[name] = child([sys.executable, os.path.abspath(__file__), "--probe"] + flags, env, 120)
+    res["style_encoder"] = child([sys.executable, os.path.join(ROOT, "tools", "style_bench.py"), "--steps", "20"], {}, 150)
+    return res
+
+
 def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
     """conv1d_tm_kernel on the single most expensive layer shape of the step: the k=11
     ResBlock convolutions of HiFi-GAN stage 2 (C=128, L=64*F; 22% of all FLOPs).  Timed live
@@ -285,7 +351,12 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default=os.environ.get("EV_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16", "fp32_ffma"])
+    ap.add_argument("--probe", action="store_true", help="internal: short child measurement for the experiments block")
+    ap.add_argument("--no-experiments", action="store_true", help="skip the opt-in-mode block measured after the headline")
     args = ap.parse_args()
+    if args.probe:
+        probe(args)
+        return
     if args.impl == "engine":
         args.warmup = max(args.warmup, 3)
 
@@ -440,6 +511,11 @@ def main():
                                     "sample": "8 full forward passes of the same workload on the host CPU (oracle/jets_oracle.py, "
                                               "torch CPU, %d threads = fastest of calibration %s ms; %d usable CPUs); %.0f ms each"
                                               % (r["cores"], json.dumps(r["calib"]), r["usable"], r["sec_per_step"] * 1e3)}
+        if world == 1 and not args.no_experiments and os.environ.get("EV_BENCH_EXPERIMENTS", "1") != "0":
+            try:
+                line["experiments"] = experiments()
+            except Exception as e:      # never let the secondary block cost the headline line
+                line["experiments"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

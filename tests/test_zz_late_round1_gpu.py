@@ -120,7 +120,7 @@ def test_opt_in_launch_modes_are_bitwise_identical(model, dev, tmp_path, knobs):
     from conftest import GOLDEN, ROOT
     src, dst = os.path.join(GOLDEN, "b3_padded.npz"), str(tmp_path / "knobs.npz")
     env = dict(os.environ, **knobs)
-    subprocess.run([sys.executable, "-c", _KNOB_CHILD, ROOT, src, dst], env=env, check=True, timeout=600)
+    subprocess.run([sys.executable, "-c", _KNOB_CHILD, ROOT, src, dst], env=env, check=True, timeout=240)
     got = np.load(dst)
     g = load_golden("b3_padded")
     try:
