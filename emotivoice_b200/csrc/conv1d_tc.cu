@@ -564,7 +564,7 @@ static int validate_conv1d_tc(const ConvParams& p, int mode) {
 
 // K granules per stage decide how the (channel block, tap) reduction is ordered, so they must be a function
 // of the layer shape alone: 8 if a (widest-N, one-accumulator) tile fits with them in 1x mode, else 4.
-static int shape_kbg(const ConvParams& p, int mode) {
+int tc_shape_kbg(const ConvParams& p, int mode) {
   tc::Plan pl;
   const int bn_max = p.Cout <= 128 ? p.Cout : 128;
   return (mode != 1 && tc::make_plan(p, mode, bn_max, 1, 8, 4, &pl)) ? 8 : 4;
@@ -593,7 +593,7 @@ static int apply_ksplit(const ConvParams& p, int mode, tc::Plan* pl) {
 
 // Plan with a prescribed tile shape (the autotuner's candidates): false if it does not fit.
 static bool plan_with_shape(const ConvParams& p, int mode, int BN, int mt, tc::Plan* out) {
-  const int kbg = shape_kbg(p, mode);
+  const int kbg = tc_shape_kbg(p, mode);
   tc::Plan pl;
   if (!tc::make_plan(p, mode, BN, mt, kbg, 4, &pl) && !tc::make_plan(p, mode, BN, mt, kbg, 2, &pl)) return false;
   if (apply_ksplit(p, mode, &pl) != EV_OK) return false;
@@ -619,7 +619,7 @@ static int plan_conv1d_tc(const ConvParams& p, int mode, tc::Plan* out) {
   while (BN >= 64 && (BN / 2) % 16 == 0 && tiles128 * ((p.Cout + BN - 1) / BN) < bn_thresh) BN /= 2;
   int mt = tiles128 >= 4 * mt_thresh ? 4 : (tiles128 >= 2 * mt_thresh ? 2 : 1);
   tc::Plan pl;
-  const int kbg = shape_kbg(p, mode);
+  const int kbg = tc_shape_kbg(p, mode);
   for (;; mt >>= 1) {
     if (tc::make_plan(p, mode, BN, mt, kbg, 4, &pl)) break;
     if (tc::make_plan(p, mode, BN, mt, kbg, 2, &pl)) break;

@@ -400,6 +400,28 @@ static int conv_x(int mode, const float* w_tc, const float* w_h, const float* x,
   return launch_conv1d_tc(p, mode == 3 ? 1 : (mode == 2 ? 2 : 0), st);
 }
 
+// EV_FUSE_RES=1: run each ResBlock layer (conv pair + residual) as one kernel where resblock_tc.cu supports the shape
+// (opt-in until validated on hardware; bitwise equal to the two-launch path by construction)
+static inline bool fuse_res() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EV_FUSE_RES"); v = (e && atoi(e) > 0) ? 1 : 0; }
+  return v == 1;
+}
+
+// the ResBlock layer through the fused kernel; returns false when the pair has to run as two convolutions
+static bool try_resblock_pair(int mode, const ConvW& c1, const ConvW& c2, const float* src, float* dst, int B, int L, int C,
+                              const int32_t* lens, int lens_mul, int acc, float div, cudaStream_t st, int* rc) {
+  if (mode == 0 || c1.K != c2.K || !c1.w_tc || !c2.w_tc) return false;
+  int tcm = mode == 3 ? 1 : (mode == 2 ? 2 : 0);
+  if (tcm == 2 && (!c1.w_h || !c2.w_h || (C % 16))) tcm = 1;      // like conv_x: layers without bf16 weights run 3xTF32
+  ResPairParams p;
+  p.x = src; p.w1 = tcm == 2 ? c1.w_h : c1.w_tc; p.b1 = c1.b; p.w2 = tcm == 2 ? c2.w_h : c2.w_tc; p.b2 = c2.b; p.out = dst;
+  p.B = B; p.L = L; p.C = C; p.K = c1.K; p.dil = c1.dil; p.lens = lens; p.lens_mul = lens_mul; p.slope = 0.1f; p.acc = acc; p.div = div;
+  if (!resblock_pair_supported(p, tcm)) return false;
+  *rc = launch_resblock_pair(p, tcm, st);
+  return true;
+}
+
 static inline int body_mode(const ev_ctx* c) {
   return c->precision == EV_PREC_FP32_FFMA ? 0 : (c->precision == EV_PREC_TF32 ? 1 : (c->precision == EV_PREC_BF16 ? 2 : 3));
 }
@@ -691,15 +713,21 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
       for (int l = 0; l < g.n_dil; ++l, ++rb) {
         const ConvW& c1 = ctx->rb_c1[rb];
         const ConvW& c2 = ctx->rb_c2[rb];
-        // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
-        EV_TRY(conv_x(mode, c1.w_tc, c1.w_h, src, c1.w, c1.b, 0, nullptr, v.Tm[cj], B, L, C, C, c1.K, c1.dil, mel_lens, mul,
-                      EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, cs));
         const bool last = (l == g.n_dil - 1);
         float* dst = last ? v.ACC : ((l & 1) ? v.R2[cj] : v.R1[cj]);
         int acc = EV_ACC_STORE;
         if (last && j > 0) acc = (j == g.n_resk - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;   // xs += ...; x = xs / n (:120-126)
         const float div = (float)g.n_resk;
         if (last && g.n_resk == 1) acc = EV_ACC_STORE;
+        int frc = EV_OK;
+        if (fuse_res() && !par && try_resblock_pair(mode, c1, c2, src, dst, B, L, C, mel_lens, mul, acc, div, cs, &frc)) {
+          EV_TRY(frc);
+          src = dst;
+          continue;
+        }
+        // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
+        EV_TRY(conv_x(mode, c1.w_tc, c1.w_h, src, c1.w, c1.b, 0, nullptr, v.Tm[cj], B, L, C, C, c1.K, c1.dil, mel_lens, mul,
+                      EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, cs));
         if (last && j > 0) EV_TRY(edge(pool, chain_st[(j - 1) % 3], cs));   // xs accumulation in ResBlock order
         EV_TRY(conv_x(mode, c2.w_tc, c2.w_h, v.Tm[cj], c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
                       EV_ACT_NONE, acc, div, cs));
@@ -747,6 +775,25 @@ int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int split3
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.in_act = EV_ACT_NONE;
   p.ksplit = ksplit; p.splitk_ws = nullptr; p.splitk_cap = (size_t)-1;   // "scratch of any size is available"
   return debug_tc_plan(p, split3, out11);
+}
+
+int ev_op_resblock_pair(const float* x, const float* w1_tc, const float* b1, const float* w2_tc, const float* b2, int split3,
+                        float* out, int B, int L, int C, int K, int dil, const int32_t* lens, int lens_mul, int acc, float div,
+                        void* stream) {
+  EV_CHECK_ARG(x && w1_tc && b1 && w2_tc && b2 && out, "ev_op_resblock_pair: null argument");
+  ResPairParams p;
+  p.x = x; p.w1 = w1_tc; p.b1 = b1; p.w2 = w2_tc; p.b2 = b2; p.out = out;
+  p.B = B; p.L = L; p.C = C; p.K = K; p.dil = dil; p.lens = lens; p.lens_mul = lens_mul; p.slope = 0.1f; p.acc = acc; p.div = div;
+  return launch_resblock_pair(p, split3 == 2 ? 2 : (split3 ? 1 : 0), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_debug_resblock_plan(int B, int L, int C, int K, int dil, int split3, int* out11) {
+  EV_CHECK_ARG(out11, "ev_debug_resblock_plan: null output");
+  static float dummy_in, dummy_out;       // only their (distinct) addresses matter to the planner
+  ResPairParams p;
+  p.x = &dummy_in; p.w1 = nullptr; p.b1 = nullptr; p.w2 = nullptr; p.b2 = nullptr; p.out = &dummy_out;
+  p.B = B; p.L = L; p.C = C; p.K = K; p.dil = dil; p.lens = nullptr; p.lens_mul = 1; p.slope = 0.1f; p.acc = EV_ACC_STORE; p.div = 1.f;
+  return debug_resblock_plan(p, split3 == 2 ? 2 : (split3 ? 1 : 0), out11);
 }
 
 int ev_set_precision(ev_ctx* ctx, int precision) {

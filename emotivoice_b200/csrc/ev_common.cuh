@@ -66,6 +66,26 @@ int launch_conv1d(const ConvParams& p, cudaStream_t st);
 // (p.w then in the bf16 layout [Cout/BNp][K][Cin/8][BNp][8 bf16]).
 int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st);
 int debug_tc_plan(const ConvParams& p, int mode, int* v11);   // host-only: the plan launch_conv1d_tc would use
+int tc_shape_kbg(const ConvParams& p, int mode);               // K granules per stage: a function of the layer shape only
+
+// One ResBlock1 layer  out = [acc]( x + c2(lrelu(c1(lrelu(x)))) )  as one tcgen05 kernel (resblock_tc.cu); opt-in.
+struct ResPairParams {
+  const float* x;      // (B, L, C): the layer input, also the residual
+  const float* w1;     // c1 weights, tensor-core layout (k taps, dilation dil)
+  const float* b1;
+  const float* w2;     // c2 weights (k taps, dilation 1)
+  const float* b2;
+  float* out;          // (B, L, C); must not alias x
+  int B, L, C, K, dil;
+  const int32_t* lens; // valid rows per item = lens[b]*lens_mul (null: L)
+  int lens_mul;
+  float slope;         // LeakyReLU slope of both prologues (0.1)
+  int acc;             // EV_ACC_* applied to `out` like conv1d's epilogue
+  float div;
+};
+bool resblock_pair_supported(const ResPairParams& p, int mode);
+int launch_resblock_pair(const ResPairParams& p, int mode, cudaStream_t st);   // mode as launch_conv1d_tc
+int debug_resblock_plan(const ResPairParams& p, int mode, int* v11);
 
 // ---------------------------------------------------------------------------------
 // acoustic-model kernels (am_kernels.cu)

@@ -106,12 +106,13 @@ np.savez(sys.argv[3], **res)
 """
 
 
-@pytest.mark.parametrize("knobs", [{"EV_PDL": "1"}, {"EV_AUTOTUNE": "2"}, {"EV_PDL": "1", "EV_AUTOTUNE": "1"}],
-                         ids=["pdl", "autotune", "pdl+autotune"])
+@pytest.mark.parametrize("knobs", [{"EV_PDL": "1"}, {"EV_AUTOTUNE": "2"}, {"EV_PDL": "1", "EV_AUTOTUNE": "1"}, {"EV_FUSE_RES": "1"}],
+                         ids=["pdl", "autotune", "pdl+autotune", "fuse_res"])
 def test_opt_in_launch_modes_are_bitwise_identical(model, dev, tmp_path, knobs):
     """EV_PDL=1 launches the tensor-core convolutions with programmatic stream serialization (set-up and weight prefetch
     of launch n+1 overlap the tail of launch n); EV_AUTOTUNE=1 picks each layer's N-tile width / accumulators per tile by
-    measurement.  Neither reorders any output element's reduction, so every output bit must equal the default mode's;
+    measurement; EV_FUSE_RES=1 runs each ResBlock layer of the 32/64-channel stages as one kernel (csrc/resblock_tc.cu).
+    None of them reorders any output element's reduction, so every output bit must equal the default mode's;
     a missing griddepcontrol.wait or a tile-shape-dependent result would show up here as a mismatch."""
     import os
     import subprocess
@@ -197,3 +198,53 @@ def test_style_encoder_padding_is_invisible_and_errors_are_loud(lib, dev):
         m(**bad)
     with pytest.raises(RuntimeError):
         m(**{k: g[k] for k in STYLE_KEYS})           # CPU tensors: no CPU path
+
+
+# ---- fused ResBlock layer (csrc/resblock_tc.cu, opt-in EV_FUSE_RES=1): must be BITWISE the two-launch path ----------------
+
+RP_CASES = [
+    # B, L, C, K, dil, acc
+    (1, 300, 32, 3, 1, 0),          # two tiles, one per CTA
+    (2, 5000, 32, 11, 5, 0),        # widest halo, ragged lens
+    (3, 70000, 32, 7, 3, 1),        # persistent: several tiles per CTA, MT > 1, accumulate mode
+    (2, 20000, 64, 11, 5, 2),       # 3xTF32: MT = 1, accumulate + divide
+    (2, 9000, 64, 3, 3, 0),
+    (1, 4000, 128, 7, 3, 0),        # 3xTF32 does not fit at C = 128 (EV_EINVAL); tf32 / bf16 do
+]
+
+
+@pytest.mark.parametrize("split3", [1, 0, 2])
+@pytest.mark.parametrize("B,L,C,K,dil,acc", RP_CASES)
+def test_resblock_pair_is_bitwise_the_two_launch_path(lib, dev, B, L, C, K, dil, acc, split3):
+    import math
+    from emotivoice_b200 import _abi, packing
+    g = torch.Generator().manual_seed(L + C + K + dil)
+    x = torch.randn(B, L, C, generator=g).to(dev)
+    w1 = torch.randn(K, C, C, generator=g) / math.sqrt(C * K)
+    w2 = torch.randn(K, C, C, generator=g) / math.sqrt(C * K)
+    b1, b2 = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+    prev = torch.randn(B, L, C, generator=g).to(dev)
+    lens = None
+    if B > 1:
+        lens = torch.tensor([L // 4 - 3 * b for b in range(B)], dtype=torch.int32).to(dev)      # valid rows = lens * 4
+        lens[0] = L // 4
+    pack = packing.to_tc16_layout if split3 == 2 else packing.to_tc_layout
+    w1t, w2t = pack(w1).to(dev), pack(w2).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ptr = lambda t: None if t is None else t.data_ptr()
+    # reference: xt = c1(lrelu(x)) ; out = [acc](c2(lrelu(xt)) + x)
+    xt = torch.full_like(x, float("nan"))
+    ref = prev.clone()
+    _abi.check(lib.ev_op_conv1d_tc(ptr(x), ptr(w1t), split3, ptr(b1), 0, None, ptr(xt), B, L, C, C, K, dil, ptr(lens), 4,
+                                   _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, None, 0, st))
+    _abi.check(lib.ev_op_conv1d_tc(ptr(xt), ptr(w2t), split3, ptr(b2), 0, ptr(x), ptr(ref), B, L, C, C, K, 1, ptr(lens), 4,
+                                   _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, acc, 3.0, None, 0, st))
+    out = prev.clone()
+    rc = lib.ev_op_resblock_pair(ptr(x), ptr(w1t), ptr(b1), ptr(w2t), ptr(b2), split3, ptr(out), B, L, C, K, dil, ptr(lens), 4, acc, 3.0, st)
+    if C == 128 and split3 == 1:
+        assert rc != 0          # documented limit: the 3xTF32 operand tile of c2 does not fit next to the rings
+        return
+    _abi.check(rc)
+    torch.cuda.synchronize()
+    assert torch.isfinite(ref).all()
+    assert torch.equal(out, ref)
