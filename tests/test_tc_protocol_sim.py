@@ -1,0 +1,350 @@
+"""Discrete-event model of the mbarrier protocols of the two tcgen05 kernels (csrc/conv1d_tc.cu, csrc/resblock_tc.cu).
+
+Both deadlocks of round 1 were protocol bugs that a GPU can only show as a hang (producer groups running two ring phases
+ahead of a parity wait; epilogue warps releasing an accumulator they never waited for).  This model replays the kernels' role
+loops -- producers (in groups), weight loader, MMA issuer, epilogue warps -- as coroutines over barriers with the hardware's
+semantics (arrival count, phase bit, `try_wait.parity(P)` passes iff the current phase parity != P; `tcgen05.commit` arrives
+when every MMA issued before it has completed; MMAs read their operands as late as their completion) under many random
+schedules, and checks: no deadlock, every slot holds the expected contents when it is read, no slot is overwritten before its
+last reader is done.  The role loops are transcribed from the kernels; the planner (ring depths, groups) is the real one.
+"""
+import ctypes
+import random
+
+import pytest
+
+from emotivoice_b200 import _abi
+
+NEPI_WARPS = 8
+NPWARPS = 6
+
+
+class Bar:
+    def __init__(self, count):
+        self.count, self.pending, self.phase = count, count, 0
+
+    def arrive(self):
+        self.pending -= 1
+        assert self.pending >= 0, "more arrivals than the barrier expects in one phase"
+        if self.pending == 0:
+            self.phase += 1
+            self.pending = self.count
+
+    def passes(self, parity):
+        return (self.phase & 1) != parity
+
+
+class Sim:
+    """Cooperative scheduler.  Roles are generators yielding ('wait', bar, parity) | ('arrive', bar) | ('write', slot, tag)
+    | ('read', slot, tag) | ('mma_read', slot, tag) | ('commit', bar).  MMA reads are deferred to the next commit's
+    completion, and commits complete in order at a random later time: the most adversarial timing the hardware allows."""
+
+    def __init__(self, seed):
+        self.rng = random.Random(seed)
+        self.slots = {}
+        self.roles = []
+        self.inflight = []           # [(reads, bars)] groups of MMAs closed by a commit, oldest first
+        self.open_reads = []
+
+    def add(self, name, gen):
+        self.roles.append([name, gen, None])
+
+    def _complete_oldest(self):
+        reads, bars = self.inflight.pop(0)
+        for slot, tag in reads:
+            assert self.slots.get(slot) == tag, "MMA read %s: holds %r, expected %r" % (slot, self.slots.get(slot), tag)
+        for b in bars:
+            b.arrive()
+
+    def run(self, max_steps=2_000_000):
+        live = list(self.roles)
+        for _ in range(max_steps):
+            if not live and not self.inflight:
+                return
+            runnable = [r for r in live if r[2] is None or r[2][0].passes(r[2][1])]
+            if self.inflight and (not runnable or self.rng.random() < 0.3):
+                self._complete_oldest()
+                continue
+            if not runnable:
+                raise AssertionError("deadlock: %r" % ([(r[0], r[2][1], r[2][0].phase) for r in live],))
+            role = self.rng.choice(runnable)
+            name, gen = role[0], role[1]
+            role[2] = None
+            try:
+                ev = next(gen)
+            except StopIteration:
+                live.remove(role)
+                continue
+            kind = ev[0]
+            if kind == "wait":
+                role[2] = (ev[1], ev[2])
+            elif kind == "arrive":
+                ev[1].arrive()
+            elif kind == "write":
+                self.slots[ev[1]] = ev[2]
+            elif kind == "read":
+                assert self.slots.get(ev[1]) == ev[2], "%s read %s: holds %r, expected %r" % (name, ev[1], self.slots.get(ev[1]), ev[2])
+            elif kind == "mma_read":
+                self.open_reads.append((ev[1], ev[2]))
+            elif kind == "commit":
+                if self.inflight and not self.open_reads:
+                    self.inflight[-1][1].append(ev[1])      # back-to-back commits track the same MMAs
+                else:
+                    self.inflight.append((self.open_reads, [ev[1]]))
+                    self.open_reads = []
+        raise AssertionError("simulation did not finish")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# conv1d_tc.cu
+# ------------------------------------------------------------------------------------------------------------------
+def sim_conv(seed, tiles, n_cb, K, a_stages, b_stages, ngroups, epi_idle_warps=0, idle_warps_skip_wait=False):
+    """tiles: list of booleans (True = active tile, False = padding tile that every role skips)."""
+    sim = Sim(seed)
+    wpg = NPWARPS // ngroups
+    a_full = [Bar(wpg) for _ in range(a_stages)]            # one arrival per producer warp here (the kernel: per thread)
+    a_empty = [Bar(1) for _ in range(a_stages)]
+    b_full = [Bar(1) for _ in range(b_stages)]
+    b_empty = [Bar(1) for _ in range(b_stages)]
+    acc_full = [Bar(1), Bar(1)]
+    acc_empty = [Bar(NEPI_WARPS), Bar(NEPI_WARPS)]
+
+    def producer(grp, w):
+        a_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            for cb in range(n_cb):
+                if a_cnt % ngroups == grp:
+                    s = a_cnt % a_stages
+                    yield ("wait", a_empty[s], ((a_cnt // a_stages) & 1) ^ 1)
+                    if w == 0:
+                        yield ("write", ("A", s), (ti, cb))
+                    yield ("arrive", a_full[s])
+                a_cnt += 1
+
+    def loader():
+        b_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            for cb in range(n_cb):
+                for j in range(K):
+                    sb = b_cnt % b_stages
+                    yield ("wait", b_empty[sb], ((b_cnt // b_stages) & 1) ^ 1)
+                    yield ("write", ("B", sb), (ti, cb, j))
+                    yield ("arrive", b_full[sb])           # expect_tx + complete_tx of the bulk copy
+                    b_cnt += 1
+
+    def mma():
+        a_cnt = b_cnt = tile_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            buf = tile_cnt & 1
+            yield ("wait", acc_empty[buf], ((tile_cnt >> 1) & 1) ^ 1)
+            for cb in range(n_cb):
+                sa = a_cnt % a_stages
+                yield ("wait", a_full[sa], (a_cnt // a_stages) & 1)
+                for j in range(K):
+                    sb = b_cnt % b_stages
+                    yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
+                    yield ("mma_read", ("A", sa), (ti, cb))
+                    yield ("mma_read", ("B", sb), (ti, cb, j))
+                    yield ("commit", b_empty[sb])
+                    b_cnt += 1
+                yield ("commit", a_empty[sa])
+                a_cnt += 1
+            yield ("write", ("ACC", buf), ti)                # (written as the MMAs complete; conservatively at issue)
+            yield ("commit", acc_full[buf])
+            tile_cnt += 1
+
+    def epilogue(w):
+        tile_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            buf = tile_cnt & 1
+            if not (idle_warps_skip_wait and w < epi_idle_warps):
+                yield ("wait", acc_full[buf], (tile_cnt >> 1) & 1)  # idle warps (no columns) wait too: the round-1 fix
+            if w >= epi_idle_warps:
+                yield ("read", ("ACC", buf), ti)
+            yield ("arrive", acc_empty[buf])
+            tile_cnt += 1
+
+    for g in range(ngroups):
+        for w in range(wpg):
+            sim.add("producer%d.%d" % (g, w), producer(g, w))
+    sim.add("loader", loader())
+    sim.add("mma", mma())
+    for w in range(NEPI_WARPS):
+        sim.add("epilogue%d" % w, epilogue(w))
+    sim.run()
+
+
+def _tc_plan(lib, B, L, Cin, Cout, K, dil, mode, ksplit=0):
+    v = (ctypes.c_int * 11)()
+    assert lib.ev_debug_tc_plan(B, L, Cin, Cout, K, dil, mode, ksplit, v) == 0
+    return dict(zip("BN MT KBG a_stages b_stages groups ksplit tmem smem tiles rows_pad".split(), list(v)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from emotivoice_b200 import build
+    build.build(verbose=False)
+    return _abi.load()
+
+
+@pytest.mark.parametrize("shape", [(1, 537, 384, 1152, 1, 1), (1, 537, 1536, 384, 3, 1), (1, 34368, 128, 128, 11, 5),
+                                   (1, 137472, 32, 32, 3, 1), (1, 4296, 256, 256, 7, 3), (1, 100, 384, 384, 3, 1)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_conv_protocol_with_the_real_plans(lib, shape, mode):
+    B, L, Cin, Cout, K, dil = shape
+    pl = _tc_plan(lib, B, L, Cin, Cout, K, dil, mode)
+    cpg = 8 if mode == 2 else 4
+    n_cb = -(-Cin // (cpg * pl["KBG"]))
+    for seed in range(6):
+        rng = random.Random(seed)
+        tiles = [rng.random() > 0.2 for _ in range(rng.randint(1, 5))]       # tiles of ONE persistent CTA, some of them padding
+        sim_conv(seed, tiles, n_cb, K, pl["a_stages"], pl["b_stages"], pl["groups"], epi_idle_warps=4 if Cout <= 32 else 0)
+
+
+def test_conv_protocol_model_catches_the_round1_bugs():
+    """The model is only worth something if it fails on the two protocols that hung the GPU in round 1."""
+    with pytest.raises(AssertionError):                       # 6 producer groups on a 2-deep ring: parity cannot tell phases apart
+        for seed in range(20):
+            sim_conv(seed, [True, True, True], n_cb=12, K=3, a_stages=2, b_stages=4, ngroups=6)
+    with pytest.raises(AssertionError):                       # column-less epilogue warps handing back an accumulator they never waited for
+        for seed in range(50):
+            sim_conv(seed, [True] * 6, n_cb=2, K=3, a_stages=2, b_stages=4, ngroups=2, epi_idle_warps=4, idle_warps_skip_wait=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# resblock_tc.cu
+# ------------------------------------------------------------------------------------------------------------------
+def sim_pair(seed, tiles, n_cb, K, a_stages, b_stages, ngroups, idle_warps=0):
+    sim = Sim(seed)
+    wpg = NPWARPS // ngroups
+    a_full = [Bar(wpg) for _ in range(a_stages)]
+    a_empty = [Bar(1) for _ in range(a_stages)]
+    b_full = [Bar(1) for _ in range(b_stages)]
+    b_empty = [Bar(1) for _ in range(b_stages)]
+    acc1_full, acc1_empty = Bar(1), Bar(NEPI_WARPS)
+    a2_full, a2_empty = Bar(NEPI_WARPS), Bar(1)              # kernel: one arrival per epilogue THREAD; per warp here
+    acc2_full, acc2_empty = Bar(1), Bar(NEPI_WARPS)
+
+    def producer(grp, w):
+        a_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            for cb in range(n_cb):
+                if a_cnt % ngroups == grp:
+                    s = a_cnt % a_stages
+                    yield ("wait", a_empty[s], ((a_cnt // a_stages) & 1) ^ 1)
+                    if w == 0:
+                        yield ("write", ("A1", s), (ti, cb))
+                    yield ("arrive", a_full[s])
+                a_cnt += 1
+
+    def loader():
+        b_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            for conv in range(2):
+                for cb in range(n_cb):
+                    for j in range(K):
+                        sb = b_cnt % b_stages
+                        yield ("wait", b_empty[sb], ((b_cnt // b_stages) & 1) ^ 1)
+                        yield ("write", ("B", sb), (ti, conv, cb, j))
+                        yield ("arrive", b_full[sb])
+                        b_cnt += 1
+
+    def mma():
+        a_cnt = b_cnt = tile_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            par = tile_cnt & 1
+            yield ("wait", acc1_empty, par ^ 1)
+            for cb in range(n_cb):
+                sa = a_cnt % a_stages
+                yield ("wait", a_full[sa], (a_cnt // a_stages) & 1)
+                for j in range(K):
+                    sb = b_cnt % b_stages
+                    yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
+                    yield ("mma_read", ("A1", sa), (ti, cb))
+                    yield ("mma_read", ("B", sb), (ti, 0, cb, j))
+                    yield ("commit", b_empty[sb])
+                    b_cnt += 1
+                yield ("commit", a_empty[sa])
+                a_cnt += 1
+            yield ("write", ("ACC1",), ti)
+            yield ("commit", acc1_full)
+            yield ("wait", acc2_empty, par ^ 1)
+            yield ("wait", a2_full, par)
+            for cb in range(n_cb):
+                for j in range(K):
+                    sb = b_cnt % b_stages
+                    yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
+                    yield ("mma_read", ("A2",), ti)
+                    yield ("mma_read", ("B", sb), (ti, 1, cb, j))
+                    yield ("commit", b_empty[sb])
+                    b_cnt += 1
+            yield ("write", ("ACC2",), ti)
+            yield ("commit", a2_empty)
+            yield ("commit", acc2_full)
+            tile_cnt += 1
+
+    def epilogue(w):
+        tile_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            par = tile_cnt & 1
+            yield ("wait", a2_empty, par ^ 1)
+            yield ("wait", acc1_full, par)
+            if w >= idle_warps:
+                yield ("read", ("ACC1",), ti)
+            if w == 0:
+                yield ("write", ("A2",), ti)
+            yield ("arrive", a2_full)
+            yield ("arrive", acc1_empty)
+            yield ("wait", acc2_full, par)
+            if w >= idle_warps:
+                yield ("read", ("ACC2",), ti)
+            yield ("arrive", acc2_empty)
+            tile_cnt += 1
+
+    for g in range(ngroups):
+        for w in range(wpg):
+            sim.add("producer%d.%d" % (g, w), producer(g, w))
+    sim.add("loader", loader())
+    sim.add("mma", mma())
+    for w in range(NEPI_WARPS):
+        sim.add("epilogue%d" % w, epilogue(w))
+    sim.run()
+
+
+@pytest.mark.parametrize("C,K,dil", [(32, 3, 1), (32, 11, 5), (64, 7, 3), (64, 11, 5), (128, 11, 1)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_resblock_pair_protocol_with_the_real_plans(lib, C, K, dil, mode):
+    v = (ctypes.c_int * 11)()
+    if lib.ev_debug_resblock_plan(1, 137472, C, K, dil, mode, v) != 0:
+        assert C == 128 and mode == 1
+        return
+    pl = dict(zip("MT KBG a_stages b_stages groups tmem smem tiles R rows1_pad rows2_pad".split(), list(v)))
+    cpg = 8 if mode == 2 else 4
+    n_cb = -(-C // (cpg * pl["KBG"]))
+    for seed in range(6):
+        rng = random.Random(100 + seed)
+        tiles = [rng.random() > 0.2 for _ in range(rng.randint(1, 5))]
+        sim_pair(seed, tiles, n_cb, K, pl["a_stages"], pl["b_stages"], pl["groups"], idle_warps=4 if C == 32 else 0)
+
+
+def test_pair_protocol_model_is_sensitive():
+    """The pair model must fail on a ring that is too shallow for the producer grouping, like the conv model does."""
+    with pytest.raises(AssertionError):
+        for seed in range(20):
+            sim_pair(seed, [True, True, True], n_cb=8, K=3, a_stages=2, b_stages=4, ngroups=6)
