@@ -38,7 +38,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--precisions", default="fp32,tf32", help="comma separated: fp32,tf32,bf16")
     args = ap.parse_args()
+    precisions = tuple(args.precisions.split(","))
     build.build(verbose=False)
     peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
@@ -49,14 +51,14 @@ def main():
     model.eval()
     flush_buf = torch.empty(64 * 1024 * 1024, device=dev)
     flush = flush_buf.zero_
-    res = {"peaks": peaks, "cfg3": {}, "cfg4": []}
+    res = {"peaks": peaks, "env": {k: v for k, v in os.environ.items() if k.startswith("EV_")}, "cfg3": {}, "cfg4": []}
 
     # ---- cfg3: batch 32, 20..200 phonemes -------------------------------------------------
     import numpy as np
     rng = np.random.default_rng(32)
     lens = sorted(rng.integers(20, 201, size=32).tolist(), reverse=True)
     batch = {k: v.to(dev) for k, v in synth.make_batch(lens, seed=3232).items()}
-    for prec in ("fp32", "tf32"):
+    for prec in precisions:
         model.precision = prec
         t, out = timed(lambda: model(**batch), 5, flush)
         frames = int(out["mel_lengths"].sum())
@@ -74,7 +76,7 @@ def main():
     # ---- cfg4: vocoder-only sweep ------------------------------------------------------------
     points = [(1, 256), (1, 1024), (1, 4096), (8, 1024), (32, 512), (32, 1024)] if args.quick else \
         [(1, 256), (1, 512), (1, 1024), (1, 2048), (1, 4096), (4, 1024), (8, 1024), (16, 1024), (32, 512), (32, 1024), (64, 512), (128, 256)]
-    for prec in ("fp32", "tf32"):
+    for prec in precisions:
         model.precision = prec
         for B, F in points:
             mel = synth.make_mel(B, F, seed=B * 7 + F).to(dev)
