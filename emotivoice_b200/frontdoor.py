@@ -11,6 +11,7 @@ engine's batches are bitwise equal to B=1 runs, micro-batching is
 Pure host code: no CUDA, no torch ops beyond tensor construction.  The style / content vectors come
 from the caller (the simbert encoder is out of scope).
 
+Prompt side (s8f rank 1): ``PromptEmbeddingCache`` -- batched, cached ``get_style_embedding``.
 Output side (s8f rank 2): ``fetch_pcm16`` (GPU int16 conversion + one pinned device->host copy + per-item trim) and
 ``pcm16_to_wav_bytes`` (the 16 kHz mono PCM16 RIFF image the front-ends emit).
 """
@@ -179,3 +180,54 @@ def fetch_pcm16(model, out, hop=256):
     B, n = pcm.shape[0], int(pcm.shape[-1])
     arr = host.numpy().reshape(B, n)
     return [arr[b, :(n if lens is None else min(n, lens[b] * hop))].copy() for b in range(B)]
+
+
+# ---- prompt / content embeddings ("batched, prompt-embedding cache") -----------------------------
+
+class PromptEmbeddingCache:
+    """The callers' ``get_style_embedding`` (inference_am_vocoder_joint.py:25-38) for many texts at once, with a cache.
+
+    The reference tokenises ONE text and runs the BERT style encoder on the CPU, twice per utterance (prompt and content,
+    :106-107), recomputing identical prompts ("Happy", "Sad", ... repeat for every line).  Here all texts of a call that are
+    not cached go through the tokenizer as one right-padded batch and through ``style_encoder`` as ONE forward; results are
+    kept (LRU, on the encoder's device) keyed by the text.  Batching is invisible: the engine's padded batches are bitwise
+    equal to single-item calls.
+
+    ``tokenizer(list_of_str, return_tensors="pt", padding=True)`` -> dict with input_ids / token_type_ids / attention_mask
+    (a transformers tokenizer, as in the reference); ``style_encoder(**those)`` -> dict with "pooled_output" (B, 768)
+    (``emotivoice_b200.style.StyleEncoder`` or the reference's own module).
+    """
+
+    def __init__(self, tokenizer, style_encoder, device=None, max_entries=4096):
+        from collections import OrderedDict
+        self._tok, self._enc, self._device = tokenizer, style_encoder, device
+        self._max = int(max_entries)
+        self._cache = OrderedDict()
+        self._lock = threading.Lock()
+        self.hits = self.misses = self.forwards = 0
+
+    def embed(self, texts):
+        """list of str -> (len(texts), D) float32 tensor, row i = pooled_output of texts[i]."""
+        texts = list(texts)
+        with self._lock:
+            missing = [t for t in dict.fromkeys(texts) if t not in self._cache]
+            self.hits += sum(1 for t in texts if t in self._cache)
+            self.misses += len(texts) - sum(1 for t in texts if t in self._cache)
+        if missing:
+            enc = self._tok(missing, return_tensors="pt", padding=True)
+            keys = ("input_ids", "token_type_ids", "attention_mask")
+            args = {k: (enc[k].to(self._device) if self._device is not None else enc[k]) for k in keys}
+            with torch.no_grad():
+                pooled = self._enc(**args)["pooled_output"].detach()
+            with self._lock:
+                self.forwards += 1
+                for i, t in enumerate(missing):
+                    self._cache[t] = pooled[i].clone()
+                while len(self._cache) > max(self._max, len(set(texts))):
+                    self._cache.popitem(last=False)
+        with self._lock:
+            rows = []
+            for t in texts:
+                self._cache.move_to_end(t)
+                rows.append(self._cache[t])
+        return torch.stack(rows)

@@ -127,3 +127,31 @@ def test_wav_container_is_the_canonical_pcm16_file():
         fd.pcm16_to_wav_bytes(np.zeros(4, np.float32))
     with pytest.raises(ValueError):
         fd.pcm16_to_wav_bytes(np.zeros((2, 4), np.int16))
+
+
+def test_prompt_embedding_cache_batches_dedups_and_evicts():
+    calls = []
+
+    def tokenizer(texts, return_tensors="pt", padding=True):
+        n = max(len(t) for t in texts)
+        ids = torch.zeros((len(texts), n), dtype=torch.long)
+        mask = torch.zeros_like(ids)
+        for i, t in enumerate(texts):
+            ids[i, :len(t)] = torch.tensor([ord(c) for c in t])
+            mask[i, :len(t)] = 1
+        return {"input_ids": ids, "token_type_ids": torch.zeros_like(ids), "attention_mask": mask}
+
+    def encoder(input_ids, token_type_ids, attention_mask):
+        calls.append(int(input_ids.shape[0]))
+        s = (input_ids * attention_mask).sum(1, keepdim=True).float()
+        return {"pooled_output": s.repeat(1, 4) / 1000.0}
+
+    cache = fd.PromptEmbeddingCache(tokenizer, encoder, max_entries=3)
+    e = cache.embed(["Happy", "Sad", "Happy", "hello world"])
+    assert e.shape == (4, 4) and torch.equal(e[0], e[2]) and not torch.equal(e[0], e[1])
+    assert calls == [3] and cache.forwards == 1 and (cache.hits, cache.misses) == (0, 4)      # one forward for the 3 distinct texts
+    e2 = cache.embed(["Sad", "Happy"])
+    assert calls == [3] and torch.equal(e2[0], e[1]) and cache.hits == 2                       # served from the cache
+    cache.embed(["a", "b"])                                                                    # 5 distinct texts > 3 entries: LRU eviction
+    assert calls == [3, 2] and len(cache._cache) == 3 and "hello world" not in cache._cache
+    assert torch.equal(cache.embed(["hello world"])[0], e[3]) and calls == [3, 2, 1]
