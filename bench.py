@@ -236,15 +236,17 @@ def probe(args):
                       "gpu_launches_per_step": (_abi.launch_count() - l0) / len(ev), "parity": parity_vs_reference_fixture(out)}))
 
 
-def experiments(budget_s=300.0):
+def experiments(budget_s=360.0):
     """Opt-in modes measured AFTER the headline numbers are final, each in its own process under a timeout, so a failure
     or a hang in an experimental path cannot touch `value` / `e2e`.  Reported under "experiments"; never part of them."""
     runs = [("tf32", ["--precision", "tf32"], {}), ("bf16", ["--precision", "bf16"], {}),
             ("fp32+pdl", ["--precision", "fp32"], {"EV_PDL": "1"}),
+            ("fp32+pdl_all", ["--precision", "fp32"], {"EV_PDL": "2"}),
             ("fp32+autotune", ["--precision", "fp32"], {"EV_AUTOTUNE": "2"}),
             ("fp32+pdl+autotune", ["--precision", "fp32"], {"EV_PDL": "1", "EV_AUTOTUNE": "1"}),
             ("fp32+fuse_res", ["--precision", "fp32"], {"EV_FUSE_RES": "1"}),
-            ("tf32+fuse_res", ["--precision", "tf32"], {"EV_FUSE_RES": "1"})]
+            ("tf32+fuse_res", ["--precision", "tf32"], {"EV_FUSE_RES": "1"}),
+            ("fp32+all", ["--precision", "fp32"], {"EV_PDL": "2", "EV_AUTOTUNE": "1", "EV_FUSE_RES": "1"})]
     res = {"note": "opt-in / secondary modes of the same B=1 workload, 10 timed steps each, separate processes; not part of value or e2e"}
     t_end = time.time() + budget_s
 

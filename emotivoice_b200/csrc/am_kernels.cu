@@ -22,12 +22,13 @@ __device__ __forceinline__ float warp_max(float v) {
 // layer of the encoder: x = word_emb[id] + alpha * pe[t]  (model_open_source.py:107,
 // encoder.py:257-261), which is also written back as the residual stream.
 // ---------------------------------------------------------------------------------------------
-template <int NV>  // float4 per lane
+template <int NV, bool PDL>  // float4 per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__ ids,
                                                         const float* __restrict__ emb, const float* __restrict__ pe,
                                                         const float* __restrict__ alpha, float* __restrict__ x_out,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         float* __restrict__ y, int rows, int L) {
+  pdl_entry<PDL>();
   constexpr int C = NV * 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -85,12 +86,12 @@ int launch_layernorm(const float* x, const int64_t* ids, const float* emb, const
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb);
   switch (C / 128) {
-    case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    case 3: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    case 4: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    case 5: layernorm_kernel<5><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    default: layernorm_kernel<6><<<grid, 256, 0, st>>>(x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    case 1: launch_k(layernorm_kernel<1, true>, layernorm_kernel<1, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    case 2: launch_k(layernorm_kernel<2, true>, layernorm_kernel<2, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    case 3: launch_k(layernorm_kernel<3, true>, layernorm_kernel<3, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    case 4: launch_k(layernorm_kernel<4, true>, layernorm_kernel<4, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    case 5: launch_k(layernorm_kernel<5, true>, layernorm_kernel<5, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    default: launch_k(layernorm_kernel<6, true>, layernorm_kernel<6, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
   }
   EV_CUDA_LAUNCH_CHECK("layernorm_kernel");
   return EV_OK;
@@ -104,9 +105,10 @@ int launch_layernorm(const float* x, const int64_t* ids, const float* emb, const
 // [h*DK, (h+1)*DK) of each third (encoder.py:72-82).  Query rows >= key_len are computed like
 // the reference computes them (they attend to the valid keys).
 // ---------------------------------------------------------------------------------------------
-template <int DK, int BQ>
+template <int DK, int BQ, bool PDL>
 __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ key_lens,
                                                         float* __restrict__ ctx, int L, int H) {
+  pdl_entry<PDL>();
   constexpr int BK = 64, LDQ = BQ + 1, LDT = BK + 1;
   constexpr int RQ = BQ / 16;   // query rows per thread
   constexpr int OC = DK / 8;    // output columns per thread
@@ -239,11 +241,12 @@ static int launch_attention_dk(const float* qkv, const int32_t* key_lens, float*
   const size_t smem = (size_t)(DK * (BQ + 1) + DK * 65 + 64 * DK + BQ * 65) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attention_kernel<DK, BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(attention_kernel<DK, BQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(attention_kernel<DK, BQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
   dim3 grid((L + BQ - 1) / BQ, heads, B);
-  attention_kernel<DK, BQ><<<grid, 128, smem, st>>>(qkv, key_lens, ctx, L, H);
+  launch_k(attention_kernel<DK, BQ, true>, attention_kernel<DK, BQ, false>, grid, 128, smem, st, qkv, key_lens, ctx, L, H);
   EV_CUDA_LAUNCH_CHECK("attention_kernel");
   return EV_OK;
 }
@@ -270,9 +273,11 @@ int launch_attention(const float* qkv, const int32_t* key_lens, float* ctx, int 
 // The 2304->384 projection (:111) is split: W_x x_t + (W_c c_b + bias); the second term is a
 // per-utterance bias computed once per item by the generic GEMM on this gathered vector.
 // ---------------------------------------------------------------------------------------------
+template <bool PDL>
 __global__ void cond_gather_kernel(const int64_t* __restrict__ spk, const float* __restrict__ spk_emb,
                                    const float* __restrict__ style, const float* __restrict__ content,
                                    float* __restrict__ out, int H, int bert) {
+  pdl_entry<PDL>();
   const int b = blockIdx.x;
   const int W = H + 2 * bert;
   for (int i = threadIdx.x; i < W; i += blockDim.x) {
@@ -285,7 +290,7 @@ __global__ void cond_gather_kernel(const int64_t* __restrict__ spk, const float*
 }
 int launch_cond_gather(const int64_t* spk, const float* spk_emb, const float* style, const float* content,
                        float* out, int B, int H, int bert, cudaStream_t st) {
-  cond_gather_kernel<<<B, 256, 0, st>>>(spk, spk_emb, style, content, out, H, bert);
+  launch_k(cond_gather_kernel<true>, cond_gather_kernel<false>, B, 256, 0, st, spk, spk_emb, style, content, out, H, bert);
   EV_CUDA_LAUNCH_CHECK("cond_gather_kernel");
   return EV_OK;
 }
@@ -296,9 +301,11 @@ int launch_cond_gather(const int64_t* spk, const float* spk_emb, const float* st
 // per (8 output columns, batch item); the K axis is split over the CTA's threads and reduced in a
 // fixed order (deterministic).  w is (K, N) row-major.
 // ---------------------------------------------------------------------------------------------
+template <bool PDL>
 __global__ void __launch_bounds__(256) cond_gemv_kernel(const float* __restrict__ c, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ out, int K,
                                                         int N) {
+  pdl_entry<PDL>();
   __shared__ float red[8][8][33];
   const int b = blockIdx.y, n0 = blockIdx.x * 8;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -329,7 +336,7 @@ __global__ void __launch_bounds__(256) cond_gemv_kernel(const float* __restrict_
 int launch_cond_gemv(const float* c, const float* w, const float* bias, float* out, int B, int K, int N, cudaStream_t st) {
   EV_CHECK_ARG(N % 8 == 0 && B > 0 && B <= 65535, "cond_gemv: N=%d B=%d", N, B);
   dim3 grid(N / 8, B);
-  cond_gemv_kernel<<<grid, 256, 0, st>>>(c, w, bias, out, K, N);
+  launch_k(cond_gemv_kernel<true>, cond_gemv_kernel<false>, grid, 256, 0, st, c, w, bias, out, K, N);
   EV_CUDA_LAUNCH_CHECK("cond_gemv_kernel");
   return EV_OK;
 }
@@ -338,10 +345,12 @@ int launch_cond_gemv(const float* c, const float* w, const float* bias, float* o
 // Predictor head: Linear(C -> 1) + output mask (variance.py:46-56, :119-124).
 // mode 0: float (pitch / energy);  mode 1: duration = clamp(rint(exp(y) - 1), 0) as int64.
 // ---------------------------------------------------------------------------------------------
+template <bool PDL>
 __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ bias, const int32_t* __restrict__ lens,
                                                      int rows, int T, int C, int mode, float* __restrict__ out_f,
                                                      int64_t* __restrict__ out_i) {
+  pdl_entry<PDL>();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -367,13 +376,15 @@ int launch_rowdot(const float* x, const float* w, const float* b, const int32_t*
                   int mode, float* out_f, int64_t* out_i, cudaStream_t st) {
   EV_CHECK_ARG(C % 4 == 0, "rowdot: C=%d", C);
   const int rows = B * T;
-  rowdot_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, b, lens, rows, T, C, mode, out_f, out_i);
+  launch_k(rowdot_kernel<true>, rowdot_kernel<false>, (rows + 7) / 8, 256, 0, st, x, w, b, lens, rows, T, C, mode, out_f, out_i);
   EV_CUDA_LAUNCH_CHECK("rowdot_kernel");
   return EV_OK;
 }
 
 // lengths arrive as int64 (inference_am_vocoder_joint.py:114); the kernels take int32 clamped to [0, T]
+template <bool PDL>
 __global__ void lens_to_i32_kernel(const int64_t* __restrict__ lens, int32_t* __restrict__ out, int B, int T) {
+  pdl_entry<PDL>();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     long long v = lens[i];
@@ -381,14 +392,16 @@ __global__ void lens_to_i32_kernel(const int64_t* __restrict__ lens, int32_t* __
   }
 }
 int launch_lens_to_i32(const int64_t* lens, int32_t* out, int B, int T, cudaStream_t st) {
-  lens_to_i32_kernel<<<(B + 127) / 128, 128, 0, st>>>(lens, out, B, T);
+  launch_k(lens_to_i32_kernel<true>, lens_to_i32_kernel<false>, (B + 127) / 128, 128, 0, st, lens, out, B, T);
   EV_CUDA_LAUNCH_CHECK("lens_to_i32_kernel");
   return EV_OK;
 }
 
 // masked_fill(x_masks, 0) on the predictors' input (variance.py:38-39, :109-110)
+template <bool PDL>
 __global__ void mask_rows_kernel(const float4* __restrict__ x, const int32_t* __restrict__ lens, float4* __restrict__ y,
                                  int T, int C4, size_t n4) {
+  pdl_entry<PDL>();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const size_t row = i / C4;
@@ -398,7 +411,7 @@ __global__ void mask_rows_kernel(const float4* __restrict__ x, const int32_t* __
 int launch_mask_rows(const float* x, const int32_t* lens, float* y, int B, int T, int C, cudaStream_t st) {
   EV_CHECK_ARG(C % 4 == 0, "mask_rows: C=%d", C);
   const size_t n4 = (size_t)B * T * C / 4;
-  mask_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float4*)x, lens, (float4*)y, T, C / 4, n4);
+  launch_k(mask_rows_kernel<true>, mask_rows_kernel<false>, (unsigned)((n4 + 255) / 256), 256, 0, st, (const float4*)x, lens, (float4*)y, T, C / 4, n4);
   EV_CUDA_LAUNCH_CHECK("mask_rows_kernel");
   return EV_OK;
 }
@@ -407,10 +420,12 @@ int launch_mask_rows(const float* x, const int32_t* lens, float* y, int B, int T
 // x += pitch_embed(p) + energy_embed(e): two Conv1d(1 -> C, k=K, pad=(K-1)/2) on the predicted
 // scalar tracks (model_open_source.py:131-134).  wp/we are tap-major (K, C).
 // ---------------------------------------------------------------------------------------------
+template <bool PDL>
 __global__ void var_embed_add_kernel(float* __restrict__ x, const float* __restrict__ pitch,
                                      const float* __restrict__ energy, const float* __restrict__ wp,
                                      const float* __restrict__ bp, const float* __restrict__ we,
                                      const float* __restrict__ be, int T, int C, int K) {
+  pdl_entry<PDL>();
   const int row = blockIdx.x;   // b*T + t
   const int b = row / T, t = row % T;
   __shared__ float ps[16], es[16];
@@ -434,7 +449,7 @@ __global__ void var_embed_add_kernel(float* __restrict__ x, const float* __restr
 int launch_var_embed_add(float* x, const float* pitch, const float* energy, const float* wp, const float* bp,
                          const float* we, const float* be, int B, int T, int C, int K, cudaStream_t st) {
   EV_CHECK_ARG(K <= 16, "var_embed: K=%d > 16", K);
-  var_embed_add_kernel<<<B * T, 128, 0, st>>>(x, pitch, energy, wp, bp, we, be, T, C, K);
+  launch_k(var_embed_add_kernel<true>, var_embed_add_kernel<false>, B * T, 128, 0, st, x, pitch, energy, wp, bp, we, be, T, C, K);
   EV_CUDA_LAUNCH_CHECK("var_embed_add_kernel");
   return EV_OK;
 }
@@ -445,10 +460,12 @@ int launch_var_embed_add(float* x, const float* pitch, const float* energy, cons
 // c = cumsum(ds) - ds/2; mel_lens[b] = sum_t ds; mel_lens[B] = max_b.  One CTA (B*T is tiny).
 // Integer-valued fp32 sums are exact below 2^24 frames.
 // ---------------------------------------------------------------------------------------------
+template <bool PDL>
 __global__ void __launch_bounds__(1024) duration_scan_kernel(const int64_t* __restrict__ dur,
                                                              const int32_t* __restrict__ lens, int invariant, int B, int T,
                                                              float* __restrict__ centers, float* __restrict__ ds_f,
                                                              int32_t* __restrict__ mel_lens) {
+  pdl_entry<PDL>();
   __shared__ unsigned long long s_total;
   __shared__ int s_max;
   const int tid = threadIdx.x, nw = blockDim.x >> 5, lane = tid & 31, wid = tid >> 5;
@@ -500,7 +517,7 @@ __global__ void __launch_bounds__(1024) duration_scan_kernel(const int64_t* __re
 }
 int launch_duration_scan(const int64_t* dur, const int32_t* lens, int invariant, int B, int T, float* centers,
                          float* ds_f, int32_t* mel_lens, cudaStream_t st) {
-  duration_scan_kernel<<<1, 1024, 0, st>>>(dur, lens, invariant, B, T, centers, ds_f, mel_lens);
+  launch_k(duration_scan_kernel<true>, duration_scan_kernel<false>, 1, 1024, 0, st, dur, lens, invariant, B, T, centers, ds_f, mel_lens);
   EV_CUDA_LAUNCH_CHECK("duration_scan_kernel");
   return EV_OK;
 }
@@ -516,12 +533,13 @@ int launch_duration_scan(const int64_t* dur, const int32_t* lens, int invariant,
 // ---------------------------------------------------------------------------------------------
 constexpr int GU_FT = 16;   // frames per CTA
 constexpr int GU_TT = 16;   // tokens per smem chunk
-template <int NC>           // channels per thread: H = NC * 128
+template <int NC, bool PDL>           // channels per thread: H = NC * 128
 __global__ void __launch_bounds__(128) gauss_upsample_kernel(const float* __restrict__ hs, const float* __restrict__ centers,
                                                              const int32_t* __restrict__ lens,
                                                              const int32_t* __restrict__ mel_lens, int T, int F,
                                                              int invariant, const float* __restrict__ pe,
                                                              const float* __restrict__ alpha, float* __restrict__ out) {
+  pdl_entry<PDL>();
   constexpr int H = NC * 128;
   __shared__ float s_w[GU_FT][GU_TT];
   __shared__ float s_max[GU_FT], s_inv[GU_FT];
@@ -622,10 +640,10 @@ int launch_gauss_upsample(const float* hs, const float* centers, const int32_t* 
   EV_CHECK_ARG(B <= 65535, "gauss_upsample: B too large");
   dim3 grid((F + GU_FT - 1) / GU_FT, B);
   switch (H / 128) {
-    case 1: gauss_upsample_kernel<1><<<grid, 128, 0, st>>>(hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
-    case 2: gauss_upsample_kernel<2><<<grid, 128, 0, st>>>(hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
-    case 3: gauss_upsample_kernel<3><<<grid, 128, 0, st>>>(hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
-    default: gauss_upsample_kernel<4><<<grid, 128, 0, st>>>(hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
+    case 1: launch_k(gauss_upsample_kernel<1, true>, gauss_upsample_kernel<1, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
+    case 2: launch_k(gauss_upsample_kernel<2, true>, gauss_upsample_kernel<2, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
+    case 3: launch_k(gauss_upsample_kernel<3, true>, gauss_upsample_kernel<3, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
+    default: launch_k(gauss_upsample_kernel<4, true>, gauss_upsample_kernel<4, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
   }
   EV_CUDA_LAUNCH_CHECK("gauss_upsample_kernel");
   return EV_OK;

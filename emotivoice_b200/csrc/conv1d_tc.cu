@@ -49,7 +49,6 @@ struct Plan {
   int tmem_cols;
   int tiles_m, tiles_n, total_tiles;
   int smem_total;
-  int pdl;             // launched with programmatic stream serialization (EV_PDL=1): see the note in the kernel
 };
 
 // smem map: [0,288) barriers | [512,516) tmem base | 1024: epilogue staging (8 warps x 4 KB) | A ring | B ring
@@ -91,7 +90,6 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN,
   q.ksplit = 1;
   q.total_tiles = p.B * q.tiles_m * q.tiles_n;
   q.smem_total = 1024 + STAGING_BYTES + q.a_stages * q.a_stage_bytes + q.b_stages * q.b_stage_bytes;
-  q.pdl = 0;
   *o = q;
   return true;
 }
@@ -103,7 +101,9 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN,
 //                 three MMAs per K step into the same fp32 TMEM accumulator.  Weights arrive pre-split
 //                 (two planes, packing.to_tc_layout); activations are split by the producer warps.
 // MT: 128-row accumulators per tile.  KBG: 16-byte K granules (4 tf32 or 8 bf16 channels each) per pipeline stage.
-template <int MODE, int MT, int KBG>
+// PDLM: programmatic dependent launch mode (EV_PDL): 0 = plain launch (the default path; no extra instructions),
+//       1 = convolutions only, 2 = every kernel of the engine launches this way (see the note after the set-up below).
+template <int MODE, int MT, int KBG, int PDLM>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Plan pl) {
   constexpr bool SPLIT3 = (MODE == 1);
   constexpr bool BF16 = (MODE == 2);
@@ -145,14 +145,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Programmatic dependent launch (opt-in, EV_PDL=1).  The grid is persistent (<= one CTA per SM, all resident), so it
-  // lets the NEXT launch in the stream start as soon as SMs free up: that kernel's CTAs run their set-up (barriers, TMEM)
-  // and its loader warp prefetches the first weight stages -- none of which depends on this grid -- while this grid's tail
-  // is still running.  Everything that touches activations (producers: x; epilogue: res / out / split-K partials) first
-  // executes griddepcontrol.wait, which returns once the preceding grid has completed and its writes are visible.
-  // The loader and the MMA issuer read only weights and p.lens; p.lens must therefore not be written by the launch
-  // immediately before a convolution (the engine writes it at the start of a phase, kernels earlier).
-  if (pl.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Programmatic dependent launch (opt-in, EV_PDL).  The grid is persistent (<= one CTA per SM, all resident), so it lets
+  // the NEXT launch in the stream start as soon as SMs free up: that kernel's CTAs run their set-up (barriers, TMEM) while
+  // this grid's tail is still running.  Everything that touches activations (producers: x; epilogue: res / out / split-K
+  // partials) first executes griddepcontrol.wait, which returns once the preceding grid has completed and its writes are
+  // visible.  PDLM == 1 (only the convolutions launch this way, so the launch before a convolution's predecessor has fully
+  // completed): the loader and the MMA issuer, which read only weights and p.lens, do not wait and the first weight stages
+  // are prefetched under the predecessor's tail.  PDLM == 2 (every kernel launches this way, p.lens may come from a grid
+  // that is still running two launches upstream): every role waits.
+  if (PDLM) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int n_cb = (p.Cin + KB - 1) / KB;
   const int halo = ((p.K - 1) / 2) * p.dil;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
 
   if (warp < NEPI / 32) {
     // ============================ epilogue warps ==============================================
-    if (pl.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (PDLM) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int quad = warp & 3, chalf = warp >> 2;
     float* stg = reinterpret_cast<float*>(staging + warp * (32 * 32 * 4));
     const int rr = lane >> 3, cq = lane & 7;         // coalesced phase: 4 rows x 8 float4 per instruction
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
     }
   } else if (warp < MMA_WARP) {
     // ============================ A producers ===================================================
-    if (pl.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (PDLM) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int pwarp = warp - NEPI / 32;
     const int wpg = NPWARPS / pl.ngroups;          // warps per group
     const int grp = pwarp / wpg;
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   } else if (warp == MMA_WARP) {
     // ============================ MMA issuer =====================================================
     if (lane == 0) {
+      if (PDLM == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
       const uint32_t a_lbo = (uint32_t)pl.rows_pad * 16u, b_lbo = (uint32_t)BN * 16u;
       int a_cnt = 0, b_cnt = 0, tile_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   } else {
     // ============================ weight loader ==================================================
     if (lane == 0) {
+      if (PDLM == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
       // w_tc layout: [plane (hi, lo)][N tile of BNp = min(Cout,128)][tap][Cin/CPG granules][BNp][16 bytes]
       // (4 fp32 or 8 bf16 per granule; granule-major inside a tile)
       const int cin4 = p.Cin / CPG;
@@ -463,7 +466,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
 // Second half of a K-split convolution: out = epi( sum_z partial[z] ) with the slices added in the
 // fixed order z = 0..S-1 (deterministic, batch invariant), then bias / activation / residual /
 // accumulate exactly like the fused epilogue.  One float4 per thread.
+template <bool PDL>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(ConvParams p, int S) {
+  pdl_entry<PDL>();
   const size_t per = (size_t)p.B * p.L * p.Cout;
   const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= per) return;
@@ -517,40 +522,39 @@ static int sm_count() {
   return n;
 }
 
-template <int MODE, int MT, int KBG>
-static int launch_tc_variant(const ConvParams& p, const tc::Plan& pl, cudaStream_t st) {
+template <int MODE, int MT, int KBG, int PDLM>
+static int launch_tc_pdl(const ConvParams& p, const tc::Plan& pl, cudaStream_t st) {
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(tc::conv1d_tc_kernel<MODE, MT, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc::conv1d_tc_kernel<MODE, MT, KBG, PDLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   const int grid = pl.total_tiles < sm_count() ? pl.total_tiles : sm_count();
-  if (pl.pdl) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(tc::NTHREADS);
-    cfg.dynamicSmemBytes = (size_t)pl.smem_total;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, tc::conv1d_tc_kernel<MODE, MT, KBG>, p, pl);
+  if (PDLM) {
+    const cudaError_t e = launch_with_pdl(tc::conv1d_tc_kernel<MODE, MT, KBG, PDLM>, dim3((unsigned)grid), dim3(tc::NTHREADS),
+                                          (size_t)pl.smem_total, st, p, pl);
     if (e != cudaSuccess) { set_error("conv1d_tc_kernel (PDL launch): %s", cudaGetErrorString(e)); return EV_ECUDA; }
     count_launch();
     return EV_OK;
   }
-  tc::conv1d_tc_kernel<MODE, MT, KBG><<<grid, tc::NTHREADS, pl.smem_total, st>>>(p, pl);
+  tc::conv1d_tc_kernel<MODE, MT, KBG, PDLM><<<grid, tc::NTHREADS, pl.smem_total, st>>>(p, pl);
   EV_CUDA_LAUNCH_CHECK("conv1d_tc_kernel");
   return EV_OK;
 }
 
+// pdl: 0 for the tuner's timing launches and the default path, else pdl_mode()
+template <int MODE, int MT, int KBG>
+static int launch_tc_variant(const ConvParams& p, const tc::Plan& pl, cudaStream_t st, int pdl) {
+  if (pdl >= 2) return launch_tc_pdl<MODE, MT, KBG, 2>(p, pl, st);
+  if (pdl == 1) return launch_tc_pdl<MODE, MT, KBG, 1>(p, pl, st);
+  return launch_tc_pdl<MODE, MT, KBG, 0>(p, pl, st);
+}
+
 template <int MODE, int KBG>
-static int launch_tc_mt(const ConvParams& p, const tc::Plan& pl, cudaStream_t st) {
-  if (pl.mt == 4) return launch_tc_variant<MODE, 4, KBG>(p, pl, st);
-  if (pl.mt == 2) return launch_tc_variant<MODE, 2, KBG>(p, pl, st);
-  return launch_tc_variant<MODE, 1, KBG>(p, pl, st);
+static int launch_tc_mt(const ConvParams& p, const tc::Plan& pl, cudaStream_t st, int pdl) {
+  if (pl.mt == 4) return launch_tc_variant<MODE, 4, KBG>(p, pl, st, pdl);
+  if (pl.mt == 2) return launch_tc_variant<MODE, 2, KBG>(p, pl, st, pdl);
+  return launch_tc_variant<MODE, 1, KBG>(p, pl, st, pdl);
 }
 
 static int validate_conv1d_tc(const ConvParams& p, int mode) {
@@ -639,10 +643,10 @@ int debug_tc_plan(const ConvParams& p, int mode, int* v) {
   return EV_OK;
 }
 
-static int dispatch_tc(const ConvParams& p, int mode, const tc::Plan& pl, cudaStream_t st) {
-  if (mode == 1) return launch_tc_mt<1, 4>(p, pl, st);
-  if (mode == 2) return pl.kbg == 8 ? launch_tc_mt<2, 8>(p, pl, st) : launch_tc_mt<2, 4>(p, pl, st);
-  return pl.kbg == 8 ? launch_tc_mt<0, 8>(p, pl, st) : launch_tc_mt<0, 4>(p, pl, st);
+static int dispatch_tc(const ConvParams& p, int mode, const tc::Plan& pl, cudaStream_t st, int pdl = 0) {
+  if (mode == 1) return launch_tc_mt<1, 4>(p, pl, st, pdl);
+  if (mode == 2) return pl.kbg == 8 ? launch_tc_mt<2, 8>(p, pl, st, pdl) : launch_tc_mt<2, 4>(p, pl, st, pdl);
+  return pl.kbg == 8 ? launch_tc_mt<0, 8>(p, pl, st, pdl) : launch_tc_mt<0, 4>(p, pl, st, pdl);
 }
 
 // ---- opt-in online tile-shape tuner (EV_AUTOTUNE=1; =2 also logs its choices to stderr) -------------------------------
@@ -732,13 +736,11 @@ int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st) {
     tc::Plan tuned;
     if (choice.first && plan_with_shape(p, mode, choice.first, choice.second, &tuned)) pl = tuned;
   }
-  static const int pdl = env_int("EV_PDL", 0);      // opt-in until it has been measured on hardware
-  pl.pdl = pdl ? 1 : 0;
   const size_t per = (size_t)p.B * p.L * p.Cout;
-  const int rc = dispatch_tc(p, mode, pl, st);
+  const int rc = dispatch_tc(p, mode, pl, st, pdl_mode());      // EV_PDL: opt-in until it has been measured on hardware
   if (rc != EV_OK || pl.ksplit == 1) return rc;
   const size_t n4 = per / 4;
-  tc::splitk_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(p, pl.ksplit);
+  launch_k(tc::splitk_reduce_kernel<true>, tc::splitk_reduce_kernel<false>, (unsigned)((n4 + 255) / 256), 256, 0, st, p, pl.ksplit);
   EV_CUDA_LAUNCH_CHECK("splitk_reduce_kernel");
   return EV_OK;
 }

@@ -20,8 +20,9 @@ constexpr int NTHREADS = 256;
 
 // TXN: threads along N (8 or 16); NV: float4 column groups per thread (1 or 2); TM: rows per thread.
 //   BN = TXN*4*NV,  BM = (256/TXN)*TM.
-template <int TXN, int NV, int TM>
+template <int TXN, int NV, int TM, bool PDL>
 __global__ void __launch_bounds__(NTHREADS) conv1d_tm_kernel(ConvParams p, int a_ld) {
+  pdl_entry<PDL>();
   constexpr int TYN = NTHREADS / TXN;   // threads along M
   constexpr int BM = TYN * TM;
   constexpr int BN = TXN * 4 * NV;
@@ -221,12 +222,13 @@ static int launch_variant(const ConvParams& p, cudaStream_t st) {
   const size_t smem = (size_t)(2 * KC * a_ld + 2 * KC * BN) * sizeof(float);
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    cudaFuncSetAttribute(conv1d_tm_kernel<TXN, NV, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(conv1d_tm_kernel<TXN, NV, TM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(conv1d_tm_kernel<TXN, NV, TM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_set = true;
   }
   EV_CHECK_ARG(smem <= 96 * 1024, "conv1d: smem %zu too large", smem);
   dim3 grid((p.L + BM - 1) / BM, (p.Cout + BN - 1) / BN, p.B);
-  conv1d_tm_kernel<TXN, NV, TM><<<grid, NTHREADS, smem, st>>>(p, a_ld);
+  launch_k(conv1d_tm_kernel<TXN, NV, TM, true>, conv1d_tm_kernel<TXN, NV, TM, false>, grid, NTHREADS, smem, st, p, a_ld);
   EV_CUDA_LAUNCH_CHECK("conv1d_tm_kernel");
   return EV_OK;
 }

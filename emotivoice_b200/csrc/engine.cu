@@ -26,6 +26,10 @@ void set_error(const char* fmt, ...) {
   g_err = buf;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int pdl_mode() {
+  static const int v = [] { const char* e = getenv("EV_PDL"); return (e && *e) ? atoi(e) : 0; }();
+  return v;
+}
 
 struct Tensor {
   const float* p = nullptr;

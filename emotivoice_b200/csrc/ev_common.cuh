@@ -37,6 +37,46 @@ void count_launch(int n = 1);
   } while (0)
 
 // ---------------------------------------------------------------------------------
+// Programmatic dependent launch (opt-in).  EV_PDL=1: the tensor-core convolutions only (conv1d_tc.cu);
+// EV_PDL=2: every kernel of the engine.  A kernel compiled with PDL = true starts with
+// griddepcontrol.launch_dependents (the next launch in the stream may be scheduled as soon as every CTA of this grid
+// has started) followed by griddepcontrol.wait (returns once the preceding grid has completed and its writes are
+// visible) -- before its first memory access, so stream order semantics are unchanged; what is gained is the launch
+// latency and, for the convolutions, the set-up that runs before the wait.  The PDL = false instantiations are the
+// kernels the default path launches: their code is unchanged by the template parameter.
+// ---------------------------------------------------------------------------------
+template <bool PDL>
+__device__ __forceinline__ void pdl_entry() {
+  if (PDL) asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+}
+int pdl_mode();      // 0 (default), 1, 2: the value of EV_PDL, read once
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_with_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+// launches `plain` exactly like `plain<<<grid, block, smem, st>>>(args...)`, or `with_pdl` with the attribute when EV_PDL >= 2;
+// launch errors surface through cudaGetLastError (EV_CUDA_LAUNCH_CHECK follows every call)
+template <typename K, typename... Args>
+inline void launch_k(K with_pdl, K plain, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  if (pdl_mode() >= 2) {
+    (void)launch_with_pdl(with_pdl, grid, block, smem, st, args...);
+  } else {
+    plain<<<grid, block, smem, st>>>(args...);
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // generic time-major conv (conv1d_tm.cu)
 // ---------------------------------------------------------------------------------
 struct ConvParams {

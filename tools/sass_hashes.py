@@ -1,0 +1,76 @@
+"""Per-kernel hashes of the SASS instruction streams of the engine library, to prove that a refactor left the device code
+of the default path untouched (round 1: the kernels were templated on a launch-mode flag after the GPU budget had ended;
+the flag-off instantiations must be -- and are -- byte-identical to the revision that passed on the B200).
+
+    python tools/sass_hashes.py                      # print {kernel: md5 of its instruction text}
+    python tools/sass_hashes.py --write profiles/r01_sass_default_kernel_hashes.json      # after a GPU-validated change
+
+Kernel names are demangled and the trailing launch-mode template argument of the default instantiation (", false>" / ", 0>")
+is dropped, so hashes taken before and after the templating are comparable.  Opt-in instantiations (true / 1 / 2) are skipped.
+"""
+import argparse
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "emotivoice_b200", "lib", "libemotivoice_b200.so")
+OPT_IN = ("resblock_pair_kernel", "bert_embed_ln_kernel", "row_gemv_kernel")      # kernels no default code path launches
+
+
+def kernel_hashes(path=LIB):
+    txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    funcs, cur, body = {}, None, []
+    for ln in txt.splitlines():
+        m = re.match(r"\s*Function : (\S+)", ln)
+        if m:
+            if cur:
+                funcs[cur] = hashlib.md5("\n".join(body).encode()).hexdigest()
+            cur, body = m.group(1), []
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", ln)
+        if m and cur:
+            body.append(m.group(1).strip())
+    if cur:
+        funcs[cur] = hashlib.md5("\n".join(body).encode()).hexdigest()
+    names = subprocess.run(["c++filt"], input="\n".join(funcs), capture_output=True, text=True, check=True).stdout.splitlines()
+    out = {}
+    for n, h in zip(names, funcs.values()):
+        n = n.split("(")[0].replace("void ", "")
+        if any(k in n for k in OPT_IN):
+            continue
+        m = re.match(r"(.*)<(.*)>$", n)
+        if m:
+            args = [a.strip() for a in m.group(2).split(",")]
+            if "conv1d_tc_kernel" in n and len(args) == 4:      # <MODE, MT, KBG, PDLM>: keep PDLM = 0 only
+                if args[-1] != "0":
+                    continue
+                args = args[:-1]
+            elif args[-1] == "true":                             # <..., bool PDL>
+                continue
+            elif args[-1] == "false":
+                args = args[:-1]
+            n = m.group(1) + ("<" + ", ".join(args) + ">" if args else "")
+        out[n] = h
+    return dict(sorted(out.items()))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--write", default="")
+    ap.add_argument("--lib", default=LIB)
+    a = ap.parse_args()
+    h = kernel_hashes(a.lib)
+    if a.write:
+        with open(a.write, "w") as f:
+            json.dump(h, f, indent=1)
+        print("wrote %d kernel hashes to %s" % (len(h), a.write))
+    else:
+        json.dump(h, sys.stdout, indent=1)
+
+
+if __name__ == "__main__":
+    main()
