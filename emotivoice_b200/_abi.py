@@ -71,7 +71,7 @@ SIGNATURES = {
     "ev_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ev_op_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ev_op_gauss_upsample": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "ev_style_create": (_i, [ctypes.POINTER(_vp), _i, _vp]),
+    "ev_style_create": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(EvStyleConfig)]),
     "ev_style_destroy": (None, [_vp]),
     "ev_style_bind_weights": (_i, [_vp, _vp, _sz, _vp, _i]),
     "ev_style_set_precision": (_i, [_vp, _i]),
