@@ -243,9 +243,7 @@ def experiments(budget_s=360.0):
             ("fp32+pdl", ["--precision", "fp32"], {"EV_PDL": "1"}),
             ("fp32+pdl_all", ["--precision", "fp32"], {"EV_PDL": "2"}),
             ("fp32+autotune", ["--precision", "fp32"], {"EV_AUTOTUNE": "2"}),
-            ("fp32+pdl+autotune", ["--precision", "fp32"], {"EV_PDL": "1", "EV_AUTOTUNE": "1"}),
             ("fp32+fuse_res", ["--precision", "fp32"], {"EV_FUSE_RES": "1"}),
-            ("tf32+fuse_res", ["--precision", "tf32"], {"EV_FUSE_RES": "1"}),
             ("fp32+all", ["--precision", "fp32"], {"EV_PDL": "2", "EV_AUTOTUNE": "1", "EV_FUSE_RES": "1"})]
     res = {"note": "opt-in / secondary modes of the same B=1 workload, 10 timed steps each, separate processes; not part of value or e2e"}
     t_end = time.time() + budget_s
