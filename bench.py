@@ -236,7 +236,7 @@ def probe(args):
                       "gpu_launches_per_step": (_abi.launch_count() - l0) / len(ev), "parity": parity_vs_reference_fixture(out)}))
 
 
-def experiments(budget_s=360.0):
+def experiments(budget_s=300.0):
     """Opt-in modes measured AFTER the headline numbers are final, each in its own process under a timeout, so a failure
     or a hang in an experimental path cannot touch `value` / `e2e`.  Reported under "experiments"; never part of them."""
     runs = [("tf32", ["--precision", "tf32"], {}), ("bf16", ["--precision", "bf16"], {}),
@@ -266,7 +266,7 @@ def experiments(budget_s=360.0):
         return d
 
     for name, flags, env in runs:
-        res[name] = child([sys.executable, os.path.abspath(__file__), "--probe"] + flags, env, 120)
+        res[name] = child([sys.executable, os.path.abspath(__file__), "--probe"] + flags, env, 90)
     res["style_encoder"] = child([sys.executable, os.path.join(ROOT, "tools", "style_bench.py"), "--steps", "20"], {}, 150)
     return res
 
