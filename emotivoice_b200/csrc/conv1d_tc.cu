@@ -52,7 +52,7 @@ struct Plan {
 };
 
 // smem map: [0,288) barriers | [512,516) tmem base | 1024: epilogue staging (8 warps x 4 KB) | A ring | B ring
-__host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN, int mt, int kbg, int min_b_stages, Plan* o) {
+__host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN, int mt, int kbg, int min_b_stages, Plan* o, int b_target = 4) {
   Plan q;
   q.planes = mode == 1 ? 2 : 1;
   const int cpg = mode == 2 ? 8 : 4;      // channels per 16-byte granule (bf16 : tf32)
@@ -77,7 +77,7 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN,
   q.a_stages = 2;
   q.b_stages = 2;
   while (q.b_stages < MAX_B_STAGES && q.b_stages < n_cb * p.K &&
-         q.a_stages * q.a_stage_bytes + (q.b_stages + 1) * q.b_stage_bytes <= budget && q.b_stages < 4) ++q.b_stages;
+         q.a_stages * q.a_stage_bytes + (q.b_stages + 1) * q.b_stage_bytes <= budget && q.b_stages < b_target) ++q.b_stages;
   while (q.a_stages < MAX_A_STAGES && q.a_stages < n_cb &&
          (q.a_stages + 1) * q.a_stage_bytes + q.b_stages * q.b_stage_bytes <= budget && q.a_stages < 6) ++q.a_stages;
   while (q.b_stages < MAX_B_STAGES && q.b_stages < n_cb * p.K &&
@@ -596,10 +596,11 @@ static int apply_ksplit(const ConvParams& p, int mode, tc::Plan* pl) {
 }
 
 // Plan with a prescribed tile shape (the autotuner's candidates): false if it does not fit.
-static bool plan_with_shape(const ConvParams& p, int mode, int BN, int mt, tc::Plan* out) {
+// b_target: depth the weight ring reaches before the activation ring grows (4 = the default split; 8 = weight-stream heavy)
+static bool plan_with_shape(const ConvParams& p, int mode, int BN, int mt, int b_target, tc::Plan* out) {
   const int kbg = tc_shape_kbg(p, mode);
   tc::Plan pl;
-  if (!tc::make_plan(p, mode, BN, mt, kbg, 4, &pl) && !tc::make_plan(p, mode, BN, mt, kbg, 2, &pl)) return false;
+  if (!tc::make_plan(p, mode, BN, mt, kbg, 4, &pl, b_target) && !tc::make_plan(p, mode, BN, mt, kbg, 2, &pl, b_target)) return false;
   if (apply_ksplit(p, mode, &pl) != EV_OK) return false;
   *out = pl;
   return true;
@@ -659,7 +660,8 @@ static int dispatch_tc(const ConvParams& p, int mode, const tc::Plan& pl, cudaSt
 namespace {
 typedef std::tuple<int, int, int, int, int, int, int, int> TuneKey;     // mode, Cin, Cout, K, dil, ksplit, has_lens, bucket
 std::mutex g_tune_mu;
-std::map<TuneKey, std::pair<int, int>> g_tuned;                          // -> (BN, mt); (0, 0) = keep the default plan
+struct TuneChoice { int BN = 0, mt = 0, b_target = 4; };                    // BN == 0: keep the default plan
+std::map<TuneKey, TuneChoice> g_tuned;
 
 int tile_bucket(long long tiles128) {      // half-octave buckets: 1,2,3,4,6,8,12,16,24,...
   int b = 0;
@@ -679,8 +681,8 @@ float time_plan(const ConvParams& q, int mode, const tc::Plan& pl, cudaStream_t 
   return ms;
 }
 
-std::pair<int, int> tune(const ConvParams& p, int mode, const tc::Plan& dflt, cudaStream_t st, int verbose) {
-  std::pair<int, int> best(0, 0);
+TuneChoice tune(const ConvParams& p, int mode, const tc::Plan& dflt, cudaStream_t st, int verbose) {
+  TuneChoice best;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   float* scratch = nullptr;
   ConvParams q = p;
@@ -697,17 +699,22 @@ std::pair<int, int> tune(const ConvParams& p, int mode, const tc::Plan& dflt, cu
     if (best_ms > 0.f) {
       const int bn_max = p.Cout <= 128 ? p.Cout : 128;
       for (int BN = bn_max; BN >= 32 && BN % 16 == 0; BN /= 2)
-        for (int mt = 1; mt <= 4; mt *= 2) {
-          if (BN == dflt.BN && mt == dflt.mt) continue;
-          if ((long long)tc::BM * (mt / 2) >= p.L && mt > 1) continue;          // more accumulators than rows
-          tc::Plan pl;
-          if (!plan_with_shape(p, mode, BN, mt, &pl)) continue;
-          const float ms = time_plan(q, mode, pl, st, e0, e1);
-          if (verbose) fprintf(stderr, " | BN %d MT %d %.1f", BN, mt, ms * 1000.f / 3.f);
-          if (ms > 0.f && ms < best_ms * 0.97f) { best_ms = ms; best = std::make_pair(BN, mt); }   // 3 % hysteresis for the default
-        }
+        for (int mt = 1; mt <= 4; mt *= 2)
+          for (int bt = 4; bt <= 8; bt += 4) {
+            if ((long long)tc::BM * (mt / 2) >= p.L && mt > 1) continue;          // more accumulators than rows
+            tc::Plan pl;
+            if (!plan_with_shape(p, mode, BN, mt, bt, &pl)) continue;
+            if (pl.BN == dflt.BN && pl.mt == dflt.mt && pl.a_stages == dflt.a_stages && pl.b_stages == dflt.b_stages) continue;
+            if (bt == 8 && pl.b_stages <= 4) continue;                             // same rings as the bt = 4 candidate
+            const float ms = time_plan(q, mode, pl, st, e0, e1);
+            if (verbose) fprintf(stderr, " | BN %d MT %d A%d B%d %.1f", BN, mt, pl.a_stages, pl.b_stages, ms * 1000.f / 3.f);
+            if (ms > 0.f && ms < best_ms * 0.97f) {      // 3 % hysteresis for the default
+              best_ms = ms;
+              best.BN = BN; best.mt = mt; best.b_target = bt;
+            }
+          }
     }
-    if (verbose) fprintf(stderr, " -> BN %d MT %d\n", best.first ? best.first : dflt.BN, best.first ? best.second : dflt.mt);
+    if (verbose) fprintf(stderr, " -> BN %d MT %d Btarget %d\n", best.BN ? best.BN : dflt.BN, best.BN ? best.mt : dflt.mt, best.b_target);
   }
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
@@ -726,7 +733,7 @@ int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st) {
   if (autotune) {
     const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
     const TuneKey key(mode, p.Cin, p.Cout, p.K, p.dil, pl.ksplit, p.lens ? 1 : 0, tile_bucket(tiles128));
-    std::pair<int, int> choice;
+    TuneChoice choice;
     {
       std::lock_guard<std::mutex> lock(g_tune_mu);
       auto it = g_tuned.find(key);
@@ -734,7 +741,7 @@ int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st) {
       choice = it->second;
     }
     tc::Plan tuned;
-    if (choice.first && plan_with_shape(p, mode, choice.first, choice.second, &tuned)) pl = tuned;
+    if (choice.BN && plan_with_shape(p, mode, choice.BN, choice.mt, choice.b_target, &tuned)) pl = tuned;
   }
   const size_t per = (size_t)p.B * p.L * p.Cout;
   const int rc = dispatch_tc(p, mode, pl, st, pdl_mode());      // EV_PDL: opt-in until it has been measured on hardware
