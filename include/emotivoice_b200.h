@@ -239,6 +239,18 @@ EV_API size_t ev_style_workspace_bytes(const ev_style_ctx* ctx, int B, int N);
 EV_API int ev_style_forward(ev_style_ctx* ctx, const int64_t* ids, const int64_t* type_ids, const int64_t* lens, int B, int N,
                             float* pooled, float* heads, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training-mode alignment helpers (not used by any inference path) --------------------------------
+ * viterbi_decode (alignment.py:124-142): monotonic alignment search per item on log_p_attn (B, T_mel, T_inp) float32 restricted
+ * to [:feats_lens[b], :text_lens[b]].  path (B, T_mel) int32 (token per frame, -1 past the item), durations (B, T_inp) float32
+ * = bincount(path), bin_loss (B) = -mean_j log_p[j, path[j]] per item (the reference averages them over B).
+ * Bit-exact paths / durations vs the reference's numba loop (float64 scores, float32 row-0 sums, ties -> smaller index).
+ * workspace: B*T_mel*T_inp bytes. */
+EV_API int ev_op_mas(const float* log_p_attn, const int64_t* text_lens, const int64_t* feats_lens, int B, int T_mel, int T_inp,
+                     int32_t* path, float* durations, float* bin_loss, uint8_t* workspace, size_t workspace_bytes, void* stream);
+/* average_by_duration (alignment.py:145-177): out (B, T_inp) = per-token mean of xs (B, T_mel) over the token's frames. */
+EV_API int ev_op_average_by_duration(const float* durations, const float* xs, const int64_t* text_lens, const int64_t* feats_lens,
+                                     int B, int T_mel, int T_inp, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

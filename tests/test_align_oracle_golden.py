@@ -1,0 +1,23 @@
+"""Pins oracle/align_oracle.py (monotonic alignment search, durations, bin loss, per-token averaging: SURVEY.md s8f rank 4)
+against fixtures generated from the reference's own numba functions (alignment.py:90-177) by oracle/make_golden_align.py.
+Paths and durations are integers: bit-exact.  bin_loss / averages are float32 means: 1e-6."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import align_oracle as AO
+
+
+@pytest.mark.parametrize("name", ["align_b3", "align_b2_ties", "align_b4_long"])
+def test_alignment_oracle_matches_reference_fixture(name):
+    g = {k: v.numpy() for k, v in load_golden(name).items()}
+    tt, tf = g["text_lengths"].tolist(), g["feats_lengths"].tolist()
+    ds, bl = AO.viterbi_decode(g["log_p_attn"], tt, tf)
+    assert np.array_equal(ds, g["durations"])
+    assert abs(float(bl) - float(g["bin_loss"])) <= 1e-6 * abs(float(g["bin_loss"]))
+    for b in range(len(tt)):
+        path = AO.monotonic_alignment_search(g["log_p_attn"][b, :tf[b], :tt[b]])
+        assert np.array_equal(path, g["paths"][b, :tf[b]])
+        assert path[0] == 0 and path[-1] == tt[b] - 1 and (np.diff(path) >= 0).all() and (np.diff(path) <= 1).all()      # monotonic, surjective
+        assert ds[b].sum() == tf[b]
+    assert np.abs(AO.average_by_duration(ds, g["xs"], tt, tf) - g["averaged"]).max() <= 1e-6

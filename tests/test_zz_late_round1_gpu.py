@@ -249,3 +249,20 @@ def test_resblock_pair_is_bitwise_the_two_launch_path(lib, dev, B, L, C, K, dil,
     torch.cuda.synchronize()
     assert torch.isfinite(ref).all()
     assert torch.equal(out, ref)
+
+
+# ---- training-mode alignment helpers: integer outputs bit-exact vs the reference's numba loops -----
+
+@pytest.mark.parametrize("name", ["align_b3", "align_b2_ties", "align_b4_long"])
+def test_alignment_helpers_match_reference_fixture(lib, dev, name):
+    from emotivoice_b200 import align
+    g = load_golden(name)
+    ds, bin_loss, path = align.viterbi_decode(g["log_p_attn"].to(dev), g["text_lengths"].to(dev), g["feats_lengths"].to(dev), return_path=True)
+    torch.cuda.synchronize()
+    assert torch.equal(path.cpu(), g["paths"])                         # monotonic alignment search: bit-exact (ties included)
+    assert torch.equal(ds.cpu(), g["durations"])
+    assert abs(float(bin_loss) - float(g["bin_loss"])) <= 1e-6 * abs(float(g["bin_loss"]))
+    avg = align.average_by_duration(ds, g["xs"].to(dev), g["text_lengths"].to(dev), g["feats_lengths"].to(dev))
+    assert (avg.cpu() - g["averaged"]).abs().max() <= 1e-6
+    with pytest.raises(RuntimeError):
+        align.viterbi_decode(g["log_p_attn"], g["text_lengths"], g["feats_lengths"])      # CPU tensors: no CPU path

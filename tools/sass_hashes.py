@@ -18,7 +18,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "emotivoice_b200", "lib", "libemotivoice_b200.so")
-OPT_IN = ("resblock_pair_kernel", "bert_embed_ln_kernel", "row_gemv_kernel")      # kernels no default code path launches
+OPT_IN = ("resblock_pair_kernel", "bert_embed_ln_kernel", "row_gemv_kernel", "mas_kernel", "avg_by_duration_kernel")      # kernels no default code path launches
 
 
 def kernel_hashes(path=LIB):
