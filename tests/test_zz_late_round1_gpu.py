@@ -106,9 +106,9 @@ np.savez(sys.argv[3], **res)
 """
 
 
-@pytest.mark.parametrize("knobs", [{"EV_PDL": "1"}, {"EV_PDL": "2"}, {"EV_AUTOTUNE": "2"}, {"EV_PDL": "1", "EV_AUTOTUNE": "1"},
-                                   {"EV_FUSE_RES": "1"}, {"EV_PDL": "2", "EV_AUTOTUNE": "1", "EV_FUSE_RES": "1"}],
-                         ids=["pdl", "pdl_all", "autotune", "pdl+autotune", "fuse_res", "all"])
+@pytest.mark.parametrize("knobs", [{"EV_PDL": "1"}, {"EV_PDL": "2"}, {"EV_AUTOTUNE": "2"}, {"EV_FUSE_RES": "1"},
+                                   {"EV_PDL": "2", "EV_AUTOTUNE": "1", "EV_FUSE_RES": "1"}],
+                         ids=["pdl", "pdl_all", "autotune", "fuse_res", "all"])
 def test_opt_in_launch_modes_are_bitwise_identical(model, dev, tmp_path, knobs):
     """EV_PDL=1 launches the tensor-core convolutions with programmatic stream serialization (set-up and weight prefetch
     of launch n+1 overlap the tail of launch n), EV_PDL=2 every kernel of the engine; EV_AUTOTUNE=1 picks each layer's N-tile width / accumulators per tile by
