@@ -28,7 +28,7 @@ EV_FUSE_RES=1 timeout 400 python tools/sweep.py --quick --precisions fp32,tf32,b
 step "5. launch list of one B=1 step, default vs EV_FUSE_RES=1 (ncu, per-launch durations)"
 for mode in default fuse; do
   if [ "$mode" = fuse ]; then export EV_FUSE_RES=1; else unset EV_FUSE_RES; fi
-  timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file "$OUT/launches_$mode.csv" \
+  timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file "$OUT/launches_$mode.csv" \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-experiments > "$OUT/ncu_$mode.log" 2>&1
   echo "ncu $mode exit $?" | tee -a "$OUT/checklist.log"
 done
