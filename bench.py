@@ -219,8 +219,28 @@ def probe(args):
     model.load_state_dict(synth.make_state_dict(conf))
     model.eval()
     model.precision = args.precision
-    batch = {k: v.to(dev) for k, v in synth.make_batch([N_PHONEMES], seed=synth.SEED).items()}
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    if args.probe_workload == "voc":
+        # cfg4 point (BASELINE.json configs[3]): vocoder only, batch 8 x 1024 frames; layer-granular traffic accounting of SURVEY s8d
+        B, F = 8, 1024
+        mel = synth.make_mel(B, F, seed=B * 7 + F).to(dev)
+        for _ in range(2):
+            model.generator(mel)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b in ev:
+            flush_buf.zero_()
+            a.record()
+            model.generator(mel)
+            b.record()
+        torch.cuda.synchronize()
+        sec = sum(a.elapsed_time(b) for a, b in ev) / len(ev) * 1e-3
+        peaks = _peaks()
+        print(json.dumps({"workload": "vocoder only, B=8, F=1024", "ms_per_step": sec * 1e3, "mel_frames_per_sec": B * F / sec,
+                          "tflops_algorithmic": B * F * 614105088.0 / sec / 1e12, "gbs_layer_granular": B * F * 5010752.0 / sec / 1e9,
+                          "frac_hbm_layer_granular": B * F * 5010752.0 / sec / 1e9 / peaks["hbm_gbs"]}))
+        return
+    batch = {k: v.to(dev) for k, v in synth.make_batch([N_PHONEMES], seed=synth.SEED).items()}
     for _ in range(3):
         out = model(**batch)
     torch.cuda.synchronize()
@@ -236,7 +256,7 @@ def probe(args):
                       "gpu_launches_per_step": (_abi.launch_count() - l0) / len(ev), "parity": parity_vs_reference_fixture(out)}))
 
 
-def experiments(budget_s=300.0):
+def experiments(budget_s=330.0):
     """Opt-in modes measured AFTER the headline numbers are final, each in its own process under a timeout, so a failure
     or a hang in an experimental path cannot touch `value` / `e2e`.  Reported under "experiments"; never part of them."""
     runs = [("tf32", ["--precision", "tf32"], {}), ("bf16", ["--precision", "bf16"], {}),
@@ -267,6 +287,9 @@ def experiments(budget_s=300.0):
 
     for name, flags, env in runs:
         res[name] = child([sys.executable, os.path.abspath(__file__), "--probe"] + flags, env, 90)
+    for name, prec, env in (("voc_b8_f1024_fp32", "fp32", {}), ("voc_b8_f1024_fp32+fuse_res", "fp32", {"EV_FUSE_RES": "1"}),
+                            ("voc_b8_f1024_tf32", "tf32", {}), ("voc_b8_f1024_tf32+fuse_res", "tf32", {"EV_FUSE_RES": "1"})):
+        res[name] = child([sys.executable, os.path.abspath(__file__), "--probe", "--probe-workload", "voc", "--precision", prec], env, 90)
     res["style_encoder"] = child([sys.executable, os.path.join(ROOT, "tools", "style_bench.py"), "--steps", "20"], {}, 150)
     return res
 
@@ -354,6 +377,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default=os.environ.get("EV_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16", "fp32_ffma"])
     ap.add_argument("--probe", action="store_true", help="internal: short child measurement for the experiments block")
+    ap.add_argument("--probe-workload", default="b1", choices=["b1", "voc"])
     ap.add_argument("--no-experiments", action="store_true", help="skip the opt-in-mode block measured after the headline")
     args = ap.parse_args()
     if args.probe:
