@@ -26,6 +26,13 @@ void set_error(const char* fmt, ...) {
   g_err = buf;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+static thread_local cudaError_t g_parked_launch_error = cudaSuccess;
+void park_launch_error(cudaError_t e) { if (e != cudaSuccess) g_parked_launch_error = e; }
+cudaError_t take_launch_error() {
+  const cudaError_t e = g_parked_launch_error;
+  g_parked_launch_error = cudaSuccess;
+  return e;
+}
 int pdl_mode() {
   static const int v = [] { const char* e = getenv("EV_PDL"); return (e && *e) ? atoi(e) : 0; }();
   return v;

@@ -11,6 +11,9 @@ namespace ev {
 // thread-local error string behind ev_last_error()
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// an error returned by cudaLaunchKernelEx (opt-in launch modes) is parked here and picked up by EV_CUDA_LAUNCH_CHECK
+void park_launch_error(cudaError_t e);
+cudaError_t take_launch_error();
 
 #define EV_CHECK_ARG(cond, ...)                      \
   do {                                               \
@@ -23,6 +26,7 @@ void count_launch(int n = 1);
 #define EV_CUDA_LAUNCH_CHECK(what)                                                        \
   do {                                                                                    \
     cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ == cudaSuccess) e__ = ev::take_launch_error();                                \
     if (e__ != cudaSuccess) {                                                             \
       ev::set_error("%s: %s", what, cudaGetErrorString(e__));                             \
       return EV_ECUDA;                                                                    \
@@ -70,7 +74,7 @@ inline cudaError_t launch_with_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 blo
 template <typename K, typename... Args>
 inline void launch_k(K with_pdl, K plain, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   if (pdl_mode() >= 2) {
-    (void)launch_with_pdl(with_pdl, grid, block, smem, st, args...);
+    park_launch_error(launch_with_pdl(with_pdl, grid, block, smem, st, args...));
   } else {
     plain<<<grid, block, smem, st>>>(args...);
   }
