@@ -33,4 +33,11 @@ for mode in default fuse; do
   echo "ncu $mode exit $?" | tee -a "$OUT/checklist.log"
 done
 unset EV_FUSE_RES
+
+step "6. fused ResBlock layer vs the two launches, per vocoder stage shape of the bench utterance (and at batch 8)"
+for args in "fp32 32 3 1 137472" "fp32 32 11 5 137472" "fp32 64 7 3 68736" "fp32 64 11 5 68736" "tf32 128 11 5 34368" "tf32 64 7 3 68736" \
+            "bf16 32 11 5 137472" "fp32 32 11 5 137472 8" "fp32 64 7 3 68736 8" "tf32 128 7 3 34368 8"; do
+  timeout 120 python tools/profile_resblock.py $args >> "$OUT/resblock_pairs.jsonl" 2>> "$OUT/resblock_pairs.err"; echo "$args -> exit $?" | tee -a "$OUT/checklist.log"
+done
+tail -12 "$OUT/resblock_pairs.jsonl" | tee -a "$OUT/checklist.log"
 step "done"
