@@ -10,9 +10,20 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "ev_common.cuh"
 
 namespace ev {
+
+// NVTX range per stage of the path (the reference has no tracing at all).  Costs nothing without a tool attached;
+// with one, `ncu --nvtx --nvtx-include "voc:stage1/"` selects the kernels of a stage.  Popped on every return path.
+struct Range {
+  explicit Range(const char* name) { nvtxRangePushA(name); }
+  ~Range() { nvtxRangePop(); }
+  Range(const Range&) = delete;
+  Range& operator=(const Range&) = delete;
+};
 
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
@@ -612,6 +623,7 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   // the duration-critical prefix is fp32-accurate in every mode: 3xTF32 on the tensor cores, or FFMA
   const int prefix_mode = (ctx->precision == EV_PREC_FP32_FFMA) ? 0 : 3;
 
+  Range r_phase("ev:am_phase1");
   // encoder: x = word_emb[ids] + alpha*pe (model_open_source.py:107, encoder.py:257-261), fused with LN1 of layer 0
   EV_TRY(launch_layernorm(nullptr, ling, ctx->emb_word, ctx->pe, ctx->enc.alpha, b.x, ctx->enc.layers[0].ln1w,
                           ctx->enc.layers[0].ln1b, b.y, B * T, T, H, st));
@@ -666,6 +678,7 @@ int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens,
   if (cv.off > workspace_bytes) { set_error("ev_am_phase2: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
   const int32_t* flens = invariant ? mel_lens : nullptr;
   g_split_ws.p = b.part; g_split_ws.cap = b.part_cap; g_split_ws.ksplit = 2;
+  Range r_phase("ev:am_phase2");
   // length regulator + the decoder's positional encoding (alignment.py:198-211, encoder.py:257-261)
   EV_TRY(launch_gauss_upsample(b1.hs, b1.centers, lens, mel_lens, B, T, H, F, invariant, ctx->pe, ctx->dec.alpha, b.x, st));
   // decoder (model_open_source.py:146: mask None in the reference; per-item lengths under the invariant contract)
@@ -695,6 +708,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
     EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm[0], B, g.n_mels, F, st));
     m = v.Tm[0];
   }
+  Range r_phase("ev:vocoder");
   // conv_pre (hifigan/models.py:116)
   const int mode = body_mode(ctx);
   EV_TRY(conv_x(mode, ctx->pre.w_tc, ctx->pre.w_h, m, ctx->pre.w, ctx->pre.b, 0, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1,
@@ -706,7 +720,10 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   EventPool pool;
   int L = F, mul = 1;
   size_t rb = 0;
+  static const char* const kStageNames[8] = {"voc:stage1", "voc:stage2", "voc:stage3", "voc:stage4", "voc:stage5", "voc:stage6",
+                                             "voc:stage7", "voc:stage8"};
   for (int s = 0; s < g.n_ups; ++s) {
+    Range r_stage(kStageNames[s & 7]);
     const UpW& u = ctx->ups[s];
     g_split_ws.ksplit = 0;
     // x = ups[i](leaky_relu(x, 0.1)) (:118-119): polyphase-packed transposed conv, output viewed (L, rate*Cout)

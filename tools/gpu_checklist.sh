@@ -40,4 +40,9 @@ for args in "fp32 32 3 1 137472" "fp32 32 11 5 137472" "fp32 64 7 3 68736" "fp32
   timeout 120 python tools/profile_resblock.py $args >> "$OUT/resblock_pairs.jsonl" 2>> "$OUT/resblock_pairs.err"; echo "$args -> exit $?" | tee -a "$OUT/checklist.log"
 done
 tail -12 "$OUT/resblock_pairs.jsonl" | tee -a "$OUT/checklist.log"
+step "7. compute-sanitizer (memcheck) over the operator tests and one small forward (slow; bounded)"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_ops_gpu.py -m gpu -x -q > "$OUT/sanitizer_ops.log" 2>&1
+echo "memcheck ops exit $?" | tee -a "$OUT/checklist.log"; tail -5 "$OUT/sanitizer_ops.log" | tee -a "$OUT/checklist.log"
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/sanitizer_smoke.log" 2>&1
+echo "memcheck smoke exit $?" | tee -a "$OUT/checklist.log"; tail -5 "$OUT/sanitizer_smoke.log" | tee -a "$OUT/checklist.log"
 step "done"
