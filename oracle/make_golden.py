@@ -79,6 +79,28 @@ def main():
     np.savez_compressed(os.path.join(out_dir, name + ".npz"), mel=mel.numpy(), wav=w.numpy())
     meta["cases"][name] = dict(batch=B, frames=Fr, seed=synth.SEED + 7, wav_absmax=float(w.abs().max()))
     print(name, "oracle==reference OK")
+    # length regulator edge cases (GaussianUpsampling.forward, alignment.py:180-211), the reference module itself
+    if refshim.REF_ROOT not in sys.path:
+        sys.path.insert(0, refshim.REF_ROOT)
+    from models.prompt_tts_modified.modules.alignment import GaussianUpsampling
+    up = GaussianUpsampling()
+    g = torch.Generator().manual_seed(99)
+    hs = torch.randn(3, 6, 16, generator=g)
+    valid = torch.tensor([[1, 1, 1, 1, 1, 1], [1, 1, 1, 0, 0, 0], [1, 0, 0, 0, 0, 0]], dtype=torch.bool)
+    edge = {
+        "all_zero": torch.zeros(3, 6, dtype=torch.int64),                                   # :187-191 -> every token gets 1 (pads included)
+        "zero_tokens": torch.tensor([[0, 3, 0, 2, 0, 1], [2, 0, 0, 0, 0, 0], [4, 0, 0, 0, 0, 0]]),   # zero-duration tokens still get weight
+        "one_item_zero": torch.tensor([[1, 2, 1, 1, 2, 1], [0, 0, 0, 0, 0, 0], [3, 0, 0, 0, 0, 0]]),  # batch sum != 0: the guard does NOT fire
+    }
+    arrays = {"hs": hs.numpy(), "valid": valid.numpy()}
+    for name, ds in edge.items():
+        with torch.no_grad():
+            want = up(hs.clone(), ds.clone(), None, valid)
+        got, mel_lens = O.gaussian_upsampling(hs.clone(), ds.clone(), valid)
+        assert want.shape == got.shape and torch.equal(torch.nan_to_num(want, nan=7.0), torch.nan_to_num(got, nan=7.0)), name
+        arrays["ds_" + name], arrays["out_" + name], arrays["mel_lens_" + name] = ds.numpy(), want.numpy(), mel_lens.numpy()
+        print("upsample edge", name, tuple(want.shape), "oracle==reference OK")
+    np.savez_compressed(os.path.join(out_dir, "upsample_edge.npz"), **arrays)
     with open(os.path.join(out_dir, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
 

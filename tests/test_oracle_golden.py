@@ -64,3 +64,15 @@ def test_padded_batch_is_not_batch_invariant_in_reference(sd, conf):
         diffs.append(rel_max(g["mel"][b, :Fb], r["dec_outputs"][0]))
     assert diffs[longest] < 1e-4
     assert max(d for i, d in enumerate(diffs) if i != longest) > 1e-3
+
+
+@pytest.mark.parametrize("case", ["all_zero", "zero_tokens", "one_item_zero"])
+def test_length_regulator_edge_cases_match_reference_fixture(case):
+    """GaussianUpsampling.forward (alignment.py:180-211) on the durations a bad predictor can emit: all zero (the batch-wide
+    guard of :187-191 turns every duration, pads included, into 1), zero-duration tokens (they still receive weight), and one
+    all-zero item inside a non-zero batch (the guard does not fire).  Fixture: the reference module itself (oracle/make_golden.py)."""
+    g = load_golden("upsample_edge")
+    out, mel_lens = O.gaussian_upsampling(g["hs"].clone(), g["ds_" + case].clone(), g["valid"])
+    assert torch.equal(mel_lens, g["mel_lens_" + case])
+    assert out.shape == g["out_" + case].shape
+    assert torch.equal(torch.nan_to_num(out, nan=7.0), torch.nan_to_num(g["out_" + case], nan=7.0))
