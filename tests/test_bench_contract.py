@@ -48,3 +48,26 @@ def test_reference_arm_runs_on_cpu_and_prints_one_json_line():
     assert d["impl"] == "reference" and d["steps"] == 1 and d["warmup"] == 1 and d["gpu_launches"] == 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_embedded_child_scripts_and_gpu_only_tools_compile():
+    """Scripts that only ever run on the GPU box (child processes of the late GPU tests, the profiling tools, the checklist)
+    must at least parse here: a syntax error there would cost a GPU call to find."""
+    import ast
+    import importlib.util
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("late_gpu_tests", os.path.join(root, "tests", "test_zz_late_round1_gpu.py"))
+    src = open(spec.origin).read()
+    tree = ast.parse(src)
+    children = [n for n in tree.body if isinstance(n, ast.Assign) and isinstance(n.value, ast.Constant) and isinstance(n.value.value, str)
+                and n.targets[0].id.endswith("_CHILD")]
+    assert len(children) >= 2
+    for n in children:
+        compile(n.value.value, n.targets[0].id, "exec")
+    for tool in sorted(os.listdir(os.path.join(root, "tools"))):
+        path = os.path.join(root, "tools", tool)
+        if tool.endswith(".py"):
+            ast.parse(open(path).read(), filename=tool)
+        elif tool.endswith(".sh"):
+            assert subprocess.run(["bash", "-n", path]).returncode == 0, tool
