@@ -71,3 +71,51 @@ def test_embedded_child_scripts_and_gpu_only_tools_compile():
             ast.parse(open(path).read(), filename=tool)
         elif tool.endswith(".sh"):
             assert subprocess.run(["bash", "-n", path]).returncode == 0, tool
+
+
+def _unbound_names(src, fname="<src>"):
+    import ast
+    import builtins
+    tree = ast.parse(src, fname)
+    bound = set(dir(builtins))
+    for n in ast.walk(tree):
+        if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef, ast.ClassDef)):
+            bound.add(n.name)
+            if not isinstance(n, ast.ClassDef):
+                a = n.args
+                for x in a.args + a.kwonlyargs + a.posonlyargs: bound.add(x.arg)
+                if a.vararg: bound.add(a.vararg.arg)
+                if a.kwarg: bound.add(a.kwarg.arg)
+        elif isinstance(n, ast.Lambda):
+            a = n.args
+            for x in a.args + a.kwonlyargs + a.posonlyargs: bound.add(x.arg)
+            if a.vararg: bound.add(a.vararg.arg)
+            if a.kwarg: bound.add(a.kwarg.arg)
+        elif isinstance(n, ast.Import):
+            for al in n.names: bound.add((al.asname or al.name).split(".")[0])
+        elif isinstance(n, ast.ImportFrom):
+            for al in n.names: bound.add(al.asname or al.name)
+        elif isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+            bound.add(n.id)
+        elif isinstance(n, ast.ExceptHandler) and n.name:
+            bound.add(n.name)
+        elif isinstance(n, ast.Global):
+            bound.update(n.names)
+    bad = sorted({n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id not in bound})
+    return bad
+
+
+def test_no_unbound_names_in_code_that_only_runs_on_the_gpu_box():
+    """A crude static scan (every loaded name must be bound somewhere in its module): catches typos in the tools, the child
+    scripts of the late GPU tests and the GPU-only branches of bench.py without a GPU."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    for d in ("tools", "emotivoice_b200", "tests"):
+        files += [os.path.join(root, d, f) for f in sorted(os.listdir(os.path.join(root, d))) if f.endswith(".py")]
+    for f in files:
+        assert [n for n in _unbound_names(open(f).read(), f) if n != "__file__"] == [], f
+    late = ast.parse(open(os.path.join(root, "tests", "test_zz_late_round1_gpu.py")).read())
+    for n in late.body:
+        if isinstance(n, ast.Assign) and isinstance(n.value, ast.Constant) and isinstance(n.value.value, str) and n.targets[0].id.endswith("_CHILD"):
+            assert _unbound_names(n.value.value) == [], n.targets[0].id
