@@ -1,24 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- mel-frames/s and RTF of JETSGenerator.forward (PromptTTS AM + HiFi-GAN).
+"""bench.py -- mel-frames/s and RTF of JETSGenerator.forward (PromptTTS AM + HiFi-GAN) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp32|tf32|bf16|fp32_ffma]
-                    [--no-experiments]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp32|tf32|bf16|fp32_ffma] [--lean]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU, NCCL)
 
-Workload (BASELINE.json configs[1], the configuration `metric` is quoted on): batch = 1,
-one 100-phoneme utterance (seed 1234 -> 537 mel frames = 8.6 s of 16 kHz audio), fp32,
-full acoustic model + vocoder, seeded synthetic weights of the released architecture.
-A "step" is one forward() over that batch.
+Headline workload (BASELINE.json configs[1], the configuration `metric` is quoted on): batch = 1, one 100-phoneme utterance
+per step, fp32, full acoustic model + vocoder, seeded synthetic weights of the released architecture.  The steps walk a
+seeded corpus of DISTINCT utterances (synth.corpus_utterance: utterance i is the same whatever the corpus size or world
+size) that runner.plan_shards deals over the ranks, so every rank synthesises different audio; there is no data-path
+collective, only the one-time NCCL weight broadcast (raw parameters + the packed blob rank 0 built).  Weak scaling: K steps
+per rank.
 
-* default arm: the engine (emotivoice_b200 -> libemotivoice_b200.so, sm_100a kernels).
-  `value` is measured with inputs resident in HBM; `e2e` with inputs in pinned host memory
-  (H2D inside the timed region) and the waveform read back to pinned host memory (D2H).
-* --impl reference: the reference's algorithm on the host CPU (oracle/jets_oracle.py, the
-  torch-CPU restatement pinned bit-exactly to the unmodified reference; the reference tree
-  itself is Python and does not travel to the GPU box), all host threads.
-At N=1, after the headline numbers are final, an "experiments" block re-measures the workload in the other precision modes
-and the opt-in modes (EV_PDL, EV_AUTOTUNE, EV_FUSE_RES) plus the style encoder, each in a separate process under a timeout.
-Under torchrun every rank runs the same per-GPU workload (weak scaling) after a one-time
-NCCL weight broadcast from rank 0; time = max over ranks (CUDA events).
+* `value`: mel-frames/s with each step's inputs already resident in HBM; per-step CUDA-event pairs on the launching stream,
+  L2 flushed (256 MiB write) between steps outside the pairs; whole job = sum of frames over ranks / max over ranks of time.
+* `e2e`: the same steps through the public API from HOST data: collate -> pinned host tensors -> H2D -> forward ->
+  fp32 waveform D2H into pinned memory, all inside the timed region (host preparation included: the start event is
+  recorded before it).
+* `b1`, `b32`, `voc`, `cfg5`: compact secondary measurements of the other BASELINE.json configurations, taken after the
+  headline numbers are final (each guarded: a failure there costs a sub-object, never the line):
+    b1   = configs[1] on the committed fixture utterance (latency, parity against the UNMODIFIED reference's output)
+    b32  = configs[2]: one batch of 32 mixed EN/ZH utterances, 20-200 phonemes, bf16 (and the headline precision)
+    voc  = configs[3]: vocoder-only points, layer-granular HBM fraction (SURVEY.md s8d accounting)
+    cfg5 = configs[4]: a fixed 256-utterance-per-GPU... see `cfg5_block` -- corpus sharded over the ranks in B=32
+           buckets, wall-clock end to end (pinned int16 D2H), with a digest that is identical for every world size iff
+           every utterance's PCM is bit-identical.
+* --impl reference: the reference's algorithm on the host CPU (oracle/jets_oracle.py, the torch-CPU restatement pinned
+  bit-exactly to the unmodified reference, which is Python and cannot travel to the GPU box), all usable host threads,
+  same corpus, same unit (B=1 per step as every reference caller runs), rank 0 only.
+
+The LAST stdout line is ONE compact JSON object (< 4 KB, checked by tests/test_bench_contract.py); everything longer goes
+to gpurun_out/bench_detail_n<N>.json and stderr.
 """
 import argparse
 import json
@@ -38,7 +49,14 @@ import torch  # noqa: E402
 
 N_PHONEMES = 100
 SR, HOP = 16000, 256
-WORKLOAD = "cfg2: batch=1, 100-phoneme utterance (seed 1234), fp32, PromptTTS AM + HiFi-GAN"
+WORKLOAD = ("cfg2: batch=1, one 100-phoneme utterance per step (distinct seeded utterances, LPT-sharded over ranks), fp32, "
+            "PromptTTS AM + HiFi-GAN")
+# identical on both arms (the driver compares it): everything arm-specific lives in `detail`
+CONFIG = {"workload": WORKLOAD, "batch": 1, "phonemes_per_utterance": N_PHONEMES, "corpus_seed": 1234,
+          "l2": "flushed between timed steps", "timing": "per-step CUDA events, max over ranks"}
+VOC_FLOP_PER_FRAME = 614105088.0
+VOC_BYTES_PER_FRAME = 5010752.0        # layer-granular fp32 activation traffic per mel frame
+MAX_LINE = 4096
 
 
 def _peaks():
@@ -49,6 +67,15 @@ def _peaks():
         return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
                     bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def _r(x, n=4):
+    """round to n significant digits (keeps the JSON line short)"""
+    if x is None or isinstance(x, (bool, int, str)):
+        return x
+    if x == 0 or not math.isfinite(x):
+        return x
+    return float("%.*g" % (n, x))
 
 
 class ClockSampler:
@@ -122,10 +149,9 @@ def usable_cpus():
 
 
 def pick_cpu_threads(sd, conf):
-    """The reference's own hint is `torch.set_num_threads(4)  # faster` (inference_tts.py:186):
-    more threads is not monotonically better for these small convolutions.  Calibrate on a short
-    vocoder-only sample and keep the fastest thread count <= the usable CPUs, so the CPU baseline
-    is the best the host can do, not an oversubscribed one."""
+    """The reference's own hint is `torch.set_num_threads(4)  # faster` (inference_tts.py:186): more threads is not
+    monotonically better for these small convolutions.  Calibrate on a short vocoder-only sample and keep the fastest
+    thread count <= the usable CPUs, so the CPU baseline is the best the host can do, not an oversubscribed one."""
     from emotivoice_b200 import synth
     from oracle import jets_oracle as O
     n = usable_cpus()
@@ -147,165 +173,117 @@ def pick_cpu_threads(sd, conf):
     return best, n, log
 
 
-def cpu_reference_run(steps, warmup):
-    """The reference's algorithm on the host CPU (oracle port), best thread count <= usable CPUs."""
+def cpu_reference_run(steps, warmup, first_index=0):
+    """The reference's algorithm on the host CPU (oracle port): `steps` utterances of the bench corpus, B=1 each (how every
+    reference caller runs), best thread count <= usable CPUs."""
     from emotivoice_b200.config import default_config
     from emotivoice_b200 import synth
     from oracle import jets_oracle as O
     conf = default_config()
     sd = synth.make_state_dict(conf)
     cores, usable, calib = pick_cpu_threads(sd, conf)
-    batch = synth.make_batch([N_PHONEMES], seed=synth.SEED)
-    frames = 0
-    for _ in range(max(1, warmup)):
-        frames = int(O.jets_forward(sd, conf, **batch)["dec_outputs"].shape[1])
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.jets_forward(sd, conf, **batch)
-    dt = (time.perf_counter() - t0) / steps
-    return dict(frames=frames, sec_per_step=dt, fps=frames / dt, cores=cores, usable=usable, calib=calib)
+    utt = lambda i: synth.collate_utterances([synth.corpus_utterance(i, n_phonemes=N_PHONEMES)])
+    for w in range(max(1, warmup)):
+        O.jets_forward(sd, conf, **utt(first_index + w))
+    frames, t = 0, 0.0
+    for s in range(steps):
+        batch = utt(first_index + warmup + s)
+        t0 = time.perf_counter()
+        out = O.jets_forward(sd, conf, **batch)
+        t += time.perf_counter() - t0
+        frames += int(out["dec_outputs"].shape[1])
+    return dict(frames=frames, seconds=t, fps=frames / t, cores=cores, usable=usable, calib=calib, steps=steps)
+
+
+def emit(line, detail=None, n_gpus=1):
+    """ONE compact JSON line on stdout (the driver parses the last line); the long form to gpurun_out/ and stderr."""
+    s = json.dumps(line, separators=(",", ":"))
+    if len(s) >= MAX_LINE:       # never let a secondary block cost the headline: drop the optional sub-objects, largest first
+        for k in sorted(("cfg5", "voc", "b32", "b1", "parity"), key=lambda k: -len(json.dumps(line.get(k, None)))):
+            if k in line:
+                line[k] = {"dropped": "line too long; see bench_detail"}
+                s = json.dumps(line, separators=(",", ":"))
+                if len(s) < MAX_LINE:
+                    break
+    if detail is not None:
+        try:
+            d = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, "bench_detail_n%d.json" % n_gpus), "w") as f:
+                json.dump({"line": line, "detail": detail}, f, indent=1)
+        except Exception:
+            pass
+        sys.stderr.write("[bench detail] " + json.dumps(detail) + "\n")
+        sys.stderr.flush()
+    sys.stdout.write(s + "\n")
+    sys.stdout.flush()
 
 
 def reference_arm(args, rank):
     if rank != 0:
         return
-    steps, warm = max(1, args.steps), max(1, args.warmup)   # ~1 s of host CPU work per step
+    steps, warm = max(1, args.steps), max(1, args.warmup)   # ~0.3 s of host CPU work per step
     r = cpu_reference_run(steps, warm)
     audio_s = r["frames"] * HOP / SR
     line = {
         "impl": "reference", "metric": "mel_frames_per_sec", "value": r["fps"], "unit": "mel-frames/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["sec_per_step"] * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["seconds"] / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames": r["frames"], "audio_seconds": audio_s, "device": "host CPU"},
-        "rtf": r["sec_per_step"] / audio_s, "x_realtime": audio_s / r["sec_per_step"],
+        "config": CONFIG,
+        "rtf": _r(r["seconds"] / audio_s), "x_realtime": _r(audio_s / r["seconds"]),
         "cpu_baseline": {"value": r["fps"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port",
-                         "sample": "%d full forward passes of the bench workload (oracle/jets_oracle.py, torch %s CPU, %d threads "
-                                   "= fastest of the calibration %s ms on a 48-frame vocoder sample; %d usable CPUs)"
-                                   % (steps, torch.__version__, r["cores"], json.dumps(r["calib"]), r["usable"])},
+                         "sample": "%d B=1 forwards over corpus utterances %d.. (oracle/jets_oracle.py, torch %s CPU, %d threads of %d usable)"
+                                   % (steps, warm, torch.__version__, r["cores"], r["usable"])},
         "e2e": {"value": r["fps"], "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "detail": {"device": "host CPU", "frames": r["frames"], "thread_calibration_ms": r["calib"]},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
-def parity_vs_reference_fixture(out):
-    """The bench workload is the committed fixture tests/golden/b1_t100.npz (inputs + outputs of the
-    UNMODIFIED reference, oracle/make_golden.py): report the engine's distance from it."""
+def parity_vs_fixture(model, dev):
+    """tests/golden/b1_t100.npz holds inputs + outputs of the UNMODIFIED reference (oracle/make_golden.py) for the cfg2
+    utterance: the engine's distance from it, with the tolerance this precision is held to."""
     import numpy as np
     path = os.path.join(ROOT, "tests", "golden", "b1_t100.npz")
     if not os.path.exists(path):
         return None
     z = np.load(path)
+    keys = ("inputs_ling", "input_lengths", "inputs_speaker", "inputs_style_embedding", "inputs_content_embedding")
+    out = model(**{k: torch.from_numpy(z[k]).to(dev) for k in keys})
     mel, wav, dur = torch.from_numpy(z["mel"]), torch.from_numpy(z["wav"]), torch.from_numpy(z["durations"])
     m, w = out["dec_outputs"].cpu(), out["wav_predictions"].cpu()
     ok = bool(torch.equal(out["log_duration_predictions"].cpu(), dur))
-    res = {"reference": "tests/golden/b1_t100.npz (unmodified reference, CPU fp32)", "durations_identical": ok}
+    res = {"vs": "reference fixture b1_t100", "dur_equal": ok}
     if ok and m.shape == mel.shape:
-        res["mel_max_abs_err_over_max_abs"] = float((m - mel).abs().max() / mel.abs().max())
-        res["wav_rms_err_over_rms"] = float((w - wav).double().pow(2).mean().sqrt() / wav.double().pow(2).mean().sqrt())
+        res["mel_relmax"] = _r(float((m - mel).abs().max() / mel.abs().max()), 3)
+        res["wav_relrms"] = _r(float((w - wav).double().pow(2).mean().sqrt() / wav.double().pow(2).mean().sqrt()), 3)
     return res
 
 
-def probe(args):
-    """Child mode of `experiments()`: a short B=1 measurement of the same workload (3 warm-up + 10 timed forwards, L2
-    flushed, CUDA events) in whatever mode the environment / --precision select; prints one small JSON object."""
-    import __graft_entry__  # noqa: F401
-    from emotivoice_b200.config import default_config
-    from emotivoice_b200 import synth, _abi
-    from emotivoice_b200.modules import JETSGenerator
-    dev = torch.device("cuda", 0)
-    conf = default_config()
-    model = JETSGenerator(conf).to(dev)
-    model.load_state_dict(synth.make_state_dict(conf))
-    model.eval()
-    model.precision = args.precision
-    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    if args.probe_workload == "voc":
-        # cfg4 point (BASELINE.json configs[3]): vocoder only, batch 8 x 1024 frames; layer-granular traffic accounting of SURVEY s8d
-        B, F = 8, 1024
-        mel = synth.make_mel(B, F, seed=B * 7 + F).to(dev)
-        for _ in range(2):
-            model.generator(mel)
-        torch.cuda.synchronize()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
-        for a, b in ev:
-            flush_buf.zero_()
-            a.record()
-            model.generator(mel)
-            b.record()
-        torch.cuda.synchronize()
-        sec = sum(a.elapsed_time(b) for a, b in ev) / len(ev) * 1e-3
-        peaks = _peaks()
-        print(json.dumps({"workload": "vocoder only, B=8, F=1024", "ms_per_step": sec * 1e3, "mel_frames_per_sec": B * F / sec,
-                          "tflops_algorithmic": B * F * 614105088.0 / sec / 1e12, "gbs_layer_granular": B * F * 5010752.0 / sec / 1e9,
-                          "frac_hbm_layer_granular": B * F * 5010752.0 / sec / 1e9 / peaks["hbm_gbs"]}))
-        return
-    batch = {k: v.to(dev) for k, v in synth.make_batch([N_PHONEMES], seed=synth.SEED).items()}
-    for _ in range(3):
-        out = model(**batch)
-    torch.cuda.synchronize()
-    l0 = _abi.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
-    for a, b in ev:
-        flush_buf.zero_()
+def timed_forwards(fn, n, flush):
+    """n x (flush; event; fn(i); event) -> list of seconds; synchronises once at the end."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    outs = []
+    for i, (a, b) in enumerate(ev):
+        flush()
         a.record()
-        out = model(**batch)
+        outs.append(fn(i))
         b.record()
     torch.cuda.synchronize()
-    print(json.dumps({"ms_per_step": sum(a.elapsed_time(b) for a, b in ev) / len(ev),
-                      "gpu_launches_per_step": (_abi.launch_count() - l0) / len(ev), "parity": parity_vs_reference_fixture(out)}))
-
-
-def experiments(budget_s=330.0):
-    """Opt-in modes measured AFTER the headline numbers are final, each in its own process under a timeout, so a failure
-    or a hang in an experimental path cannot touch `value` / `e2e`.  Reported under "experiments"; never part of them."""
-    runs = [("tf32", ["--precision", "tf32"], {}), ("bf16", ["--precision", "bf16"], {}),
-            ("fp32+pdl", ["--precision", "fp32"], {"EV_PDL": "1"}),
-            ("fp32+pdl_all", ["--precision", "fp32"], {"EV_PDL": "2"}),
-            ("fp32+autotune", ["--precision", "fp32"], {"EV_AUTOTUNE": "2"}),
-            ("fp32+fuse_res", ["--precision", "fp32"], {"EV_FUSE_RES": "1"}),
-            ("fp32+all", ["--precision", "fp32"], {"EV_PDL": "2", "EV_AUTOTUNE": "1", "EV_FUSE_RES": "1"})]
-    res = {"note": "opt-in / secondary modes of the same B=1 workload, 10 timed steps each, separate processes; not part of value or e2e"}
-    t_end = time.time() + budget_s
-
-    def child(cmd, env_extra, timeout):
-        left = t_end - time.time()
-        if left < 20:
-            return {"skipped": "time budget of the experiments block spent"}
-        try:
-            r = subprocess.run(cmd, env=dict(os.environ, **env_extra), capture_output=True, text=True, timeout=min(timeout, left))
-        except subprocess.TimeoutExpired:
-            return {"error": "timeout"}
-        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-        if r.returncode != 0 or not lines:
-            return {"error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-300:])}
-        d = json.loads(lines[-1])
-        tune = [ln[len("[ev autotune] "):] for ln in r.stderr.splitlines() if ln.startswith("[ev autotune]")]
-        if tune:
-            d["autotune_log"] = tune
-        return d
-
-    for name, flags, env in runs:
-        res[name] = child([sys.executable, os.path.abspath(__file__), "--probe"] + flags, env, 90)
-    for name, prec, env in (("voc_b8_f1024_fp32", "fp32", {}), ("voc_b8_f1024_fp32+fuse_res", "fp32", {"EV_FUSE_RES": "1"}),
-                            ("voc_b8_f1024_tf32", "tf32", {}), ("voc_b8_f1024_tf32+fuse_res", "tf32", {"EV_FUSE_RES": "1"})):
-        res[name] = child([sys.executable, os.path.abspath(__file__), "--probe", "--probe-workload", "voc", "--precision", prec], env, 90)
-    res["style_encoder"] = child([sys.executable, os.path.join(ROOT, "tools", "style_bench.py"), "--steps", "20"], {}, 150)
-    return res
+    return [a.elapsed_time(b) * 1e-3 for a, b in ev], outs
 
 
 def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
-    """conv1d_tm_kernel on the single most expensive layer shape of the step: the k=11
-    ResBlock convolutions of HiFi-GAN stage 2 (C=128, L=64*F; 22% of all FLOPs).  Timed live
-    with CUDA events on the launching stream, L2 flushed before every launch."""
-    from emotivoice_b200 import _abi
+    """The single most expensive layer shape of the step: the k=11 ResBlock convolutions of HiFi-GAN stage 2 (C=128,
+    L=64*F; 22% of all FLOPs).  Timed live with CUDA events on the launching stream, L2 flushed before every launch."""
+    from emotivoice_b200 import _abi, packing
     C, K, L = 128, 11, 64 * frames
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1, L, C, generator=g).to(dev)
     w = torch.randn(K, C, C, generator=g) / math.sqrt(C * K)
     use_tc = precision in ("fp32", "tf32", "bf16")
     if use_tc:
-        from emotivoice_b200 import packing
         w = packing.to_tc16_layout(w) if precision == "bf16" else packing.to_tc_layout(w)
     w = w.to(dev)
     split3 = {"fp32": 1, "tf32": 0, "bf16": 2}.get(precision, 0)
@@ -332,57 +310,132 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
     flops = 2.0 * L * C * C * K
     alg_bytes = 4.0 * (L * C * 3) + 4.0 * K * C * C
     achieved = flops / t / 1e12
-    ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-    if use_tc:
-        mma_mult = 3 if split3 == 1 else 1
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes/launch from the committed ncu --set full capture
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(precision, {}).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        return {
-            "kernel": "conv1d_tc_kernel<%s> (tcgen05 kind::tf32, %s; HiFi-GAN stage-2 ResBlock conv, C=128, k=11, L=%d)"
-                      % (split3, ("1xTF32", "3xTF32 fp32 emulation", "bf16 operands")[split3], L),
-            "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes/launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(precision, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    mma_mult = 3 if precision == "fp32" else 1
+    roof = {"bound": "tensor", "achieved": _r(achieved), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-            "peak_source": "%s bf16 burst (MEASURED_PEAKS.json). `achieved` counts ALGORITHMIC flops (2*L*Cin*Cout*k); the tensor "
-                           "pipe executes %dx that in tf32 MMAs at half the bf16 rate, so tensor-pipe occupancy ~ %d*frac"
-                           % (peaks["source"], mma_mult, 2 * mma_mult),
-            "tensor_pipe_frac_est": (1 if split3 == 2 else 2 * mma_mult) * achieved / peaks["bf16_tflops"],
-            "flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
-            "avg_launch_ms": t * 1e3, "hbm_gbs_at_algorithmic_bytes": alg_bytes / t / 1e9,
-            "hbm_frac_at_algorithmic_bytes": alg_bytes / t / 1e9 / peaks["hbm_gbs"],
-        }
-    return {
-        "kernel": "conv1d_tm_kernel<16,2,8> (HiFi-GAN stage-2 ResBlock conv, C=128, k=11, L=%d)" % L,
-        "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_tflops"], "traffic": None,
-        "peak_source": "%s bf16 burst (MEASURED_PEAKS.json)" % peaks["source"],
-        "note": "round-1 kernel is an fp32 FFMA implicit GEMM (exact fp32 parity path); against the fp32 FFMA "
-                "ceiling of 148 SMs x 128 lanes x 2 x 1.965 GHz = %.1f TFLOP/s it reaches frac_fp32_ffma" % ffma_peak,
-        "frac_fp32_ffma": achieved / ffma_peak,
-        "flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
-        "avg_launch_ms": t * 1e3, "hbm_gbs_at_algorithmic_bytes": alg_bytes / t / 1e9,
-    }
+            "kernel": "conv C=128 k=11 L=%d %s" % (L, precision), "ms": _r(t * 1e3),
+            "peak_is": "%s bf16 burst; tf32 MMAs run at half that rate and this mode executes %dx the algorithmic FLOPs" % (peaks["source"], mma_mult),
+            "frac_vs_tf32_executed": _r(2 * mma_mult * achieved / peaks["bf16_tflops"]) if precision in ("fp32", "tf32") else None,
+            "alg_gbs": _r(alg_bytes / t / 1e9)}
+    full = dict(roof, flops_per_launch=flops, algorithmic_bytes_per_launch=alg_bytes, times_ms=[x * 1e3 for x in times])
+    return roof, full
+
+
+def b32_block(model, dev, flush, headline_precision, conf, sd_cpu):
+    """BASELINE.json configs[2]: batch 32, mixed EN/ZH, 20-200 phonemes, bf16.  Device-timed; parity of 3 items against the
+    CPU oracle's B=1 fp32 runs (the batch-invariant contract: every item equals the reference's B=1 call)."""
+    from emotivoice_b200 import synth
+    utts = [synth.corpus_utterance(10_000 + i) for i in range(32)]
+    utts.sort(key=lambda u: -len(u["ids"]))
+    batch = {k: v.to(dev) for k, v in synth.collate_utterances(utts).items()}
+    res = {"phonemes": "U{20..200}, 16 EN + 16 ZH"}
+    for prec in ("bf16", headline_precision):
+        model.precision = prec
+        for _ in range(2):
+            out = model(**batch)
+        ts, outs = timed_forwards(lambda i: model(**batch), 5, flush)
+        out = outs[-1]
+        t = statistics.median(ts)
+        valid = int(out["mel_lengths_host"].sum())
+        padded = int(32 * out["dec_outputs"].shape[1])
+        res[prec] = {"ms": _r(t * 1e3), "valid_fps": _r(valid / t), "x_rt": _r(valid * HOP / SR / t)}
+        res["valid_frames"], res["padded_frames"] = valid, padded
+        if prec == "bf16":
+            from oracle import jets_oracle as O
+            errs, dur_ok = [], True
+            for b in (0, 15, 31):
+                ref = O.jets_forward(sd_cpu, conf, **synth.collate_utterances([utts[b]]))
+                Fb = int(ref["dec_outputs"].shape[1])
+                dur_ok = dur_ok and bool(torch.equal(out["log_duration_predictions"][b, :len(utts[b]["ids"])].cpu(), ref["log_duration_predictions"][0]))
+                if int(out["mel_lengths_host"][b]) == Fb:
+                    w, rw = out["wav_predictions"][b, 0, :Fb * HOP].cpu(), ref["wav_predictions"][0, 0]
+                    errs.append(float((w - rw).double().pow(2).mean().sqrt() / rw.double().pow(2).mean().sqrt()))
+            res["parity_bf16_vs_oracle_b1"] = {"items": 3, "dur_equal": dur_ok, "wav_relrms_max": _r(max(errs), 3) if errs else None, "tol": 2e-2}
+    model.precision = headline_precision
+    return res
+
+
+def voc_block(model, dev, flush, peaks, headline_precision, lean):
+    """BASELINE.json configs[3]: vocoder-only points with the layer-granular traffic accounting of SURVEY.md s8d."""
+    from emotivoice_b200 import synth
+    res = {}
+    points = [(8, 1024)] if lean else [(1, 1024), (8, 1024), (32, 1024)]
+    for prec in dict.fromkeys((headline_precision, "tf32", "bf16")):
+        model.precision = prec
+        for (B, F) in points:
+            mel = synth.make_mel(B, F, seed=B * 7 + F).to(dev)
+            model.generator(mel)
+            ts, _ = timed_forwards(lambda i: model.generator(mel), 3, flush)
+            t = statistics.median(ts)
+            res["%s_b%d_f%d" % (prec, B, F)] = {"ms": _r(t * 1e3), "fps": _r(B * F / t), "tflops": _r(B * F * VOC_FLOP_PER_FRAME / t / 1e12),
+                                               "hbm_frac": _r(B * F * VOC_BYTES_PER_FRAME / t / 1e9 / peaks["hbm_gbs"], 3)}
+            del mel
+    model.precision = headline_precision
+    res["hbm_frac_is"] = "5,010,752 B/frame (fp32 layer-granular) / time / %s GB/s" % peaks["hbm_gbs"]
+    return res
+
+
+def cfg5_block(model, dev, rank, world, dist, per_gpu=256, total_fixed=None):
+    """BASELINE.json configs[4] (offline batch over the GPUs), scaled to fit a bench run: the first `world * per_gpu`
+    utterances of the seeded 20-200-phoneme corpus (weak scaling; utterance i is the same at every world size), dealt to the
+    ranks by runner.plan_shards (LPT), synthesised in B=32 length buckets with pinned int16 D2H; wall clock per rank over
+    its whole shard (host collate, H2D, forward with its length sync, PCM conversion, D2H, trimming + hashing).
+    `digest_first` covers utterances 0..per_gpu-1, present at every world size: equal digests across N = bit-identical PCM."""
+    from emotivoice_b200 import synth, runner
+    n = total_fixed or world * per_gpu
+    lens = synth.corpus_lengths(n)
+    mine = runner.plan_shards(lens, world)[rank]
+    utts = {i: synth.corpus_utterance(i) for i in mine}
+    ulist = [utts.get(i) or {"ids": [0] * lens[i]} for i in range(n)]        # placeholders keep global indices
+    # warm-up: two buckets (allocator, pinned pools)
+    runner.synthesize_corpus(model, ulist, dev, batch_size=32, indices=mine[:64], keep_pcm=False)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    st = {}
+    t0 = time.perf_counter()
+    res = runner.synthesize_corpus(model, ulist, dev, batch_size=32, indices=mine, keep_pcm=False, stats=st)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    frames = sum(v[1] for v in res.values())
+    pairs = [(i, v[2]) for i, v in res.items() if i < per_gpu]
+    rec = dict(rank=rank, wall_s=wall, frames=frames, utts=len(res), pairs=pairs, stats=st)
+    if dist is not None:
+        allrec = [None] * world
+        dist.all_gather_object(allrec, rec)
+    else:
+        allrec = [rec]
+    if rank != 0:
+        return None, None
+    tmax = max(r["wall_s"] for r in allrec)
+    tot_frames = sum(r["frames"] for r in allrec)
+    tot_utts = sum(r["utts"] for r in allrec)
+    digest = runner.combine_digests([tuple(p) for r in allrec for p in r["pairs"]])
+    slow = max(allrec, key=lambda r: r["wall_s"])["stats"]
+    out = {"utts": tot_utts, "per_gpu": per_gpu, "batch": 32, "wall_s": _r(tmax), "utt_per_s": _r(tot_utts / tmax),
+           "fps": _r(tot_frames / tmax), "x_rt": _r(tot_frames * HOP / SR / tmax), "rank_wall_min_s": _r(min(r["wall_s"] for r in allrec)),
+           "host_collate_s": _r(slow["collate_s"], 3), "host_finish_s": _r(slow["finish_s"], 3),
+           "digest_first%d" % per_gpu: digest[:16]}
+    return out, allrec
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default=os.environ.get("EV_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16", "fp32_ffma"])
-    ap.add_argument("--probe", action="store_true", help="internal: short child measurement for the experiments block")
-    ap.add_argument("--probe-workload", default="b1", choices=["b1", "voc"])
-    ap.add_argument("--no-experiments", action="store_true", help="skip the opt-in-mode block measured after the headline")
+    ap.add_argument("--lean", action="store_true", help="headline + roofline + cpu_baseline only (no b32 / voc / cfg5 blocks)")
     args = ap.parse_args()
-    if args.probe:
-        probe(args)
-        return
     if args.impl == "engine":
         args.warmup = max(args.warmup, 3)
 
@@ -406,31 +459,42 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
-        dist.barrier()
+        dist.barrier()                              # also creates the communicator, so the broadcast below times the copy only
 
     from emotivoice_b200.config import default_config
     from emotivoice_b200 import synth, _abi, runner
     from emotivoice_b200.modules import JETSGenerator
 
     conf = default_config()
-    sd = synth.make_state_dict(conf) if rank == 0 else None
-    bcast_ms = None
+    sd_cpu = synth.make_state_dict(conf) if rank == 0 else None
+    t_setup0 = time.perf_counter()
+    model = JETSGenerator(conf).to(dev)
+    bcast = None
     if world > 1:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        sd = runner.broadcast_state_dict(sd, conf, dev, src=0)     # one-time NCCL weight broadcast
+        sd = runner.broadcast_state_dict(sd_cpu, conf, dev, src=0)     # raw parameters (213 MB), one NCCL broadcast
+        model.load_state_dict(sd)
         torch.cuda.synchronize()
-        bcast_ms = (time.perf_counter() - t0) * 1e3
-    model = JETSGenerator(conf).to(dev)
-    model.load_state_dict(sd)
+        t1 = time.perf_counter()
+        nbytes = runner.broadcast_engine(model, dev, src=0)            # rank 0 packs once; the packed blob, one NCCL broadcast
+        torch.cuda.synchronize()
+        bcast = {"raw_ms": _r((t1 - t0) * 1e3), "pack_and_blob_ms": _r((time.perf_counter() - t1) * 1e3), "blob_mb": _r(nbytes / 1e6)}
+    else:
+        model.load_state_dict(sd_cpu)
     model.eval()
     model.precision = args.precision
     lib = _abi.load()
+    setup_s = time.perf_counter() - t_setup0
 
-    batch_cpu = synth.make_batch([N_PHONEMES], seed=synth.SEED)
-    batch_dev = {k: v.to(dev) for k, v in batch_cpu.items()}
-    batch_pin = {k: v.pin_memory() for k, v in batch_cpu.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in batch_pin.values())
+    # ---- this rank's shard of the corpus ------------------------------------------------------------
+    n_steps = args.warmup + args.steps
+    total = world * n_steps
+    shard = runner.plan_shards(synth.corpus_lengths(total, n_phonemes=N_PHONEMES), world)[rank]
+    assert len(shard) == n_steps
+    utts = [synth.corpus_utterance(i, n_phonemes=N_PHONEMES) for i in shard]
+    dev_batches = [{k: v.to(dev) for k, v in synth.collate_utterances([u]).items()} for u in utts]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in dev_batches[0].values())
 
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
 
@@ -443,15 +507,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up -----------------------------------------------------------------------
-    out = None
-    for _ in range(args.warmup):
-        out = model(**batch_dev)
+    for s in range(args.warmup):
+        out = model(**dev_batches[s])
     torch.cuda.synchronize()
-    parity = parity_vs_reference_fixture(out) if rank == 0 else None
-    frames = int(out["dec_outputs"].shape[1])
-    n_samples = int(out["wav_predictions"].shape[-1])
-    wav_pin = torch.empty((1, 1, n_samples), dtype=torch.float32).pin_memory()
-    audio_s = frames * HOP / SR
+    parity = parity_vs_fixture(model, dev) if rank == 0 else None
 
     # ---- timed: inputs resident in HBM -------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -459,93 +518,131 @@ def main():
         sampler.start()
     barrier()
     l0 = _abi.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush()
-        ev[s][0].record()
-        out = model(**batch_dev)
-        ev[s][1].record()
+    ts, outs = timed_forwards(lambda s: model(**dev_batches[args.warmup + s]), args.steps, flush)
     barrier()
     wall = time.perf_counter() - wall0
     launches = _abi.launch_count() - l0
-    dev_s = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    dev_s = sum(ts)
+    frames = sum(int(o["dec_outputs"].shape[1]) for o in outs)
+    n_samples = sum(int(o["wav_predictions"].shape[-1]) for o in outs)
+    del outs
 
-    # ---- timed: end to end (pinned host inputs -> device, waveform -> pinned host) -------------------
-    for _ in range(2):
-        o = model(**{k: v.to(dev, non_blocking=True) for k, v in batch_pin.items()})
-        wav_pin.copy_(o["wav_predictions"], non_blocking=True)
+    # ---- timed: end to end from host data (collate -> pinned -> H2D -> forward -> wav D2H pinned) --------
+    max_samples = 1 << 20
+    wav_pin = torch.empty((max_samples,), dtype=torch.float32).pin_memory()
+
+    def e2e_step(s):
+        batch = synth.collate_utterances([utts[args.warmup + s]], pin=True)
+        o = model(**{k: v.to(dev, non_blocking=True) for k, v in batch.items()})
+        w = o["wav_predictions"].reshape(-1)
+        wav_pin[:w.numel()].copy_(w, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller holds the waveform on the host before the next request starts
+        return int(o["dec_outputs"].shape[1])
+
+    for s in range(2):
+        e2e_step(s)
     barrier()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for s in range(args.steps):
-        flush()
-        ev2[s][0].record()
-        o = model(**{k: v.to(dev, non_blocking=True) for k, v in batch_pin.items()})
-        wav_pin.copy_(o["wav_predictions"], non_blocking=True)
-        ev2[s][1].record()
+    ts2, fr2 = timed_forwards(e2e_step, args.steps, flush)
     barrier()
-    e2e_s = sum(a.elapsed_time(b) for a, b in ev2) * 1e-3
+    e2e_s, e2e_frames = sum(ts2), sum(fr2)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- max over ranks ------------------------------------------------------------------
-    t = torch.tensor([dev_s, e2e_s, float(frames)], dtype=torch.float64, device=dev)
+    # ---- whole job: sum of frames over ranks / max over ranks of time ------------------------------------------
+    t = torch.tensor([dev_s, e2e_s, float(frames), float(e2e_frames), float(launches)], dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_s, e2e_s, total_frames = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        dev_s, e2e_s = float(tmax[0]), float(tmax[1])
+        total_frames, total_e2e_frames, total_launches = float(tsum[2]), float(tsum[3]), int(tsum[4])
     else:
-        total_frames = float(frames)
+        total_frames, total_e2e_frames, total_launches = float(frames), float(e2e_frames), int(launches)
 
+    line, detail = None, {}
     if rank == 0:
         peaks = _peaks()
-        value = total_frames * args.steps / dev_s
-        e2e_val = total_frames * args.steps / e2e_s
-        ms_step = dev_s / args.steps * 1e3
-        roof = dominant_kernel_roofline(lib, dev, frames, peaks, flush, args.precision)
+        value = total_frames / dev_s
+        audio_s = frames * HOP / SR
         line = {
-            "metric": "mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": "mel_frames_per_sec", "value": _r(value, 6), "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": _r(dev_s / args.steps * 1e3, 5), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": {"fp32": "fp32 (fp32 storage; GEMM-shaped layers on tcgen05 as 3xTF32 fp32 emulation, fp32 accumulation in TMEM; "
-                              "everything else fp32 FFMA)",
-                      "tf32": "tf32 (fp32 storage; decoder+vocoder GEMMs on tcgen05 with tf32 operands rounded to nearest, fp32 "
-                              "accumulation; duration prefix 3xTF32)",
-                      "bf16": "bf16 (fp32 storage; decoder+vocoder GEMMs on tcgen05 kind::f16 with bf16 operands, fp32 accumulation; "
-                              "duration prefix 3xTF32)",
-                      "fp32_ffma": "fp32 (FFMA kernels, no tensor cores)"}[args.precision],
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "precision": args.precision, "frames_per_step_per_gpu": frames, "audio_seconds_per_step_per_gpu": audio_s,
-                       "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
-                       "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks",
-                       "weights": "seeded synthetic, 53.3 M params fp32",
-                       "weight_broadcast_ms": bcast_ms},
-            "rtf": (dev_s / args.steps) / audio_s, "x_realtime": audio_s / (dev_s / args.steps),
-            "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
+            "dtype": {"fp32": "fp32 (3xTF32 on tcgen05, fp32 accumulate)", "tf32": "tf32", "bf16": "bf16 (fp32 accumulate)",
+                      "fp32_ffma": "fp32 (FFMA)"}[args.precision],
+            "data": "synthetic", "config": CONFIG,
+            "rtf": _r(dev_s / audio_s), "x_realtime": _r(audio_s / dev_s),
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": n_samples * 4, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "x_realtime": audio_s / (e2e_s / args.steps)},
-            "gpu_launches": int(launches),
+            "e2e": {"value": _r(total_e2e_frames / e2e_s, 6), "unit": "mel-frames/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": int(n_samples * 4 // args.steps), "ms_per_step": _r(e2e_s / args.steps * 1e3, 5),
+                    "x_realtime": _r(audio_s / e2e_s)},
+            "gpu_launches": total_launches,
             "parity": parity,
-            "roofline": roof,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(steps=8, warmup=1)
-            line["cpu_baseline"] = {"value": r["fps"], "unit": "mel-frames/s", "cores": r["cores"], "kind": "port",
-                                    "sample": "8 full forward passes of the same workload on the host CPU (oracle/jets_oracle.py, "
-                                              "torch CPU, %d threads = fastest of calibration %s ms; %d usable CPUs); %.0f ms each"
-                                              % (r["cores"], json.dumps(r["calib"]), r["usable"], r["sec_per_step"] * 1e3)}
-        if world == 1 and not args.no_experiments and os.environ.get("EV_BENCH_EXPERIMENTS", "1") != "0":
-            try:
-                line["experiments"] = experiments()
-            except Exception as e:      # never let the secondary block cost the headline line
-                line["experiments"] = {"error": repr(e)}
-        print(json.dumps(line), flush=True)
+        detail.update(precision=args.precision, frames_rank0=frames, audio_seconds_rank0=audio_s, wall_ms_per_step_incl_flush=wall / args.steps * 1e3,
+                      weight_broadcast=bcast, setup_s=setup_s, step_ms_rank0=[x * 1e3 for x in ts], e2e_step_ms_rank0=[x * 1e3 for x in ts2],
+                      launches_per_step=total_launches / (args.steps * world), peaks=peaks)
+        if bcast:
+            line["weights"] = bcast
+        try:
+            roof, roof_full = dominant_kernel_roofline(lib, dev, frames // args.steps, peaks, flush, args.precision)
+            line["roofline"] = roof
+            detail["roofline"] = roof_full
+        except Exception as e:
+            line["roofline"] = {"bound": "tensor", "achieved": None, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": None,
+                                "traffic": None, "error": repr(e)[:200]}
+
+    # ---- secondary blocks (the headline numbers above are final) ---------------------------------------
+    if not args.lean:
+        if rank == 0:
+            for name, fn in (("b1", lambda: b1_block(model, dev, flush, line["parity"])),
+                             ("b32", lambda: b32_block(model, dev, flush, args.precision, conf, sd_cpu)),
+                             ("voc", lambda: voc_block(model, dev, flush, peaks, args.precision, world > 1))):
+                try:
+                    line[name] = fn()
+                except Exception as e:
+                    line[name] = {"error": repr(e)[:200]}
+                torch.cuda.empty_cache()
+        try:
+            c5, recs = cfg5_block(model, dev, rank, world, dist)
+            if rank == 0:
+                line["cfg5"] = c5
+                detail["cfg5_ranks"] = [{k: v for k, v in r.items() if k != "pairs"} for r in recs]
+        except Exception as e:
+            if rank == 0:
+                line["cfg5"] = {"error": repr(e)[:200]}
+
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return
+    # the other ranks have left: the host cores are free for the CPU baseline
+    if not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(steps=12, warmup=1)
+            line["cpu_baseline"] = {"value": _r(r["fps"], 5), "unit": "mel-frames/s", "cores": r["cores"], "kind": "port",
+                                    "sample": "12 B=1 forwards over corpus utterances (oracle/jets_oracle.py, torch CPU, %d threads of %d usable), %.0f ms each"
+                                              % (r["cores"], r["usable"], r["seconds"] / r["steps"] * 1e3)}
+            detail["cpu_baseline"] = r
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "mel-frames/s", "cores": 0, "kind": "port", "sample": "failed: " + repr(e)[:120]}
+    emit(line, detail, world)
+
+
+def b1_block(model, dev, flush, parity):
+    """configs[1] on the committed fixture utterance (537 frames): device and end-to-end latency of ONE fixed utterance."""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "b1_t100.npz"))
+    keys = ("inputs_ling", "input_lengths", "inputs_speaker", "inputs_style_embedding", "inputs_content_embedding")
+    batch = {k: torch.from_numpy(z[k]).to(dev) for k in keys}
+    for _ in range(2):
+        out = model(**batch)
+    ts, outs = timed_forwards(lambda i: model(**batch), 10, flush)
+    frames = int(outs[-1]["dec_outputs"].shape[1])
+    t = statistics.median(ts)
+    return {"frames": frames, "ms": _r(t * 1e3), "x_rt": _r(frames * HOP / SR / t), "ms_min": _r(min(ts) * 1e3)}
 
 
 if __name__ == "__main__":

@@ -66,8 +66,6 @@ SIGNATURES = {
     "ev_op_conv1d_tc": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _i, _i, _f, _vp, _sz, _vp]),
     "ev_set_precision": (_i, [_vp, _i]),
     "ev_debug_tc_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
-    "ev_op_resblock_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _vp]),
-    "ev_debug_resblock_plan": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
     "ev_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ev_op_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ev_op_gauss_upsample": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

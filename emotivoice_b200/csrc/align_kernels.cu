@@ -79,11 +79,8 @@ int launch_mas(const float* log_p, const int64_t* text_lens, const int64_t* feat
   EV_CHECK_ARG(B > 0 && T_mel > 0 && T_inp > 0, "mas: B=%d T_mel=%d T_inp=%d", B, T_mel, T_inp);
   const size_t smem = (size_t)T_inp * (2 * sizeof(double) + sizeof(int));
   EV_CHECK_ARG(smem <= 200 * 1024, "mas: %d tokens exceed the shared-memory budget", T_inp);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_devs{0};
+  if (first_use_on_device(attr_devs)) cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   mas_kernel<<<B, 256, smem, st>>>(log_p, text_lens, feats_lens, T_mel, T_inp, path, durations, bin_loss, dec_ws);
   EV_CUDA_LAUNCH_CHECK("mas_kernel");
   return EV_OK;
@@ -141,12 +138,14 @@ int ev_op_mas(const float* log_p_attn, const int64_t* text_lens, const int64_t* 
               int32_t* path, float* durations, float* bin_loss, uint8_t* workspace, size_t workspace_bytes, void* stream) {
   EV_CHECK_ARG(log_p_attn && text_lens && feats_lens && path && durations && bin_loss && workspace, "ev_op_mas: null argument");
   EV_CHECK_ARG(workspace_bytes >= (size_t)B * T_mel * T_inp, "ev_op_mas: workspace %zu < %zu bytes", workspace_bytes, (size_t)B * T_mel * T_inp);
+  EV_TRY(use_device_of(log_p_attn));
   return launch_mas(log_p_attn, text_lens, feats_lens, B, T_mel, T_inp, path, durations, bin_loss, workspace, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ev_op_average_by_duration(const float* durations, const float* xs, const int64_t* text_lens, const int64_t* feats_lens, int B,
                               int T_mel, int T_inp, float* out, void* stream) {
   EV_CHECK_ARG(durations && xs && text_lens && feats_lens && out, "ev_op_average_by_duration: null argument");
+  EV_TRY(use_device_of(durations));
   return launch_avg_by_duration(durations, xs, text_lens, feats_lens, B, T_mel, T_inp, out, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ emb, const float* __restrict__ pe,
                                                         const float* __restrict__ alpha, float* __restrict__ x_out,
                                                         const float* __restrict__ w, const float* __restrict__ b,
-                                                        float* __restrict__ y, int rows, int L) {
+                                                        float* __restrict__ y, int rows, int L, int n_emb) {
   pdl_entry<PDL>();
   constexpr int C = NV * 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   if (ids) {
     const int t = row % L;
     const float a = *alpha;
-    const float* e = emb + (size_t)ids[row] * C;
+    // out-of-range ids are reported by validate_inputs_kernel (the host raises); clamped here so the read stays in bounds
+    const long long id = ids[row];
+    const float* e = emb + (size_t)(id < 0 ? 0 : (id >= n_emb ? n_emb - 1 : id)) * C;
     const float* pr = pe + (size_t)t * C;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -80,18 +82,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 int launch_layernorm(const float* x, const int64_t* ids, const float* emb, const float* pe, const float* alpha,
                      float* x_out, const float* w, const float* b, float* y, int rows, int L, int C,
-                     cudaStream_t st) {
+                     cudaStream_t st, int n_emb) {
   EV_CHECK_ARG(rows > 0, "layernorm: rows=%d", rows);
+  EV_CHECK_ARG(!ids || n_emb > 0, "layernorm: embedding prologue without a table size");
   EV_CHECK_ARG(C % 128 == 0 && C <= 768, "layernorm: C=%d must be a multiple of 128 and <= 768", C);
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb);
   switch (C / 128) {
-    case 1: launch_k(layernorm_kernel<1, true>, layernorm_kernel<1, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    case 2: launch_k(layernorm_kernel<2, true>, layernorm_kernel<2, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    case 3: launch_k(layernorm_kernel<3, true>, layernorm_kernel<3, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    case 4: launch_k(layernorm_kernel<4, true>, layernorm_kernel<4, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    case 5: launch_k(layernorm_kernel<5, true>, layernorm_kernel<5, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
-    default: launch_k(layernorm_kernel<6, true>, layernorm_kernel<6, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L); break;
+    case 1: launch_k(layernorm_kernel<1, true>, layernorm_kernel<1, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L, n_emb); break;
+    case 2: launch_k(layernorm_kernel<2, true>, layernorm_kernel<2, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L, n_emb); break;
+    case 3: launch_k(layernorm_kernel<3, true>, layernorm_kernel<3, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L, n_emb); break;
+    case 4: launch_k(layernorm_kernel<4, true>, layernorm_kernel<4, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L, n_emb); break;
+    case 5: launch_k(layernorm_kernel<5, true>, layernorm_kernel<5, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L, n_emb); break;
+    default: launch_k(layernorm_kernel<6, true>, layernorm_kernel<6, false>, grid, 256, 0, st, x, ids, emb, pe, alpha, x_out, w, b, y, rows, L, n_emb); break;
   }
   EV_CUDA_LAUNCH_CHECK("layernorm_kernel");
   return EV_OK;
@@ -239,11 +242,10 @@ template <int DK, int BQ>
 static int launch_attention_dk(const float* qkv, const int32_t* key_lens, float* ctx, int B, int L, int H, int heads,
                                cudaStream_t st) {
   const size_t smem = (size_t)(DK * (BQ + 1) + DK * 65 + 64 * DK + BQ * 65) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devs{0};
+  if (first_use_on_device(attr_devs)) {
     cudaFuncSetAttribute(attention_kernel<DK, BQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(attention_kernel<DK, BQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
   }
   dim3 grid((L + BQ - 1) / BQ, heads, B);
   launch_k(attention_kernel<DK, BQ, true>, attention_kernel<DK, BQ, false>, grid, 128, smem, st, qkv, key_lens, ctx, L, H);
@@ -276,21 +278,23 @@ int launch_attention(const float* qkv, const int32_t* key_lens, float* ctx, int 
 template <bool PDL>
 __global__ void cond_gather_kernel(const int64_t* __restrict__ spk, const float* __restrict__ spk_emb,
                                    const float* __restrict__ style, const float* __restrict__ content,
-                                   float* __restrict__ out, int H, int bert) {
+                                   float* __restrict__ out, int H, int bert, int n_spk) {
   pdl_entry<PDL>();
   const int b = blockIdx.x;
   const int W = H + 2 * bert;
+  const long long sid_raw = spk[b];      // range errors are reported by validate_inputs_kernel; clamp keeps the read in bounds
+  const size_t sid = (size_t)(sid_raw < 0 ? 0 : (sid_raw >= n_spk ? n_spk - 1 : sid_raw));
   for (int i = threadIdx.x; i < W; i += blockDim.x) {
     float v;
-    if (i < H) v = spk_emb[(size_t)spk[b] * H + i];
+    if (i < H) v = spk_emb[sid * H + i];
     else if (i < H + bert) v = style[(size_t)b * bert + (i - H)];
     else v = content[(size_t)b * bert + (i - H - bert)];
     out[(size_t)b * W + i] = v;
   }
 }
 int launch_cond_gather(const int64_t* spk, const float* spk_emb, const float* style, const float* content,
-                       float* out, int B, int H, int bert, cudaStream_t st) {
-  launch_k(cond_gather_kernel<true>, cond_gather_kernel<false>, B, 256, 0, st, spk, spk_emb, style, content, out, H, bert);
+                       float* out, int B, int H, int bert, int n_spk, cudaStream_t st) {
+  launch_k(cond_gather_kernel<true>, cond_gather_kernel<false>, B, 256, 0, st, spk, spk_emb, style, content, out, H, bert, n_spk);
   EV_CUDA_LAUNCH_CHECK("cond_gather_kernel");
   return EV_OK;
 }
@@ -381,19 +385,41 @@ int launch_rowdot(const float* x, const float* w, const float* b, const int32_t*
   return EV_OK;
 }
 
-// lengths arrive as int64 (inference_am_vocoder_joint.py:114); the kernels take int32 clamped to [0, T]
+// Input validation + length conversion, ONE CTA (B*T is a few thousand elements at most).  The reference raises
+// IndexError from nn.Embedding for a bad token / speaker id and a shape error for a bad length; here the kernels index
+// raw device memory, so this kernel reports range errors in a status word that the host reads with the mel lengths at
+// the path's single sync (no extra round trip), and every consumer clamps so nothing is read out of bounds meanwhile.
+// status bits: 1 = token id outside [0, n_vocab), 2 = speaker id outside [0, n_speaker), 4 = length outside [1, T].
+// lens arrive as int64 (inference_am_vocoder_joint.py:114); the kernels take int32 clamped to [0, T].
 template <bool PDL>
-__global__ void lens_to_i32_kernel(const int64_t* __restrict__ lens, int32_t* __restrict__ out, int B, int T) {
+__global__ void __launch_bounds__(1024) validate_inputs_kernel(const int64_t* __restrict__ ling, const int64_t* __restrict__ lens,
+                                                               const int64_t* __restrict__ spk, int32_t* __restrict__ lens_out,
+                                                               int32_t* __restrict__ status, int B, int T, int n_vocab, int n_spk) {
   pdl_entry<PDL>();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) {
-    long long v = lens[i];
-    out[i] = (int32_t)(v < 0 ? 0 : (v > T ? T : v));
+  __shared__ int s_flags;
+  if (threadIdx.x == 0) s_flags = 0;
+  __syncthreads();
+  int flags = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const long long v = lens[i];
+    if (v < 1 || v > T) flags |= 4;
+    lens_out[i] = (int32_t)(v < 0 ? 0 : (v > T ? T : v));
+    if (spk) { const long long sp = spk[i]; if (sp < 0 || sp >= n_spk) flags |= 2; }
   }
+  if (ling)
+    for (int i = threadIdx.x; i < B * T; i += blockDim.x) {
+      const long long id = ling[i];
+      if (id < 0 || id >= n_vocab) flags |= 1;
+    }
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if ((threadIdx.x & 31) == 0 && flags) atomicOr(&s_flags, flags);
+  __syncthreads();
+  if (threadIdx.x == 0 && status) *status = s_flags;
 }
-int launch_lens_to_i32(const int64_t* lens, int32_t* out, int B, int T, cudaStream_t st) {
-  launch_k(lens_to_i32_kernel<true>, lens_to_i32_kernel<false>, (B + 127) / 128, 128, 0, st, lens, out, B, T);
-  EV_CUDA_LAUNCH_CHECK("lens_to_i32_kernel");
+int launch_validate_inputs(const int64_t* ling, const int64_t* lens, const int64_t* spk, int32_t* lens_out, int32_t* status, int B,
+                           int T, int n_vocab, int n_spk, cudaStream_t st) {
+  launch_k(validate_inputs_kernel<true>, validate_inputs_kernel<false>, 1, 1024, 0, st, ling, lens, spk, lens_out, status, B, T, n_vocab, n_spk);
+  EV_CUDA_LAUNCH_CHECK("validate_inputs_kernel");
   return EV_OK;
 }
 

@@ -27,9 +27,6 @@
 // released by tcgen05.commit), accumulators (acc_full/acc_empty).
 #include <cstdio>
 #include <cstdlib>
-#include <map>
-#include <mutex>
-#include <tuple>
 
 #include "ev_common.cuh"
 #include "tc_common.cuh"
@@ -511,24 +508,11 @@ static int env_int(const char* name, int dflt) {
   return (e && *e) ? atoi(e) : dflt;
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 template <int MODE, int MT, int KBG, int PDLM>
 static int launch_tc_pdl(const ConvParams& p, const tc::Plan& pl, cudaStream_t st) {
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devs{0};   // per instantiation; function attributes are per device
+  if (first_use_on_device(attr_devs))
     cudaFuncSetAttribute(tc::conv1d_tc_kernel<MODE, MT, KBG, PDLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
-  }
   const int grid = pl.total_tiles < sm_count() ? pl.total_tiles : sm_count();
   if (PDLM) {
     const cudaError_t e = launch_with_pdl(tc::conv1d_tc_kernel<MODE, MT, KBG, PDLM>, dim3((unsigned)grid), dim3(tc::NTHREADS),
@@ -542,7 +526,7 @@ static int launch_tc_pdl(const ConvParams& p, const tc::Plan& pl, cudaStream_t s
   return EV_OK;
 }
 
-// pdl: 0 for the tuner's timing launches and the default path, else pdl_mode()
+// pdl: 0 for the default path, else pdl_mode()
 template <int MODE, int MT, int KBG>
 static int launch_tc_variant(const ConvParams& p, const tc::Plan& pl, cudaStream_t st, int pdl) {
   if (pdl >= 2) return launch_tc_pdl<MODE, MT, KBG, 2>(p, pl, st);
@@ -595,17 +579,6 @@ static int apply_ksplit(const ConvParams& p, int mode, tc::Plan* pl) {
   return EV_OK;
 }
 
-// Plan with a prescribed tile shape (the autotuner's candidates): false if it does not fit.
-// b_target: depth the weight ring reaches before the activation ring grows (4 = the default split; 8 = weight-stream heavy)
-static bool plan_with_shape(const ConvParams& p, int mode, int BN, int mt, int b_target, tc::Plan* out) {
-  const int kbg = tc_shape_kbg(p, mode);
-  tc::Plan pl;
-  if (!tc::make_plan(p, mode, BN, mt, kbg, 4, &pl, b_target) && !tc::make_plan(p, mode, BN, mt, kbg, 2, &pl, b_target)) return false;
-  if (apply_ksplit(p, mode, &pl) != EV_OK) return false;
-  *out = pl;
-  return true;
-}
-
 // Tile / pipeline plan of one launch (pure host arithmetic; also exported as ev_debug_tc_plan so the CPU tests
 // can check the invariants the kernel's barrier protocol and the batch-invariance contract rely on).
 static int plan_conv1d_tc(const ConvParams& p, int mode, tc::Plan* out) {
@@ -650,99 +623,11 @@ static int dispatch_tc(const ConvParams& p, int mode, const tc::Plan& pl, cudaSt
   return pl.kbg == 8 ? launch_tc_mt<0, 8>(p, pl, st, pdl) : launch_tc_mt<0, 4>(p, pl, st, pdl);
 }
 
-// ---- opt-in online tile-shape tuner (EV_AUTOTUNE=1; =2 also logs its choices to stderr) -------------------------------
-// The N-tile width and the accumulators per tile change how a layer is cut into CTAs (SM fill, weight bytes streamed per
-// output row, A staging replicated per N tile) but never the order of any output element's reduction, so every
-// candidate is bitwise equivalent and the fastest one can be picked by measurement.  The first launch of a
-// (mode, layer shape, K-split, half-octave bucket of the tile count) times each candidate that fits (one warm-up + 3 timed
-// launches into a scratch output, CUDA events on the caller's stream, synchronising: this is a one-off per key) and the
-// choice is cached for the life of the process.  Default off until it has been validated on hardware.
-namespace {
-typedef std::tuple<int, int, int, int, int, int, int, int> TuneKey;     // mode, Cin, Cout, K, dil, ksplit, has_lens, bucket
-std::mutex g_tune_mu;
-struct TuneChoice { int BN = 0, mt = 0, b_target = 4; };                    // BN == 0: keep the default plan
-std::map<TuneKey, TuneChoice> g_tuned;
-
-int tile_bucket(long long tiles128) {      // half-octave buckets: 1,2,3,4,6,8,12,16,24,...
-  int b = 0;
-  long long lo = 1;
-  while (lo * 2 <= tiles128) { lo *= 2; b += 2; }
-  return b + (tiles128 * 2 >= lo * 3 ? 1 : 0);
-}
-
-float time_plan(const ConvParams& q, int mode, const tc::Plan& pl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
-  if (dispatch_tc(q, mode, pl, st) != EV_OK) return -1.f;     // warm-up (also faults in the kernel image / smem attribute)
-  if (cudaEventRecord(e0, st) != cudaSuccess) return -1.f;
-  for (int r = 0; r < 3; ++r)
-    if (dispatch_tc(q, mode, pl, st) != EV_OK) return -1.f;
-  if (cudaEventRecord(e1, st) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
-  float ms = -1.f;
-  if (cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) return -1.f;
-  return ms;
-}
-
-TuneChoice tune(const ConvParams& p, int mode, const tc::Plan& dflt, cudaStream_t st, int verbose) {
-  TuneChoice best;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  float* scratch = nullptr;
-  ConvParams q = p;
-  const size_t per = (size_t)p.B * p.L * p.Cout;
-  // the timed launches must not touch the caller's output (it may be an accumulate target or alias the residual)
-  if (dflt.ksplit == 1) {
-    if (cudaMalloc(&scratch, per * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return best; }
-    q.out = scratch;
-  }   // K-split launches only write the partial buffers, which are scratch by contract
-  if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
-    float best_ms = time_plan(q, mode, dflt, st, e0, e1);
-    if (verbose) fprintf(stderr, "[ev autotune] mode %d Cin %d Cout %d K %d dil %d B %d L %d S %d: default BN %d MT %d %.1f us", mode, p.Cin,
-                         p.Cout, p.K, p.dil, p.B, p.L, dflt.ksplit, dflt.BN, dflt.mt, best_ms * 1000.f / 3.f);
-    if (best_ms > 0.f) {
-      const int bn_max = p.Cout <= 128 ? p.Cout : 128;
-      for (int BN = bn_max; BN >= 32 && BN % 16 == 0; BN /= 2)
-        for (int mt = 1; mt <= 4; mt *= 2)
-          for (int bt = 4; bt <= 8; bt += 4) {
-            if ((long long)tc::BM * (mt / 2) >= p.L && mt > 1) continue;          // more accumulators than rows
-            tc::Plan pl;
-            if (!plan_with_shape(p, mode, BN, mt, bt, &pl)) continue;
-            if (pl.BN == dflt.BN && pl.mt == dflt.mt && pl.a_stages == dflt.a_stages && pl.b_stages == dflt.b_stages) continue;
-            if (bt == 8 && pl.b_stages <= 4) continue;                             // same rings as the bt = 4 candidate
-            const float ms = time_plan(q, mode, pl, st, e0, e1);
-            if (verbose) fprintf(stderr, " | BN %d MT %d A%d B%d %.1f", BN, mt, pl.a_stages, pl.b_stages, ms * 1000.f / 3.f);
-            if (ms > 0.f && ms < best_ms * 0.97f) {      // 3 % hysteresis for the default
-              best_ms = ms;
-              best.BN = BN; best.mt = mt; best.b_target = bt;
-            }
-          }
-    }
-    if (verbose) fprintf(stderr, " -> BN %d MT %d Btarget %d\n", best.BN ? best.BN : dflt.BN, best.BN ? best.mt : dflt.mt, best.b_target);
-  }
-  if (e0) cudaEventDestroy(e0);
-  if (e1) cudaEventDestroy(e1);
-  if (scratch) { cudaStreamSynchronize(st); cudaFree(scratch); }
-  cudaGetLastError();
-  return best;
-}
-}  // namespace
-
 // p.w must be in the tensor-core layout [plane][Cout/BNp][K][Cin/4][BNp][4] (packing.py: to_tc_layout);
 // mode 0: 1xTF32, 1: 3xTF32 fp32 emulation (reads both planes), 2: bf16 operands (p.w in the bf16 tc layout).
 int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st) {
   tc::Plan pl;
   EV_TRY(plan_conv1d_tc(p, mode, &pl));
-  static const int autotune = env_int("EV_AUTOTUNE", 0);
-  if (autotune) {
-    const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
-    const TuneKey key(mode, p.Cin, p.Cout, p.K, p.dil, pl.ksplit, p.lens ? 1 : 0, tile_bucket(tiles128));
-    TuneChoice choice;
-    {
-      std::lock_guard<std::mutex> lock(g_tune_mu);
-      auto it = g_tuned.find(key);
-      if (it == g_tuned.end()) it = g_tuned.emplace(key, tune(p, mode, pl, st, autotune > 1)).first;
-      choice = it->second;
-    }
-    tc::Plan tuned;
-    if (choice.BN && plan_with_shape(p, mode, choice.BN, choice.mt, choice.b_target, &tuned)) pl = tuned;
-  }
   const size_t per = (size_t)p.B * p.L * p.Cout;
   const int rc = dispatch_tc(p, mode, pl, st, pdl_mode());      // EV_PDL: opt-in until it has been measured on hardware
   if (rc != EV_OK || pl.ksplit == 1) return rc;

@@ -220,11 +220,10 @@ static int launch_variant(const ConvParams& p, cudaStream_t st) {
   EV_CHECK_ARG(rows_a <= 6 * NTHREADS / 4, "conv1d: receptive field too wide for the tile (rows_a=%d)", rows_a);
   const int a_ld = ((rows_a + 7) / 8) * 8 + 2;   // == 2 (mod 8): conflict-free transposed stores
   const size_t smem = (size_t)(2 * KC * a_ld + 2 * KC * BN) * sizeof(float);
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devs{0};   // per instantiation
+  if (first_use_on_device(attr_devs)) {
     cudaFuncSetAttribute(conv1d_tm_kernel<TXN, NV, TM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(conv1d_tm_kernel<TXN, NV, TM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
   }
   EV_CHECK_ARG(smem <= 96 * 1024, "conv1d: smem %zu too large", smem);
   dim3 grid((p.L + BM - 1) / BM, (p.Cout + BN - 1) / BN, p.B);

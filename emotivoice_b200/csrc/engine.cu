@@ -44,6 +44,31 @@ cudaError_t take_launch_error() {
   g_parked_launch_error = cudaSuccess;
   return e;
 }
+int sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    cache[dev & 63].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+int use_device_of(const void* dev_ptr) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, dev_ptr);
+  if (e == cudaSuccess && at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+    set_error("pointer %p is not device memory (there is no CPU path in this library)", dev_ptr);
+    return EV_EINVAL;
+  }
+  int cur = -1;
+  if (e == cudaSuccess) e = cudaGetDevice(&cur);
+  if (e == cudaSuccess && cur != at.device) e = cudaSetDevice(at.device);
+  if (e != cudaSuccess) { set_error("selecting the device of %p: %s", dev_ptr, cudaGetErrorString(e)); cudaGetLastError(); return EV_ECUDA; }
+  return EV_OK;
+}
 int pdl_mode() {
   static const int v = [] { const char* e = getenv("EV_PDL"); return (e && *e) ? atoi(e) : 0; }();
   return v;
@@ -110,9 +135,6 @@ struct ev_ctx {
   int post_k = 7;
   int total_up = 1;
   int max_stage_width = 0;   // max over stages of prod(rates so far) * channels
-  // two auxiliary streams: at small batch the three ResBlocks of a stage (and the three predictors) are
-  // independent chains of small launches; running them side by side fills the SMs the single chain leaves idle
-  cudaStream_t aux[2] = {nullptr, nullptr};
 };
 
 namespace ev {
@@ -142,8 +164,7 @@ struct Phase2Bufs {
 struct VocBufs {
   float *X, *ACC, *part;
   size_t part_cap;
-  float *Tm[3], *R1[3], *R2[3];   // per-ResBlock chain scratch (chains 1,2 alias chain 0 when run sequentially)
-  bool concurrent;
+  float *Tm, *R1, *R2;   // ResBlock chain scratch
 };
 
 static void carve_phase1(const ev_ctx* c, Carver& cv, int B, int T, Phase1Bufs* o) {
@@ -173,54 +194,15 @@ static void carve_phase2(const ev_ctx* c, Carver& cv, int B, int F, Phase2Bufs* 
   o->part_cap = 8 * n * 4 * H;
   o->part = cv.take(o->part_cap);
 }
-// ResBlock chains run concurrently (3x the chain scratch) only while the whole call is small: that is where a
-// single chain cannot fill the GPU, and where the extra scratch is cheap.
-// EXPERIMENTAL (off by default, EV_STREAMS=1 enables): the first on-device trial of the multi-stream path hung,
-// so until that is understood every chain runs on the caller's stream.
-static inline int streams_mask() {     // bit 0: predictor chains, bit 1: ResBlock chains
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("EV_STREAMS"); v = e ? atoi(e) : 0; }
-  return v;
-}
-static inline bool voc_concurrent(int B, int F) { return (streams_mask() & 2) && (long long)B * F <= 4096; }
-
 static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
   const size_t n = (size_t)B * F * (size_t)c->max_stage_width;
-  o->concurrent = voc_concurrent(B, F);
   o->X = cv.take(n);
   o->ACC = cv.take(n);
   o->part_cap = n / 2;                  // split-K partials of the first (widest-channel) stage: 2 slices of B*r0*F*C1
   o->part = cv.take(o->part_cap);
-  for (int i = 0; i < 3; ++i) {
-    if (i == 0 || o->concurrent) {
-      o->Tm[i] = cv.take(n);
-      o->R1[i] = cv.take(n);
-      o->R2[i] = cv.take(n);
-    } else {
-      o->Tm[i] = o->Tm[0]; o->R1[i] = o->R1[0]; o->R2[i] = o->R2[0];
-    }
-  }
-}
-
-// fork/join helpers: events are created per call (cheap, timing disabled) so concurrent callers never share one
-struct EventPool {
-  std::vector<cudaEvent_t> evs;
-  cudaEvent_t get() {
-    cudaEvent_t e = nullptr;
-    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    evs.push_back(e);
-    return e;
-  }
-  ~EventPool() { for (auto e : evs) cudaEventDestroy(e); }   // deferred by the runtime until the event completes
-};
-static int edge(EventPool& pool, cudaStream_t from, cudaStream_t to) {   // work queued on `to` after this waits for `from`
-  if (from == to) return EV_OK;
-  cudaEvent_t e = pool.get();
-  if (!e || cudaEventRecord(e, from) != cudaSuccess || cudaStreamWaitEvent(to, e, 0) != cudaSuccess) {
-    set_error("stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return EV_ECUDA;
-  }
-  return EV_OK;
+  o->Tm = cv.take(n);
+  o->R1 = cv.take(n);
+  o->R2 = cv.take(n);
 }
 
 static int find(ev_ctx* c, const std::string& name, uint64_t expect, const float** out) {
@@ -422,28 +404,6 @@ static int conv_x(int mode, const float* w_tc, const float* w_h, const float* x,
   return launch_conv1d_tc(p, mode == 3 ? 1 : (mode == 2 ? 2 : 0), st);
 }
 
-// EV_FUSE_RES=1: run each ResBlock layer (conv pair + residual) as one kernel where resblock_tc.cu supports the shape
-// (opt-in until validated on hardware; bitwise equal to the two-launch path by construction)
-static inline bool fuse_res() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("EV_FUSE_RES"); v = (e && atoi(e) > 0) ? 1 : 0; }
-  return v == 1;
-}
-
-// the ResBlock layer through the fused kernel; returns false when the pair has to run as two convolutions
-static bool try_resblock_pair(int mode, const ConvW& c1, const ConvW& c2, const float* src, float* dst, int B, int L, int C,
-                              const int32_t* lens, int lens_mul, int acc, float div, cudaStream_t st, int* rc) {
-  if (mode == 0 || c1.K != c2.K || !c1.w_tc || !c2.w_tc) return false;
-  int tcm = mode == 3 ? 1 : (mode == 2 ? 2 : 0);
-  if (tcm == 2 && (!c1.w_h || !c2.w_h || (C % 16))) tcm = 1;      // like conv_x: layers without bf16 weights run 3xTF32
-  ResPairParams p;
-  p.x = src; p.w1 = tcm == 2 ? c1.w_h : c1.w_tc; p.b1 = c1.b; p.w2 = tcm == 2 ? c2.w_h : c2.w_tc; p.b2 = c2.b; p.out = dst;
-  p.B = B; p.L = L; p.C = C; p.K = c1.K; p.dil = c1.dil; p.lens = lens; p.lens_mul = lens_mul; p.slope = 0.1f; p.acc = acc; p.div = div;
-  if (!resblock_pair_supported(p, tcm)) return false;
-  *rc = launch_resblock_pair(p, tcm, st);
-  return true;
-}
-
 static inline int body_mode(const ev_ctx* c) {
   return c->precision == EV_PREC_FP32_FFMA ? 0 : (c->precision == EV_PREC_TF32 ? 1 : (c->precision == EV_PREC_BF16 ? 2 : 3));
 }
@@ -482,7 +442,7 @@ static int run_predictor(const ev_ctx* c, const PredW& p, const float* in, float
                          const int32_t* lens, const int32_t* conv_lens, int mode, float* out_f, int64_t* out_i,
                          int cmode, cudaStream_t st) {
   const int H = c->cfg.hidden, K = c->cfg.pred_kernel;
-  g_split_ws.ksplit = (streams_mask() & 1) ? 0 : 2;   // concurrent predictor chains would share the split-K scratch
+  g_split_ws.ksplit = 2;
   const float* cur = in;
   for (size_t i = 0; i < p.w.size(); ++i) {
     EV_TRY(conv_x(cmode, p.w_tc[i], nullptr, cur, p.w[i], p.b[i], 0, nullptr, t1, B, T, H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
@@ -523,23 +483,11 @@ int ev_create(ev_ctx** out, int device, const ev_config* cfg) {
   ev_ctx* c = new ev_ctx();
   c->cfg = *cfg;
   c->device = device;
-  {   // auxiliary streams live on the engine's device, whatever device is current for the caller
-    int prev = -1;
-    cudaGetDevice(&prev);
-    if (prev != device) cudaSetDevice(device);
-    for (int i = 0; i < 2; ++i)
-      if (cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking) != cudaSuccess) c->aux[i] = nullptr;
-    if (prev >= 0 && prev != device) cudaSetDevice(prev);
-    cudaGetLastError();
-  }
   *out = c;
   return EV_OK;
 }
 
 void ev_destroy(ev_ctx* ctx) {
-  if (!ctx) return;
-  for (int i = 0; i < 2; ++i)
-    if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
   delete ctx;
 }
 
@@ -617,7 +565,8 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   if (cv.off > workspace_bytes) { set_error("ev_am_phase1: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
   EV_TRY(use_device(ctx));
   g_split_ws.p = b.part; g_split_ws.cap = b.part_cap; g_split_ws.ksplit = 2;
-  EV_TRY(launch_lens_to_i32(lens64, lens32_out, B, T, st));
+  // lengths -> int32, plus range checks of ids / speakers / lengths into the status word mel_lens_out[B + 1]
+  EV_TRY(launch_validate_inputs(ling, lens64, spk, lens32_out, mel_lens_out + B + 1, B, T, g.n_vocab, g.n_speaker, st));
   const int32_t* lens = lens32_out;
   const int32_t* conv_lens = invariant ? lens : nullptr;
   // the duration-critical prefix is fp32-accurate in every mode: 3xTF32 on the tensor cores, or FFMA
@@ -626,10 +575,10 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   Range r_phase("ev:am_phase1");
   // encoder: x = word_emb[ids] + alpha*pe (model_open_source.py:107, encoder.py:257-261), fused with LN1 of layer 0
   EV_TRY(launch_layernorm(nullptr, ling, ctx->emb_word, ctx->pe, ctx->enc.alpha, b.x, ctx->enc.layers[0].ln1w,
-                          ctx->enc.layers[0].ln1b, b.y, B * T, T, H, st));
+                          ctx->enc.layers[0].ln1b, b.y, B * T, T, H, st, g.n_vocab));
   EV_TRY(run_stack(ctx, ctx->enc, b.x, b.y, b.qkv, b.ctx, b.h, B, T, lens, conv_lens, true, prefix_mode, st));
   // conditioning (model_open_source.py:109-111): per-utterance bias + W_x x
-  EV_TRY(launch_cond_gather(spk, ctx->emb_spk, style, content, b.cond_in, B, H, g.bert_dim, st));
+  EV_TRY(launch_cond_gather(spk, ctx->emb_spk, style, content, b.cond_in, B, H, g.bert_dim, g.n_speaker, st));
   EV_TRY(launch_cond_gemv(b.cond_in, ctx->cond_wc, ctx->cond_b, b.cond_bias, B, H + 2 * g.bert_dim, H, st));
   EV_TRY(conv_x(prefix_mode, ctx->cond_wx_tc, nullptr, b.y, ctx->cond_wx, b.cond_bias, H, nullptr, b.hs, B, T, H, H, 1, 1, conv_lens, 1,
                 EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
@@ -639,19 +588,9 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
     EV_TRY(launch_mask_rows(b.hs, lens, b.pm, B, T, H, st));
     pin = b.pm;
   }
-  {
-    // three independent predictor chains: pitch on the caller's stream, energy / duration on the auxiliary ones
-    EventPool pool;
-    const bool fork = (streams_mask() & 1) && ctx->aux[0] && ctx->aux[1];
-    cudaStream_t s1 = fork ? ctx->aux[0] : st, s2 = fork ? ctx->aux[1] : st;
-    EV_TRY(edge(pool, st, s1));
-    EV_TRY(edge(pool, st, s2));
-    EV_TRY(run_predictor(ctx, ctx->pitch, pin, b.p1[0], b.p2[0], B, T, lens, conv_lens, 0, pitch_out, nullptr, prefix_mode, st));
-    EV_TRY(run_predictor(ctx, ctx->energy, pin, b.p1[1], b.p2[1], B, T, lens, conv_lens, 0, energy_out, nullptr, prefix_mode, s1));
-    EV_TRY(run_predictor(ctx, ctx->dur, pin, b.p1[2], b.p2[2], B, T, lens, conv_lens, 1, nullptr, dur_out, prefix_mode, s2));
-    EV_TRY(edge(pool, s1, st));
-    EV_TRY(edge(pool, s2, st));
-  }
+  EV_TRY(run_predictor(ctx, ctx->pitch, pin, b.p1[0], b.p2[0], B, T, lens, conv_lens, 0, pitch_out, nullptr, prefix_mode, st));
+  EV_TRY(run_predictor(ctx, ctx->energy, pin, b.p1[1], b.p2[1], B, T, lens, conv_lens, 0, energy_out, nullptr, prefix_mode, st));
+  EV_TRY(run_predictor(ctx, ctx->dur, pin, b.p1[2], b.p2[2], B, T, lens, conv_lens, 1, nullptr, dur_out, prefix_mode, st));
   // x = x + pitch_embed + energy_embed (model_open_source.py:131-134)
   EV_TRY(launch_var_embed_add(b.hs, pitch_out, energy_out, ctx->pemb_w, ctx->pemb_b, ctx->eemb_w, ctx->eemb_b, B, T, H,
                               g.embed_kernel, st));
@@ -705,19 +644,14 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   g_split_ws.p = v.part; g_split_ws.cap = v.part_cap; g_split_ws.ksplit = 0;
   const float* m = mel;
   if (!mel_time_major) {
-    EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm[0], B, g.n_mels, F, st));
-    m = v.Tm[0];
+    EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm, B, g.n_mels, F, st));
+    m = v.Tm;
   }
   Range r_phase("ev:vocoder");
   // conv_pre (hifigan/models.py:116)
   const int mode = body_mode(ctx);
   EV_TRY(conv_x(mode, ctx->pre.w_tc, ctx->pre.w_h, m, ctx->pre.w, ctx->pre.b, 0, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1,
                 mel_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
-  // chain j of a stage (ResBlock j) runs on its own stream when the call is small; the xs accumulation
-  // (xs = r0; xs += r1; xs += r2; x = xs / 3, :120-126) keeps its order through events
-  const bool par = v.concurrent && g.n_resk <= 3 && ctx->aux[0] && ctx->aux[1];
-  cudaStream_t chain_st[3] = {st, par ? ctx->aux[0] : st, par ? ctx->aux[1] : st};
-  EventPool pool;
   int L = F, mul = 1;
   size_t rb = 0;
   static const char* const kStageNames[8] = {"voc:stage1", "voc:stage2", "voc:stage3", "voc:stage4", "voc:stage5", "voc:stage6",
@@ -725,44 +659,33 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   for (int s = 0; s < g.n_ups; ++s) {
     Range r_stage(kStageNames[s & 7]);
     const UpW& u = ctx->ups[s];
+    // no K-split in the vocoder: outputs are large, the partial-sum traffic costs more than the shorter reduction gains
+    // (measured: 2-slice K-split of stage 1 gains 4.6 % at batch 1 and costs 6 % at batch 32)
     g_split_ws.ksplit = 0;
     // x = ups[i](leaky_relu(x, 0.1)) (:118-119): polyphase-packed transposed conv, output viewed (L, rate*Cout)
     EV_TRY(conv_x(mode, u.w_tc, u.w_h, v.ACC, u.w, u.b, 0, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, mel_lens, mul,
                   EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
     L *= u.rate; mul *= u.rate;
     const int C = u.cout;
-    // no K-split in the vocoder: outputs are large, the partial-sum traffic costs more than the shorter reduction gains
-    g_split_ws.ksplit = 0;   // measured: 2-slice K-split of stage 1 gains 4.6 % at batch 1 and costs 6 % at batch 32 -> off
-    for (int j = 1; j < 3; ++j) EV_TRY(edge(pool, st, chain_st[j]));   // fork: X (and the previous stage) is ready
     for (int j = 0; j < g.n_resk; ++j) {
-      cudaStream_t cs = chain_st[j % 3];
-      const int cj = par ? j % 3 : 0;
       const float* src = v.X;
       for (int l = 0; l < g.n_dil; ++l, ++rb) {
         const ConvW& c1 = ctx->rb_c1[rb];
         const ConvW& c2 = ctx->rb_c2[rb];
         const bool last = (l == g.n_dil - 1);
-        float* dst = last ? v.ACC : ((l & 1) ? v.R2[cj] : v.R1[cj]);
+        float* dst = last ? v.ACC : ((l & 1) ? v.R2 : v.R1);
         int acc = EV_ACC_STORE;
         if (last && j > 0) acc = (j == g.n_resk - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;   // xs += ...; x = xs / n (:120-126)
         const float div = (float)g.n_resk;
         if (last && g.n_resk == 1) acc = EV_ACC_STORE;
-        int frc = EV_OK;
-        if (fuse_res() && !par && try_resblock_pair(mode, c1, c2, src, dst, B, L, C, mel_lens, mul, acc, div, cs, &frc)) {
-          EV_TRY(frc);
-          src = dst;
-          continue;
-        }
         // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
-        EV_TRY(conv_x(mode, c1.w_tc, c1.w_h, src, c1.w, c1.b, 0, nullptr, v.Tm[cj], B, L, C, C, c1.K, c1.dil, mel_lens, mul,
-                      EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, cs));
-        if (last && j > 0) EV_TRY(edge(pool, chain_st[(j - 1) % 3], cs));   // xs accumulation in ResBlock order
-        EV_TRY(conv_x(mode, c2.w_tc, c2.w_h, v.Tm[cj], c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
-                      EV_ACT_NONE, acc, div, cs));
+        EV_TRY(conv_x(mode, c1.w_tc, c1.w_h, src, c1.w, c1.b, 0, nullptr, v.Tm, B, L, C, C, c1.K, c1.dil, mel_lens, mul,
+                      EV_ACT_LRELU, 0.1f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+        EV_TRY(conv_x(mode, c2.w_tc, c2.w_h, v.Tm, c2.w, c2.b, 0, src, dst, B, L, C, C, c2.K, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+                      EV_ACT_NONE, acc, div, st));
         src = dst;
       }
     }
-    EV_TRY(edge(pool, chain_st[(g.n_resk - 1) % 3], st));   // the stage output (ACC) is complete
   }
   // x = leaky_relu(x) [slope 0.01]; conv_post; tanh (:127-129)
   EV_CHECK_ARG(mul == ctx->total_up, "ev_vocoder: internal rate mismatch");
@@ -773,6 +696,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
 
 int ev_wav_to_pcm16(const float* wav, int16_t* pcm, size_t n, void* stream) {
   EV_CHECK_ARG(wav && pcm, "ev_wav_to_pcm16: null argument");
+  EV_TRY(use_device_of(wav));
   return launch_pcm16(wav, pcm, n, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -780,6 +704,7 @@ int ev_op_conv1d(const float* x, const float* w, const float* bias, size_t bias_
                  int B, int L, int Cin, int Cout, int K, int dil, const int32_t* lens, int lens_mul, int in_act,
                  float in_slope, int out_act, int acc, float div, void* stream) {
   EV_CHECK_ARG(x && w && out, "ev_op_conv1d: null argument");
+  EV_TRY(use_device_of(x));
   return conv(x, w, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul, in_act, in_slope,
               out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -790,6 +715,7 @@ int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* 
                     void* stream) {
   g_split_ws.p = splitk_ws; g_split_ws.cap = splitk_ws ? splitk_floats : 0; g_split_ws.ksplit = splitk_ws ? 4 : 0;
   EV_CHECK_ARG(x && w_tc && out, "ev_op_conv1d_tc: null argument");
+  EV_TRY(use_device_of(x));
   EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0 && (Cout <= 128 || Cout % 128 == 0),
                "ev_op_conv1d_tc: needs Cin %% 8 == 0, Cout %% 16 == 0 and Cout <= 128 or a multiple of 128 (Cin=%d Cout=%d)", Cin, Cout);
   EV_CHECK_ARG(split3 != 2 || Cin % 16 == 0, "ev_op_conv1d_tc: the bf16 mode needs Cin %% 16 == 0 (Cin=%d)", Cin);
@@ -803,25 +729,6 @@ int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int split3
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.in_act = EV_ACT_NONE;
   p.ksplit = ksplit; p.splitk_ws = nullptr; p.splitk_cap = (size_t)-1;   // "scratch of any size is available"
   return debug_tc_plan(p, split3, out11);
-}
-
-int ev_op_resblock_pair(const float* x, const float* w1_tc, const float* b1, const float* w2_tc, const float* b2, int split3,
-                        float* out, int B, int L, int C, int K, int dil, const int32_t* lens, int lens_mul, int acc, float div,
-                        void* stream) {
-  EV_CHECK_ARG(x && w1_tc && b1 && w2_tc && b2 && out, "ev_op_resblock_pair: null argument");
-  ResPairParams p;
-  p.x = x; p.w1 = w1_tc; p.b1 = b1; p.w2 = w2_tc; p.b2 = b2; p.out = out;
-  p.B = B; p.L = L; p.C = C; p.K = K; p.dil = dil; p.lens = lens; p.lens_mul = lens_mul; p.slope = 0.1f; p.acc = acc; p.div = div;
-  return launch_resblock_pair(p, split3 == 2 ? 2 : (split3 ? 1 : 0), reinterpret_cast<cudaStream_t>(stream));
-}
-
-int ev_debug_resblock_plan(int B, int L, int C, int K, int dil, int split3, int* out11) {
-  EV_CHECK_ARG(out11, "ev_debug_resblock_plan: null output");
-  static float dummy_in, dummy_out;       // only their (distinct) addresses matter to the planner
-  ResPairParams p;
-  p.x = &dummy_in; p.w1 = nullptr; p.b1 = nullptr; p.w2 = nullptr; p.b2 = nullptr; p.out = &dummy_out;
-  p.B = B; p.L = L; p.C = C; p.K = K; p.dil = dil; p.lens = nullptr; p.lens_mul = 1; p.slope = 0.1f; p.acc = EV_ACC_STORE; p.div = 1.f;
-  return debug_resblock_plan(p, split3 == 2 ? 2 : (split3 ? 1 : 0), out11);
 }
 
 int ev_set_precision(ev_ctx* ctx, int precision) {
@@ -863,6 +770,7 @@ int ev_set_precision(ev_ctx* ctx, int precision) {
 
 int ev_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int C, void* stream) {
   EV_CHECK_ARG(x && w && b && y, "ev_op_layernorm: null argument");
+  EV_TRY(use_device_of(x));
   return launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, w, b, y, rows, rows, C,
                           reinterpret_cast<cudaStream_t>(stream));
 }
@@ -870,6 +778,7 @@ int ev_op_layernorm(const float* x, const float* w, const float* b, float* y, in
 int ev_op_attention(const float* qkv, const int32_t* key_lens, float* ctx_out, int B, int L, int H, int n_heads,
                     void* stream) {
   EV_CHECK_ARG(qkv && ctx_out, "ev_op_attention: null argument");
+  EV_TRY(use_device_of(qkv));
   return launch_attention(qkv, key_lens, ctx_out, B, L, H, n_heads, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -877,6 +786,7 @@ int ev_op_gauss_upsample(const float* hs, const int64_t* dur, const int32_t* len
                          int invariant, const float* pe, const float* alpha, float* centers_tmp, int32_t* mel_lens_tmp,
                          float* out, void* stream) {
   EV_CHECK_ARG(hs && dur && centers_tmp && mel_lens_tmp && out, "ev_op_gauss_upsample: null argument");
+  EV_TRY(use_device_of(hs));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // centers_tmp holds 2*B*T floats: centres then float durations
   EV_TRY(launch_duration_scan(dur, lens, invariant, B, T, centers_tmp, centers_tmp + (size_t)B * T, mel_lens_tmp, st));

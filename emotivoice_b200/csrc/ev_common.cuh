@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include "../../include/emotivoice_b200.h"
 
@@ -14,6 +15,19 @@ void count_launch(int n = 1);
 // an error returned by cudaLaunchKernelEx (opt-in launch modes) is parked here and picked up by EV_CUDA_LAUNCH_CHECK
 void park_launch_error(cudaError_t e);
 cudaError_t take_launch_error();
+
+// Per-device one-time set-up.  cudaFuncSetAttribute and the SM count are per device and an engine may live on any GPU of the
+// process, so "done once" is tracked per device (bit d of `mask`); a benign race sets an attribute twice.
+inline bool first_use_on_device(std::atomic<uint64_t>& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const uint64_t bit = 1ull << (d & 63);
+  if (mask.load(std::memory_order_relaxed) & bit) return false;
+  mask.fetch_or(bit, std::memory_order_relaxed);
+  return true;
+}
+int sm_count();                          // SMs of the CURRENT device (cached per device)
+int use_device_of(const void* dev_ptr);  // cudaSetDevice(the device that owns dev_ptr); EV_OK / EV_ECUDA
 
 #define EV_CHECK_ARG(cond, ...)                      \
   do {                                               \
@@ -112,41 +126,24 @@ int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st);
 int debug_tc_plan(const ConvParams& p, int mode, int* v11);   // host-only: the plan launch_conv1d_tc would use
 int tc_shape_kbg(const ConvParams& p, int mode);               // K granules per stage: a function of the layer shape only
 
-// One ResBlock1 layer  out = [acc]( x + c2(lrelu(c1(lrelu(x)))) )  as one tcgen05 kernel (resblock_tc.cu); opt-in.
-struct ResPairParams {
-  const float* x;      // (B, L, C): the layer input, also the residual
-  const float* w1;     // c1 weights, tensor-core layout (k taps, dilation dil)
-  const float* b1;
-  const float* w2;     // c2 weights (k taps, dilation 1)
-  const float* b2;
-  float* out;          // (B, L, C); must not alias x
-  int B, L, C, K, dil;
-  const int32_t* lens; // valid rows per item = lens[b]*lens_mul (null: L)
-  int lens_mul;
-  float slope;         // LeakyReLU slope of both prologues (0.1)
-  int acc;             // EV_ACC_* applied to `out` like conv1d's epilogue
-  float div;
-};
-bool resblock_pair_supported(const ResPairParams& p, int mode);
-int launch_resblock_pair(const ResPairParams& p, int mode, cudaStream_t st);   // mode as launch_conv1d_tc
-int debug_resblock_plan(const ResPairParams& p, int mode, int* v11);
-
 // ---------------------------------------------------------------------------------
 // acoustic-model kernels (am_kernels.cu)
 // ---------------------------------------------------------------------------------
 // y = LN(x) over C; optional prologue x = emb[ids] + alpha*pe[t] (written to x_out).
 int launch_layernorm(const float* x, const int64_t* ids, const float* emb, const float* pe, const float* alpha,
                      float* x_out, const float* w, const float* b, float* y, int rows, int L, int C,
-                     cudaStream_t st);
+                     cudaStream_t st, int n_emb = 0);
 int launch_attention(const float* qkv, const int32_t* key_lens, float* ctx, int B, int L, int H, int heads,
                      cudaStream_t st);
 int launch_cond_gather(const int64_t* spk, const float* spk_emb, const float* style, const float* content,
-                       float* out, int B, int H, int bert, cudaStream_t st);
+                       float* out, int B, int H, int bert, int n_spk, cudaStream_t st);
 int launch_cond_gemv(const float* c, const float* w, const float* bias, float* out, int B, int K, int N, cudaStream_t st);
 // y[row] = dot(x[row,:], w) + b ; masked rows (t >= lens[b]) -> 0.  mode 0: float out; mode 1: duration int64
 int launch_rowdot(const float* x, const float* w, const float* b, const int32_t* lens, int B, int T, int C,
                   int mode, float* out_f, int64_t* out_i, cudaStream_t st);
-int launch_lens_to_i32(const int64_t* lens, int32_t* out, int B, int T, cudaStream_t st);
+// lens -> int32 clamped to [0, T] + range checks of token / speaker ids and lengths into *status (bits 1 / 2 / 4); ling, spk, status may be null
+int launch_validate_inputs(const int64_t* ling, const int64_t* lens, const int64_t* spk, int32_t* lens_out, int32_t* status, int B,
+                           int T, int n_vocab, int n_spk, cudaStream_t st);
 // zero rows t >= lens[b] of x (B,T,C) into y (masked_fill of the predictors' input)
 int launch_mask_rows(const float* x, const int32_t* lens, float* y, int B, int T, int C, cudaStream_t st);
 int launch_var_embed_add(float* x, const float* pitch, const float* energy, const float* wp, const float* bp,

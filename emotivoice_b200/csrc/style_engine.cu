@@ -318,7 +318,13 @@ int ev_style_forward(ev_style_ctx* c, const int64_t* ids, const int64_t* type_id
   if (bf.total > workspace_bytes) { set_error("ev_style_forward: workspace %zu < %zu bytes", workspace_bytes, bf.total); return EV_EWORKSPACE; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int H = g.hidden, I = g.intermediate, rows = B * N;
-  EV_TRY(launch_lens_to_i32(lens, bf.lens32, B, N, st));
+  {   // kernels and function attributes belong to the context's device, whatever device is current for the calling thread
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e == cudaSuccess && cur != c->device) e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) { set_error("ev_style_forward: cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e)); return EV_ECUDA; }
+  }
+  EV_TRY(launch_validate_inputs(nullptr, lens, nullptr, bf.lens32, nullptr, B, N, 0, 0, st));
   EV_TRY(launch_bert_embed_ln(ids, type_ids, c->word, c->type, c->pos, c->elnw, c->elnb, bf.x, rows, N, H, st));
   for (int i = 0; i < g.n_layers; ++i) {
     const StyleLayerW& l = c->layers[i];

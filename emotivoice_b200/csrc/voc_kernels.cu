@@ -81,11 +81,10 @@ int launch_conv_post(const float* x, const float* w, const float* bias, const in
   EV_CHECK_ARG(C % 4 == 0 && C <= 128 && K <= 15 && (K & 1), "conv_post: C=%d K=%d", C, K);
   EV_CHECK_ARG(B > 0 && B <= 65535 && L > 0, "conv_post: bad shape");
   const size_t smem = (size_t)((CP_BT + K - 1) * (C + 1) + K * C) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devs{0};
+  if (first_use_on_device(attr_devs)) {
     cudaFuncSetAttribute(conv_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(conv_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_set = true;
   }
   dim3 grid((L + CP_BT - 1) / CP_BT, B);
   launch_k(conv_post_kernel<true>, conv_post_kernel<false>, grid, CP_BT, smem, st, x, w, bias, lens, lens_mul, L, C, K, slope, wav);

@@ -62,12 +62,20 @@ def collate(items, device="cpu", pad_id=0):
     for b, it in enumerate(items):
         ling[b, :len(it[0])] = it[0]
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+    def vecs(col):
+        # rows may be numpy arrays / lists, or tensors on any device (PromptEmbeddingCache.embed keeps them on the GPU)
+        rows = [it[col] for it in items]
+        if any(isinstance(r, torch.Tensor) for r in rows):
+            return torch.stack([torch.as_tensor(r, dtype=torch.float32).to(device) for r in rows])
+        return to(np.stack([np.asarray(r, dtype=np.float32) for r in rows]))
+
     return dict(
         inputs_ling=to(ling),
         input_lengths=to(np.asarray([len(it[0]) for it in items], dtype=np.int64)),
         inputs_speaker=to(np.asarray([it[1] for it in items], dtype=np.int64)),
-        inputs_style_embedding=to(np.stack([np.asarray(it[2], dtype=np.float32) for it in items])),
-        inputs_content_embedding=to(np.stack([np.asarray(it[3], dtype=np.float32) for it in items])),
+        inputs_style_embedding=vecs(2),
+        inputs_content_embedding=vecs(3),
     )
 
 
@@ -171,7 +179,7 @@ def fetch_pcm16(model, out, hop=256):
     batch into pinned memory, then per-item trimming to ``mel_lengths[b] * hop`` on the host.
     ``out`` is the dict ``model(...)`` returned.  Returns a list of 1-D int16 numpy arrays (one per batch item)."""
     wav = out["wav_predictions"]
-    pcm = model.to_pcm16(wav)                                              # (B, 1, 256 F) int16, device
+    pcm = model.to_pcm16(wav)                                              # (B, 1, 256 F) int16, device (saturating, see to_pcm16)
     host = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)
     host.copy_(pcm, non_blocking=True)
     lens = out.get("mel_lengths")
@@ -209,25 +217,31 @@ class PromptEmbeddingCache:
     def embed(self, texts):
         """list of str -> (len(texts), D) float32 tensor, row i = pooled_output of texts[i]."""
         texts = list(texts)
+        uniq = list(dict.fromkeys(texts))
+        have = {}
+        # rows are captured into a local dict inside the critical section that finds them, so a concurrent embed() that evicts
+        # them afterwards cannot make this call's final lookup fail
         with self._lock:
-            missing = [t for t in dict.fromkeys(texts) if t not in self._cache]
-            self.hits += sum(1 for t in texts if t in self._cache)
-            self.misses += len(texts) - sum(1 for t in texts if t in self._cache)
+            for t in uniq:
+                row = self._cache.get(t)
+                if row is not None:
+                    self._cache.move_to_end(t)
+                    have[t] = row
+            n_hit = sum(1 for t in texts if t in have)
+            self.hits += n_hit
+            self.misses += len(texts) - n_hit
+        missing = [t for t in uniq if t not in have]
         if missing:
             enc = self._tok(missing, return_tensors="pt", padding=True)
             keys = ("input_ids", "token_type_ids", "attention_mask")
             args = {k: (enc[k].to(self._device) if self._device is not None else enc[k]) for k in keys}
             with torch.no_grad():
                 pooled = self._enc(**args)["pooled_output"].detach()
+            fresh = {t: pooled[i].clone() for i, t in enumerate(missing)}
+            have.update(fresh)
             with self._lock:
                 self.forwards += 1
-                for i, t in enumerate(missing):
-                    self._cache[t] = pooled[i].clone()
-                while len(self._cache) > max(self._max, len(set(texts))):
+                self._cache.update(fresh)
+                while len(self._cache) > self._max:
                     self._cache.popitem(last=False)
-        with self._lock:
-            rows = []
-            for t in texts:
-                self._cache.move_to_end(t)
-                rows.append(self._cache[t])
-        return torch.stack(rows)
+        return torch.stack([have[t] for t in texts])

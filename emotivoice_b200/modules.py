@@ -64,7 +64,10 @@ def _dirty_post_hook(module, incompatible_keys):
 class _Engine:
     """One ev_ctx + its packed weight blob and positional table on one device."""
 
-    def __init__(self, conf, packed, device, precision="fp32"):
+    def __init__(self, conf, packed, device, precision="fp32", blob=None, index_meta=None):
+        """``packed``: name -> tensor dict (packing.pack_state_dict + add_tc_weights), laid into one blob here; or pass a
+        ready ``blob`` (fp32 tensor already on ``device``) with its ``index_meta`` [(name, offset, numel)] -- what the
+        other ranks of a multi-GPU run receive from rank 0 instead of re-packing (runner.broadcast_engine)."""
         self.lib = _abi.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -76,8 +79,13 @@ class _Engine:
         handle = ctypes.c_void_p()
         _abi.check(self.lib.ev_create(ctypes.byref(handle), self.index_dev, ctypes.byref(self.cfg)))
         self.handle = handle
-        blob, self.index = packing.make_blob(packed)
-        self.blob = blob.to(self.device)
+        if blob is None:
+            blob, self.index = packing.make_blob(packed)
+            self.blob = blob.to(self.device)
+        else:
+            self.index = packing.index_from_meta(index_meta)
+            self.blob = blob
+            assert blob.device == self.device and blob.dtype == torch.float32 and blob.is_contiguous()
         _abi.check(self.lib.ev_bind_weights(self.handle, self.blob.data_ptr(), self.blob.numel(),
                                             ctypes.cast(self.index, ctypes.c_void_p), len(self.index)))
         self.set_precision(precision)
@@ -88,6 +96,9 @@ class _Engine:
     def set_precision(self, precision):
         _abi.check(self.lib.ev_set_precision(self.handle, _abi.PRECISIONS[precision]))
         self.precision = precision
+
+    def index_meta(self):
+        return [(e.name.decode(), int(e.offset), int(e.numel)) for e in self.index]
 
     def ensure_pe(self, n):
         if self.pe is not None and self.pe.shape[0] >= n:
@@ -115,7 +126,7 @@ class _Engine:
         dur = torch.empty((B, T), dtype=torch.int64, device=dev)
         pitch = torch.empty((B, T), dtype=torch.float32, device=dev)
         energy = torch.empty((B, T), dtype=torch.float32, device=dev)
-        meta = torch.empty((2 * B + 1,), dtype=torch.int32, device=dev)      # lens32 | mel_lens (B+1)
+        meta = torch.empty((2 * B + 2,), dtype=torch.int32, device=dev)      # lens32 (B) | mel_lens (B) | max | input status
         n1 = lib.ev_phase1_workspace_bytes(self.handle, B, T)
         ws1 = torch.empty((n1,), dtype=torch.uint8, device=dev)
         st = self._stream()
@@ -126,6 +137,13 @@ class _Engine:
                                     energy.data_ptr(), lens32_ptr, mel_lens_ptr, ws1.data_ptr(), n1, st))
         # the path's single host sync: the output length is data dependent (alignment.py:194-195)
         mel_lens_host = meta[B:].cpu()
+        status = int(mel_lens_host[B + 1])
+        if status:      # what nn.Embedding / the mask construction raise in the reference (checked on the device, read with the lengths)
+            if status & 1:
+                raise IndexError("inputs_ling holds token ids outside [0, %d)" % int(self.cfg.n_vocab))
+            if status & 2:
+                raise IndexError("inputs_speaker holds ids outside [0, %d)" % int(self.cfg.n_speaker))
+            raise RuntimeError("input_lengths must lie in [1, %d] (the padded width of inputs_ling)" % T)
         F = int(mel_lens_host[B])
         self.ensure_pe(F)
         n2 = lib.ev_phase2_workspace_bytes(self.handle, B, F)
@@ -195,6 +213,15 @@ class _EngineOwner(nn.Module):
 
     def _pack(self):
         raise NotImplementedError
+
+    def attach_packed(self, blob, index_meta):
+        """Adopt a packed weight blob produced elsewhere (rank 0 of a multi-GPU run) instead of packing this module's own
+        parameters: ``blob`` is already on the module's device.  The caller guarantees it corresponds to the parameters."""
+        dev = next(self.parameters()).device
+        with self._ev_lock:
+            self._ev_engine = _Engine(self.config, None, dev, self._ev_precision, blob=blob, index_meta=index_meta)
+            self._ev_dirty = False
+        return self._ev_engine
 
     def _engine(self):
         eng = self._ev_engine
@@ -302,9 +329,13 @@ def _am_forward(eng, inputs_ling, input_lengths, inputs_speaker, style, content,
     spk = _prep(inputs_speaker, torch.int64, dev)
     style = _prep(style, torch.float32, dev)
     content = _prep(content, torch.float32, dev)
-    if ling.dim() != 2 or lens.shape[0] != ling.shape[0] or spk.shape[0] != ling.shape[0]:
+    if ling.dim() != 2 or lens.dim() != 1 or lens.shape[0] != ling.shape[0] or spk.numel() != ling.shape[0]:
         raise RuntimeError("shape mismatch: inputs_ling %s, input_lengths %s, inputs_speaker %s"
                            % (tuple(ling.shape), tuple(lens.shape), tuple(spk.shape)))
+    want = (ling.shape[0], int(eng.cfg.bert_dim))
+    if tuple(style.shape) != want or tuple(content.shape) != want:
+        raise RuntimeError("inputs_style_embedding %s / inputs_content_embedding %s must both be %s"
+                           % (tuple(style.shape), tuple(content.shape), want))
     r = eng.acoustic(ling, lens, spk, style, content, invariant)
     out = {
         "mel_targets": None,
@@ -321,6 +352,7 @@ def _am_forward(eng, inputs_ling, input_lengths, inputs_speaker, style, content,
         "log_p_attn": None,
         "bin_loss": None,
         "mel_lengths": r["mel_lens"],                  # extension: per-item frame counts (B,) int32
+        "mel_lengths_host": r["mel_lens_host"],        # extension: the same on the host (read at the path's one sync)
     }
     return out, r
 
@@ -371,7 +403,9 @@ class JETSGenerator(_EngineOwner):
 
     @torch.no_grad()
     def to_pcm16(self, wav):
-        """The callers' ``wav * 32768 -> int16`` (inference_am_vocoder_joint.py:130-131) on the GPU."""
+        """The callers' ``wav * 32768 -> int16`` (inference_am_vocoder_joint.py:130-131) on the GPU: truncation toward zero
+        like ``astype``.  Deviation: samples outside the int16 range SATURATE to [-32768, 32767] (tanh can round to exactly
+        1.0 -> 32768) where numpy's cast wraps around; for |wav| < 1 the two agree bit for bit."""
         eng = self._engine()
         wav = _prep(wav, torch.float32, eng.device)
         pcm = torch.empty(wav.shape, dtype=torch.int16, device=eng.device)

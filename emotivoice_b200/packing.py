@@ -230,6 +230,16 @@ def make_blob(packed, align=64):
     return blob, index
 
 
+def index_from_meta(meta):
+    """[(name, offset, numel)] -> the ctypes index ``make_blob`` builds (for a blob received from another rank)."""
+    index = (WeightEntry * len(meta))()
+    for i, (k, off, n) in enumerate(meta):
+        index[i].name = k.encode()
+        index[i].offset = int(off)
+        index[i].numel = int(n)
+    return index
+
+
 # ---- style encoder (simbert.py:33-72; transformers BertModel names under ``bert.``) ---------------------------------
 
 STYLE_HEADS = ("pitch", "speed", "energy", "emotion")      # order of the packed classifier columns (simbert.py:58-61)

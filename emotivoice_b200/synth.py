@@ -205,6 +205,55 @@ def slice_batch(batch, b):
     )
 
 
+# id ranges of the two symbol families in data/youdao/text/tokenlist (502 lines): ARPABET "[..]" + engsp* (EN) and pinyin
+# initials/finals + sp* (ZH); 417-501 are unused "uncasedNN" placeholders, 0 = pad "_", 1 = <sos/eos>
+EN_ID_RANGES = ((2, 70), (148, 150), (402, 402), (409, 409))
+ZH_ID_RANGES = ((71, 147), (151, 401), (403, 408), (410, 416))
+
+
+def _ids_from(ranges):
+    return np.concatenate([np.arange(lo, hi + 1) for lo, hi in ranges]).astype(np.int64)
+
+
+def corpus_utterance(index, seed=SEED, lo=20, hi=200, n_phonemes=None, n_speaker=2014, bert_dim=768):
+    """Utterance ``index`` of the seeded synthetic corpus (BASELINE.json configs[2] / [4]: 20-200 phonemes, even indices
+    drawn from the EN symbols, odd ones from the ZH symbols).  Each utterance has its own generator seeded by
+    ``(seed, index)``, so it is the same whatever the corpus size, shard or world size -- what lets a multi-GPU run check
+    that its outputs are bit-identical to a single-GPU run's."""
+    rng = np.random.default_rng([int(seed), int(index)])
+    n = int(n_phonemes) if n_phonemes is not None else int(rng.integers(lo, hi + 1))
+    pool = _ids_from(EN_ID_RANGES if index % 2 == 0 else ZH_ID_RANGES)
+    ids = pool[rng.integers(0, len(pool), size=n)]
+    ids[0] = SOS_EOS_ID
+    ids[-1] = SOS_EOS_ID
+    return dict(ids=ids, speaker=np.int64(rng.integers(0, n_speaker)),
+                style=np.tanh(rng.normal(size=bert_dim)).astype(np.float32),
+                content=np.tanh(rng.normal(size=bert_dim)).astype(np.float32), index=int(index))
+
+
+def corpus_lengths(n, seed=SEED, lo=20, hi=200, n_phonemes=None):
+    """Phoneme counts of utterances 0..n-1 without building them (the sharding plan needs only these)."""
+    if n_phonemes is not None:
+        return [int(n_phonemes)] * n
+    return [int(np.random.default_rng([int(seed), i]).integers(lo, hi + 1)) for i in range(n)]
+
+
+def collate_utterances(utts, pin=False):
+    """list of utterance dicts -> JETSGenerator.forward keyword arguments (CPU tensors, optionally pinned), padded with
+    id 0 like the reference's collate (prompt_dataset.py:183)."""
+    B, T = len(utts), max(len(u["ids"]) for u in utts)
+    ling = np.full((B, T), PAD_ID, dtype=np.int64)
+    for b, u in enumerate(utts):
+        ling[b, :len(u["ids"])] = u["ids"]
+    out = dict(
+        inputs_ling=torch.from_numpy(ling),
+        input_lengths=torch.tensor([len(u["ids"]) for u in utts], dtype=torch.int64),
+        inputs_speaker=torch.tensor([int(u["speaker"]) for u in utts], dtype=torch.int64),
+        inputs_style_embedding=torch.from_numpy(np.stack([u["style"] for u in utts])),
+        inputs_content_embedding=torch.from_numpy(np.stack([u["content"] for u in utts])))
+    return {k: v.pin_memory() for k, v in out.items()} if pin else out
+
+
 def make_mel(batch, frames, seed=SEED, n_mels=80):
     """cfg4 vocoder-only input: N(0,1)*1.2, shape (B, 80, F)."""
     rng = np.random.default_rng(seed)

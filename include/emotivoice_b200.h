@@ -128,7 +128,10 @@ EV_API size_t ev_phase2_workspace_bytes(const ev_ctx* ctx, int B, int F);
  *   style, content (B,bert) f32
  *   dur_out (B,T) i64; pitch_out / energy_out (B,T) f32;
  *   lens32_out (B) i32: lens clamped to [0,T] (input of the later phases);
- *   mel_lens_out (B+1) i32: per-item frame counts, and max over items in slot B.
+ *   mel_lens_out (B+2) i32: per-item frame counts, max over items in slot B, and in slot B+1 an input
+ *     status word the host checks at the same read-back (the reference raises IndexError from nn.Embedding
+ *     for these; the kernels clamp so nothing is read out of bounds): bit 0 = a token id outside
+ *     [0, n_vocab), bit 1 = a speaker id outside [0, n_speaker), bit 2 = a length outside [1, T].
  *   invariant != 0: batch-invariant contract (each item == the reference's B=1 call);
  *   invariant == 0: literal padded-batch forward of the reference. */
 EV_API int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens, const int64_t* spk,
@@ -187,16 +190,6 @@ EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const 
  * The CPU tests check the invariants the kernel relies on (ring depth >= producer groups, TMEM/smem limits,
  * summation-order parameters independent of batch and length). */
 EV_API int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int split3, int ksplit, int* out11);
-/* One ResBlock1 layer (hifigan/models.py:50-57) as ONE kernel: out = [acc]( x + c2(lrelu(c1(lrelu(x), dil)), 1) ), C -> C
- * channels, C in {32, 64, 128}, both weights in the tensor-core layout of ev_op_conv1d_tc, slope 0.1.  Bitwise equal to the
- * two ev_op_conv1d_tc launches it replaces.  EV_EINVAL for shapes it does not take (the engine then runs the pair unfused).
- * The engine uses it only with EV_FUSE_RES=1 (opt-in until validated on hardware). */
-EV_API int ev_op_resblock_pair(const float* x, const float* w1_tc, const float* b1, const float* w2_tc, const float* b2,
-                               int split3, float* out, int B, int L, int C, int K, int dil, const int32_t* lens, int lens_mul,
-                               int acc, float div, void* stream);
-/* Host-only: out11 = {MT, KBG, a_stages, b_stages, producer groups, tmem columns, smem bytes, tiles, rows per tile,
- * rows1_pad, rows2_pad} of the plan ev_op_resblock_pair would use. */
-EV_API int ev_debug_resblock_plan(int B, int L, int C, int K, int dil, int split3, int* out11);
 /* LayerNorm over the last dim, eps 1e-12 (encoder.py:112-127). rows x C. */
 EV_API int ev_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int C, void* stream);
 /* Multi-head self-attention core (encoder.py:84-109) on a packed (B,L,3H) q|k|v buffer. */

@@ -202,6 +202,9 @@ def test_corpus_runner_is_independent_of_batching(model, dev):
         assert one[i][1] == five[i][1] == sharded[i][1] and one[i][0].shape == (one[i][1] * 256,)
         assert np.array_equal(one[i][0], five[i][0]) and np.array_equal(one[i][0], sharded[i][0])
         assert one[i][0].dtype == np.int16
+        assert one[i][2] == five[i][2] == sharded[i][2] == runner.utterance_digest(one[i][0])
+    digest = runner.combine_digests([(i, v[2]) for i, v in one.items()])
+    assert digest == runner.combine_digests([(i, v[2]) for i, v in reversed(list(sharded.items()))])
 
 
 def test_minimal_and_long_sequences(conf, sd, dev, lib):
@@ -223,3 +226,29 @@ def test_minimal_and_long_sequences(conf, sd, dev, lib):
     assert out["dec_outputs"].shape[1] > 5000                       # the table had to grow
     assert torch.equal(out["log_duration_predictions"].cpu(), ref["log_duration_predictions"])
     assert rel_max(out["dec_outputs"].cpu(), ref["dec_outputs"]) <= MEL_TOL
+
+
+def test_bad_inputs_raise_like_the_reference(model, dev):
+    """The reference's nn.Embedding raises IndexError for an out-of-range token / speaker id and its mask construction needs
+    1 <= length <= T; the engine's kernels index raw memory, so they clamp and report through the status word that the host
+    reads with the mel lengths (no extra sync).  Shape errors of the style / content vectors are host checks."""
+    good = {k: v.to(dev) for k, v in synth.make_batch([12, 9], seed=4).items()}
+    model(**good)
+    bad = dict(good, inputs_ling=good["inputs_ling"].clone())
+    bad["inputs_ling"][1, 3] = 502
+    with pytest.raises(IndexError):
+        model(**bad)
+    bad = dict(good, inputs_ling=good["inputs_ling"].clone())
+    bad["inputs_ling"][0, 0] = -1
+    with pytest.raises(IndexError):
+        model(**bad)
+    with pytest.raises(IndexError):
+        model(**dict(good, inputs_speaker=torch.tensor([0, 2014], device=dev)))
+    with pytest.raises(RuntimeError):
+        model(**dict(good, input_lengths=torch.tensor([12, 0], device=dev)))
+    with pytest.raises(RuntimeError):
+        model(**dict(good, input_lengths=torch.tensor([13, 9], device=dev)))
+    with pytest.raises(RuntimeError):
+        model(**dict(good, inputs_style_embedding=good["inputs_style_embedding"][:, :700].contiguous()))
+    out = model(**good)          # the engine is still usable afterwards
+    assert torch.isfinite(out["wav_predictions"]).all()

@@ -155,3 +155,29 @@ def test_prompt_embedding_cache_batches_dedups_and_evicts():
     cache.embed(["a", "b"])                                                                    # 5 distinct texts > 3 entries: LRU eviction
     assert calls == [3, 2] and len(cache._cache) == 3 and "hello world" not in cache._cache
     assert torch.equal(cache.embed(["hello world"])[0], e[3]) and calls == [3, 2, 1]
+
+
+def test_collate_accepts_tensor_rows_and_cache_rows_survive_eviction():
+    """PromptEmbeddingCache.embed returns tensors (on the encoder's device); collate must take them, and embed must
+    not lose its own rows when the cache is smaller than the request."""
+    import numpy as np
+    import torch
+    from emotivoice_b200 import frontdoor
+    items = [(np.arange(5), 1, torch.ones(8), np.zeros(8, np.float32)), (np.arange(3), 2, torch.zeros(8), torch.ones(8))]
+    b = frontdoor.collate(items)
+    assert b["inputs_style_embedding"].shape == (2, 8) and b["inputs_content_embedding"].dtype == torch.float32
+    assert b["inputs_ling"].shape == (2, 5) and b["input_lengths"].tolist() == [5, 3]
+
+    class Tok:
+        def __call__(self, texts, return_tensors="pt", padding=True):
+            ids = torch.tensor([[len(t)] for t in texts])
+            return {"input_ids": ids, "token_type_ids": torch.zeros_like(ids), "attention_mask": torch.ones_like(ids)}
+
+    def enc(input_ids, token_type_ids, attention_mask):
+        return {"pooled_output": input_ids.float().repeat(1, 4)}
+
+    cache = frontdoor.PromptEmbeddingCache(Tok(), enc, max_entries=2)
+    out = cache.embed(["a", "bb", "ccc", "a", "dddd"])          # more distinct texts than the cache holds
+    assert out[:, 0].tolist() == [1.0, 2.0, 3.0, 1.0, 4.0]
+    assert len(cache._cache) == 2 and cache.forwards == 1
+    assert cache.embed(["dddd", "a"])[:, 0].tolist() == [4.0, 1.0]

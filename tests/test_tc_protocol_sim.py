@@ -217,134 +217,3 @@ def test_conv_protocol_model_catches_the_round1_bugs():
     with pytest.raises(AssertionError):                       # column-less epilogue warps handing back an accumulator they never waited for
         for seed in range(50):
             sim_conv(seed, [True] * 6, n_cb=2, K=3, a_stages=2, b_stages=4, ngroups=2, epi_idle_warps=4, idle_warps_skip_wait=True)
-
-
-# ------------------------------------------------------------------------------------------------------------------
-# resblock_tc.cu
-# ------------------------------------------------------------------------------------------------------------------
-def sim_pair(seed, tiles, n_cb, K, a_stages, b_stages, ngroups, idle_warps=0):
-    sim = Sim(seed)
-    wpg = NPWARPS // ngroups
-    a_full = [Bar(wpg) for _ in range(a_stages)]
-    a_empty = [Bar(1) for _ in range(a_stages)]
-    b_full = [Bar(1) for _ in range(b_stages)]
-    b_empty = [Bar(1) for _ in range(b_stages)]
-    acc1_full, acc1_empty = Bar(1), Bar(NEPI_WARPS)
-    a2_full, a2_empty = Bar(NEPI_WARPS), Bar(1)              # kernel: one arrival per epilogue THREAD; per warp here
-    acc2_full, acc2_empty = Bar(1), Bar(NEPI_WARPS)
-
-    def producer(grp, w):
-        a_cnt = 0
-        for ti, active in enumerate(tiles):
-            if not active:
-                continue
-            for cb in range(n_cb):
-                if a_cnt % ngroups == grp:
-                    s = a_cnt % a_stages
-                    yield ("wait", a_empty[s], ((a_cnt // a_stages) & 1) ^ 1)
-                    if w == 0:
-                        yield ("write", ("A1", s), (ti, cb))
-                    yield ("arrive", a_full[s])
-                a_cnt += 1
-
-    def loader():
-        b_cnt = 0
-        for ti, active in enumerate(tiles):
-            if not active:
-                continue
-            for conv in range(2):
-                for cb in range(n_cb):
-                    for j in range(K):
-                        sb = b_cnt % b_stages
-                        yield ("wait", b_empty[sb], ((b_cnt // b_stages) & 1) ^ 1)
-                        yield ("write", ("B", sb), (ti, conv, cb, j))
-                        yield ("arrive", b_full[sb])
-                        b_cnt += 1
-
-    def mma():
-        a_cnt = b_cnt = tile_cnt = 0
-        for ti, active in enumerate(tiles):
-            if not active:
-                continue
-            par = tile_cnt & 1
-            yield ("wait", acc1_empty, par ^ 1)
-            for cb in range(n_cb):
-                sa = a_cnt % a_stages
-                yield ("wait", a_full[sa], (a_cnt // a_stages) & 1)
-                for j in range(K):
-                    sb = b_cnt % b_stages
-                    yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
-                    yield ("mma_read", ("A1", sa), (ti, cb))
-                    yield ("mma_read", ("B", sb), (ti, 0, cb, j))
-                    yield ("commit", b_empty[sb])
-                    b_cnt += 1
-                yield ("commit", a_empty[sa])
-                a_cnt += 1
-            yield ("write", ("ACC1",), ti)
-            yield ("commit", acc1_full)
-            yield ("wait", acc2_empty, par ^ 1)
-            yield ("wait", a2_full, par)
-            for cb in range(n_cb):
-                for j in range(K):
-                    sb = b_cnt % b_stages
-                    yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
-                    yield ("mma_read", ("A2",), ti)
-                    yield ("mma_read", ("B", sb), (ti, 1, cb, j))
-                    yield ("commit", b_empty[sb])
-                    b_cnt += 1
-            yield ("write", ("ACC2",), ti)
-            yield ("commit", a2_empty)
-            yield ("commit", acc2_full)
-            tile_cnt += 1
-
-    def epilogue(w):
-        tile_cnt = 0
-        for ti, active in enumerate(tiles):
-            if not active:
-                continue
-            par = tile_cnt & 1
-            yield ("wait", a2_empty, par ^ 1)
-            yield ("wait", acc1_full, par)
-            if w >= idle_warps:
-                yield ("read", ("ACC1",), ti)
-            if w == 0:
-                yield ("write", ("A2",), ti)
-            yield ("arrive", a2_full)
-            yield ("arrive", acc1_empty)
-            yield ("wait", acc2_full, par)
-            if w >= idle_warps:
-                yield ("read", ("ACC2",), ti)
-            yield ("arrive", acc2_empty)
-            tile_cnt += 1
-
-    for g in range(ngroups):
-        for w in range(wpg):
-            sim.add("producer%d.%d" % (g, w), producer(g, w))
-    sim.add("loader", loader())
-    sim.add("mma", mma())
-    for w in range(NEPI_WARPS):
-        sim.add("epilogue%d" % w, epilogue(w))
-    sim.run()
-
-
-@pytest.mark.parametrize("C,K,dil", [(32, 3, 1), (32, 11, 5), (64, 7, 3), (64, 11, 5), (128, 11, 1)])
-@pytest.mark.parametrize("mode", [0, 1, 2])
-def test_resblock_pair_protocol_with_the_real_plans(lib, C, K, dil, mode):
-    v = (ctypes.c_int * 11)()
-    if lib.ev_debug_resblock_plan(1, 137472, C, K, dil, mode, v) != 0:
-        assert C == 128 and mode == 1
-        return
-    pl = dict(zip("MT KBG a_stages b_stages groups tmem smem tiles R rows1_pad rows2_pad".split(), list(v)))
-    cpg = 8 if mode == 2 else 4
-    n_cb = -(-C // (cpg * pl["KBG"]))
-    for seed in range(6):
-        rng = random.Random(100 + seed)
-        tiles = [rng.random() > 0.2 for _ in range(rng.randint(1, 5))]
-        sim_pair(seed, tiles, n_cb, K, pl["a_stages"], pl["b_stages"], pl["groups"], idle_warps=4 if C == 32 else 0)
-
-
-def test_pair_protocol_model_is_sensitive():
-    """The pair model must fail on a ring that is too shallow for the producer grouping, like the conv model does."""
-    with pytest.raises(AssertionError):
-        for seed in range(20):
-            sim_pair(seed, [True, True, True], n_cb=8, K=3, a_stages=2, b_stages=4, ngroups=6)
