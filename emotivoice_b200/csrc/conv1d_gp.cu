@@ -1,0 +1,670 @@
+// HiFi-GAN convolutions on "granule-planar" activations (sm_100a): tcgen05.mma implicit GEMM whose A operand is fed by
+// bulk async copies (cp.async.bulk -> mbarrier complete_tx) instead of a register round trip, and whose epilogue stores
+// straight from the TMEM lane layout with fully coalesced 16-byte accesses -- no shared-memory transpose on either side.
+//
+// Layout (GP): an activation tensor (B, L, C) is stored as [b][g = C / cpg][l][cpg] with 16-byte granules
+// (cpg = 4 fp32 or 8 bf16 channels): every granule is a contiguous plane of L x 16 bytes.  That is exactly the no-swizzle
+// K-major UMMA operand layout of conv1d_tc.cu (element (row r, granule g) at (g * rows_pad + r) * 16), so
+//   * the A stage of a tile = KBG contiguous runs of `rows x 16 B`  -> KBG bulk copies issued by ONE thread, as many stages
+//     in flight as shared memory holds (the round-1 kernel had six warps doing ldg -> cvt -> st.shared, 86 % no-eligible);
+//   * tap j of a dilated convolution is still the same staged tile with the descriptor start advanced by j*dil rows;
+//   * tcgen05.ld gives thread = row, registers = consecutive channels: 4 (fp32) / 8 (bf16) consecutive registers are one
+//     granule, consecutive lanes are consecutive rows -> each st.global.v4 of a warp covers 512 contiguous bytes.
+// What still has to touch the operand between the copy and the MMA -- LeakyReLU of the input, zeroing of rows outside
+// [0, len) (the convolution's zero padding and the batch-invariant contract), round-to-nearest tf32 and the hi/lo split of
+// the 3xTF32 fp32 emulation -- is an IN-PLACE pass over the staged tile by four "transform" warps: shared memory to shared
+// memory (29-cycle latency instead of a global-memory round trip), conflict-free (consecutive lanes = consecutive 16 B).
+// HBM therefore holds plain activation values (fp32, or bf16 in the bf16 mode): residuals stay exact, one copy per tensor.
+//
+// Roles (480 threads): warps 0-7 epilogue, 8-11 transform, 12 A loader (one lane), 13 weight loader (one lane),
+// 14 TMEM allocation + MMA issue (one lane).  mbarrier pipelines: a_full (copy landed) -> a_ready (transformed) -> a_empty
+// (tcgen05.commit), b_full / b_empty, acc_full / acc_empty (two accumulator sets in TMEM: epilogue of tile i overlaps the
+// main loop of tile i+1).  Persistent CTAs, static round-robin tile order.
+//
+// out[b, m*rate + n / CoutR, n % CoutR] = epi( bias[n] + sum_j sum_ci w[j][ci][n] * act_in(x[b, m + (j-(K-1)/2)*dil, ci]) )
+// rate > 1 is the polyphase form of ConvTranspose1d (packing.polyphase_pack): the GEMM's N = rate * CoutR columns are the
+// `rate` output phases of each input row.  Replaces hifigan/models.py:50-57 (ResBlock1 convs), :116 (conv_pre), :118-119 (ups).
+#include "ev_common.cuh"
+#include "tc_common.cuh"
+
+namespace ev {
+namespace gp {
+
+using namespace tc;
+
+constexpr int NEPI_WARPS = 8;
+constexpr int NTW = 4;                       // transform warps
+constexpr int W_XFORM = NEPI_WARPS;          // warps 8..11
+constexpr int W_ALOAD = W_XFORM + NTW;       // 12
+constexpr int W_BLOAD = W_ALOAD + 1;         // 13
+constexpr int W_MMA = W_BLOAD + 1;           // 14
+constexpr int GP_THREADS = (W_MMA + 1) * 32; // 480
+constexpr int MAX_A = 8, MAX_B = 8;
+constexpr int SMEM_HEAD = 1024;              // barriers + TMEM slot
+constexpr int XF_UNROLL = 4;
+
+struct GPlan {
+  int BN, mt, kbg, planes;
+  int rows_pad;
+  int a_plane_bytes, b_plane_bytes, a_stage_bytes, b_stage_bytes;
+  int a_stages, b_stages;
+  int tmem_cols;
+  int tiles_m, tiles_n, total_tiles;
+  int smem_total;
+};
+
+__host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int BN, int mt, int kbg, GPlan* o) {
+  GPlan q;
+  q.planes = mode == 1 ? 2 : 1;
+  const int cpg = mode == 2 ? 8 : 4;
+  q.kbg = kbg; q.mt = mt; q.BN = BN;
+  if (2 * mt * BN > 512) return false;
+  q.tmem_cols = 32;
+  while (q.tmem_cols < 2 * mt * BN) q.tmem_cols <<= 1;
+  const int rows = BM * mt + (p.K - 1) * p.dil;
+  q.rows_pad = (rows + 7) / 8 * 8;
+  q.a_plane_bytes = kbg * q.rows_pad * 16;
+  q.b_plane_bytes = kbg * BN * 16;
+  q.a_stage_bytes = q.planes * q.a_plane_bytes;
+  q.b_stage_bytes = q.planes * q.b_plane_bytes;
+  const int budget = 227 * 1024 - SMEM_HEAD;
+  const int n_cb = (p.Cin + cpg * kbg - 1) / (cpg * kbg);
+  const int b_max = n_cb * p.K < MAX_B ? n_cb * p.K : MAX_B;
+  q.a_stages = 2;
+  q.b_stages = b_max < 2 ? b_max : 2;
+  if (q.a_stages * q.a_stage_bytes + q.b_stages * q.b_stage_bytes > budget) return false;
+  auto fits = [&](int a, int b) { return a * q.a_stage_bytes + b * q.b_stage_bytes <= budget; };
+  // the weight ring turns over K times per activation stage: first 4 weight stages, then up to 4 activation stages (they
+  // prefetch ACROSS tiles: the ring is not bounded by the channel blocks of one tile), then whatever still fits
+  while (q.b_stages < b_max && q.b_stages < 4 && fits(q.a_stages, q.b_stages + 1)) ++q.b_stages;
+  while (q.a_stages < 4 && fits(q.a_stages + 1, q.b_stages)) ++q.a_stages;
+  while (q.b_stages < b_max && fits(q.a_stages, q.b_stages + 1)) ++q.b_stages;
+  while (q.a_stages < MAX_A && fits(q.a_stages + 1, q.b_stages)) ++q.a_stages;
+  q.tiles_m = (p.L + BM * mt - 1) / (BM * mt);
+  q.tiles_n = (p.Cout + BN - 1) / BN;
+  q.total_tiles = p.B * q.tiles_m * q.tiles_n;
+  q.smem_total = SMEM_HEAD + q.a_stages * q.a_stage_bytes + q.b_stages * q.b_stage_bytes;
+  *o = q;
+  return true;
+}
+
+__device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// MODE 0: one tf32 MMA per K step; 1: 3xTF32 fp32 emulation (hi/lo planes, three MMAs per K step); 2: bf16 operands,
+// bf16 activations in HBM (kind::f16, 8 channels per granule).  Accumulation is fp32 in TMEM in every mode.
+template <int MODE, int MT, int KBG>
+__global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p, GPlan pl) {
+  constexpr bool SPLIT3 = (MODE == 1);
+  constexpr bool BF16 = (MODE == 2);
+  constexpr int PLANES = SPLIT3 ? 2 : 1;
+  constexpr int CPG = BF16 ? 8 : 4;
+  constexpr int KB = CPG * KBG;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int BN = pl.BN;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 512);     // barriers occupy [0, 8 * 44) = 352 B
+  uint8_t* a_tiles = smem_raw + SMEM_HEAD;
+  uint8_t* b_tiles = a_tiles + pl.a_stages * pl.a_stage_bytes;
+  const uint32_t bar_base = smem_u32(bars);
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_ready = [&](int s) { return bar_base + 8u * (MAX_A + s); };
+  auto a_empty = [&](int s) { return bar_base + 8u * (2 * MAX_A + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (3 * MAX_A + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (3 * MAX_A + MAX_B + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (3 * MAX_A + 2 * MAX_B + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (3 * MAX_A + 2 * MAX_B + 2 + s); };
+
+  if (tid == 0) {
+    for (int s = 0; s < pl.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_ready(s), NTW * 32); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < pl.b_stages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), NEPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_MMA) {   // TMEM allocation by one full warp; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pl.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Programmatic dependent launch: harmless without the launch attribute.  With it, the next kernel in the stream may start
+  // its set-up (barriers, TMEM, first weight stages) while this grid's tail is still running; everything that touches
+  // activations executes griddepcontrol.wait first (returns once the preceding grid has completed and flushed).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int n_cb = (p.Cin + KB - 1) / KB;
+  const int halo = ((p.K - 1) / 2) * p.dil;
+  const int rows_a = BM * MT + (p.K - 1) * p.dil;
+  const int tiles_per_b = pl.tiles_m * pl.tiles_n;
+  const int gin = p.Cin / CPG;                // input granule planes per item
+
+  auto decode = [&](int tile, int& b, int& t0, int& n0, int& len) {
+    b = tile / tiles_per_b;
+    const int r = tile - b * tiles_per_b;
+    const int tm = r / pl.tiles_n, tn = r - tm * pl.tiles_n;
+    t0 = tm * (BM * MT);
+    n0 = tn * BN;
+    len = p.lens ? min(p.L, p.lens[b] * p.lens_mul) : p.L;
+  };
+
+  if (warp < NEPI_WARPS) {
+    // ============================ epilogue warps ==============================================
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int quad = warp & 3, half = warp >> 2;
+    const int nchunks = BN / 32;
+    const int coutR = p.Cout / p.rate;
+    const int gout = coutR / CPG;              // output granule planes per item
+    const size_t Lout = (size_t)p.L * p.rate;
+    const int accm = p.acc;
+    const bool has_res = p.res != nullptr;
+    int tile_cnt = 0;
+    for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+      int b, t0, n0, len;
+      decode(tile, b, t0, n0, len);
+      if (t0 >= len) continue;                 // padding tile: no MMA work was issued, nothing is stored (rows >= len are undefined)
+      const int buf = tile_cnt & 1;
+      bool waited = false;
+#pragma unroll 1
+      for (int item = half; item < MT * nchunks; item += 2) {
+        const int mt = item / nchunks, c = (item - mt * nchunks) * 32;
+        const int row = t0 + mt * BM + quad * 32 + lane;         // this thread's GEMM row (input-resolution time step)
+        const bool ok = row < len;
+        const int n = n0 + c;                                     // first of this thread's 32 columns
+        const int phase = n / coutR, co = n - phase * coutR;
+        const size_t orow = (size_t)row * p.rate + phase;
+        // 16-byte granule q of this chunk lives at plane (co/CPG + q), row orow
+        const size_t gbase = ((size_t)b * gout + co / CPG) * Lout + orow;
+        constexpr int NG = 32 / CPG;                              // granules per 32-column chunk: 8 (fp32) / 4 (bf16)
+        uint4 rq[NG];
+        if (has_res) {
+#pragma unroll
+          for (int q = 0; q < NG; ++q) {
+            rq[q] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) rq[q] = *(reinterpret_cast<const uint4*>(p.res) + gbase + (size_t)q * Lout);
+          }
+        }
+        if (!waited) {
+          mbar_wait(acc_full(buf), (tile_cnt >> 1) & 1);
+          tc_fence_after();
+          waited = true;
+        }
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * MT * BN + mt * BN + c), 32, v);
+        if (ok) {
+          if (p.bias) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
+              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+            }
+          }
+          if (has_res) {
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+              if (BF16) {
+                const uint32_t w4[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[8 * q + 2 * e] += __uint_as_float(w4[e] << 16);
+                  v[8 * q + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+                }
+              } else {
+                v[4 * q] += __uint_as_float(rq[q].x); v[4 * q + 1] += __uint_as_float(rq[q].y);
+                v[4 * q + 2] += __uint_as_float(rq[q].z); v[4 * q + 3] += __uint_as_float(rq[q].w);
+              }
+            }
+          }
+          if (accm != EV_ACC_STORE) {     // the xs += / xs /= n accumulation of the last layer of a ResBlock (2 launches in 18): loaded late to keep
+            uint4 oq[NG];                 // the common path's register footprint small
+#pragma unroll
+            for (int q = 0; q < NG; ++q) oq[q] = *(reinterpret_cast<const uint4*>(p.out) + gbase + (size_t)q * Lout);
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+              if (BF16) {
+                const uint32_t w4[4] = {oq[q].x, oq[q].y, oq[q].z, oq[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[8 * q + 2 * e] += __uint_as_float(w4[e] << 16);
+                  v[8 * q + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+                }
+              } else {
+                v[4 * q] += __uint_as_float(oq[q].x); v[4 * q + 1] += __uint_as_float(oq[q].y);
+                v[4 * q + 2] += __uint_as_float(oq[q].z); v[4 * q + 3] += __uint_as_float(oq[q].w);
+              }
+            }
+            if (accm == EV_ACC_ADD_DIV) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] /= p.div;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < NG; ++q) {
+            uint4 o;
+            if (BF16) {
+              o.x = pack_bf16(v[8 * q], v[8 * q + 1]); o.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+              o.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); o.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+            } else {
+              o.x = __float_as_uint(v[4 * q]); o.y = __float_as_uint(v[4 * q + 1]);
+              o.z = __float_as_uint(v[4 * q + 2]); o.w = __float_as_uint(v[4 * q + 3]);
+            }
+            *(reinterpret_cast<uint4*>(p.out) + gbase + (size_t)q * Lout) = o;
+          }
+        }
+      }
+      if (!waited) {     // a warp without work items in this tile still follows the accumulator phases
+        mbar_wait(acc_full(buf), (tile_cnt >> 1) & 1);
+        tc_fence_after();
+      }
+      // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+      ++tile_cnt;
+    }
+  } else if (warp < W_ALOAD) {
+    // ============================ transform warps: in-place pass over the landed A stage =======================
+    const int xt = (warp - W_XFORM) * 32 + lane;      // 0..127
+    const bool lrelu = (p.in_act == EV_ACT_LRELU);
+    const float slope = p.in_slope;
+    int a_cnt = 0;
+    for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+      int b, t0, n0, len;
+      decode(tile, b, t0, n0, len);
+      if (t0 >= len) continue;
+      const int row0 = t0 - halo;
+      for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
+        const int s = a_cnt % pl.a_stages;
+        const int ngran = min(KB, p.Cin - cb * KB) / CPG;
+        uint8_t* base = a_tiles + s * pl.a_stage_bytes;
+        mbar_wait(a_full(s), (a_cnt / pl.a_stages) & 1);
+        for (int g = 0; g < ngran; ++g) {
+          uint8_t* gb = base + (size_t)g * pl.rows_pad * 16;
+          for (int r0 = 0; r0 < rows_a; r0 += NTW * 32 * XF_UNROLL) {
+            uint4 v[XF_UNROLL];
+#pragma unroll
+            for (int u = 0; u < XF_UNROLL; ++u) {
+              const int r = r0 + u * (NTW * 32) + xt;
+              const int row = row0 + r;
+              v[u] = make_uint4(0u, 0u, 0u, 0u);
+              if (r < rows_a && row >= 0 && row < len) v[u] = *reinterpret_cast<const uint4*>(gb + r * 16);
+            }
+#pragma unroll
+            for (int u = 0; u < XF_UNROLL; ++u) {
+              const int r = r0 + u * (NTW * 32) + xt;
+              if (r >= rows_a) continue;
+              if (BF16) {
+                if (lrelu) {
+                  uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float lo = lrelu_f(__uint_as_float(w4[e] << 16), slope);
+                    const float hi = lrelu_f(__uint_as_float(w4[e] & 0xffff0000u), slope);
+                    w4[e] = pack_bf16(lo, hi);
+                  }
+                  v[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+                *reinterpret_cast<uint4*>(gb + r * 16) = v[u];
+              } else {
+                float4 t = make_float4(__uint_as_float(v[u].x), __uint_as_float(v[u].y), __uint_as_float(v[u].z), __uint_as_float(v[u].w));
+                if (lrelu) { t.x = lrelu_f(t.x, slope); t.y = lrelu_f(t.y, slope); t.z = lrelu_f(t.z, slope); t.w = lrelu_f(t.w, slope); }
+                // round to nearest tf32 (the MMA would otherwise truncate the low 13 mantissa bits)
+                const float4 h = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
+                *reinterpret_cast<float4*>(gb + r * 16) = h;
+                if (SPLIT3) {
+                  const float4 l = make_float4(to_tf32(t.x - h.x), to_tf32(t.y - h.y), to_tf32(t.z - h.z), to_tf32(t.w - h.w));
+                  *reinterpret_cast<float4*>(gb + pl.a_plane_bytes + r * 16) = l;
+                }
+              }
+            }
+          }
+        }
+        fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(a_ready(s));
+      }
+    }
+  } else if (warp == W_ALOAD) {
+    // ============================ A loader: one thread, KBG bulk copies per stage ================================
+    if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      int a_cnt = 0;
+      for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+        int b, t0, n0, len;
+        decode(tile, b, t0, n0, len);
+        if (t0 >= len) continue;
+        const int r_lo = max(t0 - halo, 0);
+        const int r_hi = min(t0 - halo + rows_a, len);      // len <= L: never past the plane
+        const uint32_t nbytes = (uint32_t)(r_hi - r_lo) * 16u;
+        const uint32_t roff = (uint32_t)(r_lo - (t0 - halo)) * 16u;
+        const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x) + ((size_t)b * gin * p.L + r_lo) * 16;
+        for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
+          const int s = a_cnt % pl.a_stages;
+          const int ngran = min(KB, p.Cin - cb * KB) / CPG;
+          mbar_wait(a_empty(s), ((a_cnt / pl.a_stages) & 1) ^ 1);
+          mbar_expect_tx(a_full(s), (uint32_t)ngran * nbytes);
+          const uint32_t dst = smem_u32(a_tiles + s * pl.a_stage_bytes) + roff;
+          const uint8_t* src = xb + (size_t)(cb * KBG) * p.L * 16;
+          for (int g = 0; g < ngran; ++g)
+            bulk_g2s(dst + (uint32_t)(g * pl.rows_pad * 16), src + (size_t)g * p.L * 16, nbytes, a_full(s));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W_BLOAD) {
+    // ============================ weight loader (weights are constants: no dependency wait) ========================
+    if (lane == 0) {
+      // w layout: [plane (hi, lo)][N tile of BNp = min(Cout,128)][tap][Cin/CPG granules][BNp][16 bytes]
+      const int bnp = p.Cout < 128 ? p.Cout : 128;
+      const size_t plane = (size_t)p.K * p.Cin * p.Cout;
+      const size_t tile_stride = (size_t)p.K * gin * bnp * 4;      // 4-byte words per packed N tile
+      int b_cnt = 0;
+      for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+        int b, t0, n0, len;
+        decode(tile, b, t0, n0, len);
+        if (t0 >= len) continue;
+        const float* wt = p.w + (size_t)(n0 / bnp) * tile_stride + (size_t)(n0 % bnp) * 4;
+        for (int cb = 0; cb < n_cb; ++cb) {
+          const int ngran = min(KB, p.Cin - cb * KB) / CPG;
+          for (int j = 0; j < p.K; ++j, ++b_cnt) {
+            const int sb = b_cnt % pl.b_stages;
+            mbar_wait(b_empty(sb), ((b_cnt / pl.b_stages) & 1) ^ 1);
+            mbar_expect_tx(b_full(sb), (uint32_t)(PLANES * ngran * BN * 16));
+            const uint32_t dst = smem_u32(b_tiles + sb * pl.b_stage_bytes);
+            const float* src = wt + ((size_t)j * gin + (size_t)cb * KBG) * bnp * 4;
+            if (BN == bnp) {
+              bulk_g2s(dst, src, (uint32_t)(ngran * BN * 16), b_full(sb));
+              if (SPLIT3) bulk_g2s(dst + (uint32_t)pl.b_plane_bytes, src + plane, (uint32_t)(ngran * BN * 16), b_full(sb));
+            } else {
+              for (int g = 0; g < ngran; ++g) {
+                bulk_g2s(dst + (uint32_t)(g * BN * 16), src + (size_t)g * bnp * 4, (uint32_t)(BN * 16), b_full(sb));
+                if (SPLIT3) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane + (size_t)g * bnp * 4, (uint32_t)(BN * 16), b_full(sb));
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ MMA issuer =====================================================
+    if (lane == 0) {
+      const uint32_t a_lbo = (uint32_t)pl.rows_pad * 16u, b_lbo = (uint32_t)BN * 16u;
+      const uint32_t fmt = BF16 ? 1u : 2u;      // instruction descriptor: D=F32 [4,6)=1, A/B format [7,10) / [10,13), N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int a_cnt = 0, b_cnt = 0, tile_cnt = 0;
+      for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
+        int b, t0, n0, len;
+        decode(tile, b, t0, n0, len);
+        if (t0 >= len) continue;
+        const int buf = tile_cnt & 1;
+        mbar_wait(acc_empty(buf), ((tile_cnt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * MT * BN);
+        for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
+          const int sa = a_cnt % pl.a_stages;
+          const int nk8 = min(KB, p.Cin - cb * KB) / (2 * CPG);   // MMA K steps: two 16-byte granules each
+          mbar_wait(a_ready(sa), (a_cnt / pl.a_stages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_tiles + sa * pl.a_stage_bytes);
+          for (int j = 0; j < p.K; ++j, ++b_cnt) {
+            const int sb = b_cnt % pl.b_stages;
+            mbar_wait(b_full(sb), (b_cnt / pl.b_stages) & 1);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(b_tiles + sb * pl.b_stage_bytes);
+            for (int k8 = 0; k8 < nk8; ++k8) {
+              const uint32_t b_off = (uint32_t)(2 * k8) * b_lbo;
+              const uint64_t b_hi = make_desc(b_addr + b_off, b_lbo, 128u);
+              const uint64_t b_lo = make_desc(b_addr + pl.b_plane_bytes + b_off, b_lbo, 128u);
+              const uint32_t first = (cb | j | k8) != 0 ? 1u : 0u;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
+                const uint32_t a_off = (uint32_t)((2 * k8) * pl.rows_pad + mt * BM + j * p.dil) * 16u;
+                const uint64_t a_hi = make_desc(a_addr + a_off, a_lbo, 128u);
+                const uint32_t d = d_base + (uint32_t)(mt * BN);
+                if (SPLIT3) {
+                  const uint64_t a_lo = make_desc(a_addr + pl.a_plane_bytes + a_off, a_lbo, 128u);
+                  umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
+                  umma_tf32(d, a_hi, b_lo, idesc, 1u);
+                  umma_tf32(d, a_hi, b_hi, idesc, 1u);
+                } else if (BF16) {
+                  umma_bf16(d, a_hi, b_hi, idesc, first);
+                } else {
+                  umma_tf32(d, a_hi, b_hi, idesc, first);
+                }
+              }
+            }
+            umma_commit(b_empty(sb));     // weight stage free once these MMAs have read it
+          }
+          umma_commit(a_empty(sa));       // activation stage free
+        }
+        umma_commit(acc_full(buf));       // accumulators of this tile complete -> epilogue
+        ++tile_cnt;
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pl.tmem_cols));
+  }
+}
+
+// ---- layout conversion at the vocoder's boundary ---------------------------------------------------------------------
+// in[b*sb + t*st + c*sc] fp32 (time-major (B,F,C): st = C, sc = 1; channels-first (B,C,F): st = 1, sc = F)  ->  GP.
+template <bool BF16>
+__global__ void __launch_bounds__(256) to_gp_kernel(const float* __restrict__ in, long long sb, long long st_, long long sc, void* __restrict__ out,
+                                                    int B, int L, int C) {
+  asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+  constexpr int CPG = BF16 ? 8 : 4;
+  const int G = C / CPG;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (b, g, t), t fastest
+  if (i >= (size_t)B * G * L) return;
+  const int t = (int)(i % L);
+  const int g = (int)((i / L) % G);
+  const int b = (int)(i / ((size_t)L * G));
+  const float* src = in + (size_t)b * sb + (size_t)t * st_ + (size_t)(g * CPG) * sc;
+  float v[CPG];
+#pragma unroll
+  for (int e = 0; e < CPG; ++e) v[e] = src[(size_t)e * sc];
+  uint4 o;
+  if (BF16) {
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[CPG - 4], v[CPG - 3]); o.w = pack_bf16(v[CPG - 2], v[CPG - 1]);
+  } else {
+    o.x = __float_as_uint(v[0]); o.y = __float_as_uint(v[1]); o.z = __float_as_uint(v[2]); o.w = __float_as_uint(v[3]);
+  }
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+// wav[b,t] = tanh( bias + sum_j sum_c w[j][c] * lrelu(x[b, t+j-(K-1)/2, c]) ) on a GP input (hifigan/models.py:127-129:
+// F.leaky_relu default slope 0.01, Conv1d(C,1,7,pad 3), tanh).  HBM-bound: each CTA stages (256 + K - 1) rows once, already
+// activated; rows >= len read as zero padding and are written as zeros.  Same summation order as conv_post_kernel.
+constexpr int GPP_BT = 256;
+template <bool BF16>
+__global__ void __launch_bounds__(GPP_BT) conv_post_gp_kernel(const void* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                              const int32_t* __restrict__ lens, int lens_mul, int L, int C, int K, float slope,
+                                                              float* __restrict__ wav) {
+  asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+  constexpr int CPG = BF16 ? 8 : 4;
+  extern __shared__ __align__(16) float gpp_smem[];
+  const int rows = GPP_BT + K - 1;
+  float* xs = gpp_smem;                 // [C][rows] channel-major: conflict-free for consecutive rows
+  float* ws = gpp_smem + (size_t)C * rows;   // [K][C]
+  const int b = blockIdx.y, t0 = blockIdx.x * GPP_BT;
+  const int len = lens ? min(L, lens[b] * lens_mul) : L;
+  const int halo = (K - 1) / 2;
+  const int G = C / CPG;
+  const uint4* xb = reinterpret_cast<const uint4*>(x) + (size_t)b * G * L;
+  for (int i = threadIdx.x; i < G * rows; i += GPP_BT) {
+    const int g = i / rows, r = i - g * rows;
+    const int row = t0 - halo + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row >= 0 && row < len) v = xb[(size_t)g * L + row];
+    float f[CPG];
+    if (BF16) {
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { f[2 * e] = __uint_as_float(w4[e] << 16); f[2 * e + 1] = __uint_as_float(w4[e] & 0xffff0000u); }
+    } else {
+      f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+    }
+#pragma unroll
+    for (int e = 0; e < CPG; ++e) xs[(size_t)(g * CPG + e) * rows + r] = lrelu_f(f[e], slope);
+  }
+  for (int i = threadIdx.x; i < K * C; i += GPP_BT) ws[i] = w[i];
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
+  float acc = 0.f;
+  for (int j = 0; j < K; ++j) {
+    const float* wr = ws + j * C;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) acc = fmaf(xs[(size_t)c * rows + threadIdx.x + j], wr[c], acc);
+  }
+  wav[(size_t)b * L + t] = t < len ? tanhf(acc + bias[0]) : 0.f;
+}
+
+}  // namespace gp
+
+static int validate_gp(const GpConvParams& p, int mode) {
+  EV_CHECK_ARG(p.B > 0 && p.L > 0, "conv1d_gp: bad problem B=%d L=%d", p.B, p.L);
+  EV_CHECK_ARG(mode >= 0 && mode <= 2, "conv1d_gp: mode %d", mode);
+  EV_CHECK_ARG(p.Cin % (mode == 2 ? 16 : 8) == 0, "conv1d_gp: Cin=%d must be a multiple of %d", p.Cin, mode == 2 ? 16 : 8);
+  EV_CHECK_ARG(p.Cout % 32 == 0 && (p.Cout <= 128 || p.Cout % 128 == 0), "conv1d_gp: Cout=%d must be a multiple of 32, and of 128 above 128", p.Cout);
+  EV_CHECK_ARG(p.rate >= 1 && p.Cout % p.rate == 0 && (p.Cout / p.rate) % 32 == 0, "conv1d_gp: rate=%d does not split Cout=%d into multiples of 32", p.rate, p.Cout);
+  EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_gp: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
+  EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_gp: unsupported input activation");
+  EV_CHECK_ARG(p.rate == 1 || (!p.res && p.acc == EV_ACC_STORE), "conv1d_gp: residual / accumulate need rate == 1");
+  EV_CHECK_ARG((long long)p.L * p.rate < (1ll << 31), "conv1d_gp: output too long");
+  return EV_OK;
+}
+
+// K granules per stage decide the order of the (channel block, tap, k-step) reduction, so they are a function of the layer
+// shape alone (never of batch or length): 8 outside the 3xTF32 mode if a one-accumulator tile fits with them, else 4.
+static int gp_shape_kbg(const GpConvParams& p, int mode) {
+  gp::GPlan pl;
+  const int bn_max = p.Cout <= 128 ? p.Cout : 128;
+  return (mode != 1 && gp::make_gplan(p, mode, bn_max, 1, 8, &pl)) ? 8 : 4;
+}
+
+// Tile shape: none of these choices changes the order in which any output element's K reduction is summed, so results are
+// bitwise independent of batch size / sequence length (batch-invariant contract).
+//  * rows per tile: as many 128-row accumulators (MT) as still leave about one tile per SM; one weight tile from L2 then
+//    feeds MT MMAs and the (K-1)*dil halo rows are amortised over MT*128 rows.
+//  * N tile: min(C_out, 128) = the weight packing tile (one bulk copy per weight stage), halved while the launch would
+//    otherwise leave a quarter of the SMs without a tile (HiFi-GAN stage 1 at batch 1: 68 tiles -> 136).
+static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out) {
+  EV_TRY(validate_gp(p, mode));
+  const int nsm = sm_count();
+  const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
+  int BN = p.Cout <= 128 ? p.Cout : 128;
+  int mt = 1;
+  {
+    const long long nt = (p.Cout + BN - 1) / BN;
+    if (tiles128 * nt >= 4ll * nsm) mt = 4;
+    else if (tiles128 * nt >= 2ll * nsm) mt = 2;
+  }
+  while (BN >= 64 && ((long long)((p.L + tc::BM * mt - 1) / (tc::BM * mt)) * p.B) * ((p.Cout + BN - 1) / BN) * 4 < 3ll * nsm) BN /= 2;
+  const int kbg = gp_shape_kbg(p, mode);
+  gp::GPlan pl;
+  for (;; mt >>= 1) {
+    if (gp::make_gplan(p, mode, BN, mt, kbg, &pl)) break;
+    if (mt == 1) { set_error("conv1d_gp: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
+  }
+  *out = pl;
+  return EV_OK;
+}
+
+int debug_gp_plan(const GpConvParams& p, int mode, int* v) {
+  gp::GPlan pl;
+  const int rc = plan_gp(p, mode, &pl);
+  if (rc != EV_OK) return rc;
+  v[0] = pl.BN; v[1] = pl.mt; v[2] = pl.kbg; v[3] = pl.a_stages; v[4] = pl.b_stages; v[5] = gp::NTW;
+  v[6] = pl.planes; v[7] = pl.tmem_cols; v[8] = pl.smem_total; v[9] = pl.total_tiles; v[10] = pl.rows_pad;
+  return EV_OK;
+}
+
+template <int MODE, int MT, int KBG>
+static int launch_gp_variant(const GpConvParams& p, const gp::GPlan& pl, cudaStream_t st) {
+  static std::atomic<uint64_t> attr_devs{0};
+  if (first_use_on_device(attr_devs))
+    cudaFuncSetAttribute(gp::conv1d_gp_kernel<MODE, MT, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const int nsm = sm_count();
+  const int grid = pl.total_tiles < nsm ? pl.total_tiles : nsm;
+  if (pdl_mode()) {
+    const cudaError_t e = launch_with_pdl(gp::conv1d_gp_kernel<MODE, MT, KBG>, dim3((unsigned)grid), dim3(gp::GP_THREADS), (size_t)pl.smem_total, st, p, pl);
+    if (e != cudaSuccess) { set_error("conv1d_gp_kernel (PDL launch): %s", cudaGetErrorString(e)); return EV_ECUDA; }
+    count_launch();
+    return EV_OK;
+  }
+  gp::conv1d_gp_kernel<MODE, MT, KBG><<<grid, gp::GP_THREADS, pl.smem_total, st>>>(p, pl);
+  EV_CUDA_LAUNCH_CHECK("conv1d_gp_kernel");
+  return EV_OK;
+}
+
+template <int MODE, int KBG>
+static int launch_gp_mt(const GpConvParams& p, const gp::GPlan& pl, cudaStream_t st) {
+  if (pl.mt == 4) return launch_gp_variant<MODE, 4, KBG>(p, pl, st);
+  if (pl.mt == 2) return launch_gp_variant<MODE, 2, KBG>(p, pl, st);
+  return launch_gp_variant<MODE, 1, KBG>(p, pl, st);
+}
+
+int launch_conv1d_gp(const GpConvParams& p, int mode, cudaStream_t st) {
+  gp::GPlan pl;
+  EV_TRY(plan_gp(p, mode, &pl));
+  if (mode == 1) return launch_gp_mt<1, 4>(p, pl, st);
+  if (mode == 2) return pl.kbg == 8 ? launch_gp_mt<2, 8>(p, pl, st) : launch_gp_mt<2, 4>(p, pl, st);
+  return pl.kbg == 8 ? launch_gp_mt<0, 8>(p, pl, st) : launch_gp_mt<0, 4>(p, pl, st);
+}
+
+int launch_to_gp(const float* in, long long sb, long long st_, long long sc, void* out, int B, int L, int C, int bf16, cudaStream_t st) {
+  EV_CHECK_ARG(B > 0 && L > 0 && C % (bf16 ? 8 : 4) == 0, "to_gp: B=%d L=%d C=%d", B, L, C);
+  const size_t n = (size_t)B * (C / (bf16 ? 8 : 4)) * L;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  cudaError_t e = cudaSuccess;
+  if (pdl_mode()) {
+    e = bf16 ? launch_with_pdl(gp::to_gp_kernel<true>, dim3(grid), dim3(256), 0, st, in, sb, st_, sc, out, B, L, C)
+             : launch_with_pdl(gp::to_gp_kernel<false>, dim3(grid), dim3(256), 0, st, in, sb, st_, sc, out, B, L, C);
+  } else if (bf16) {
+    gp::to_gp_kernel<true><<<grid, 256, 0, st>>>(in, sb, st_, sc, out, B, L, C);
+  } else {
+    gp::to_gp_kernel<false><<<grid, 256, 0, st>>>(in, sb, st_, sc, out, B, L, C);
+  }
+  park_launch_error(e);
+  EV_CUDA_LAUNCH_CHECK("to_gp_kernel");
+  return EV_OK;
+}
+
+int launch_conv_post_gp(const void* x, int bf16, const float* w, const float* bias, const int32_t* lens, int lens_mul, int B, int L, int C, int K,
+                        float slope, float* wav, cudaStream_t st) {
+  EV_CHECK_ARG(C % (bf16 ? 8 : 4) == 0 && C <= 128 && K <= 15 && (K & 1), "conv_post_gp: C=%d K=%d", C, K);
+  EV_CHECK_ARG(B > 0 && B <= 65535 && L > 0, "conv_post_gp: bad shape");
+  const size_t smem = (size_t)(C * (gp::GPP_BT + K - 1) + K * C) * sizeof(float);
+  static std::atomic<uint64_t> attr_devs{0};
+  if (first_use_on_device(attr_devs)) {
+    cudaFuncSetAttribute(gp::conv_post_gp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(gp::conv_post_gp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  }
+  dim3 grid((L + gp::GPP_BT - 1) / gp::GPP_BT, B);
+  cudaError_t e = cudaSuccess;
+  if (pdl_mode()) {
+    e = bf16 ? launch_with_pdl(gp::conv_post_gp_kernel<true>, grid, dim3(gp::GPP_BT), smem, st, x, w, bias, lens, lens_mul, L, C, K, slope, wav)
+             : launch_with_pdl(gp::conv_post_gp_kernel<false>, grid, dim3(gp::GPP_BT), smem, st, x, w, bias, lens, lens_mul, L, C, K, slope, wav);
+  } else if (bf16) {
+    gp::conv_post_gp_kernel<true><<<grid, gp::GPP_BT, smem, st>>>(x, w, bias, lens, lens_mul, L, C, K, slope, wav);
+  } else {
+    gp::conv_post_gp_kernel<false><<<grid, gp::GPP_BT, smem, st>>>(x, w, bias, lens, lens_mul, L, C, K, slope, wav);
+  }
+  park_launch_error(e);
+  EV_CUDA_LAUNCH_CHECK("conv_post_gp_kernel");
+  return EV_OK;
+}
+
+}  // namespace ev

@@ -404,6 +404,24 @@ static int conv_x(int mode, const float* w_tc, const float* w_h, const float* x,
   return launch_conv1d_tc(p, mode == 3 ? 1 : (mode == 2 ? 2 : 0), st);
 }
 
+// HiFi-GAN convolution on granule-planar activations (conv1d_gp.cu).  mode as conv_x: 1 = tf32, 2 = bf16 (bf16 activations), 3 = 3xTF32.
+static int conv_gp(int mode, const float* w_tc, const float* w_h, const void* x, const float* bias, const void* res, void* out, int B, int L,
+                   int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act, float in_slope, int acc, float div,
+                   cudaStream_t st) {
+  GpConvParams p;
+  p.x = x; p.w = (mode == 2) ? w_h : w_tc; p.bias = bias; p.res = res; p.out = out;
+  p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.rate = rate;
+  p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope; p.acc = acc; p.div = div;
+  return launch_conv1d_gp(p, mode == 3 ? 1 : (mode == 2 ? 2 : 0), st);
+}
+
+// The vocoder runs on granule-planar activations whenever it runs on the tensor cores (every mode but "fp32_ffma");
+// EV_VOC_LAYOUT=tm keeps the round-1 time-major path (conv1d_tc.cu) for A/B measurements.
+static inline bool voc_gp_enabled() {
+  static const int v = [] { const char* e = getenv("EV_VOC_LAYOUT"); return (e && e[0] == 't') ? 0 : 1; }();
+  return v == 1;
+}
+
 static inline int body_mode(const ev_ctx* c) {
   return c->precision == EV_PREC_FP32_FFMA ? 0 : (c->precision == EV_PREC_TF32 ? 1 : (c->precision == EV_PREC_BF16 ? 2 : 3));
 }
@@ -641,6 +659,50 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   VocBufs v;
   carve_voc(ctx, cv, B, F, &v);
   if (cv.off > workspace_bytes) { set_error("ev_vocoder: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
+  const int mode = body_mode(ctx);
+  if (mode != 0 && voc_gp_enabled()) {
+    // ---- granule-planar path: [b][C/cpg][l][cpg] activations, bulk-copied A operands, direct coalesced epilogues ----
+    Range r_phase("ev:vocoder");
+    const int bf = (mode == 2) ? 1 : 0;
+    // mel (B,F,n_mels) time-major or (B,n_mels,F) channels-first -> GP
+    EV_TRY(launch_to_gp(mel, (long long)F * g.n_mels, mel_time_major ? g.n_mels : 1, mel_time_major ? 1 : F, v.Tm, B, F, g.n_mels, bf, st));
+    // conv_pre (hifigan/models.py:116)
+    EV_TRY(conv_gp(mode, ctx->pre.w_tc, ctx->pre.w_h, v.Tm, ctx->pre.b, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1, 1, mel_lens, 1,
+                   EV_ACT_NONE, 0.f, EV_ACC_STORE, 1.f, st));
+    int L = F, mul = 1;
+    size_t rb = 0;
+    static const char* const kNames[8] = {"voc:stage1", "voc:stage2", "voc:stage3", "voc:stage4", "voc:stage5", "voc:stage6", "voc:stage7", "voc:stage8"};
+    for (int s = 0; s < g.n_ups; ++s) {
+      Range r_stage(kNames[s & 7]);
+      const UpW& u = ctx->ups[s];
+      // x = ups[i](leaky_relu(x, 0.1)) (:118-119): polyphase transposed conv, the `rate` output phases are GEMM column groups
+      EV_TRY(conv_gp(mode, u.w_tc, u.w_h, v.ACC, u.b, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, u.rate, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+                     EV_ACC_STORE, 1.f, st));
+      L *= u.rate; mul *= u.rate;
+      const int C = u.cout;
+      for (int j = 0; j < g.n_resk; ++j) {
+        const float* src = v.X;
+        for (int l = 0; l < g.n_dil; ++l, ++rb) {
+          const ConvW& c1 = ctx->rb_c1[rb];
+          const ConvW& c2 = ctx->rb_c2[rb];
+          const bool last = (l == g.n_dil - 1);
+          float* dst = last ? v.ACC : ((l & 1) ? v.R2 : v.R1);
+          int acc = EV_ACC_STORE;
+          if (last && j > 0) acc = (j == g.n_resk - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;   // xs += ...; x = xs / n (:120-126)
+          if (last && g.n_resk == 1) acc = EV_ACC_STORE;
+          // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
+          EV_TRY(conv_gp(mode, c1.w_tc, c1.w_h, src, c1.b, nullptr, v.Tm, B, L, C, C, c1.K, c1.dil, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+                         EV_ACC_STORE, 1.f, st));
+          EV_TRY(conv_gp(mode, c2.w_tc, c2.w_h, v.Tm, c2.b, src, dst, B, L, C, C, c2.K, 1, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f, acc,
+                         (float)g.n_resk, st));
+          src = dst;
+        }
+      }
+    }
+    EV_CHECK_ARG(mul == ctx->total_up, "ev_vocoder: internal rate mismatch");
+    // x = leaky_relu(x) [slope 0.01]; conv_post; tanh (:127-129)
+    return launch_conv_post_gp(v.ACC, bf, ctx->post_w, ctx->post_b, mel_lens, mul, B, L, ctx->ups.back().cout, ctx->post_k, 0.01f, wav_out, st);
+  }
   g_split_ws.p = v.part; g_split_ws.cap = v.part_cap; g_split_ws.ksplit = 0;
   const float* m = mel;
   if (!mel_time_major) {
@@ -649,7 +711,6 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
   }
   Range r_phase("ev:vocoder");
   // conv_pre (hifigan/models.py:116)
-  const int mode = body_mode(ctx);
   EV_TRY(conv_x(mode, ctx->pre.w_tc, ctx->pre.w_h, m, ctx->pre.w, ctx->pre.b, 0, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1,
                 mel_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
   int L = F, mul = 1;
@@ -729,6 +790,36 @@ int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int split3
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.in_act = EV_ACT_NONE;
   p.ksplit = ksplit; p.splitk_ws = nullptr; p.splitk_cap = (size_t)-1;   // "scratch of any size is available"
   return debug_tc_plan(p, split3, out11);
+}
+
+int ev_op_conv1d_gp(const void* x, const float* w, int mode, const float* bias, const void* res, void* out, int B, int L, int Cin, int Cout,
+                    int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act, float in_slope, int acc, float div, void* stream) {
+  EV_CHECK_ARG(x && w && out, "ev_op_conv1d_gp: null argument");
+  EV_TRY(use_device_of(x));
+  GpConvParams p;
+  p.x = x; p.w = w; p.bias = bias; p.res = res; p.out = out; p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.rate = rate;
+  p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope; p.acc = acc; p.div = div;
+  return launch_conv1d_gp(p, mode, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_debug_gp_plan(int B, int L, int Cin, int Cout, int K, int dil, int rate, int mode, int* out11) {
+  EV_CHECK_ARG(out11, "ev_debug_gp_plan: null output");
+  GpConvParams p{};
+  p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.rate = rate; p.in_act = EV_ACT_NONE; p.acc = EV_ACC_STORE;
+  return debug_gp_plan(p, mode, out11);
+}
+
+int ev_op_to_gp(const float* in, long long stride_b, long long stride_t, long long stride_c, void* out, int B, int L, int C, int bf16, void* stream) {
+  EV_CHECK_ARG(in && out, "ev_op_to_gp: null argument");
+  EV_TRY(use_device_of(in));
+  return launch_to_gp(in, stride_b, stride_t, stride_c, out, B, L, C, bf16, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_conv_post_gp(const void* x, int bf16, const float* w, const float* bias, const int32_t* lens, int lens_mul, int B, int L, int C, int K,
+                       float slope, float* wav, void* stream) {
+  EV_CHECK_ARG(x && w && bias && wav, "ev_op_conv_post_gp: null argument");
+  EV_TRY(use_device_of(x));
+  return launch_conv_post_gp(x, bf16, w, bias, lens, lens_mul, B, L, C, K, slope, wav, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ev_set_precision(ev_ctx* ctx, int precision) {

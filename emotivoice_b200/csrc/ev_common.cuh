@@ -127,6 +127,32 @@ int debug_tc_plan(const ConvParams& p, int mode, int* v11);   // host-only: the 
 int tc_shape_kbg(const ConvParams& p, int mode);               // K granules per stage: a function of the layer shape only
 
 // ---------------------------------------------------------------------------------
+// HiFi-GAN convolutions on granule-planar activations (conv1d_gp.cu): [b][C/cpg][L][cpg], 16-byte granules of 4 fp32 or
+// 8 bf16 channels; the A operand is bulk-copied, the epilogue stores straight from the TMEM lane layout.
+// ---------------------------------------------------------------------------------
+struct GpConvParams {
+  const void* x;       // GP (B, Cin/cpg, L, cpg)
+  const float* w;      // tensor-core weight layout of conv1d_tc (mode 0/1: two tf32 planes; mode 2: bf16)
+  const float* bias;   // (Cout) fp32 or null
+  const void* res;     // GP, shape of the output, or null (rate == 1 only)
+  void* out;           // GP (B, (Cout/rate)/cpg, L*rate, cpg)
+  int B, L, Cin, Cout, K, dil;
+  int rate;            // polyphase ConvTranspose1d: the Cout GEMM columns are `rate` output phases of Cout/rate channels
+  const int32_t* lens; // valid input rows per item = lens[b]*lens_mul (null: L); rows >= len are neither read nor written
+  int lens_mul;
+  int in_act;          // EV_ACT_NONE / EV_ACT_LRELU
+  float in_slope;
+  int acc;             // EV_ACC_*
+  float div;
+};
+int launch_conv1d_gp(const GpConvParams& p, int mode, cudaStream_t st);    // mode 0: tf32, 1: 3xTF32 (fp32 activations); 2: bf16 activations
+int debug_gp_plan(const GpConvParams& p, int mode, int* v11);
+// fp32 in[b*sb + t*st + c*sc] -> GP (fp32, or bf16 when bf16 != 0)
+int launch_to_gp(const float* in, long long sb, long long st_, long long sc, void* out, int B, int L, int C, int bf16, cudaStream_t st);
+int launch_conv_post_gp(const void* x, int bf16, const float* w, const float* bias, const int32_t* lens, int lens_mul, int B, int L, int C, int K,
+                        float slope, float* wav, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------
 // acoustic-model kernels (am_kernels.cu)
 // ---------------------------------------------------------------------------------
 // y = LN(x) over C; optional prologue x = emb[ids] + alpha*pe[t] (written to x_out).

@@ -190,6 +190,24 @@ EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const 
  * The CPU tests check the invariants the kernel relies on (ring depth >= producer groups, TMEM/smem limits,
  * summation-order parameters independent of batch and length). */
 EV_API int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int split3, int ksplit, int* out11);
+/* HiFi-GAN convolution on GRANULE-PLANAR activations (csrc/conv1d_gp.cu; what ev_vocoder runs in every tensor-core mode).
+ * Layout: a (B, L, C) tensor is stored [b][C/cpg][l][cpg] in 16-byte granules, cpg = 4 fp32 (mode 0 tf32, 1 3xTF32) or 8 bf16
+ * (mode 2).  w: the ev_op_conv1d_tc weight layout of that mode.  rate > 1: polyphase ConvTranspose1d, the Cout GEMM columns
+ * are `rate` phases of Cout/rate channels, out is (B, (Cout/rate)/cpg, L*rate, cpg).  res (rate == 1): same shape as out.
+ * Rows >= lens[b]*lens_mul are neither read (they count as zero padding) nor written.  Replaces hifigan/models.py:50-57,
+ * :116, :118-119. */
+EV_API int ev_op_conv1d_gp(const void* x, const float* w, int mode, const float* bias, const void* res, void* out, int B, int L,
+                           int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act,
+                           float in_slope, int acc, float div, void* stream);
+/* Host-only: out11 = {BN, MT, KBG, a_stages, b_stages, transform warps, planes, tmem columns, smem bytes, tiles, rows_pad}. */
+EV_API int ev_debug_gp_plan(int B, int L, int Cin, int Cout, int K, int dil, int rate, int mode, int* out11);
+/* fp32 in[b*stride_b + t*stride_t + c*stride_c] -> granule-planar (fp32, or bf16 when bf16 != 0): the vocoder's input boundary
+ * (hifigan/models.py:115 takes (B, n_mels, F); jets.py:62 hands over dec_outputs (B, F, n_mels) transposed). */
+EV_API int ev_op_to_gp(const float* in, long long stride_b, long long stride_t, long long stride_c, void* out, int B, int L, int C,
+                       int bf16, void* stream);
+/* wav[b,t] = tanh(bias + conv_post(leaky_relu(x, slope))) on a granule-planar input (hifigan/models.py:127-129). */
+EV_API int ev_op_conv_post_gp(const void* x, int bf16, const float* w, const float* bias, const int32_t* lens, int lens_mul, int B,
+                              int L, int C, int K, float slope, float* wav, void* stream);
 /* LayerNorm over the last dim, eps 1e-12 (encoder.py:112-127). rows x C. */
 EV_API int ev_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int C, void* stream);
 /* Multi-head self-attention core (encoder.py:84-109) on a packed (B,L,3H) q|k|v buffer. */

@@ -1,0 +1,90 @@
+"""Granule-planar HiFi-GAN convolution kernel (csrc/conv1d_gp.cu) on the B200.
+
+* operator level (tools/gp_check.py, run as a child under a timeout so a pipeline deadlock cannot take pytest with it):
+  BITWISE equality with the round-1 time-major tensor-core kernel in the tf32 and 3xTF32 modes (same reduction order, same
+  roundings) over ragged lengths, residual / accumulate epilogues, the polyphase ConvTranspose1d form; the bf16-storage mode
+  against a torch reference on bf16-rounded operands (<= 1.2e-2 of max|ref|: one bf16 output rounding);
+  rows >= len are never written; the boundary kernels (to_gp, conv_post_gp).
+* end to end: the vocoder on the GP path (the default) is BITWISE the round-1 time-major path (EV_VOC_LAYOUT=tm) in the
+  fp32 and tf32 modes; bf16 storage against the unmodified reference's fixture within the bf16 tolerance."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden, rel_max, rel_rms
+
+pytestmark = pytest.mark.gpu
+KEYS = ("inputs_ling", "input_lengths", "inputs_speaker", "inputs_style_embedding", "inputs_content_embedding")
+
+
+def test_gp_operator_check_tool(lib):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gp_check.py")], capture_output=True, text=True, timeout=420)
+    print(r.stdout[-6000:], r.stderr[-2000:])
+    rows = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and "GP_CHECK_OK" in r.stdout, [x for x in rows if not x.get("ok", True)]
+    assert len([x for x in rows if "case" in x]) == 39
+
+
+_TM_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from emotivoice_b200.config import default_config
+from emotivoice_b200 import synth
+from emotivoice_b200.modules import JETSGenerator
+conf = default_config()
+m = JETSGenerator(conf).to("cuda:0"); m.load_state_dict(synth.make_state_dict(conf)); m.eval()
+z = np.load(sys.argv[2])
+keys = ("inputs_ling", "input_lengths", "inputs_speaker", "inputs_style_embedding", "inputs_content_embedding")
+res = {}
+for prec in ("fp32", "tf32"):
+    m.precision = prec
+    out = m(**{k: torch.from_numpy(z[k]).cuda() for k in keys})
+    torch.cuda.synchronize()
+    res[prec + "_wav"] = out["wav_predictions"].cpu().numpy(); res[prec + "_lens"] = out["mel_lengths"].cpu().numpy()
+np.savez(sys.argv[3], **res)
+"""
+
+
+def test_vocoder_on_the_gp_path_is_bitwise_the_time_major_path(model, dev, tmp_path):
+    src, dst = os.path.join(GOLDEN, "b3_padded.npz"), str(tmp_path / "tm.npz")
+    subprocess.run([sys.executable, "-c", _TM_CHILD, ROOT, src, dst], env=dict(os.environ, EV_VOC_LAYOUT="tm"), check=True, timeout=300)
+    got = np.load(dst)
+    g = load_golden("b3_padded")
+    try:
+        for prec in ("fp32", "tf32"):
+            model.precision = prec
+            out = model(**{k: g[k].to(dev) for k in KEYS})
+            wav = out["wav_predictions"].cpu().numpy()
+            for b, n in enumerate(got[prec + "_lens"].tolist()):        # the GP path leaves rows >= len of its scratch undefined; the waveform is zero there in both
+                assert np.array_equal(wav[b, 0, :n * 256], got[prec + "_wav"][b, 0, :n * 256]), (prec, b)
+                assert not wav[b, 0, n * 256:].any()
+    finally:
+        model.precision = "fp32"
+
+
+@pytest.mark.parametrize("name", ["b1_t12", "b1_t50", "b1_t100"])
+def test_bf16_storage_mode_against_the_reference_fixture(model, dev, name):
+    """ "bf16": bf16 operands AND bf16 activations in HBM through the vocoder (fp32 accumulation in TMEM; the duration prefix
+    stays 3xTF32, so durations are identical).  Tolerance: mel <= 2e-2 of max|mel|, wav rms <= 2e-2 of rms."""
+    g = load_golden(name)
+    try:
+        model.precision = "bf16"
+        out = model(**{k: g[k].to(dev) for k in KEYS})
+        assert torch.equal(out["log_duration_predictions"].cpu(), g["durations"])
+        e_mel, e_wav = rel_max(out["dec_outputs"].cpu(), g["mel"]), rel_rms(out["wav_predictions"].cpu(), g["wav"])
+        print(name, "bf16 storage: mel rel-max %.2e wav rel-rms %.2e" % (e_mel, e_wav))
+        assert e_mel <= 2e-2 and e_wav <= 2e-2
+    finally:
+        model.precision = "fp32"
+
+
+def test_generator_alone_takes_channels_first_mel_on_the_gp_path(model, dev):
+    """hifigan/models.py:115: Generator.forward takes (B, n_mels, F); the GP boundary kernel reads it with strides."""
+    g = load_golden("voc_b2_f40")
+    wav = model.generator(g["mel"].to(dev))
+    assert rel_rms(wav.cpu(), g["wav"]) <= 1e-4

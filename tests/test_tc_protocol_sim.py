@@ -1,4 +1,4 @@
-"""Discrete-event model of the mbarrier protocols of the two tcgen05 kernels (csrc/conv1d_tc.cu, csrc/resblock_tc.cu).
+"""Discrete-event model of the mbarrier protocols of the two tcgen05 kernels (csrc/conv1d_tc.cu, csrc/conv1d_gp.cu).
 
 Both deadlocks of round 1 were protocol bugs that a GPU can only show as a hang (producer groups running two ring phases
 ahead of a parity wait; epilogue warps releasing an accumulator they never waited for).  This model replays the kernels' role
@@ -217,3 +217,158 @@ def test_conv_protocol_model_catches_the_round1_bugs():
     with pytest.raises(AssertionError):                       # column-less epilogue warps handing back an accumulator they never waited for
         for seed in range(50):
             sim_conv(seed, [True] * 6, n_cb=2, K=3, a_stages=2, b_stages=4, ngroups=2, epi_idle_warps=4, idle_warps_skip_wait=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# conv1d_gp.cu: A loader (bulk copies) -> a_full -> transform warps (in place) -> a_ready -> MMA -> a_empty -> A loader
+# ------------------------------------------------------------------------------------------------------------------
+NTW = 4
+
+
+def sim_gp(seed, tiles, n_cb, K, a_stages, b_stages, n_work_items=2, skip_idle_wait=False):
+    """tiles: list of booleans (True = active tile, False = padding tile that every role skips).  n_work_items: epilogue
+    work items (MT * BN/32) per lane quadrant; warp `half` of a quadrant takes items half, half+2, ...: with one item the
+    second warp of each quadrant has nothing to read but must still follow the accumulator phases."""
+    sim = Sim(seed)
+    a_full = [Bar(1) for _ in range(a_stages)]
+    a_ready = [Bar(NTW) for _ in range(a_stages)]           # one arrival per transform warp here (the kernel: per thread)
+    a_empty = [Bar(1) for _ in range(a_stages)]
+    b_full = [Bar(1) for _ in range(b_stages)]
+    b_empty = [Bar(1) for _ in range(b_stages)]
+    acc_full = [Bar(1), Bar(1)]
+    acc_empty = [Bar(NEPI_WARPS), Bar(NEPI_WARPS)]
+
+    def aloader():
+        a_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            for cb in range(n_cb):
+                s = a_cnt % a_stages
+                yield ("wait", a_empty[s], ((a_cnt // a_stages) & 1) ^ 1)
+                yield ("write", ("A", s), ("raw", ti, cb))       # expect_tx + the bulk copies' complete_tx
+                yield ("arrive", a_full[s])
+                a_cnt += 1
+
+    def xform(w):
+        a_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            for cb in range(n_cb):
+                s = a_cnt % a_stages
+                yield ("wait", a_full[s], (a_cnt // a_stages) & 1)
+                yield ("read", ("A", s), ("raw", ti, cb) if w == 0 else sim.slots.get(("A", s)))
+                if w == 0:
+                    yield ("write", ("A", s), ("op", ti, cb))
+                yield ("arrive", a_ready[s])
+                a_cnt += 1
+
+    def bloader():
+        b_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            for cb in range(n_cb):
+                for j in range(K):
+                    sb = b_cnt % b_stages
+                    yield ("wait", b_empty[sb], ((b_cnt // b_stages) & 1) ^ 1)
+                    yield ("write", ("B", sb), (ti, cb, j))
+                    yield ("arrive", b_full[sb])
+                    b_cnt += 1
+
+    def mma():
+        a_cnt = b_cnt = tile_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            buf = tile_cnt & 1
+            yield ("wait", acc_empty[buf], ((tile_cnt >> 1) & 1) ^ 1)
+            for cb in range(n_cb):
+                sa = a_cnt % a_stages
+                yield ("wait", a_ready[sa], (a_cnt // a_stages) & 1)
+                for j in range(K):
+                    sb = b_cnt % b_stages
+                    yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
+                    yield ("mma_read", ("A", sa), ("op", ti, cb))
+                    yield ("mma_read", ("B", sb), (ti, cb, j))
+                    yield ("commit", b_empty[sb])
+                    b_cnt += 1
+                yield ("commit", a_empty[sa])
+                a_cnt += 1
+            yield ("write", ("ACC", buf), ti)
+            yield ("commit", acc_full[buf])
+            tile_cnt += 1
+
+    def epilogue(w):
+        half = w >> 2
+        has_work = half < n_work_items
+        tile_cnt = 0
+        for ti, active in enumerate(tiles):
+            if not active:
+                continue
+            buf = tile_cnt & 1
+            if has_work or not skip_idle_wait:
+                yield ("wait", acc_full[buf], (tile_cnt >> 1) & 1)
+            if has_work:
+                yield ("read", ("ACC", buf), ti)
+            yield ("arrive", acc_empty[buf])
+            tile_cnt += 1
+
+    sim.add("aloader", aloader())
+    for w in range(NTW):
+        sim.add("xform%d" % w, xform(w))
+    sim.add("bloader", bloader())
+    sim.add("mma", mma())
+    for w in range(NEPI_WARPS):
+        sim.add("epilogue%d" % w, epilogue(w))
+    sim.run()
+
+
+def _gp_plan(lib, B, L, Cin, Cout, K, dil, rate, mode):
+    v = (ctypes.c_int * 11)()
+    assert lib.ev_debug_gp_plan(B, L, Cin, Cout, K, dil, rate, mode, v) == 0, lib.ev_last_error()
+    return dict(zip("BN MT KBG a_stages b_stages ntw planes tmem smem tiles rows_pad".split(), list(v)))
+
+
+GP_SHAPES = [(1, 537, 80, 512, 7, 1, 1), (1, 537, 512, 2048, 3, 1, 8), (1, 4296, 256, 256, 11, 5, 1), (1, 34368, 128, 128, 11, 1, 1),
+             (1, 34368, 128, 128, 3, 1, 2), (1, 68736, 64, 64, 7, 3, 1), (1, 137472, 32, 32, 3, 1, 1), (32, 262144, 32, 32, 11, 5, 1),
+             (8, 65536, 128, 128, 11, 5, 1), (128, 32768, 256, 256, 7, 1, 1)]
+
+
+@pytest.mark.parametrize("shape", GP_SHAPES)
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_gp_plans_respect_the_hardware_limits_and_the_protocol(lib, shape, mode):
+    B, L, Cin, Cout, K, dil, rate = shape
+    pl = _gp_plan(lib, B, L, Cin, Cout, K, dil, rate, mode)
+    cpg = 8 if mode == 2 else 4
+    assert pl["smem"] <= 227 * 1024 and 2 <= pl["a_stages"] <= 8 and 1 <= pl["b_stages"] <= 8
+    assert pl["tmem"] in (32, 64, 128, 256, 512) and 2 * pl["MT"] * pl["BN"] <= pl["tmem"]
+    assert pl["BN"] % 32 == 0 and Cout % pl["BN"] == 0 and pl["planes"] == (2 if mode == 1 else 1)
+    rows = 128 * pl["MT"] + (K - 1) * dil
+    assert pl["rows_pad"] >= rows and pl["rows_pad"] % 8 == 0
+    # one stage's transaction count must fit the mbarrier tx-count field (2^20 - 1 bytes)
+    assert pl["KBG"] * pl["rows_pad"] * 16 < (1 << 20) and pl["planes"] * pl["KBG"] * pl["BN"] * 16 < (1 << 20)
+    n_cb = -(-Cin // (cpg * pl["KBG"]))
+    items = pl["MT"] * (pl["BN"] // 32)
+    for seed in range(5):
+        rng = random.Random(seed)
+        tiles = [rng.random() > 0.2 for _ in range(rng.randint(1, 5))]
+        sim_gp(seed, tiles, min(n_cb, 6), K, pl["a_stages"], pl["b_stages"], n_work_items=items)
+
+
+def test_gp_summation_order_parameters_do_not_depend_on_batch_or_length(lib):
+    """KBG (channels per pipeline stage) fixes the order of each output element's reduction: it must be a function of the
+    layer shape only, or a batch would not be bitwise equal to its items' B=1 runs."""
+    for (Cin, Cout, K, dil, rate) in [(80, 512, 7, 1, 1), (512, 2048, 3, 1, 8), (256, 256, 11, 5, 1), (128, 128, 7, 3, 1), (32, 32, 11, 5, 1)]:
+        for mode in (0, 1, 2):
+            kbgs = {_gp_plan(lib, B, L, Cin, Cout, K, dil, rate, mode)["KBG"] for (B, L) in [(1, 64), (1, 5000), (3, 70000), (32, 300000)]}
+            assert len(kbgs) == 1, (Cin, Cout, K, dil, mode, kbgs)
+
+
+def test_gp_protocol_model_is_sensitive():
+    """The model must fail when an epilogue warp without work items releases an accumulator set it never waited for
+    (the round-1 hang), which is why the kernel's idle warps still wait on acc_full."""
+    with pytest.raises(AssertionError):
+        for seed in range(40):
+            sim_gp(seed, [True] * 5, n_cb=1, K=1, a_stages=2, b_stages=2, n_work_items=1, skip_idle_wait=True)
