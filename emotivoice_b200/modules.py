@@ -33,6 +33,18 @@ class _Holder(nn.Module):
         raise RuntimeError("parameter holder: compute happens in libemotivoice_b200.so")
 
 
+def _bucket(nbytes):
+    """Workspace sizes are rounded up to a geometric series (x1.125 steps, 2 MiB granularity): utterances of similar length
+    then request IDENTICAL sizes, so torch's caching allocator serves them from its pool instead of calling cudaMalloc
+    (a device-synchronising, ~1-2 ms call) whenever a request is a little larger than anything it has cached."""
+    g = 2 << 20
+    n = max(int(nbytes), g)
+    b = g
+    while b < n:
+        b = (b + (b >> 3) + g - 1) // g * g
+    return b
+
+
 def _register(root, dotted, tensor):
     parts = dotted.split(".")
     mod = root
@@ -127,7 +139,7 @@ class _Engine:
         pitch = torch.empty((B, T), dtype=torch.float32, device=dev)
         energy = torch.empty((B, T), dtype=torch.float32, device=dev)
         meta = torch.empty((2 * B + 2,), dtype=torch.int32, device=dev)      # lens32 (B) | mel_lens (B) | max | input status
-        n1 = lib.ev_phase1_workspace_bytes(self.handle, B, T)
+        n1 = _bucket(lib.ev_phase1_workspace_bytes(self.handle, B, T))
         ws1 = torch.empty((n1,), dtype=torch.uint8, device=dev)
         st = self._stream()
         lens32_ptr = meta.data_ptr()
@@ -146,7 +158,7 @@ class _Engine:
             raise RuntimeError("input_lengths must lie in [1, %d] (the padded width of inputs_ling)" % T)
         F = int(mel_lens_host[B])
         self.ensure_pe(F)
-        n2 = lib.ev_phase2_workspace_bytes(self.handle, B, F)
+        n2 = _bucket(lib.ev_phase2_workspace_bytes(self.handle, B, F))
         ws2 = torch.empty((n2,), dtype=torch.uint8, device=dev)
         mel = torch.empty((B, F, int(self.cfg.n_mels)), dtype=torch.float32, device=dev)
         _abi.check(lib.ev_am_phase2(self.handle, ws1.data_ptr(), lens32_ptr, mel_lens_ptr, B, T, F, int(invariant),
@@ -161,7 +173,7 @@ class _Engine:
         else:
             B, _, F = mel.shape
         if ws is None:
-            n = lib.ev_phase2_workspace_bytes(self.handle, B, F)
+            n = _bucket(lib.ev_phase2_workspace_bytes(self.handle, B, F))
             ws = torch.empty((n,), dtype=torch.uint8, device=dev)
         wav = torch.empty((B, 1, F * self.total_up), dtype=torch.float32, device=dev)
         _abi.check(lib.ev_vocoder(self.handle, mel.data_ptr(), int(bool(time_major)), mel_lens_ptr, B, F,
