@@ -57,7 +57,8 @@ def main():
             xg = layout.to_gp(x, bf).to(dev)
             rg = layout.to_gp(res, bf).to(dev) if use_res else None
             og = layout.to_gp(prev, bf).to(dev)
-            rc = lib.ev_op_conv1d_gp(ptr(xg), ptr(w_l), mode, ptr(bias.to(dev)), ptr(rg), ptr(og), B, L, Cin, Cout, K, dil, rate, ptr(lens), lens_mul,
+            bias_d = bias.to(dev)          # keep every device tensor alive across the launch: a temporary's block would be recycled
+            rc = lib.ev_op_conv1d_gp(ptr(xg), ptr(w_l), mode, ptr(bias_d), ptr(rg), ptr(og), B, L, Cin, Cout, K, dil, rate, ptr(lens), lens_mul,
                                      _abi.ACT_LRELU, 0.1, acc, 3.0, st)
             torch.cuda.synchronize()
             if rc != 0:
@@ -72,7 +73,7 @@ def main():
                 xt = x.to(dev)
                 ref = prev.reshape(B, L, Cout).clone().to(dev)
                 rt = res.reshape(B, L, Cout).to(dev) if use_res else None
-                _abi.check(lib.ev_op_conv1d_tc(ptr(xt), ptr(w_l), 1 if mode == 1 else 0, ptr(bias.to(dev)), 0, ptr(rt), ptr(ref), B, L, Cin, Cout, K, dil,
+                _abi.check(lib.ev_op_conv1d_tc(ptr(xt), ptr(w_l), 1 if mode == 1 else 0, ptr(bias_d), 0, ptr(rt), ptr(ref), B, L, Cin, Cout, K, dil,
                                                ptr(lens), lens_mul, _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, acc, 3.0, None, 0, st))
                 torch.cuda.synchronize()
                 ref = ref.cpu().reshape(B, L * rate, coutR)
@@ -110,9 +111,10 @@ def main():
     # boundary kernels
     g = torch.Generator().manual_seed(5)
     mel = torch.randn(2, 80, 37, generator=g)
+    mel_d = mel.to(dev)
     for bf in (0, 1):
         outg = torch.empty((2, 80 // (8 if bf else 4), 37, 8 if bf else 4), dtype=torch.bfloat16 if bf else torch.float32, device=dev)
-        _abi.check(lib.ev_op_to_gp(ptr(mel.to(dev)), 80 * 37, 1, 37, ptr(outg), 2, 37, 80, bf, st))
+        _abi.check(lib.ev_op_to_gp(ptr(mel_d), 80 * 37, 1, 37, ptr(outg), 2, 37, 80, bf, st))
         torch.cuda.synchronize()
         eq = torch.equal(outg.cpu(), layout.to_gp(mel.transpose(1, 2).contiguous(), bool(bf)))
         print(json.dumps({"to_gp_channels_first": eq, "bf16": bf}), flush=True)
@@ -121,14 +123,13 @@ def main():
     w = torch.randn(7, 32, generator=g) * 0.1
     b1 = torch.randn(1, generator=g)
     lens = torch.tensor([20, 13], dtype=torch.int32, device=dev)
-    wav_old = torch.empty(2, 5000, device=dev)
-    from emotivoice_b200._abi import load
-    # old time-major conv_post through the vocoder is not exported as an op: compare with torch
+    w_d, b1_d = w.to(dev), b1.to(dev)
+    # the time-major conv_post is not exported as an op: compare with torch
     ref = torch.tanh(F.conv1d(F.leaky_relu(x, 0.01).transpose(1, 2), w.t().unsqueeze(0), b1, padding=3))[:, 0]
     for bf in (0, 1):
         xg = layout.to_gp(x, bool(bf)).to(dev)
         wav = torch.empty(2, 5000, device=dev)
-        _abi.check(lib.ev_op_conv_post_gp(ptr(xg), bf, ptr(w.to(dev)), ptr(b1.to(dev)), ptr(lens), 256, 2, 5000, 32, 7, 0.01, ptr(wav), st))
+        _abi.check(lib.ev_op_conv_post_gp(ptr(xg), bf, ptr(w_d), ptr(b1_d), ptr(lens), 256, 2, 5000, 32, 7, 0.01, ptr(wav), st))
         torch.cuda.synchronize()
         e = max(float((wav[b, :int(lens[b]) * 256 - 3].cpu() - ref[b, :int(lens[b]) * 256 - 3]).abs().max()) for b in range(2))
         z = bool((wav[1, 13 * 256:] == 0).all())

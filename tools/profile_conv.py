@@ -1,43 +1,64 @@
 """Launch one conv shape through the C ABI a few times (for ncu / timing).
-usage: python tools/profile_conv.py MODE C K DIL L [B] [reps]   MODE in {ffma, tf32, fp32, bf16};  C may be "Cin:Cout"."""
+
+usage: python tools/profile_conv.py MODE C K DIL L [B] [reps]
+  MODE in {ffma, tf32, fp32, bf16}            round-1 time-major kernels (conv1d_tm / conv1d_tc)
+          {gp:tf32, gp:fp32, gp:bf16}         granule-planar kernel (conv1d_gp), the vocoder's default path
+  C may be "Cin:Cout" (or "Cin:Cout:rate" for the polyphase ConvTranspose1d form, gp only).
+Prints per-launch times (L2 flushed before each), algorithmic TFLOP/s and layer-granular GB/s (in + out + residual, weights once)."""
+import json
 import math
-import sys
 import os
+import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from emotivoice_b200 import _abi, packing, build
+from emotivoice_b200 import _abi, build, layout, packing
 
 build.build(verbose=False)
 lib = _abi.load()
 mode, K, dil, L = sys.argv[1], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
-Cin, Cout = (int(v) for v in sys.argv[2].split(":")) if ":" in sys.argv[2] else (int(sys.argv[2]), int(sys.argv[2]))
-C = Cout
+cs = [int(v) for v in sys.argv[2].split(":")]
+Cin, Cout, rate = (cs[0], cs[0], 1) if len(cs) == 1 else ((cs[0], cs[1], 1) if len(cs) == 2 else tuple(cs))
 B = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 reps = int(sys.argv[7]) if len(sys.argv) > 7 else 5
+gp = mode.startswith("gp:")
+prec = mode[3:] if gp else mode
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
-x = torch.randn(B, L, Cin, generator=g).to(dev)
+x = torch.randn(B, L, Cin, generator=g)
 w = torch.randn(K, Cin, Cout, generator=g) / math.sqrt(Cin * K)
-wd = (packing.to_tc16_layout(w) if mode == "bf16" else (packing.to_tc_layout(w) if mode != "ffma" else w)).to(dev)
-b = torch.randn(C, generator=g).to(dev)
-res = torch.randn(B, L, C, generator=g).to(dev)
-out = torch.empty(B, L, C, device=dev)
+wd = (packing.to_tc16_layout(w) if prec == "bf16" else (packing.to_tc_layout(w) if prec != "ffma" else w)).to(dev)
+b = torch.randn(Cout, generator=g).to(dev)
+coutR = Cout // rate
+res = torch.randn(B, L * rate, coutR, generator=g) if rate == 1 else None
+esize = 2 if (gp and prec == "bf16") else 4
+if gp:
+    xd = layout.to_gp(x, prec == "bf16").to(dev)
+    rd = layout.to_gp(res, prec == "bf16").to(dev) if res is not None else None
+    out = torch.empty_like(layout.to_gp(torch.zeros(B, L * rate, coutR), prec == "bf16")).to(dev)
+else:
+    xd, rd, out = x.to(dev), res.to(dev), torch.empty(B, L, Cout, device=dev)
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 st = torch.cuda.current_stream().cuda_stream
+ptr = lambda t: None if t is None else t.data_ptr()
 ts = []
 for i in range(reps):
     flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    if mode == "ffma":
-        _abi.check(lib.ev_op_conv1d(x.data_ptr(), wd.data_ptr(), b.data_ptr(), 0, res.data_ptr(), out.data_ptr(), B, L, Cin, Cout, K, dil,
-                                    None, 1, 1, 0.1, 0, 0, 1.0, st))
+    if gp:
+        _abi.check(lib.ev_op_conv1d_gp(ptr(xd), ptr(wd), {"tf32": 0, "fp32": 1, "bf16": 2}[prec], ptr(b), ptr(rd), ptr(out), B, L, Cin, Cout, K, dil, rate,
+                                       None, 1, 1, 0.1, 0, 1.0, st))
+    elif mode == "ffma":
+        _abi.check(lib.ev_op_conv1d(ptr(xd), ptr(wd), ptr(b), 0, ptr(rd), ptr(out), B, L, Cin, Cout, K, dil, None, 1, 1, 0.1, 0, 0, 1.0, st))
     else:
-        _abi.check(lib.ev_op_conv1d_tc(x.data_ptr(), wd.data_ptr(), {"fp32": 1, "tf32": 0, "bf16": 2}[mode], b.data_ptr(), 0, res.data_ptr(),
-                                       out.data_ptr(), B, L, Cin, Cout, K, dil, None, 1, 1, 0.1, 0, 0, 1.0, None, 0, st))
+        _abi.check(lib.ev_op_conv1d_tc(ptr(xd), ptr(wd), {"fp32": 1, "tf32": 0, "bf16": 2}[mode], ptr(b), 0, ptr(rd), ptr(out), B, L, Cin, Cout, K, dil,
+                                       None, 1, 1, 0.1, 0, 0, 1.0, None, 0, st))
     e1.record()
     e1.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
 fl = 2.0 * B * L * Cin * Cout * K
-print("%s C=%d:%d K=%d dil=%d L=%d B=%d: %s us  -> %.1f TFLOP/s (best)" % (mode, Cin, Cout, K, dil, L, B, ["%.1f" % t for t in ts], fl / min(ts) / 1e6))
+by = esize * B * L * (Cin + Cout * (2 if res is not None else 1)) + 4.0 * K * Cin * Cout
+best = min(ts[1:]) if len(ts) > 1 else ts[0]
+print(json.dumps({"mode": mode, "Cin": Cin, "Cout": Cout, "rate": rate, "K": K, "dil": dil, "L": L, "B": B, "us": [round(t, 1) for t in ts],
+                  "best_us": round(best, 1), "tflops": round(fl / best / 1e6, 1), "layer_gbs": round(by / best / 1e3, 1)}))
