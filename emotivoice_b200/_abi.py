@@ -72,6 +72,7 @@ SIGNATURES = {
     "ev_debug_tc_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int)]),
     "ev_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ev_op_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ev_op_attention_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ev_op_gauss_upsample": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ev_op_mas": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ev_op_average_by_duration": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -426,6 +426,11 @@ static inline int body_mode(const ev_ctx* c) {
   return c->precision == EV_PREC_FP32_FFMA ? 0 : (c->precision == EV_PREC_TF32 ? 1 : (c->precision == EV_PREC_BF16 ? 2 : 3));
 }
 
+static inline bool attn_tc_enabled() {
+  static const int v = [] { const char* e = getenv("EV_ATTN"); return (e && e[0] == 'f') ? 0 : 1; }();
+  return v == 1;
+}
+
 // Encoder.forward (encoder.py:316-324) minus the positional prologue (done by the caller of this
 // function): n x [ x += W_o Attn(LN1 x) ; x += Conv2(GELU(Conv1(LN2 x))) ], then after_norm -> y.
 static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float* qkv, float* ctxb, float* h,
@@ -439,7 +444,12 @@ static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float
     g_split_ws.ksplit = 2;   // K = H: two slices
     EV_TRY(conv_x(mode, l.wqkv_tc, l.wqkv_h, y, l.wqkv, l.bqkv, 0, nullptr, qkv, B, L, H, 3 * H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
                   EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
-    EV_TRY(launch_attention(qkv, key_lens, ctxb, B, L, H, heads, st));
+    // QK^T / softmax / PV: tcgen05 (3xTF32 where the layer runs fp32-accurate, one tf32 MMA otherwise) for d_k = 48; the fp32 FFMA
+    // flash kernel in the "fp32_ffma" mode, for other head sizes, or with EV_ATTN=ffma (A/B measurements)
+    if (mode != 0 && H / heads == 48 && attn_tc_enabled())
+      EV_TRY(launch_attention_tc(qkv, key_lens, ctxb, B, L, H, heads, mode == 3 ? 1 : 0, st));
+    else
+      EV_TRY(launch_attention(qkv, key_lens, ctxb, B, L, H, heads, st));
     EV_TRY(conv_x(mode, l.wo_tc, l.wo_h, ctxb, l.wo, l.bo, 0, x, x, B, L, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
                   EV_ACC_STORE, 1.f, st));
     EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln2w, l.ln2b, y, B * L, L, H, st));
@@ -871,6 +881,12 @@ int ev_op_attention(const float* qkv, const int32_t* key_lens, float* ctx_out, i
   EV_CHECK_ARG(qkv && ctx_out, "ev_op_attention: null argument");
   EV_TRY(use_device_of(qkv));
   return launch_attention(qkv, key_lens, ctx_out, B, L, H, n_heads, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_attention_tc(const float* qkv, const int32_t* key_lens, float* ctx_out, int B, int L, int H, int n_heads, int tc_mode, void* stream) {
+  EV_CHECK_ARG(qkv && ctx_out, "ev_op_attention_tc: null argument");
+  EV_TRY(use_device_of(qkv));
+  return launch_attention_tc(qkv, key_lens, ctx_out, B, L, H, n_heads, tc_mode, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ev_op_gauss_upsample(const float* hs, const int64_t* dur, const int32_t* lens, int B, int T, int H, int F,

@@ -161,6 +161,8 @@ int launch_layernorm(const float* x, const int64_t* ids, const float* emb, const
                      cudaStream_t st, int n_emb = 0);
 int launch_attention(const float* qkv, const int32_t* key_lens, float* ctx, int B, int L, int H, int heads,
                      cudaStream_t st);
+// tcgen05 variant (attention_tc.cu), d_k = 48 only; tc_mode 1: 3xTF32 fp32 emulation, 0: one tf32 MMA per K step
+int launch_attention_tc(const float* qkv, const int32_t* key_lens, float* ctx, int B, int L, int H, int heads, int tc_mode, cudaStream_t st);
 int launch_cond_gather(const int64_t* spk, const float* spk_emb, const float* style, const float* content,
                        float* out, int B, int H, int bert, int n_spk, cudaStream_t st);
 int launch_cond_gemv(const float* c, const float* w, const float* bias, float* out, int B, int K, int N, cudaStream_t st);

@@ -213,6 +213,11 @@ EV_API int ev_op_layernorm(const float* x, const float* w, const float* b, float
 /* Multi-head self-attention core (encoder.py:84-109) on a packed (B,L,3H) q|k|v buffer. */
 EV_API int ev_op_attention(const float* qkv, const int32_t* key_lens, float* ctx_out, int B, int L, int H,
                            int n_heads, void* stream);
+/* The same attention on the tensor cores (csrc/attention_tc.cu): QK^T and PV as tcgen05.mma with the softmax between two TMEM
+ * reads; d_k = 48 only.  tc_mode 1 = 3xTF32 fp32 emulation (what the engine uses wherever a layer runs fp32-accurate),
+ * 0 = one tf32 MMA per K step. */
+EV_API int ev_op_attention_tc(const float* qkv, const int32_t* key_lens, float* ctx_out, int B, int L, int H, int n_heads,
+                              int tc_mode, void* stream);
 /* Gaussian upsampling (alignment.py:180-211) incl. cumsum; out (B,F,H); adds alpha*pe[f] when pe != NULL.
  * centers_tmp: 2*B*T floats of scratch; mel_lens_tmp: B+1 int32 (frame counts, max in slot B). */
 EV_API int ev_op_gauss_upsample(const float* hs, const int64_t* dur, const int32_t* lens, int B, int T, int H,

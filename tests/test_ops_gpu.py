@@ -174,6 +174,44 @@ def test_attention(lib, dev, B, L, masked):
     assert rel_max(out.cpu(), ref) <= TOL
 
 
+@pytest.mark.parametrize("tc_mode,tol", [(1, 2e-5), (0, 3e-3)], ids=["3xtf32", "tf32"])
+@pytest.mark.parametrize("B,L,masked", [(1, 7, False), (1, 64, False), (1, 129, False), (2, 500, True), (3, 1300, True), (1, 2049, False), (4, 65, True)])
+def test_attention_tc(lib, dev, B, L, masked, tc_mode, tol):
+    """encoder.py:84-109 on the tensor cores (csrc/attention_tc.cu): QK^T / PV as tcgen05.mma, softmax between two TMEM reads.
+    3xTF32 is held to the fp32 FFMA kernel's tolerance class (2e-5 of max|ref|); one tf32 MMA per step to 3e-3."""
+    H, heads, dk = 384, 8, 48
+    g = torch.Generator().manual_seed(L + 17 * B)
+    qkv = torch.randn(B, L, 3 * H, generator=g)
+    lens = torch.randint(1, L + 1, (B,), generator=g, dtype=torch.int32) if masked else None
+    if masked:
+        lens[0] = L
+    q, k, v = [t.reshape(B, L, heads, dk).transpose(1, 2) for t in qkv.split(H, dim=-1)]
+    scores = q @ k.transpose(-2, -1) / math.sqrt(dk)
+    if masked:
+        m = (torch.arange(L)[None, :] >= lens[:, None])[:, None, None, :]
+        scores = scores.masked_fill(m, torch.finfo(torch.float32).min)
+        attn = torch.softmax(scores, -1).masked_fill(m, 0.0)
+    else:
+        attn = torch.softmax(scores, -1)
+    ref = (attn @ v).transpose(1, 2).reshape(B, L, H)
+    out = torch.full((B, L, H), float("nan"), device=dev)
+    qd = qkv.to(dev)
+    ld = lens.to(dev) if masked else None
+    _abi.check(lib.ev_op_attention_tc(qd.data_ptr(), _ptr(ld), out.data_ptr(), B, L, H, heads, tc_mode, _stream()))
+    torch.cuda.synchronize()
+    err = rel_max(out.cpu(), ref)
+    print("attention_tc", (B, L, masked), tc_mode, "rel-max err %.2e" % err)
+    assert err <= tol
+    # batch invariance: item 1 of a masked batch is bitwise its own B=1 call on its valid prefix
+    if masked and B > 1:
+        n = int(lens[1])
+        one = torch.empty(1, n, H, device=dev)
+        q1 = qkv[1:2, :n].contiguous().to(dev)
+        _abi.check(lib.ev_op_attention_tc(q1.data_ptr(), None, one.data_ptr(), 1, n, H, heads, tc_mode, _stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(one[0], out[1, :n])
+
+
 @pytest.mark.parametrize("invariant", [0, 1])
 def test_gauss_upsample(lib, dev, invariant):
     """alignment.py:180-211 incl. the cumsum; literal padded batch vs per-item semantics."""
