@@ -76,6 +76,8 @@ SIGNATURES = {
     "ev_op_gauss_upsample": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ev_op_mas": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ev_op_average_by_duration": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ev_op_align_logp": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ev_op_get_segments": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ev_style_create": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(EvStyleConfig)]),
     "ev_style_destroy": (None, [_vp]),
     "ev_style_bind_weights": (_i, [_vp, _vp, _sz, _vp, _i]),

@@ -128,6 +128,95 @@ int launch_avg_by_duration(const float* durations, const float* xs, const int64_
   return EV_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// AlignmentModule.forward after its convolutions (alignment.py:39-56): score[b,f,t] = -|| feats[b,f,:] - text[b,t,:] ||_2,
+// tokens t >= text_lens[b] masked to -inf (x_masks), log_softmax over t, + the beta-binomial prior (built on the host like
+// the reference builds it, -inf outside each item's (T_feats, T_text) rectangle).  One warp per frame: the frame's feature row
+// lives in registers (A = NC*128 channels), the text rows stream through L1/L2, the T scores of the frame sit in shared memory
+// for the two softmax passes.  Training only.
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(128) align_logp_kernel(const float* __restrict__ text, const float* __restrict__ feats,
+                                                         const int64_t* __restrict__ text_lens, const float* __restrict__ prior, int F, int T,
+                                                         float* __restrict__ out) {
+  constexpr int A = NC * 128;
+  extern __shared__ float alp_sc[];            // [4 warps][T]
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * 4 + warp;
+  if (f >= F) return;
+  const int tl = text_lens ? (int)min((long long)T, max(0ll, (long long)text_lens[b])) : T;
+  float* sc = alp_sc + (size_t)warp * T;
+  const float* fr = feats + ((size_t)b * F + f) * A;
+  float4 fv[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) fv[j] = *reinterpret_cast<const float4*>(fr + (lane + 32 * j) * 4);
+  float mx = -INFINITY;
+  for (int t = 0; t < tl; ++t) {
+    const float* tr = text + ((size_t)b * T + t) * A;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const float4 tv = __ldg(reinterpret_cast<const float4*>(tr + (lane + 32 * j) * 4));
+      const float dx = fv[j].x - tv.x, dy = fv[j].y - tv.y, dz = fv[j].z - tv.z, dw = fv[j].w - tv.w;
+      s += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float score = -sqrtf(s);
+    mx = fmaxf(mx, score);
+    if (lane == 0) sc[t] = score;
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int t = lane; t < tl; t += 32) sum += expf(sc[t] - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float lse = mx + logf(sum);
+  const size_t ob = ((size_t)b * F + f) * T;
+  for (int t = lane; t < T; t += 32) {
+    const float lp = t < tl ? sc[t] - lse : -INFINITY;
+    out[ob + t] = lp + (prior ? prior[ob + t] : 0.f);
+  }
+}
+
+int launch_align_logp(const float* text, const float* feats, const int64_t* text_lens, const float* prior, int B, int F, int T, int A,
+                      float* out, cudaStream_t st) {
+  EV_CHECK_ARG(B > 0 && B <= 65535 && F > 0 && T > 0 && T <= 3072, "align_logp: B=%d F=%d T=%d (T <= 3072 tokens)", B, F, T);
+  EV_CHECK_ARG(A % 128 == 0 && A <= 512, "align_logp: feature width %d must be a multiple of 128, <= 512", A);
+  dim3 grid((F + 3) / 4, B);
+  const size_t smem = (size_t)4 * T * sizeof(float);
+  switch (A / 128) {
+    case 1: align_logp_kernel<1><<<grid, 128, smem, st>>>(text, feats, text_lens, prior, F, T, out); break;
+    case 2: align_logp_kernel<2><<<grid, 128, smem, st>>>(text, feats, text_lens, prior, F, T, out); break;
+    case 3: align_logp_kernel<3><<<grid, 128, smem, st>>>(text, feats, text_lens, prior, F, T, out); break;
+    default: align_logp_kernel<4><<<grid, 128, smem, st>>>(text, feats, text_lens, prior, F, T, out); break;
+  }
+  EV_CUDA_LAUNCH_CHECK("align_logp_kernel");
+  return EV_OK;
+}
+
+// get_segments (models/hifigan/get_random_segments.py:19-27): out[b, c, i] = x[b, c, start[b] + i] while start[b] + i < T, else 0.
+// x is (B, C, T) channels-first like the reference's z = dec_outputs.transpose(1, 2) (jets.py:55-60).
+__global__ void __launch_bounds__(256) segments_kernel(const float* __restrict__ x, const int64_t* __restrict__ start, int C, int T, int seg,
+                                                       float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = (int)(i % seg);
+  const size_t bc = i / seg;
+  const int b = (int)(bc / C);
+  const long long t = (long long)start[b] + k;
+  out[i] = (t >= 0 && t < T) ? x[bc * T + t] : 0.f;
+}
+
+int launch_segments(const float* x, const int64_t* start, int B, int C, int T, int seg, float* out, cudaStream_t st) {
+  EV_CHECK_ARG(B > 0 && C > 0 && T > 0 && seg > 0, "get_segments: B=%d C=%d T=%d segment=%d", B, C, T, seg);
+  const size_t n = (size_t)B * C * seg;
+  segments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, start, C, T, seg, out, n);
+  EV_CUDA_LAUNCH_CHECK("segments_kernel");
+  return EV_OK;
+}
+
 }  // namespace ev
 
 using namespace ev;
@@ -147,6 +236,19 @@ int ev_op_average_by_duration(const float* durations, const float* xs, const int
   EV_CHECK_ARG(durations && xs && text_lens && feats_lens && out, "ev_op_average_by_duration: null argument");
   EV_TRY(use_device_of(durations));
   return launch_avg_by_duration(durations, xs, text_lens, feats_lens, B, T_mel, T_inp, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_align_logp(const float* text_feat, const float* feats_feat, const int64_t* text_lens, const float* prior, int B, int T_mel, int T_inp,
+                     int A, float* log_p_attn, void* stream) {
+  EV_CHECK_ARG(text_feat && feats_feat && log_p_attn, "ev_op_align_logp: null argument");
+  EV_TRY(use_device_of(text_feat));
+  return launch_align_logp(text_feat, feats_feat, text_lens, prior, B, T_mel, T_inp, A, log_p_attn, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_get_segments(const float* x, const int64_t* start_idxs, int B, int C, int T, int segment_size, float* out, void* stream) {
+  EV_CHECK_ARG(x && start_idxs && out, "ev_op_get_segments: null argument");
+  EV_TRY(use_device_of(x));
+  return launch_segments(x, start_idxs, B, C, T, segment_size, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -254,6 +254,17 @@ def collate_utterances(utts, pin=False):
     return {k: v.pin_memory() for k, v in out.items()} if pin else out
 
 
+def make_alignment_state_dict(adim=384, odim=80, seed=SEED + 7):
+    """Seeded weights of the reference's AlignmentModule (alignment.py:19-25), torch's default Conv1d init range."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name, cin, k in (("t_conv1", adim, 3), ("t_conv2", adim, 1), ("f_conv1", odim, 3), ("f_conv2", adim, 3), ("f_conv3", adim, 1)):
+        bound = 1.0 / math.sqrt(cin * k)
+        sd[name + ".weight"] = torch.from_numpy(rng.uniform(-bound, bound, size=(adim, cin, k)).astype(np.float32))
+        sd[name + ".bias"] = torch.from_numpy(rng.uniform(-bound, bound, size=(adim,)).astype(np.float32))
+    return sd
+
+
 def make_mel(batch, frames, seed=SEED, n_mels=80):
     """cfg4 vocoder-only input: N(0,1)*1.2, shape (B, 80, F)."""
     rng = np.random.default_rng(seed)

@@ -266,6 +266,14 @@ EV_API int ev_op_mas(const float* log_p_attn, const int64_t* text_lens, const in
 /* average_by_duration (alignment.py:145-177): out (B, T_inp) = per-token mean of xs (B, T_mel) over the token's frames. */
 EV_API int ev_op_average_by_duration(const float* durations, const float* xs, const int64_t* text_lens, const int64_t* feats_lens,
                                      int B, int T_mel, int T_inp, float* out, void* stream);
+/* AlignmentModule.forward after its convolutions (alignment.py:39-56): log_p_attn[b,f,t] = log_softmax_t( -||feats_feat[b,f,:] -
+ * text_feat[b,t,:]||_2 ) with tokens t >= text_lens[b] masked to -inf, + prior (B,T_mel,T_inp; may be NULL).  text_feat (B,T_inp,A),
+ * feats_feat (B,T_mel,A) time-major fp32, A a multiple of 128.  Training only. */
+EV_API int ev_op_align_logp(const float* text_feat, const float* feats_feat, const int64_t* text_lens, const float* prior, int B, int T_mel,
+                            int T_inp, int A, float* log_p_attn, void* stream);
+/* get_segments (models/hifigan/get_random_segments.py:19-27; jets.py:55-60): out[b,c,i] = x[b,c,start_idxs[b]+i], zero past T.
+ * x (B,C,T) channels-first, out (B,C,segment_size). */
+EV_API int ev_op_get_segments(const float* x, const int64_t* start_idxs, int B, int C, int T, int segment_size, float* out, void* stream);
 
 #ifdef __cplusplus
 }

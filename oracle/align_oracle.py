@@ -60,3 +60,35 @@ def average_by_duration(ds, xs, text_lengths, feats_lengths):
             seg = x[s:e]
             out[b, n] = seg.mean(dtype=np.float32) if len(seg) else 0.0
     return out
+
+
+def alignment_module_forward(sd, text, feats, text_lengths, feats_lengths, x_masks=None, prefix="", prior_fn=None):
+    """AlignmentModule.forward (alignment.py:33-56) as plain functional torch on the CPU.  ``sd``: the module's state dict
+    (t_conv1.weight ...).  The prior comes from ``prior_fn(text_lengths, feats_lengths)`` (the product's host code builds it with
+    the same scipy call as the reference; passing the reference's own here keeps this function a pure restatement)."""
+    import torch
+    import torch.nn.functional as F
+    g = lambda n: sd[prefix + n]
+    t = text.transpose(1, 2)
+    t = F.relu(F.conv1d(t, g("t_conv1.weight"), g("t_conv1.bias"), padding=1))
+    t = F.conv1d(t, g("t_conv2.weight"), g("t_conv2.bias")).transpose(1, 2)
+    f = feats.transpose(1, 2)
+    f = F.relu(F.conv1d(f, g("f_conv1.weight"), g("f_conv1.bias"), padding=1))
+    f = F.relu(F.conv1d(f, g("f_conv2.weight"), g("f_conv2.bias"), padding=1))
+    f = F.conv1d(f, g("f_conv3.weight"), g("f_conv3.bias")).transpose(1, 2)
+    score = -torch.norm(f.unsqueeze(2) - t.unsqueeze(1), p=2, dim=3)
+    if x_masks is not None:
+        score = score.masked_fill(x_masks.unsqueeze(-2), -np.inf)
+    lp = F.log_softmax(score, dim=-1)
+    return lp + prior_fn(text_lengths, feats_lengths).to(lp.dtype) if prior_fn is not None else lp
+
+
+def get_segments(x, start_idxs, segment_size):
+    """models/hifigan/get_random_segments.py:19-27 in numpy: (B, C, T) -> (B, C, segment_size), zero padded."""
+    B, C, T = x.shape
+    out = np.zeros((B, C, segment_size), x.dtype)
+    for b in range(B):
+        s = int(start_idxs[b])
+        seg = x[b, :, s:s + segment_size]
+        out[b, :, :seg.shape[1]] = seg
+    return out

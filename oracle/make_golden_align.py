@@ -55,5 +55,40 @@ def main():
         print(name, "ok: bin_loss %.6f, durations sum %s" % (float(bin_loss), ds.sum(1).tolist()))
 
 
+def make_module_fixture():
+    """AlignmentModule.forward + get_random_segments of the UNMODIFIED reference on seeded inputs -> tests/golden/alignmod_b3.npz."""
+    if refshim.REF_ROOT not in sys.path:
+        sys.path.insert(0, refshim.REF_ROOT)
+    from models.prompt_tts_modified.modules import alignment as R
+    from models.hifigan import get_random_segments as RS
+    from emotivoice_b200 import synth
+    adim, odim = 384, 80
+    mod = R.AlignmentModule(adim, odim).eval()
+    mod.load_state_dict(synth.make_alignment_state_dict(adim, odim), strict=True)       # seeded: the fixture need not carry the weights
+    tt, tf = [23, 9, 31], [120, 40, 187]
+    B, T, F = len(tt), max(tt), max(tf)
+    rng = np.random.default_rng(8001)
+    text = torch.from_numpy(rng.normal(size=(B, T, adim)).astype(np.float32))
+    feats = torch.from_numpy((rng.normal(size=(B, F, odim)) * 1.2).astype(np.float32))
+    tl, fl = torch.tensor(tt), torch.tensor(tf)
+    x_masks = torch.arange(T)[None, :] >= tl[:, None]                         # True = pad (model_open_source.py:164-173)
+    with torch.no_grad():
+        lp = mod(text, feats, tl, fl, x_masks)
+    sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    o = AO.alignment_module_forward(sd, text, feats, tl, fl, x_masks, prior_fn=mod._generate_prior)
+    fin = torch.isfinite(lp)
+    assert torch.equal(fin, torch.isfinite(o)) and (lp[fin] - o[fin]).abs().max() <= 1e-5, "oracle restatement differs from the reference module"
+    torch.manual_seed(99)
+    z = torch.from_numpy(rng.normal(size=(B, odim, F)).astype(np.float32))
+    seg, starts, size = RS.get_random_segments(z, fl, 32)
+    assert np.array_equal(AO.get_segments(z.numpy(), starts.numpy(), 32), seg.numpy())
+    short = RS.get_segments(z[:, :, :20], torch.tensor([0, 3, 19]), 32)        # t < segment_size: zero padded
+    arrays = {"text": text.numpy(), "feats": feats.numpy(), "text_lengths": tl.numpy().astype(np.int64), "feats_lengths": fl.numpy().astype(np.int64),
+              "log_p_attn": lp.numpy(), "z": z.numpy(), "seg": seg.numpy(), "starts": starts.numpy().astype(np.int64), "seg_short": short.numpy()}
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "alignmod_b3.npz"), **arrays)
+    print("alignmod_b3 ok: log_p_attn", tuple(lp.shape), "starts", starts.tolist())
+
+
 if __name__ == "__main__":
     main()
+    make_module_fixture()

@@ -21,3 +21,23 @@ def test_alignment_oracle_matches_reference_fixture(name):
         assert path[0] == 0 and path[-1] == tt[b] - 1 and (np.diff(path) >= 0).all() and (np.diff(path) <= 1).all()      # monotonic, surjective
         assert ds[b].sum() == tf[b]
     assert np.abs(AO.average_by_duration(ds, g["xs"], tt, tf) - g["averaged"]).max() <= 1e-6
+
+
+def test_alignment_module_oracle_matches_reference_fixture():
+    """AlignmentModule.forward (alignment.py:33-56) restated in oracle/align_oracle.py vs the unmodified reference module's
+    output (oracle/make_golden_align.py), with the product's host-side beta-binomial prior (the same scipy call as the
+    reference's); get_segments vs the reference's segments incl. the t < segment_size zero padding."""
+    import torch
+    from emotivoice_b200 import synth
+    from emotivoice_b200.align import AlignmentModule
+    g = load_golden("alignmod_b3")
+    sd = synth.make_alignment_state_dict(384, 80)
+    tl, fl = g["text_lengths"], g["feats_lengths"]
+    T = g["text"].shape[1]
+    x_masks = torch.arange(T)[None, :] >= tl[:, None]
+    prior = AlignmentModule(384, 80)._generate_prior
+    lp = AO.alignment_module_forward(sd, g["text"], g["feats"], tl, fl, x_masks, prior_fn=prior)
+    fin = torch.isfinite(g["log_p_attn"])
+    assert torch.equal(fin, torch.isfinite(lp)) and (lp[fin] - g["log_p_attn"][fin]).abs().max() <= 1e-5
+    assert np.array_equal(AO.get_segments(g["z"].numpy(), g["starts"].numpy(), 32), g["seg"].numpy())
+    assert np.array_equal(AO.get_segments(g["z"].numpy()[:, :, :20], np.array([0, 3, 19]), 32), g["seg_short"].numpy())

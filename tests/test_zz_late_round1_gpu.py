@@ -220,3 +220,27 @@ def _check_knobs_bitwise(model, dev, tmp_path, knobs):
 @pytest.mark.parametrize("knobs", [{"EV_PDL": "1"}, {"EV_PDL": "2"}], ids=["pdl", "pdl_all"])
 def test_opt_in_launch_modes_are_bitwise_identical(model, dev, tmp_path, knobs):
     _check_knobs_bitwise(model, dev, tmp_path, knobs)
+
+
+def test_alignment_module_and_segments_match_reference_fixture(lib, dev):
+    """The rest of SURVEY.md s8f rank 4: AlignmentModule.forward (five 3xTF32 convolutions on tcgen05 + the distance /
+    log-softmax kernel + the host-built prior) against the unmodified reference module's output (1e-4 on finite entries, the
+    -inf pattern identical), and get_random_segments / get_segments bit-exact (same torch RNG calls as the reference)."""
+    from emotivoice_b200 import align, synth
+    g = load_golden("alignmod_b3")
+    mod = align.AlignmentModule(384, 80).to(dev)
+    mod.load_state_dict(synth.make_alignment_state_dict(384, 80))
+    tl, fl = g["text_lengths"], g["feats_lengths"]
+    x_masks = (torch.arange(g["text"].shape[1])[None, :] >= tl[:, None]).to(dev)
+    lp = mod(g["text"].to(dev), g["feats"].to(dev), tl, fl, x_masks).cpu()
+    ref = g["log_p_attn"]
+    fin = torch.isfinite(ref)
+    assert torch.equal(fin, torch.isfinite(lp))
+    err = (lp[fin] - ref[fin]).abs().max().item()
+    print("AlignmentModule max abs err on log_p_attn: %.2e" % err)
+    assert err <= 1e-4
+    torch.manual_seed(99)
+    seg, starts, size = align.get_random_segments(g["z"].to(dev), fl.to(dev), 32)
+    assert size == 32 and torch.equal(starts.cpu(), g["starts"]) and torch.equal(seg.cpu(), g["seg"])
+    short = align.get_segments(g["z"][:, :, :20].contiguous().to(dev), torch.tensor([0, 3, 19]), 32)
+    assert torch.equal(short.cpu(), g["seg_short"])
