@@ -230,73 +230,78 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const floa
     }
   } else {
     // ================================ MMA issuer ===================================================================
-    if (lane == 0) {
+    // all 32 lanes run the warp-uniform control flow and the barrier waits; one elected lane issues the tcgen05 instructions
+    {
       // instruction descriptors: D=F32, A=B=TF32, K-major, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BKT >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DK >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
-      const uint32_t q_addr = smem_u32(q_s), p_addr = smem_u32(p_s);
-      const uint32_t q_lbo = QPAD * 16, k_lbo = KPAD * 16, v_lbo = VPAD * 16, p_lbo = BQ * 16;
+      constexpr uint32_t q_lbo = QPAD * 16, k_lbo = KPAD * 16, v_lbo = VPAD * 16, p_lbo = BQ * 16;
+      const uint64_t q_desc = make_desc(smem_u32(q_s), q_lbo, 128u), p_desc = make_desc(smem_u32(p_s), p_lbo, 128u);
+      const uint64_t k_desc0 = make_desc(0u, k_lbo, 128u), v_desc0 = make_desc(0u, v_lbo, 128u);
       mbar_wait(q_ready, 0);
       tc_fence_after();
       int cnt = 0;
-      auto issue_qk = [&](int c) {       // S[c & 1] = Q K^T with the K tile in stage c & 1
+      auto issue_qk = [&](int c, bool release_kv) {       // S[c & 1] = Q K^T with the K tile in stage c & 1
         const int s = c & 1;
         mbar_wait(kv_full(s), (c >> 1) & 1);
         mbar_wait(s_empty(s), ((c >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(k_s + (size_t)s * PL * S::k_plane);
+        const uint64_t k_desc = desc_advance(k_desc0, smem_u32(k_s + (size_t)s * PL * S::k_plane));
         const uint32_t d = tmem_base + (uint32_t)(s * BKT);
+        if (elect_one()) {
 #pragma unroll
-        for (int k8 = 0; k8 < G / 2; ++k8) {
-          const uint64_t a_hi = make_desc(q_addr + (uint32_t)(2 * k8) * q_lbo, q_lbo, 128u);
-          const uint64_t b_hi = make_desc(k_addr + (uint32_t)(2 * k8) * k_lbo, k_lbo, 128u);
-          if (SPLIT3) {
-            const uint64_t a_lo = make_desc(q_addr + S::q_plane + (uint32_t)(2 * k8) * q_lbo, q_lbo, 128u);
-            const uint64_t b_lo = make_desc(k_addr + S::k_plane + (uint32_t)(2 * k8) * k_lbo, k_lbo, 128u);
-            umma_tf32(d, a_lo, b_hi, idesc_s, k8 ? 1u : 0u);
-            umma_tf32(d, a_hi, b_lo, idesc_s, 1u);
-            umma_tf32(d, a_hi, b_hi, idesc_s, 1u);
-          } else {
-            umma_tf32(d, a_hi, b_hi, idesc_s, k8 ? 1u : 0u);
+          for (int k8 = 0; k8 < G / 2; ++k8) {
+            const uint64_t a_hi = desc_advance(q_desc, (uint32_t)(2 * k8) * q_lbo);
+            const uint64_t b_hi = desc_advance(k_desc, (uint32_t)(2 * k8) * k_lbo);
+            if (SPLIT3) {
+              const uint64_t a_lo = desc_advance(a_hi, (uint32_t)S::q_plane);
+              const uint64_t b_lo = desc_advance(b_hi, (uint32_t)S::k_plane);
+              umma_tf32(d, a_lo, b_hi, idesc_s, k8 ? 1u : 0u);
+              umma_tf32(d, a_hi, b_lo, idesc_s, 1u);
+              umma_tf32(d, a_hi, b_hi, idesc_s, 1u);
+            } else {
+              umma_tf32(d, a_hi, b_hi, idesc_s, k8 ? 1u : 0u);
+            }
           }
+          umma_commit(s_full(s));
+          if (release_kv) umma_commit(kv_empty(s));
         }
-        umma_commit(s_full(s));
+        __syncwarp();
       };
       // pass 1: maxima only; the K stage is free as soon as its MMAs have completed
-      for (int j = 0; j < nkt; ++j, ++cnt) {
-        issue_qk(cnt);
-        umma_commit(kv_empty(cnt & 1));
-      }
+      for (int j = 0; j < nkt; ++j, ++cnt) issue_qk(cnt, true);
       // pass 2
-      if (nkt > 0) issue_qk(cnt);
+      if (nkt > 0) issue_qk(cnt, false);
       for (int j = 0; j < nkt; ++j) {
         const int c = cnt + j, s = c & 1;
-        if (j + 1 < nkt) issue_qk(c + 1);          // runs under the softmax of tile j
+        if (j + 1 < nkt) issue_qk(c + 1, false);          // runs under the softmax of tile j
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(v_s + (size_t)s * PL * S::v_plane);
+        const uint64_t v_desc = desc_advance(v_desc0, smem_u32(v_s + (size_t)s * PL * S::v_plane));
         const uint32_t d = tmem_base + 128u;
+        if (elect_one()) {
 #pragma unroll
-        for (int k8 = 0; k8 < GK / 2; ++k8) {
-          const uint64_t a_hi = make_desc(p_addr + (uint32_t)(2 * k8) * p_lbo, p_lbo, 128u);
-          const uint64_t b_hi = make_desc(v_addr + (uint32_t)(2 * k8) * v_lbo, v_lbo, 128u);
-          const uint32_t acc = (j | k8) ? 1u : 0u;
-          if (SPLIT3) {
-            const uint64_t a_lo = make_desc(p_addr + S::p_plane + (uint32_t)(2 * k8) * p_lbo, p_lbo, 128u);
-            const uint64_t b_lo = make_desc(v_addr + S::v_plane + (uint32_t)(2 * k8) * v_lbo, v_lbo, 128u);
-            umma_tf32(d, a_lo, b_hi, idesc_o, acc);
-            umma_tf32(d, a_hi, b_lo, idesc_o, 1u);
-            umma_tf32(d, a_hi, b_hi, idesc_o, 1u);
-          } else {
-            umma_tf32(d, a_hi, b_hi, idesc_o, acc);
+          for (int k8 = 0; k8 < GK / 2; ++k8) {
+            const uint64_t a_hi = desc_advance(p_desc, (uint32_t)(2 * k8) * p_lbo);
+            const uint64_t b_hi = desc_advance(v_desc, (uint32_t)(2 * k8) * v_lbo);
+            const uint32_t acc = (j | k8) ? 1u : 0u;
+            if (SPLIT3) {
+              const uint64_t a_lo = desc_advance(a_hi, (uint32_t)S::p_plane);
+              const uint64_t b_lo = desc_advance(b_hi, (uint32_t)S::v_plane);
+              umma_tf32(d, a_lo, b_hi, idesc_o, acc);
+              umma_tf32(d, a_hi, b_lo, idesc_o, 1u);
+              umma_tf32(d, a_hi, b_hi, idesc_o, 1u);
+            } else {
+              umma_tf32(d, a_hi, b_hi, idesc_o, acc);
+            }
           }
+          umma_commit(p_empty);
+          umma_commit(kv_empty(s));
+          if (j == nkt - 1) umma_commit(o_full);
         }
-        umma_commit(p_empty);
-        umma_commit(kv_empty(s));
+        __syncwarp();
       }
-      if (nkt > 0) umma_commit(o_full);
     }
-    __syncwarp();
   }
 
   tc_fence_before();

@@ -392,10 +392,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
     __syncwarp();
   } else {
     // ============================ MMA issuer =====================================================
-    if (lane == 0) {
+    // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues the tcgen05 instructions.
+    {
       const uint32_t a_lbo = (uint32_t)pl.rows_pad * 16u, b_lbo = (uint32_t)BN * 16u;
       const uint32_t fmt = BF16 ? 1u : 2u;      // instruction descriptor: D=F32 [4,6)=1, A/B format [7,10) / [10,13), N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint64_t a_desc0 = make_desc(0u, a_lbo, 128u), b_desc0 = make_desc(0u, b_lbo, 128u);
+      const uint32_t a_tap = (uint32_t)p.dil * 16u;                    // bytes per tap shift
+      const uint32_t a_k8 = 2u * a_lbo, b_k8 = 2u * b_lbo;             // bytes per K step (two granules)
       int a_cnt = 0, b_cnt = 0, tile_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
         int b, t0, n0, len;
@@ -409,44 +413,47 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
           const int sa = a_cnt % pl.a_stages;
           const int nk8 = min(KB, p.Cin - cb * KB) / (2 * CPG);   // MMA K steps: two 16-byte granules each
           mbar_wait(a_ready(sa), (a_cnt / pl.a_stages) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_tiles + sa * pl.a_stage_bytes);
+          const uint64_t a_hi0 = desc_advance(a_desc0, smem_u32(a_tiles + sa * pl.a_stage_bytes));
           for (int j = 0; j < p.K; ++j, ++b_cnt) {
             const int sb = b_cnt % pl.b_stages;
             mbar_wait(b_full(sb), (b_cnt / pl.b_stages) & 1);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(b_tiles + sb * pl.b_stage_bytes);
-            for (int k8 = 0; k8 < nk8; ++k8) {
-              const uint32_t b_off = (uint32_t)(2 * k8) * b_lbo;
-              const uint64_t b_hi = make_desc(b_addr + b_off, b_lbo, 128u);
-              const uint64_t b_lo = make_desc(b_addr + pl.b_plane_bytes + b_off, b_lbo, 128u);
-              const uint32_t first = (cb | j | k8) != 0 ? 1u : 0u;
+            const uint64_t b_hi0 = desc_advance(b_desc0, smem_u32(b_tiles + sb * pl.b_stage_bytes));
+            const uint64_t a_j = desc_advance(a_hi0, (uint32_t)j * a_tap);
+            if (elect_one()) {
+              for (int k8 = 0; k8 < nk8; ++k8) {
+                const uint64_t b_hi = desc_advance(b_hi0, (uint32_t)k8 * b_k8);
+                const uint64_t a_k = desc_advance(a_j, (uint32_t)k8 * a_k8);
+                const uint32_t first = (cb | j | k8) != 0 ? 1u : 0u;
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
-                const uint32_t a_off = (uint32_t)((2 * k8) * pl.rows_pad + mt * BM + j * p.dil) * 16u;
-                const uint64_t a_hi = make_desc(a_addr + a_off, a_lbo, 128u);
-                const uint32_t d = d_base + (uint32_t)(mt * BN);
-                if (SPLIT3) {
-                  const uint64_t a_lo = make_desc(a_addr + pl.a_plane_bytes + a_off, a_lbo, 128u);
-                  umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
-                  umma_tf32(d, a_hi, b_lo, idesc, 1u);
-                  umma_tf32(d, a_hi, b_hi, idesc, 1u);
-                } else if (BF16) {
-                  umma_bf16(d, a_hi, b_hi, idesc, first);
-                } else {
-                  umma_tf32(d, a_hi, b_hi, idesc, first);
+                for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
+                  const uint64_t a_hi = desc_advance(a_k, (uint32_t)(mt * BM) * 16u);
+                  const uint32_t d = d_base + (uint32_t)(mt * BN);
+                  if (SPLIT3) {
+                    const uint64_t a_lo = desc_advance(a_hi, (uint32_t)pl.a_plane_bytes);
+                    const uint64_t b_lo = desc_advance(b_hi, (uint32_t)pl.b_plane_bytes);
+                    umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
+                    umma_tf32(d, a_hi, b_lo, idesc, 1u);
+                    umma_tf32(d, a_hi, b_hi, idesc, 1u);
+                  } else if (BF16) {
+                    umma_bf16(d, a_hi, b_hi, idesc, first);
+                  } else {
+                    umma_tf32(d, a_hi, b_hi, idesc, first);
+                  }
                 }
               }
+              umma_commit(b_empty(sb));               // weight stage free once these MMAs have read it
+              if (j == p.K - 1) {
+                umma_commit(a_empty(sa));             // activation stage free
+                if (cb == n_cb - 1) umma_commit(acc_full(buf));   // accumulators of this tile complete -> epilogue
+              }
             }
-            umma_commit(b_empty(sb));     // weight stage free once these MMAs have read it
+            __syncwarp();
           }
-          umma_commit(a_empty(sa));       // activation stage free
         }
-        umma_commit(acc_full(buf));       // accumulators of this tile complete -> epilogue
         ++tile_cnt;
       }
     }
-    __syncwarp();
   }
 
   tc_fence_before();
@@ -555,30 +562,42 @@ static int gp_shape_kbg(const GpConvParams& p, int mode) {
 }
 
 // Tile shape: none of these choices changes the order in which any output element's K reduction is summed, so results are
-// bitwise independent of batch size / sequence length (batch-invariant contract).
-//  * rows per tile: as many 128-row accumulators (MT) as still leave about one tile per SM; one weight tile from L2 then
-//    feeds MT MMAs and the (K-1)*dil halo rows are amortised over MT*128 rows.
-//  * N tile: min(C_out, 128) = the weight packing tile (one bulk copy per weight stage), halved while the launch would
-//    otherwise leave a quarter of the SMs without a tile (HiFi-GAN stage 1 at batch 1: 68 tiles -> 136).
+// bitwise independent of batch size / sequence length (batch-invariant contract) and the shape can be picked by a cost model.
+// Per tile of MT x 128 rows and BN columns, three engines run concurrently and the slowest one sets the pace:
+//   tensor core + its shared-memory operand reads:  MT * m * max(BN/2, issue) cycles per (tap, 8 channels)   (m = 3 MMAs in 3xTF32; bf16: 16 channels)
+//   weight stream L2 -> shared memory:              planes * 32 B * BN per (tap, 8 channels) at ~42 B/cycle/SM (6.3 KB/cycle chip-wide)
+//   activations HBM -> shared memory -> HBM:        MT * 128 rows * (Cin + 2 Cout) * esize at ~23 B/cycle/SM
+// plus a fixed pipeline fill / drain per tile; the launch takes ceil(tiles / SMs) such tile times.  More accumulators per tile
+// (MT) amortise the weight stream and the halo rows, a narrower N tile fills idle SMs (HiFi-GAN stage 1 at batch 1).
 static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out) {
   EV_TRY(validate_gp(p, mode));
   const int nsm = sm_count();
-  const long long tiles128 = (long long)((p.L + tc::BM - 1) / tc::BM) * p.B;
-  int BN = p.Cout <= 128 ? p.Cout : 128;
-  int mt = 1;
-  {
-    const long long nt = (p.Cout + BN - 1) / BN;
-    if (tiles128 * nt >= 4ll * nsm) mt = 4;
-    else if (tiles128 * nt >= 2ll * nsm) mt = 2;
-  }
-  while (BN >= 64 && ((long long)((p.L + tc::BM * mt - 1) / (tc::BM * mt)) * p.B) * ((p.Cout + BN - 1) / BN) * 4 < 3ll * nsm) BN /= 2;
   const int kbg = gp_shape_kbg(p, mode);
-  gp::GPlan pl;
-  for (;; mt >>= 1) {
-    if (gp::make_gplan(p, mode, BN, mt, kbg, &pl)) break;
-    if (mt == 1) { set_error("conv1d_gp: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
+  const double kc8 = (double)p.K * p.Cin / 8.0;
+  const double n_mma = (mode == 1 ? 3.0 : 1.0) * (mode == 2 ? 0.5 : 1.0) * kc8;     // MMA instructions per accumulator and tile
+  const double w_per_n = (mode == 1 ? 2.0 : 1.0) * (mode == 2 ? 16.0 : 32.0) / 42.0;
+  const double esize = mode == 2 ? 2.0 : 4.0;
+  double best = 1e300;
+  bool found = false;
+  gp::GPlan best_pl;
+  const int bn_max = p.Cout <= 128 ? p.Cout : 128;
+  for (int BN = bn_max; BN >= 32; BN /= 2) {
+    if (p.Cout % BN) continue;
+    for (int mt = 4; mt >= 1; mt >>= 1) {
+      gp::GPlan pl;
+      if (!gp::make_gplan(p, mode, BN, mt, kbg, &pl)) continue;
+      const double t_mma = mt * n_mma * (BN / 2.0 > 28.0 ? BN / 2.0 : 28.0);     // BN/2 tensor cycles per instruction, ~28 to issue one
+      const double t_w = w_per_n * BN * kc8;
+      const double t_hbm = (double)mt * tc::BM * ((double)p.Cin * (mt * tc::BM + (p.K - 1) * p.dil) / (mt * tc::BM) + 2.0 * BN) * esize / 23.0;
+      double t = t_mma > t_w ? t_mma : t_w;
+      if (t_hbm > t) t = t_hbm;
+      const double waves = (double)((pl.total_tiles + nsm - 1) / nsm);
+      const double cost = waves * (t + 3000.0);
+      if (cost < best * 0.97) { best = cost; best_pl = pl; found = true; }     // widest N / most accumulators first; 3 % hysteresis
+    }
   }
-  *out = pl;
+  if (!found) { set_error("conv1d_gp: tile does not fit in shared memory / TMEM (K=%d dil=%d Cout=%d)", p.K, p.dil, p.Cout); return EV_EINVAL; }
+  *out = best_pl;
   return EV_OK;
 }
 

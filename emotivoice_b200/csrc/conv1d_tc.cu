@@ -350,9 +350,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
     }
   } else if (warp == MMA_WARP) {
     // ============================ MMA issuer =====================================================
-    if (lane == 0) {
+    // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues the tcgen05 instructions
+    // (descriptors stay in uniform registers: no vote loop / R2UR per MMA, see tc_common.cuh: elect_one).
+    {
       if (PDLM == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
       const uint32_t a_lbo = (uint32_t)pl.rows_pad * 16u, b_lbo = (uint32_t)BN * 16u;
+      const uint64_t a_desc0 = make_desc(0u, a_lbo, 128u), b_desc0 = make_desc(0u, b_lbo, 128u);
+      const uint32_t a_tap = (uint32_t)p.dil * 16u, a_k8 = 2u * a_lbo, b_k8 = 2u * b_lbo;
       int a_cnt = 0, b_cnt = 0, tile_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
         int b, t0, n0, nt, len;
@@ -372,44 +376,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
           const int sa = a_cnt % pl.a_stages;
           const int nk8 = min(KB, p.Cin - cb * KB) / (2 * CPG);   // MMA K steps: two 16-byte granules each
           mbar_wait(a_full(sa), (a_cnt / pl.a_stages) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_tiles + sa * pl.a_stage_bytes);
+          const uint64_t a_hi0 = desc_advance(a_desc0, smem_u32(a_tiles + sa * pl.a_stage_bytes));
           for (int j = 0; j < p.K; ++j, ++b_cnt) {
             const int sb = b_cnt % pl.b_stages;
             mbar_wait(b_full(sb), (b_cnt / pl.b_stages) & 1);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(b_tiles + sb * pl.b_stage_bytes);
-            for (int k8 = 0; k8 < nk8; ++k8) {
-              const uint32_t b_off = (uint32_t)(2 * k8) * b_lbo;
-              const uint64_t b_hi = make_desc(b_addr + b_off, b_lbo, 128u);
-              const uint64_t b_lo = make_desc(b_addr + pl.b_plane_bytes + b_off, b_lbo, 128u);
-              const uint32_t first = ((cb - cb_lo) | j | k8) != 0 ? 1u : 0u;
+            const uint64_t b_hi0 = desc_advance(b_desc0, smem_u32(b_tiles + sb * pl.b_stage_bytes));
+            const uint64_t a_j = desc_advance(a_hi0, (uint32_t)j * a_tap);
+            if (elect_one()) {
+              for (int k8 = 0; k8 < nk8; ++k8) {
+                const uint64_t b_hi = desc_advance(b_hi0, (uint32_t)k8 * b_k8);
+                const uint64_t a_k = desc_advance(a_j, (uint32_t)k8 * a_k8);
+                const uint32_t first = ((cb - cb_lo) | j | k8) != 0 ? 1u : 0u;
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
-                const uint32_t a_off = (uint32_t)((2 * k8) * pl.rows_pad + mt * BM + j * p.dil) * 16u;
-                const uint64_t a_hi = make_desc(a_addr + a_off, a_lbo, 128u);
-                const uint32_t d = d_base + (uint32_t)(mt * BN);
-                if (SPLIT3) {
-                  const uint64_t a_lo = make_desc(a_addr + pl.a_plane_bytes + a_off, a_lbo, 128u);
-                  umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
-                  umma_tf32(d, a_hi, b_lo, idesc, 1u);
-                  umma_tf32(d, a_hi, b_hi, idesc, 1u);
-                } else if (BF16) {
-                  umma_bf16(d, a_hi, b_hi, idesc, first);
-                } else {
-                  umma_tf32(d, a_hi, b_hi, idesc, first);
+                for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
+                  const uint64_t a_hi = desc_advance(a_k, (uint32_t)(mt * BM) * 16u);
+                  const uint32_t d = d_base + (uint32_t)(mt * BN);
+                  if (SPLIT3) {
+                    const uint64_t a_lo = desc_advance(a_hi, (uint32_t)pl.a_plane_bytes);
+                    const uint64_t b_lo = desc_advance(b_hi, (uint32_t)pl.b_plane_bytes);
+                    umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
+                    umma_tf32(d, a_hi, b_lo, idesc, 1u);
+                    umma_tf32(d, a_hi, b_hi, idesc, 1u);
+                  } else if (BF16) {
+                    umma_bf16(d, a_hi, b_hi, idesc, first);
+                  } else {
+                    umma_tf32(d, a_hi, b_hi, idesc, first);
+                  }
                 }
               }
+              umma_commit(b_empty(sb));     // weight stage free once these MMAs have read it
+              if (j == p.K - 1) {
+                umma_commit(a_empty(sa));   // activation stage free
+                if (cb == cb_hi - 1) umma_commit(acc_full(buf));       // accumulators of this tile complete -> epilogue
+              }
             }
-            umma_commit(b_empty(sb));     // weight stage free once these MMAs have read it
+            __syncwarp();
           }
-          umma_commit(a_empty(sa));       // activation stage free
         }
-        umma_commit(acc_full(buf));       // accumulators of this tile complete -> epilogue
         ++tile_cnt;
       }
     }
-    __syncwarp();
   } else {
     // ============================ weight loader ==================================================
     if (lane == 0) {

@@ -89,6 +89,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
   return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+// One elected lane of a fully converged warp (elect.sync): the MMA-issuing warps keep ALL lanes in the (warp-uniform) control flow
+// and predicate only the tcgen05 instructions with this, so descriptors and addresses stay in uniform registers -- with an
+// `if (lane == 0)` region instead, every tcgen05.mma is wrapped in a vote loop plus R2UR moves (~10 extra instructions per MMA,
+// which makes 16-cycle N=32 MMAs issue bound).  The same lane is elected every time while the warp stays converged.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor with the start address field advanced by `bytes` (the 14-bit field holds address >> 4; shared memory is < 256 KB)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
