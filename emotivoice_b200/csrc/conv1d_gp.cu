@@ -55,8 +55,10 @@ struct GPlan {
 
 __host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int BN, int mt, int kbg, GPlan* o) {
   GPlan q;
-  q.planes = mode == 1 ? 2 : 1;
-  const int cpg = mode == 2 ? 8 : 4;
+  q.planes = mode == 1 ? 2 : 1;          // A planes in shared memory (mode 3 keeps hi / lo interleaved in ONE plane, in place)
+  const int b_planes = (mode == 1 || mode == 3) ? 2 : 1;
+  const int cpg = mode == 2 ? 8 : 4;     // channels per 16-byte granule of the ACTIVATIONS
+  const int wcpg = mode >= 2 ? 8 : 4;    // channels per 16-byte granule of the WEIGHTS (bf16 operands: 8)
   q.kbg = kbg; q.mt = mt; q.BN = BN;
   if (2 * mt * BN > 512) return false;
   q.tmem_cols = 32;
@@ -64,9 +66,9 @@ __host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int 
   const int rows = BM * mt + (p.K - 1) * p.dil;
   q.rows_pad = (rows + 7) / 8 * 8;
   q.a_plane_bytes = kbg * q.rows_pad * 16;
-  q.b_plane_bytes = kbg * BN * 16;
+  q.b_plane_bytes = (kbg * cpg / wcpg) * BN * 16;
   q.a_stage_bytes = q.planes * q.a_plane_bytes;
-  q.b_stage_bytes = q.planes * q.b_plane_bytes;
+  q.b_stage_bytes = b_planes * q.b_plane_bytes;
   const int budget = 227 * 1024 - SMEM_HEAD;
   const int n_cb = (p.Cin + cpg * kbg - 1) / (cpg * kbg);
   const int b_max = n_cb * p.K < MAX_B ? n_cb * p.K : MAX_B;
@@ -91,14 +93,20 @@ __host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int 
 __device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 // MODE 0: one tf32 MMA per K step; 1: 3xTF32 fp32 emulation (hi/lo planes, three MMAs per K step); 2: bf16 operands,
-// bf16 activations in HBM (kind::f16, 8 channels per granule).  Accumulation is fp32 in TMEM in every mode.
+// bf16 activations in HBM (kind::f16, 8 channels per granule); 3: "bf16x3": fp32 activations in HBM, every operand split
+// into bf16 hi + lo (16 significant bits), three kind::f16 MMAs per K = 16 step -- an fp32-class result (~1e-5 relative) at
+// half the tensor-core and shared-memory cost of 3xTF32.  Accumulation is fp32 in TMEM in every mode.
 template <int MODE, int MT, int KBG>
 __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p, GPlan pl) {
-  constexpr bool SPLIT3 = (MODE == 1);
-  constexpr bool BF16 = (MODE == 2);
-  constexpr int PLANES = SPLIT3 ? 2 : 1;
-  constexpr int CPG = BF16 ? 8 : 4;
+  constexpr bool SPLIT3 = (MODE == 1);     // 3xTF32: hi / lo tf32 planes
+  constexpr bool BF16 = (MODE == 2);       // bf16 activations in HBM, bf16 operands
+  constexpr bool X3B = (MODE == 3);        // fp32 activations in HBM, operands split into bf16 hi + lo: three kind::f16 MMAs per K=16 step
+  constexpr bool OP16 = BF16 || X3B;       // the MMA operands are bf16
+  constexpr int BPLANES = (SPLIT3 || X3B) ? 2 : 1;
+  constexpr int CPG = BF16 ? 8 : 4;        // channels per 16-byte granule of the activations (HBM and the staged tile)
+  constexpr int WCPG = OP16 ? 8 : 4;       // channels per 16-byte granule of the weights
   constexpr int KB = CPG * KBG;
+  static_assert(!X3B || KBG % 4 == 0, "bf16x3 consumes four fp32 granules (16 channels) per MMA K step");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -283,7 +291,31 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
         const int ngran = min(KB, p.Cin - cb * KB) / CPG;
         uint8_t* base = a_tiles + s * pl.a_stage_bytes;
         mbar_wait(a_full(s), (a_cnt / pl.a_stages) & 1);
-        for (int g = 0; g < ngran; ++g) {
+        if (X3B) {
+          // fp32 -> bf16 hi + lo in place: the granule pair (2q, 2q+1) = 8 channels becomes [hi of the 8 | lo of the 8], so the hi
+          // plane is the even granule slots and the lo plane the odd ones (descriptor LBO = two slots)
+          for (int q = 0; q < ngran / 2; ++q) {
+            uint8_t* g0 = base + (size_t)(2 * q) * pl.rows_pad * 16;
+            uint8_t* g1 = g0 + (size_t)pl.rows_pad * 16;
+            for (int r = xt; r < rows_a; r += NTW * 32) {
+              const int row = row0 + r;
+              float4 u = make_float4(0.f, 0.f, 0.f, 0.f), w = u;
+              if (row >= 0 && row < len) { u = *reinterpret_cast<const float4*>(g0 + r * 16); w = *reinterpret_cast<const float4*>(g1 + r * 16); }
+              float f[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a0 = f[2 * e], a1 = f[2 * e + 1];
+                if (lrelu) { a0 = lrelu_f(a0, slope); a1 = lrelu_f(a1, slope); }
+                hi[e] = pack_bf16(a0, a1);
+                lo[e] = pack_bf16(a0 - __uint_as_float(hi[e] << 16), a1 - __uint_as_float(hi[e] & 0xffff0000u));
+              }
+              *reinterpret_cast<uint4*>(g0 + r * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(g1 + r * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+        for (int g = 0; g < (X3B ? 0 : ngran); ++g) {
           uint8_t* gb = base + (size_t)g * pl.rows_pad * 16;
           for (int r0 = 0; r0 < rows_a; r0 += NTW * 32 * XF_UNROLL) {
             uint4 v[XF_UNROLL];
@@ -358,10 +390,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
   } else if (warp == W_BLOAD) {
     // ============================ weight loader (weights are constants: no dependency wait) ========================
     if (lane == 0) {
-      // w layout: [plane (hi, lo)][N tile of BNp = min(Cout,128)][tap][Cin/CPG granules][BNp][16 bytes]
+      // w layout: [plane (hi, lo)][N tile of BNp = min(Cout,128)][tap][Cin/WCPG granules][BNp][16 bytes] (fp32 or bf16 granules)
       const int bnp = p.Cout < 128 ? p.Cout : 128;
-      const size_t plane = (size_t)p.K * p.Cin * p.Cout;
-      const size_t tile_stride = (size_t)p.K * gin * bnp * 4;      // 4-byte words per packed N tile
+      const int win = p.Cin / WCPG;                                  // weight granules along C_in
+      const size_t plane = (size_t)p.K * win * p.Cout * 4;          // 4-byte words per plane
+      const size_t tile_stride = (size_t)p.K * win * bnp * 4;       // 4-byte words per packed N tile
+      constexpr int KBGW = KBG * CPG / WCPG;                         // weight granules per pipeline stage
       int b_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
         int b, t0, n0, len;
@@ -369,20 +403,20 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
         if (t0 >= len) continue;
         const float* wt = p.w + (size_t)(n0 / bnp) * tile_stride + (size_t)(n0 % bnp) * 4;
         for (int cb = 0; cb < n_cb; ++cb) {
-          const int ngran = min(KB, p.Cin - cb * KB) / CPG;
+          const int ngran = min(KB, p.Cin - cb * KB) / WCPG;          // weight granules of this stage
           for (int j = 0; j < p.K; ++j, ++b_cnt) {
             const int sb = b_cnt % pl.b_stages;
             mbar_wait(b_empty(sb), ((b_cnt / pl.b_stages) & 1) ^ 1);
-            mbar_expect_tx(b_full(sb), (uint32_t)(PLANES * ngran * BN * 16));
+            mbar_expect_tx(b_full(sb), (uint32_t)(BPLANES * ngran * BN * 16));
             const uint32_t dst = smem_u32(b_tiles + sb * pl.b_stage_bytes);
-            const float* src = wt + ((size_t)j * gin + (size_t)cb * KBG) * bnp * 4;
+            const float* src = wt + ((size_t)j * win + (size_t)cb * KBGW) * bnp * 4;
             if (BN == bnp) {
               bulk_g2s(dst, src, (uint32_t)(ngran * BN * 16), b_full(sb));
-              if (SPLIT3) bulk_g2s(dst + (uint32_t)pl.b_plane_bytes, src + plane, (uint32_t)(ngran * BN * 16), b_full(sb));
+              if (BPLANES == 2) bulk_g2s(dst + (uint32_t)pl.b_plane_bytes, src + plane, (uint32_t)(ngran * BN * 16), b_full(sb));
             } else {
               for (int g = 0; g < ngran; ++g) {
                 bulk_g2s(dst + (uint32_t)(g * BN * 16), src + (size_t)g * bnp * 4, (uint32_t)(BN * 16), b_full(sb));
-                if (SPLIT3) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane + (size_t)g * bnp * 4, (uint32_t)(BN * 16), b_full(sb));
+                if (BPLANES == 2) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane + (size_t)g * bnp * 4, (uint32_t)(BN * 16), b_full(sb));
               }
             }
           }
@@ -395,11 +429,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
     // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues the tcgen05 instructions.
     {
       const uint32_t a_lbo = (uint32_t)pl.rows_pad * 16u, b_lbo = (uint32_t)BN * 16u;
-      const uint32_t fmt = BF16 ? 1u : 2u;      // instruction descriptor: D=F32 [4,6)=1, A/B format [7,10) / [10,13), N>>3 [17,23), M>>4 [24,29)
+      const uint32_t fmt = OP16 ? 1u : 2u;      // instruction descriptor: D=F32 [4,6)=1, A/B format [7,10) / [10,13), N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint64_t a_desc0 = make_desc(0u, a_lbo, 128u), b_desc0 = make_desc(0u, b_lbo, 128u);
+      // bf16x3: the two K granules of one MMA are two slots apart (hi in the even slots, lo in the odd ones), one K step = 4 slots
+      const uint64_t a_desc0 = make_desc(0u, X3B ? 2u * a_lbo : a_lbo, 128u), b_desc0 = make_desc(0u, b_lbo, 128u);
       const uint32_t a_tap = (uint32_t)p.dil * 16u;                    // bytes per tap shift
-      const uint32_t a_k8 = 2u * a_lbo, b_k8 = 2u * b_lbo;             // bytes per K step (two granules)
+      const uint32_t a_k8 = (X3B ? 4u : 2u) * a_lbo, b_k8 = 2u * b_lbo;   // bytes per K step
+      const uint32_t a_lo_off = X3B ? a_lbo : (uint32_t)pl.a_plane_bytes;
       int a_cnt = 0, b_cnt = 0, tile_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
         int b, t0, n0, len;
@@ -411,7 +447,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
         const uint32_t d_base = tmem_base + (uint32_t)(buf * MT * BN);
         for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
           const int sa = a_cnt % pl.a_stages;
-          const int nk8 = min(KB, p.Cin - cb * KB) / (2 * CPG);   // MMA K steps: two 16-byte granules each
+          const int nk8 = min(KB, p.Cin - cb * KB) / (2 * WCPG);  // MMA K steps: two 16-byte operand granules each
           mbar_wait(a_ready(sa), (a_cnt / pl.a_stages) & 1);
           const uint64_t a_hi0 = desc_advance(a_desc0, smem_u32(a_tiles + sa * pl.a_stage_bytes));
           for (int j = 0; j < p.K; ++j, ++b_cnt) {
@@ -429,12 +465,18 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
                 for (int mt = 0; mt < MT; ++mt) {      // one weight tile feeds MT accumulators
                   const uint64_t a_hi = desc_advance(a_k, (uint32_t)(mt * BM) * 16u);
                   const uint32_t d = d_base + (uint32_t)(mt * BN);
-                  if (SPLIT3) {
-                    const uint64_t a_lo = desc_advance(a_hi, (uint32_t)pl.a_plane_bytes);
+                  if (SPLIT3 || X3B) {
+                    const uint64_t a_lo = desc_advance(a_hi, a_lo_off);
                     const uint64_t b_lo = desc_advance(b_hi, (uint32_t)pl.b_plane_bytes);
-                    umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
-                    umma_tf32(d, a_hi, b_lo, idesc, 1u);
-                    umma_tf32(d, a_hi, b_hi, idesc, 1u);
+                    if (X3B) {
+                      umma_bf16(d, a_lo, b_hi, idesc, first);     // small terms first
+                      umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                      umma_bf16(d, a_hi, b_hi, idesc, 1u);
+                    } else {
+                      umma_tf32(d, a_lo, b_hi, idesc, first);
+                      umma_tf32(d, a_hi, b_lo, idesc, 1u);
+                      umma_tf32(d, a_hi, b_hi, idesc, 1u);
+                    }
                   } else if (BF16) {
                     umma_bf16(d, a_hi, b_hi, idesc, first);
                   } else {
@@ -542,8 +584,8 @@ __global__ void __launch_bounds__(GPP_BT) conv_post_gp_kernel(const void* __rest
 
 static int validate_gp(const GpConvParams& p, int mode) {
   EV_CHECK_ARG(p.B > 0 && p.L > 0, "conv1d_gp: bad problem B=%d L=%d", p.B, p.L);
-  EV_CHECK_ARG(mode >= 0 && mode <= 2, "conv1d_gp: mode %d", mode);
-  EV_CHECK_ARG(p.Cin % (mode == 2 ? 16 : 8) == 0, "conv1d_gp: Cin=%d must be a multiple of %d", p.Cin, mode == 2 ? 16 : 8);
+  EV_CHECK_ARG(mode >= 0 && mode <= 3, "conv1d_gp: mode %d", mode);
+  EV_CHECK_ARG(p.Cin % (mode >= 2 ? 16 : 8) == 0, "conv1d_gp: Cin=%d must be a multiple of %d", p.Cin, mode >= 2 ? 16 : 8);
   EV_CHECK_ARG(p.Cout % 32 == 0 && (p.Cout <= 128 || p.Cout % 128 == 0), "conv1d_gp: Cout=%d must be a multiple of 32, and of 128 above 128", p.Cout);
   EV_CHECK_ARG(p.rate >= 1 && p.Cout % p.rate == 0 && (p.Cout / p.rate) % 32 == 0, "conv1d_gp: rate=%d does not split Cout=%d into multiples of 32", p.rate, p.Cout);
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_gp: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
@@ -574,8 +616,8 @@ static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out) {
   const int nsm = sm_count();
   const int kbg = gp_shape_kbg(p, mode);
   const double kc8 = (double)p.K * p.Cin / 8.0;
-  const double n_mma = (mode == 1 ? 3.0 : 1.0) * (mode == 2 ? 0.5 : 1.0) * kc8;     // MMA instructions per accumulator and tile
-  const double w_per_n = (mode == 1 ? 2.0 : 1.0) * (mode == 2 ? 16.0 : 32.0) / 42.0;
+  const double n_mma = ((mode == 1 || mode == 3) ? 3.0 : 1.0) * (mode >= 2 ? 0.5 : 1.0) * kc8;     // MMA instructions per accumulator and tile
+  const double w_per_n = ((mode == 1 || mode == 3) ? 2.0 : 1.0) * (mode >= 2 ? 16.0 : 32.0) / 42.0;
   const double esize = mode == 2 ? 2.0 : 4.0;
   double best = 1e300;
   bool found = false;
@@ -639,6 +681,7 @@ int launch_conv1d_gp(const GpConvParams& p, int mode, cudaStream_t st) {
   gp::GPlan pl;
   EV_TRY(plan_gp(p, mode, &pl));
   if (mode == 1) return launch_gp_mt<1, 4>(p, pl, st);
+  if (mode == 3) return pl.kbg == 8 ? launch_gp_mt<3, 8>(p, pl, st) : launch_gp_mt<3, 4>(p, pl, st);
   if (mode == 2) return pl.kbg == 8 ? launch_gp_mt<2, 8>(p, pl, st) : launch_gp_mt<2, 4>(p, pl, st);
   return pl.kbg == 8 ? launch_gp_mt<0, 8>(p, pl, st) : launch_gp_mt<0, 4>(p, pl, st);
 }

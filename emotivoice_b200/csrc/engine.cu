@@ -97,12 +97,14 @@ struct ConvW {
   const float *w, *b;
   const float* w_tc = nullptr;
   const float* w_h = nullptr;
+  const float* w_x2 = nullptr;     // two bf16 planes (hi, lo): the bf16x3 fp32 emulation of the granule-planar vocoder
   int K, dil, cin, cout;
 };
 struct UpW {
   const float *w, *b;
   const float* w_tc = nullptr;
   const float* w_h = nullptr;
+  const float* w_x2 = nullptr;
   int K, cin, cout_packed, rate, cout;
 };
 
@@ -319,6 +321,7 @@ static int resolve_voc(ev_ctx* c) {
   EV_TRY(find(c, "voc.pre.b", g.voc_c0, &c->pre.b));
   c->pre.w_tc = find_opt(c, "voc.pre.w.tc", (uint64_t)2 * 7 * g.n_mels * g.voc_c0);
   c->pre.w_h = find_opt(c, "voc.pre.w.tc16", (uint64_t)7 * g.n_mels * g.voc_c0 / 2);
+  c->pre.w_x2 = find_opt(c, "voc.pre.w.tc16x2", (uint64_t)7 * g.n_mels * g.voc_c0);
   c->ups.resize(g.n_ups);
   c->rb_c1.clear(); c->rb_c2.clear();
   int ch = g.voc_c0, mul = 1;
@@ -339,6 +342,7 @@ static int resolve_voc(ev_ctx* c) {
     u.w = it->second.p;
     u.w_tc = find_opt(c, q + ".w.tc", 2 * it->second.numel);
     u.w_h = find_opt(c, q + ".w.tc16", it->second.numel / 2);
+    u.w_x2 = find_opt(c, q + ".w.tc16x2", it->second.numel);
     EV_TRY(find(c, q + ".b", u.cout_packed, &u.b));
     ch = u.cout; mul *= u.rate;
     if (mul * ch > c->max_stage_width) c->max_stage_width = mul * ch;
@@ -357,6 +361,8 @@ static int resolve_voc(ev_ctx* c) {
         c2.w_tc = find_opt(c, r + ".c2." + std::to_string(l) + ".w.tc", (uint64_t)2 * k * ch * ch);
         c1.w_h = find_opt(c, r + ".c1." + std::to_string(l) + ".w.tc16", (uint64_t)k * ch * ch / 2);
         c2.w_h = find_opt(c, r + ".c2." + std::to_string(l) + ".w.tc16", (uint64_t)k * ch * ch / 2);
+        c1.w_x2 = find_opt(c, r + ".c1." + std::to_string(l) + ".w.tc16x2", (uint64_t)k * ch * ch);
+        c2.w_x2 = find_opt(c, r + ".c2." + std::to_string(l) + ".w.tc16x2", (uint64_t)k * ch * ch);
         c->rb_c1.push_back(c1); c->rb_c2.push_back(c2);
       }
   }
@@ -405,14 +411,21 @@ static int conv_x(int mode, const float* w_tc, const float* w_h, const float* x,
 }
 
 // HiFi-GAN convolution on granule-planar activations (conv1d_gp.cu).  mode as conv_x: 1 = tf32, 2 = bf16 (bf16 activations), 3 = 3xTF32.
-static int conv_gp(int mode, const float* w_tc, const float* w_h, const void* x, const float* bias, const void* res, void* out, int B, int L,
-                   int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act, float in_slope, int acc, float div,
-                   cudaStream_t st) {
+// In the fp32-accurate mode (3) the vocoder runs the "bf16x3" emulation when the blob carries the two-plane bf16 weights (half the
+// tensor-core and shared-memory cost of 3xTF32, ~1e-5 relative error; EV_VOC_FP32=tf32x3 keeps 3xTF32).
+static inline bool voc_bf16x3_enabled() {
+  static const int v = [] { const char* e = getenv("EV_VOC_FP32"); return (e && e[0] == 't') ? 0 : 1; }();
+  return v == 1;
+}
+static int conv_gp(int mode, const float* w_tc, const float* w_h, const float* w_x2, const void* x, const float* bias, const void* res, void* out,
+                   int B, int L, int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act, float in_slope, int acc,
+                   float div, cudaStream_t st) {
   GpConvParams p;
-  p.x = x; p.w = (mode == 2) ? w_h : w_tc; p.bias = bias; p.res = res; p.out = out;
+  const bool x3b = mode == 3 && w_x2 && voc_bf16x3_enabled();
+  p.x = x; p.w = x3b ? w_x2 : ((mode == 2) ? w_h : w_tc); p.bias = bias; p.res = res; p.out = out;
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.rate = rate;
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope; p.acc = acc; p.div = div;
-  return launch_conv1d_gp(p, mode == 3 ? 1 : (mode == 2 ? 2 : 0), st);
+  return launch_conv1d_gp(p, x3b ? 3 : (mode == 3 ? 1 : (mode == 2 ? 2 : 0)), st);
 }
 
 // The vocoder runs on granule-planar activations whenever it runs on the tensor cores (every mode but "fp32_ffma");
@@ -677,7 +690,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
     // mel (B,F,n_mels) time-major or (B,n_mels,F) channels-first -> GP
     EV_TRY(launch_to_gp(mel, (long long)F * g.n_mels, mel_time_major ? g.n_mels : 1, mel_time_major ? 1 : F, v.Tm, B, F, g.n_mels, bf, st));
     // conv_pre (hifigan/models.py:116)
-    EV_TRY(conv_gp(mode, ctx->pre.w_tc, ctx->pre.w_h, v.Tm, ctx->pre.b, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1, 1, mel_lens, 1,
+    EV_TRY(conv_gp(mode, ctx->pre.w_tc, ctx->pre.w_h, ctx->pre.w_x2, v.Tm, ctx->pre.b, nullptr, v.ACC, B, F, g.n_mels, g.voc_c0, ctx->pre.K, 1, 1, mel_lens, 1,
                    EV_ACT_NONE, 0.f, EV_ACC_STORE, 1.f, st));
     int L = F, mul = 1;
     size_t rb = 0;
@@ -686,7 +699,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
       Range r_stage(kNames[s & 7]);
       const UpW& u = ctx->ups[s];
       // x = ups[i](leaky_relu(x, 0.1)) (:118-119): polyphase transposed conv, the `rate` output phases are GEMM column groups
-      EV_TRY(conv_gp(mode, u.w_tc, u.w_h, v.ACC, u.b, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, u.rate, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+      EV_TRY(conv_gp(mode, u.w_tc, u.w_h, u.w_x2, v.ACC, u.b, nullptr, v.X, B, L, u.cin, u.cout_packed, u.K, 1, u.rate, mel_lens, mul, EV_ACT_LRELU, 0.1f,
                      EV_ACC_STORE, 1.f, st));
       L *= u.rate; mul *= u.rate;
       const int C = u.cout;
@@ -701,9 +714,9 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
           if (last && j > 0) acc = (j == g.n_resk - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;   // xs += ...; x = xs / n (:120-126)
           if (last && g.n_resk == 1) acc = EV_ACC_STORE;
           // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
-          EV_TRY(conv_gp(mode, c1.w_tc, c1.w_h, src, c1.b, nullptr, v.Tm, B, L, C, C, c1.K, c1.dil, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
+          EV_TRY(conv_gp(mode, c1.w_tc, c1.w_h, c1.w_x2, src, c1.b, nullptr, v.Tm, B, L, C, C, c1.K, c1.dil, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
                          EV_ACC_STORE, 1.f, st));
-          EV_TRY(conv_gp(mode, c2.w_tc, c2.w_h, v.Tm, c2.b, src, dst, B, L, C, C, c2.K, 1, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f, acc,
+          EV_TRY(conv_gp(mode, c2.w_tc, c2.w_h, c2.w_x2, v.Tm, c2.b, src, dst, B, L, C, C, c2.K, 1, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f, acc,
                          (float)g.n_resk, st));
           src = dst;
         }

@@ -84,6 +84,16 @@ def to_tc16_layout(w_kio):
     return g.to(torch.bfloat16).view(torch.float32)
 
 
+def to_tc16x2_layout(w_kio):
+    """(K, Cin, Cout) -> two bf16 planes in the tc16 layout, stacked: plane 0 = bf16(w) ("hi"), plane 1 = bf16(w - hi) ("lo").
+    The "bf16x3" fp32 emulation of the vocoder (csrc/conv1d_gp.cu MODE 3): w ~= hi + lo to 16 significant bits."""
+    if w_kio.dim() == 2:
+        w_kio = w_kio.unsqueeze(0)
+    hi = w_kio.to(torch.bfloat16)
+    lo = (w_kio - hi.float()).to(torch.bfloat16)
+    return torch.stack([to_tc16_layout(hi.float()), to_tc16_layout(lo.float())]).contiguous()
+
+
 TC_SUFFIXES = ("wqkv", "wo", "w1", "w2")
 
 
@@ -100,6 +110,8 @@ def add_tc_weights(packed):
             extra[k + ".tc"] = to_tc_layout(v)
         if (is_stack and k.startswith("dec.")) or is_voc or k == "to_mel.w":      # layers the bf16 mode runs in bf16
             extra[k + ".tc16"] = to_tc16_layout(v)
+        if is_voc:                                                                  # the vocoder's fp32 mode: bf16x3 emulation
+            extra[k + ".tc16x2"] = to_tc16x2_layout(v)
     packed.update(extra)
     return packed
 

@@ -192,7 +192,8 @@ EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const 
 EV_API int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int split3, int ksplit, int* out11);
 /* HiFi-GAN convolution on GRANULE-PLANAR activations (csrc/conv1d_gp.cu; what ev_vocoder runs in every tensor-core mode).
  * Layout: a (B, L, C) tensor is stored [b][C/cpg][l][cpg] in 16-byte granules, cpg = 4 fp32 (mode 0 tf32, 1 3xTF32) or 8 bf16
- * (mode 2).  w: the ev_op_conv1d_tc weight layout of that mode.  rate > 1: polyphase ConvTranspose1d, the Cout GEMM columns
+ * (mode 2); mode 3 = "bf16x3": fp32 activations, every operand split into bf16 hi + lo, three bf16 MMAs per K step (fp32-class
+ * result at half the cost of 3xTF32; w then holds two bf16 planes).  w: the ev_op_conv1d_tc weight layout of that mode.  rate > 1: polyphase ConvTranspose1d, the Cout GEMM columns
  * are `rate` phases of Cout/rate channels, out is (B, (Cout/rate)/cpg, L*rate, cpg).  res (rate == 1): same shape as out.
  * Rows >= lens[b]*lens_mul are neither read (they count as zero padding) nor written.  Replaces hifigan/models.py:50-57,
  * :116, :118-119. */

@@ -2,7 +2,8 @@
 
 usage: python tools/profile_conv.py MODE C K DIL L [B] [reps]
   MODE in {ffma, tf32, fp32, bf16}            round-1 time-major kernels (conv1d_tm / conv1d_tc)
-          {gp:tf32, gp:fp32, gp:bf16}         granule-planar kernel (conv1d_gp), the vocoder's default path
+          {gp:tf32, gp:fp32, gp:bf16, gp:bf16x3}   granule-planar kernel (conv1d_gp), the vocoder's default path
+                                              (gp:fp32 = 3xTF32; gp:bf16x3 = the fp32 mode's default emulation)
   C may be "Cin:Cout" (or "Cin:Cout:rate" for the polyphase ConvTranspose1d form, gp only).
 Prints per-launch times (L2 flushed before each), algorithmic TFLOP/s and layer-granular GB/s (in + out + residual, weights once)."""
 import json
@@ -27,7 +28,7 @@ dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 x = torch.randn(B, L, Cin, generator=g)
 w = torch.randn(K, Cin, Cout, generator=g) / math.sqrt(Cin * K)
-wd = (packing.to_tc16_layout(w) if prec == "bf16" else (packing.to_tc_layout(w) if prec != "ffma" else w)).to(dev)
+wd = (packing.to_tc16x2_layout(w) if prec == "bf16x3" else (packing.to_tc16_layout(w) if prec == "bf16" else (packing.to_tc_layout(w) if prec != "ffma" else w))).to(dev)
 b = torch.randn(Cout, generator=g).to(dev)
 coutR = Cout // rate
 res = torch.randn(B, L * rate, coutR, generator=g) if rate == 1 else None
@@ -47,7 +48,7 @@ for i in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if gp:
-        _abi.check(lib.ev_op_conv1d_gp(ptr(xd), ptr(wd), {"tf32": 0, "fp32": 1, "bf16": 2}[prec], ptr(b), ptr(rd), ptr(out), B, L, Cin, Cout, K, dil, rate,
+        _abi.check(lib.ev_op_conv1d_gp(ptr(xd), ptr(wd), {"tf32": 0, "fp32": 1, "bf16": 2, "bf16x3": 3}[prec], ptr(b), ptr(rd), ptr(out), B, L, Cin, Cout, K, dil, rate,
                                        None, 1, 1, 0.1, 0, 1.0, st))
     elif mode == "ffma":
         _abi.check(lib.ev_op_conv1d(ptr(xd), ptr(wd), ptr(b), 0, ptr(rd), ptr(out), B, L, Cin, Cout, K, dil, None, 1, 1, 0.1, 0, 0, 1.0, st))
