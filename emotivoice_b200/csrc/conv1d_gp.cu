@@ -624,7 +624,7 @@ static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out) {
   gp::GPlan best_pl;
   const int bn_max = p.Cout <= 128 ? p.Cout : 128;
   for (int BN = bn_max; BN >= 32; BN /= 2) {
-    if (p.Cout % BN) continue;
+    if (p.Cout % BN || BN % 32) continue;
     for (int mt = 4; mt >= 1; mt >>= 1) {
       gp::GPlan pl;
       if (!gp::make_gplan(p, mode, BN, mt, kbg, &pl)) continue;

@@ -428,6 +428,26 @@ static int conv_gp(int mode, const float* w_tc, const float* w_h, const float* w
   return launch_conv1d_gp(p, x3b ? 3 : (mode == 3 ? 1 : (mode == 2 ? 2 : 0)), st);
 }
 
+// One ResBlock layer through the fused kernel (resblock_gp.cu) where it takes the shape (C <= 128); EV_FUSE_RES=0 keeps two launches.
+static inline bool fuse_res_enabled() {
+  static const int v = [] { const char* e = getenv("EV_FUSE_RES"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v == 1;
+}
+static bool try_gp_pair(int mode, const ConvW& c1, const ConvW& c2, const void* src, void* dst, int B, int L, int C, const int32_t* lens, int lens_mul,
+                        int acc, float div, cudaStream_t st, int* rc) {
+  if (!fuse_res_enabled() || c1.K != c2.K || c2.dil != 1) return false;
+  const bool x3b = mode == 3 && c1.w_x2 && c2.w_x2 && voc_bf16x3_enabled();
+  const int gm = x3b ? 3 : (mode == 3 ? 1 : (mode == 2 ? 2 : 0));
+  GpPairParams p;
+  p.x = src; p.out = dst; p.b1 = c1.b; p.b2 = c2.b;
+  p.w1 = x3b ? c1.w_x2 : (mode == 2 ? c1.w_h : c1.w_tc);
+  p.w2 = x3b ? c2.w_x2 : (mode == 2 ? c2.w_h : c2.w_tc);
+  p.B = B; p.L = L; p.C = C; p.K = c1.K; p.dil = c1.dil; p.lens = lens; p.lens_mul = lens_mul; p.slope = 0.1f; p.acc = acc; p.div = div;
+  if (!p.w1 || !p.w2 || !gp_pair_supported(p, gm)) return false;
+  *rc = launch_gp_pair(p, gm, st);
+  return true;
+}
+
 // The vocoder runs on granule-planar activations whenever it runs on the tensor cores (every mode but "fp32_ffma");
 // EV_VOC_LAYOUT=tm keeps the round-1 time-major path (conv1d_tc.cu) for A/B measurements.
 static inline bool voc_gp_enabled() {
@@ -713,7 +733,13 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
           int acc = EV_ACC_STORE;
           if (last && j > 0) acc = (j == g.n_resk - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;   // xs += ...; x = xs / n (:120-126)
           if (last && g.n_resk == 1) acc = EV_ACC_STORE;
-          // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57)
+          // xt = c1(lrelu(x)) ; x = c2(lrelu(xt)) + x   (:50-57): one fused kernel where the shape fits, else two launches
+          int frc = EV_OK;
+          if (try_gp_pair(mode, c1, c2, src, dst, B, L, C, mel_lens, mul, acc, (float)g.n_resk, st, &frc)) {
+            EV_TRY(frc);
+            src = dst;
+            continue;
+          }
           EV_TRY(conv_gp(mode, c1.w_tc, c1.w_h, c1.w_x2, src, c1.b, nullptr, v.Tm, B, L, C, C, c1.K, c1.dil, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f,
                          EV_ACC_STORE, 1.f, st));
           EV_TRY(conv_gp(mode, c2.w_tc, c2.w_h, c2.w_x2, v.Tm, c2.b, src, dst, B, L, C, C, c2.K, 1, 1, mel_lens, mul, EV_ACT_LRELU, 0.1f, acc,
@@ -823,6 +849,24 @@ int ev_op_conv1d_gp(const void* x, const float* w, int mode, const float* bias, 
   p.x = x; p.w = w; p.bias = bias; p.res = res; p.out = out; p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.rate = rate;
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope; p.acc = acc; p.div = div;
   return launch_conv1d_gp(p, mode, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_resblock_gp(const void* x, const float* w1, const float* b1, const float* w2, const float* b2, int mode, void* out, int B, int L, int C, int K,
+                      int dil, const int32_t* lens, int lens_mul, int acc, float div, void* stream) {
+  EV_CHECK_ARG(x && w1 && b1 && w2 && b2 && out, "ev_op_resblock_gp: null argument");
+  EV_TRY(use_device_of(x));
+  GpPairParams p;
+  p.x = x; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.out = out; p.B = B; p.L = L; p.C = C; p.K = K; p.dil = dil; p.lens = lens; p.lens_mul = lens_mul;
+  p.slope = 0.1f; p.acc = acc; p.div = div;
+  return launch_gp_pair(p, mode, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_debug_resblock_gp_plan(int B, int L, int C, int K, int dil, int mode, int* out11) {
+  EV_CHECK_ARG(out11, "ev_debug_resblock_gp_plan: null output");
+  static float dummy_in, dummy_out;
+  GpPairParams p{};
+  p.x = &dummy_in; p.out = &dummy_out; p.B = B; p.L = L; p.C = C; p.K = K; p.dil = dil; p.lens_mul = 1; p.slope = 0.1f; p.acc = EV_ACC_STORE; p.div = 1.f;
+  return debug_gp_pair_plan(p, mode, out11);
 }
 
 int ev_debug_gp_plan(int B, int L, int Cin, int Cout, int K, int dil, int rate, int mode, int* out11) {

@@ -149,6 +149,25 @@ int launch_conv1d_gp(const GpConvParams& p, int mode, cudaStream_t st);    // mo
 int debug_gp_plan(const GpConvParams& p, int mode, int* v11);
 // fp32 in[b*sb + t*st + c*sc] -> GP (fp32, or bf16 when bf16 != 0)
 int launch_to_gp(const float* in, long long sb, long long st_, long long sc, void* out, int B, int L, int C, int bf16, cudaStream_t st);
+// One ResBlock1 layer  out = [acc]( x + c2(lrelu(c1(lrelu(x), dil)), 1) )  as one kernel on granule-planar activations
+// (resblock_gp.cu); bitwise equal to the two launch_conv1d_gp calls it replaces.  C in {32, 64, 96, 128}.
+struct GpPairParams {
+  const void* x;       // GP (B, C/cpg, L, cpg): the layer input, also the residual
+  const float* w1;     // c1 weights (k taps, dilation dil), tensor-core layout of the mode
+  const float* b1;
+  const float* w2;     // c2 weights (k taps, dilation 1)
+  const float* b2;
+  void* out;           // GP, same shape; must not alias x
+  int B, L, C, K, dil;
+  const int32_t* lens; // valid rows per item = lens[b]*lens_mul (null: L)
+  int lens_mul;
+  float slope;         // LeakyReLU slope of both prologues (0.1)
+  int acc;             // EV_ACC_*
+  float div;
+};
+bool gp_pair_supported(const GpPairParams& p, int mode);
+int launch_gp_pair(const GpPairParams& p, int mode, cudaStream_t st);      // mode as launch_conv1d_gp
+int debug_gp_pair_plan(const GpPairParams& p, int mode, int* v11);
 int launch_conv_post_gp(const void* x, int bf16, const float* w, const float* bias, const int32_t* lens, int lens_mul, int B, int L, int C, int K,
                         float slope, float* wav, cudaStream_t st);
 

@@ -200,6 +200,14 @@ EV_API int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int
 EV_API int ev_op_conv1d_gp(const void* x, const float* w, int mode, const float* bias, const void* res, void* out, int B, int L,
                            int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act,
                            float in_slope, int acc, float div, void* stream);
+/* One ResBlock1 layer (hifigan/models.py:50-57) as ONE kernel on granule-planar activations (csrc/resblock_gp.cu):
+ * out = [acc]( x + c2(lrelu(c1(lrelu(x), dil)), 1) ), C -> C channels (C % 32 == 0, C <= 128), slope 0.1, both weights in the layout of
+ * `mode` (as ev_op_conv1d_gp).  Bitwise equal to the two ev_op_conv1d_gp launches it replaces; EV_EINVAL for shapes it does not take
+ * (the engine then runs the pair unfused). */
+EV_API int ev_op_resblock_gp(const void* x, const float* w1, const float* b1, const float* w2, const float* b2, int mode, void* out, int B,
+                             int L, int C, int K, int dil, const int32_t* lens, int lens_mul, int acc, float div, void* stream);
+/* Host-only: out11 = {MT, KBG, x stages, weight stages, transform warps, tmem columns, smem bytes, tiles, rows per tile, rows1_pad, rows2_pad}. */
+EV_API int ev_debug_resblock_gp_plan(int B, int L, int C, int K, int dil, int mode, int* out11);
 /* Host-only: out11 = {BN, MT, KBG, a_stages, b_stages, transform warps, planes, tmem columns, smem bytes, tiles, rows_pad}. */
 EV_API int ev_debug_gp_plan(int B, int L, int Cin, int Cout, int K, int dil, int rate, int mode, int* out11);
 /* fp32 in[b*stride_b + t*stride_t + c*stride_c] -> granule-planar (fp32, or bf16 when bf16 != 0): the vocoder's input boundary

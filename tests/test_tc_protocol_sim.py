@@ -372,3 +372,146 @@ def test_gp_protocol_model_is_sensitive():
     with pytest.raises(AssertionError):
         for seed in range(40):
             sim_gp(seed, [True] * 5, n_cb=1, K=1, a_stages=2, b_stages=2, n_work_items=1, skip_idle_wait=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# resblock_gp.cu: C1(0) | C1(i+1), C2(i); epi1 writes the xt tile between them; separate epilogue warp groups
+# ------------------------------------------------------------------------------------------------------------------
+def sim_pair(seed, n_tiles, n_cb, K, a_stages, b_stages):
+    sim = Sim(seed)
+    a_full = [Bar(1) for _ in range(a_stages)]
+    a_ready = [Bar(NTW) for _ in range(a_stages)]
+    a_empty = [Bar(1) for _ in range(a_stages)]
+    b_full = [Bar(1) for _ in range(b_stages)]
+    b_empty = [Bar(1) for _ in range(b_stages)]
+    acc1_full, acc1_empty = [Bar(1), Bar(1)], [Bar(4), Bar(4)]
+    acc2_full, acc2_empty = [Bar(1), Bar(1)], [Bar(4), Bar(4)]
+    a2_full, a2_empty = Bar(4), Bar(1)                  # one arrival per epi1 warp here (the kernel: per thread)
+
+    def order():                                         # the MMA issuer's / weight loader's schedule
+        if n_tiles:
+            yield (1, 0)
+        for i in range(n_tiles):
+            if i + 1 < n_tiles:
+                yield (1, i + 1)
+            yield (2, i)
+
+    def aloader():
+        a_cnt = 0
+        for ti in range(n_tiles):
+            for cb in range(n_cb):
+                s = a_cnt % a_stages
+                yield ("wait", a_empty[s], ((a_cnt // a_stages) & 1) ^ 1)
+                yield ("write", ("X", s), ("raw", ti, cb))
+                yield ("arrive", a_full[s])
+                a_cnt += 1
+
+    def xform(w):
+        a_cnt = 0
+        for ti in range(n_tiles):
+            for cb in range(n_cb):
+                s = a_cnt % a_stages
+                yield ("wait", a_full[s], (a_cnt // a_stages) & 1)
+                if w == 0:
+                    yield ("read", ("X", s), ("raw", ti, cb))
+                    yield ("write", ("X", s), ("op", ti, cb))
+                yield ("arrive", a_ready[s])
+                a_cnt += 1
+
+    def bloader():
+        b_cnt = 0
+        for which, ti in order():
+            for cb in range(n_cb):
+                for j in range(K):
+                    sb = b_cnt % b_stages
+                    yield ("wait", b_empty[sb], ((b_cnt // b_stages) & 1) ^ 1)
+                    yield ("write", ("B", sb), (which, ti, cb, j))
+                    yield ("arrive", b_full[sb])
+                    b_cnt += 1
+
+    def mma():
+        a_cnt = b_cnt = 0
+        for which, ti in order():
+            buf = ti & 1
+            if which == 1:
+                yield ("wait", acc1_empty[buf], ((ti >> 1) & 1) ^ 1)
+                for cb in range(n_cb):
+                    sa = a_cnt % a_stages
+                    yield ("wait", a_ready[sa], (a_cnt // a_stages) & 1)
+                    for j in range(K):
+                        sb = b_cnt % b_stages
+                        yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
+                        yield ("mma_read", ("X", sa), ("op", ti, cb))
+                        yield ("mma_read", ("B", sb), (1, ti, cb, j))
+                        yield ("commit", b_empty[sb])
+                        b_cnt += 1
+                    yield ("commit", a_empty[sa])
+                    a_cnt += 1
+                yield ("write", ("ACC1", buf), ti)
+                yield ("commit", acc1_full[buf])
+            else:
+                yield ("wait", a2_full, ti & 1)
+                yield ("wait", acc2_empty[buf], ((ti >> 1) & 1) ^ 1)
+                for cb in range(n_cb):
+                    for j in range(K):
+                        sb = b_cnt % b_stages
+                        yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
+                        yield ("mma_read", ("A2",), ti)
+                        yield ("mma_read", ("B", sb), (2, ti, cb, j))
+                        yield ("commit", b_empty[sb])
+                        b_cnt += 1
+                yield ("write", ("ACC2", buf), ti)
+                yield ("commit", a2_empty)
+                yield ("commit", acc2_full[buf])
+
+    def epi1(w):
+        for ti in range(n_tiles):
+            buf = ti & 1
+            yield ("wait", acc1_full[buf], (ti >> 1) & 1)
+            yield ("wait", a2_empty, (ti & 1) ^ 1)
+            yield ("read", ("ACC1", buf), ti)
+            if w == 0:
+                yield ("write", ("A2",), ti)
+            yield ("arrive", a2_full)
+            yield ("arrive", acc1_empty[buf])
+
+    def epi2(w):
+        for ti in range(n_tiles):
+            buf = ti & 1
+            yield ("wait", acc2_full[buf], (ti >> 1) & 1)
+            yield ("read", ("ACC2", buf), ti)
+            yield ("arrive", acc2_empty[buf])
+
+    sim.add("aloader", aloader())
+    for w in range(NTW):
+        sim.add("xform%d" % w, xform(w))
+    sim.add("bloader", bloader())
+    sim.add("mma", mma())
+    for w in range(4):
+        sim.add("epi1_%d" % w, epi1(w))
+        sim.add("epi2_%d" % w, epi2(w))
+    sim.run()
+
+
+@pytest.mark.parametrize("C,K,dil", [(32, 3, 1), (32, 11, 5), (64, 7, 3), (64, 11, 5), (128, 11, 1)])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_resblock_gp_protocol_with_the_real_plans(lib, C, K, dil, mode):
+    v = (ctypes.c_int * 11)()
+    assert lib.ev_debug_resblock_gp_plan(1, 137472, C, K, dil, mode, v) == 0, lib.ev_last_error()
+    pl = dict(zip("MT KBG a_stages b_stages ntw tmem smem tiles R rows1_pad rows2_pad".split(), list(v)))
+    assert pl["smem"] <= 227 * 1024 and 4 * pl["MT"] * C <= pl["tmem"] <= 512 and pl["a_stages"] >= 2 and pl["b_stages"] >= 2
+    assert pl["R"] == 128 * pl["MT"] - (K - 1) and pl["rows1_pad"] >= 128 * pl["MT"] + (K - 1) * dil and pl["rows2_pad"] >= 128 * pl["MT"] + K - 1
+    cpg = 8 if mode == 2 else 4
+    n_cb = -(-C // (cpg * pl["KBG"]))
+    for seed in range(5):
+        sim_pair(seed, random.Random(seed).randint(1, 5), n_cb, K, pl["a_stages"], pl["b_stages"])
+
+
+def test_resblock_gp_kbg_matches_the_unfused_kernel(lib):
+    """The fused layer must reduce in the same order as the two launches it replaces: same channels per pipeline stage."""
+    for C, K, dil in [(32, 3, 1), (32, 11, 5), (64, 7, 3), (64, 11, 5), (128, 11, 5)]:
+        for mode in (0, 1, 2, 3):
+            v, u = (ctypes.c_int * 11)(), (ctypes.c_int * 11)()
+            assert lib.ev_debug_resblock_gp_plan(4, 50000, C, K, dil, mode, v) == 0
+            assert lib.ev_debug_gp_plan(4, 50000, C, C, K, dil, 1, mode, u) == 0
+            assert v[1] == u[2], (C, K, dil, mode)

@@ -127,6 +127,58 @@ def main():
             row["ok"] = bool(ok)
             ok_all = ok_all and ok
             print(json.dumps(row), flush=True)
+    # ---- fused ResBlock layer (resblock_gp.cu) against the two conv1d_gp launches it replaces: BITWISE in every mode ----
+    PAIRS = [
+        # B, L, C, K, dil, acc, ragged
+        (1, 300, 32, 3, 1, 0, 0),
+        (2, 5000, 32, 11, 5, 0, 1),
+        (3, 70000, 32, 7, 3, 1, 1),
+        (2, 20000, 64, 11, 5, 2, 1),
+        (2, 9000, 64, 3, 3, 0, 1),
+        (1, 4000, 128, 7, 3, 0, 0),
+        (2, 3000, 96, 3, 1, 1, 1),
+    ]
+    for case in (PAIRS[:3] if quick else PAIRS):
+        B, L, C, K, dil, acc, ragged = case
+        g = torch.Generator().manual_seed(sum(case) + 1)
+        x = torch.randn(B, L, C, generator=g)
+        w1 = torch.randn(K, C, C, generator=g) / math.sqrt(C * K)
+        w2 = torch.randn(K, C, C, generator=g) / math.sqrt(C * K)
+        b1, b2 = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+        prev = torch.randn(B, L, C, generator=g)
+        lens = torch.tensor([max(1, L // 4 - 3 * b) for b in range(B)], dtype=torch.int32, device=dev) if ragged else None
+        lens_mul = 4 if ragged else 1
+        for mode in (1, 0, 2, 3):
+            if mode >= 2 and C % 16:
+                continue
+            bf = mode == 2
+            pack = packing.to_tc16x2_layout if mode == 3 else (packing.to_tc16_layout if bf else packing.to_tc_layout)
+            w1d, w2d = pack(w1).to(dev), pack(w2).to(dev)
+            xg = layout.to_gp(x, bf).to(dev)
+            xt = torch.full_like(xg, float("nan"))
+            ref = layout.to_gp(prev, bf).to(dev)
+            _abi.check(lib.ev_op_conv1d_gp(ptr(xg), ptr(w1d), mode, ptr(b1), None, ptr(xt), B, L, C, C, K, dil, 1, ptr(lens), lens_mul, _abi.ACT_LRELU, 0.1,
+                                           _abi.ACC_STORE, 1.0, st))
+            _abi.check(lib.ev_op_conv1d_gp(ptr(xt), ptr(w2d), mode, ptr(b2), ptr(xg), ptr(ref), B, L, C, C, K, 1, 1, ptr(lens), lens_mul, _abi.ACT_LRELU, 0.1,
+                                           acc, 3.0, st))
+            out = layout.to_gp(prev, bf).to(dev)
+            rc = lib.ev_op_resblock_gp(ptr(xg), ptr(w1d), ptr(b1), ptr(w2d), ptr(b2), mode, ptr(out), B, L, C, K, dil, ptr(lens), lens_mul, acc, 3.0, st)
+            torch.cuda.synchronize()
+            row = {"pair": case, "mode": mode, "rc": rc}
+            if rc == 0:
+                a, r = layout.from_gp(out.cpu()), layout.from_gp(ref.cpu())
+                valid = [L] * B if lens is None else [min(L, int(v) * lens_mul) for v in lens.tolist()]
+                row["bitwise_vs_two_launches"] = all(torch.equal(a[b, :valid[b]], r[b, :valid[b]]) for b in range(B))
+                row["finite"] = all(bool(torch.isfinite(r[b, :valid[b]]).all()) for b in range(B))
+                row["max_abs_diff"] = max(float((a[b, :valid[b]] - r[b, :valid[b]]).abs().max()) for b in range(B))
+                pg = layout.from_gp(layout.to_gp(prev, bf))
+                row["pad_rows_untouched"] = all(torch.equal(a[b, valid[b]:], pg[b, valid[b]:]) for b in range(B))
+                row["ok"] = bool(row["bitwise_vs_two_launches"] and row["finite"] and row["pad_rows_untouched"])
+            else:
+                row["err"] = lib.ev_last_error().decode()
+                row["ok"] = False
+            ok_all = ok_all and row["ok"]
+            print(json.dumps(row), flush=True)
     # boundary kernels
     g = torch.Generator().manual_seed(5)
     mel = torch.randn(2, 80, 37, generator=g)

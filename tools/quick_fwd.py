@@ -17,5 +17,5 @@ for i in range(10):
     t0 = time.perf_counter(); o = m(**b); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
 wav = torch.from_numpy(z["wav"])
 err = float(((o["wav_predictions"].cpu() - wav).double().pow(2).mean().sqrt() / wav.double().pow(2).mean().sqrt()))
-print("EV_STREAMS=%s %s: median %.3f ms, dur equal %s, wav rms-rel %.2e" % (os.environ.get("EV_STREAMS", "0"), m.precision,
-      1e3 * sorted(ts)[5], bool(torch.equal(o["log_duration_predictions"].cpu(), torch.from_numpy(z["durations"]))), err), flush=True)
+print("%s: median %.3f ms, dur equal %s, wav rms-rel %.2e" % (m.precision, 1e3 * sorted(ts)[5],
+      bool(torch.equal(o["log_duration_predictions"].cpu(), torch.from_numpy(z["durations"]))), err), flush=True)
