@@ -150,7 +150,7 @@ int debug_gp_plan(const GpConvParams& p, int mode, int* v11);
 // fp32 in[b*sb + t*st + c*sc] -> GP (fp32, or bf16 when bf16 != 0)
 int launch_to_gp(const float* in, long long sb, long long st_, long long sc, void* out, int B, int L, int C, int bf16, cudaStream_t st);
 // One ResBlock1 layer  out = [acc]( x + c2(lrelu(c1(lrelu(x), dil)), 1) )  as one kernel on granule-planar activations
-// (resblock_gp.cu); bitwise equal to the two launch_conv1d_gp calls it replaces.  C in {32, 64, 96, 128}.
+// (resblock_gp.cu); bitwise equal to the two launch_conv1d_gp calls it replaces.  C in {32, 64, 128}.
 struct GpPairParams {
   const void* x;       // GP (B, C/cpg, L, cpg): the layer input, also the residual
   const float* w1;     // c1 weights (k taps, dilation dil), tensor-core layout of the mode

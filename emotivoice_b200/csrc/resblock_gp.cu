@@ -539,7 +539,7 @@ static int pair_shape_kbg(const GpPairParams& p, int mode) {
 }
 
 static bool plan_pair(const GpPairParams& p, int mode, gpp::PPlan* out) {
-  if (p.B <= 0 || p.L <= 0 || p.C % 32 || p.C > 128 || !(p.K & 1) || p.dil < 1) return false;
+  if (p.B <= 0 || p.L <= 0 || (p.C != 32 && p.C != 64 && p.C != 128) || !(p.K & 1) || p.dil < 1) return false;
   if (mode >= 2 && p.C % 16) return false;
   if (p.x == p.out) return false;
   const int kbg = pair_shape_kbg(p, mode);

@@ -201,7 +201,7 @@ EV_API int ev_op_conv1d_gp(const void* x, const float* w, int mode, const float*
                            int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act,
                            float in_slope, int acc, float div, void* stream);
 /* One ResBlock1 layer (hifigan/models.py:50-57) as ONE kernel on granule-planar activations (csrc/resblock_gp.cu):
- * out = [acc]( x + c2(lrelu(c1(lrelu(x), dil)), 1) ), C -> C channels (C % 32 == 0, C <= 128), slope 0.1, both weights in the layout of
+ * out = [acc]( x + c2(lrelu(c1(lrelu(x), dil)), 1) ), C -> C channels (C in {32, 64, 128}), slope 0.1, both weights in the layout of
  * `mode` (as ev_op_conv1d_gp).  Bitwise equal to the two ev_op_conv1d_gp launches it replaces; EV_EINVAL for shapes it does not take
  * (the engine then runs the pair unfused). */
 EV_API int ev_op_resblock_gp(const void* x, const float* w1, const float* b1, const float* w2, const float* b2, int mode, void* out, int B,

@@ -28,7 +28,7 @@ def test_gp_operator_check_tool(lib):
     print(r.stdout[-6000:], r.stderr[-2000:])
     rows = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert r.returncode == 0 and "GP_CHECK_OK" in r.stdout, [x for x in rows if not x.get("ok", True)]
-    assert len([x for x in rows if "case" in x]) == 52 and len([x for x in rows if "pair" in x]) == 28
+    assert len([x for x in rows if "case" in x]) == 52 and len([x for x in rows if "pair" in x]) == 24
 
 
 _TM_CHILD = r"""

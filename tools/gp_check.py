@@ -136,7 +136,6 @@ def main():
         (2, 20000, 64, 11, 5, 2, 1),
         (2, 9000, 64, 3, 3, 0, 1),
         (1, 4000, 128, 7, 3, 0, 0),
-        (2, 3000, 96, 3, 1, 1, 1),
     ]
     for case in (PAIRS[:3] if quick else PAIRS):
         B, L, C, K, dil, acc, ragged = case
