@@ -332,6 +332,12 @@ static int launch_atc(const float* qkv, const int32_t* key_lens, float* ctx, int
   return EV_OK;
 }
 
+void preload_attention_tc() {      // see preload_conv1d_gp
+  cudaFuncSetAttribute(atc::attention_tc_kernel<48, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Smem<48>::total(1));
+  cudaFuncSetAttribute(atc::attention_tc_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Smem<48>::total(2));
+  cudaGetLastError();
+}
+
 // tc_mode 1: 3xTF32 (fp32-accurate), 0: one tf32 MMA per K step.  Supported head size: 48.
 int launch_attention_tc(const float* qkv, const int32_t* key_lens, float* ctx, int B, int L, int H, int heads, int tc_mode, cudaStream_t st) {
   EV_CHECK_ARG(B > 0 && L > 0 && heads > 0 && H % heads == 0 && H / heads == 48, "attention_tc: needs d_k = 48 (B=%d L=%d H=%d heads=%d)", B, L, H, heads);

@@ -606,7 +606,7 @@ static int gp_shape_kbg(const GpConvParams& p, int mode) {
 // Tile shape: none of these choices changes the order in which any output element's K reduction is summed, so results are
 // bitwise independent of batch size / sequence length (batch-invariant contract) and the shape can be picked by a cost model.
 // Per tile of MT x 128 rows and BN columns, three engines run concurrently and the slowest one sets the pace:
-//   tensor core + its shared-memory operand reads:  MT * m * max(BN/2, issue) cycles per (tap, 8 channels)   (m = 3 MMAs in 3xTF32; bf16: 16 channels)
+//   tensor core + its shared-memory operand reads:  MT * m * max(BN/2, 32 + BN/4) cycles per (tap, 8 channels)   (m = 3 MMAs in 3xTF32; bf16: 16 channels)
 //   weight stream L2 -> shared memory:              planes * 32 B * BN per (tap, 8 channels) at ~42 B/cycle/SM (6.3 KB/cycle chip-wide)
 //   activations HBM -> shared memory -> HBM:        MT * 128 rows * (Cin + 2 Cout) * esize at ~23 B/cycle/SM
 // plus a fixed pipeline fill / drain per tile; the launch takes ceil(tiles / SMs) such tile times.  More accumulators per tile
@@ -623,12 +623,18 @@ static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out) {
   bool found = false;
   gp::GPlan best_pl;
   const int bn_max = p.Cout <= 128 ? p.Cout : 128;
-  for (int BN = bn_max; BN >= 32; BN /= 2) {
+  // N tile = the weight packing tile (min(C_out, 128)): ONE bulk copy per weight stage and plane.  Narrower tiles would fill idle SMs
+  // at batch 1 (stage 1: 68 tiles) but need one 1-KB copy per granule issued by a single thread -- measured 1.5x slower.
+  for (int BN = bn_max; BN >= bn_max; BN /= 2) {
     if (p.Cout % BN || BN % 32) continue;
     for (int mt = 4; mt >= 1; mt >>= 1) {
       gp::GPlan pl;
       if (!gp::make_gplan(p, mode, BN, mt, kbg, &pl)) continue;
-      const double t_mma = mt * n_mma * (BN / 2.0 > 28.0 ? BN / 2.0 : 28.0);     // BN/2 tensor cycles per instruction, ~28 to issue one
+      // per MMA instruction: BN/2 tensor cycles, but both operands come from shared memory (128 B/cycle): (128 + BN) rows x 32 B
+      // = 32 + BN/4 cycles -- the binding term below BN = 128 (a 64-wide tile costs 1.5x per FLOP, a 32-wide one 2.5x)
+      double c_mma = BN / 2.0;
+      if (32.0 + BN / 4.0 > c_mma) c_mma = 32.0 + BN / 4.0;
+      const double t_mma = mt * n_mma * c_mma;
       const double t_w = w_per_n * BN * kc8;
       const double t_hbm = (double)mt * tc::BM * ((double)p.Cin * (mt * tc::BM + (p.K - 1) * p.dil) / (mt * tc::BM) + 2.0 * BN) * esize / 23.0;
       double t = t_mma > t_w ? t_mma : t_w;
@@ -684,6 +690,25 @@ int launch_conv1d_gp(const GpConvParams& p, int mode, cudaStream_t st) {
   if (mode == 3) return pl.kbg == 8 ? launch_gp_mt<3, 8>(p, pl, st) : launch_gp_mt<3, 4>(p, pl, st);
   if (mode == 2) return pl.kbg == 8 ? launch_gp_mt<2, 8>(p, pl, st) : launch_gp_mt<2, 4>(p, pl, st);
   return pl.kbg == 8 ? launch_gp_mt<0, 8>(p, pl, st) : launch_gp_mt<0, 4>(p, pl, st);
+}
+
+// Load every instantiation's code now (CUDA loads kernels lazily, at their first launch: tens of milliseconds for a kernel of this
+// size, which would otherwise hit whichever utterance first needs a new tile shape) and set the shared-memory attribute.
+template <int MODE, int KBG>
+static void preload_gp_mode() {
+  cudaFuncSetAttribute(gp::conv1d_gp_kernel<MODE, 1, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(gp::conv1d_gp_kernel<MODE, 2, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(gp::conv1d_gp_kernel<MODE, 4, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+void preload_conv1d_gp() {
+  preload_gp_mode<0, 4>(); preload_gp_mode<0, 8>(); preload_gp_mode<1, 4>(); preload_gp_mode<2, 4>(); preload_gp_mode<2, 8>();
+  preload_gp_mode<3, 4>(); preload_gp_mode<3, 8>();
+  cudaFuncSetAttribute(gp::conv_post_gp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(gp::conv_post_gp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, gp::to_gp_kernel<false>);
+  cudaFuncGetAttributes(&fa, gp::to_gp_kernel<true>);
+  cudaGetLastError();
 }
 
 int launch_to_gp(const float* in, long long sb, long long st_, long long sc, void* out, int B, int L, int C, int bf16, cudaStream_t st) {

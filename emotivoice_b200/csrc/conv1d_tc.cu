@@ -548,6 +548,19 @@ static int launch_tc_mt(const ConvParams& p, const tc::Plan& pl, cudaStream_t st
   return launch_tc_variant<MODE, 1, KBG>(p, pl, st, pdl);
 }
 
+template <int MODE, int KBG>
+static void preload_tc_mode() {
+  cudaFuncSetAttribute(tc::conv1d_tc_kernel<MODE, 1, KBG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(tc::conv1d_tc_kernel<MODE, 2, KBG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(tc::conv1d_tc_kernel<MODE, 4, KBG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+void preload_conv1d_tc() {      // see conv1d_gp.cu: preload_conv1d_gp (the default, non-PDL instantiations)
+  preload_tc_mode<0, 4>(); preload_tc_mode<0, 8>(); preload_tc_mode<1, 4>(); preload_tc_mode<2, 4>(); preload_tc_mode<2, 8>();
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, tc::splitk_reduce_kernel<false>);
+  cudaGetLastError();
+}
+
 static int validate_conv1d_tc(const ConvParams& p, int mode) {
   EV_CHECK_ARG(p.B > 0 && p.L > 0, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
   EV_CHECK_ARG(p.Cin % (mode == 2 ? 16 : 8) == 0, "conv1d_tc: Cin=%d must be a multiple of %d", p.Cin, mode == 2 ? 16 : 8);

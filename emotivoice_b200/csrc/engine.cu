@@ -544,6 +544,16 @@ int ev_create(ev_ctx** out, int device, const ev_config* cfg) {
   ev_ctx* c = new ev_ctx();
   c->cfg = *cfg;
   c->device = device;
+  {   // CUDA loads kernel code lazily at first launch; for the large tcgen05 kernels that is tens of milliseconds each, which would
+      // land on whichever utterance first needs a new tile shape.  Load them now, once per device.
+    static std::atomic<uint64_t> loaded{0};
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device);
+    if (first_use_on_device(loaded)) { preload_conv1d_gp(); preload_resblock_gp(); preload_attention_tc(); preload_conv1d_tc(); }
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    cudaGetLastError();
+  }
   *out = c;
   return EV_OK;
 }

@@ -27,6 +27,11 @@ inline bool first_use_on_device(std::atomic<uint64_t>& mask) {
   return true;
 }
 int sm_count();                          // SMs of the CURRENT device (cached per device)
+// eager loading of the big tcgen05 kernels' code on the current device (ev_create calls them once per device)
+void preload_conv1d_gp();
+void preload_resblock_gp();
+void preload_attention_tc();
+void preload_conv1d_tc();
 int use_device_of(const void* dev_ptr);  // cudaSetDevice(the device that owns dev_ptr); EV_OK / EV_ECUDA
 
 #define EV_CHECK_ARG(cond, ...)                      \

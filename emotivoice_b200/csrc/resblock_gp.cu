@@ -598,6 +598,18 @@ static int launch_pair_mt(const GpPairParams& p, const gpp::PPlan& pl, cudaStrea
   return launch_pair_variant<MODE, 1, KBG>(p, pl, st);
 }
 
+template <int MODE, int KBG>
+static void preload_pair_mode() {
+  cudaFuncSetAttribute(gpp::resblock_gp_kernel<MODE, 1, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(gpp::resblock_gp_kernel<MODE, 2, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(gpp::resblock_gp_kernel<MODE, 4, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+void preload_resblock_gp() {      // see preload_conv1d_gp
+  preload_pair_mode<0, 4>(); preload_pair_mode<0, 8>(); preload_pair_mode<1, 4>(); preload_pair_mode<2, 4>(); preload_pair_mode<2, 8>();
+  preload_pair_mode<3, 4>(); preload_pair_mode<3, 8>();
+  cudaGetLastError();
+}
+
 int launch_gp_pair(const GpPairParams& p, int mode, cudaStream_t st) {
   gpp::PPlan pl;
   if (!plan_pair(p, mode, &pl)) { set_error("resblock_gp: shape not supported (C=%d K=%d dil=%d mode=%d)", p.C, p.K, p.dil, mode); return EV_EINVAL; }
