@@ -51,8 +51,8 @@ struct Plan {
 // smem map: [0,288) barriers | [512,516) tmem base | 1024: epilogue staging (8 warps x 4 KB) | A ring | B ring
 __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN, int mt, int kbg, int min_b_stages, Plan* o, int b_target = 4) {
   Plan q;
-  q.planes = mode == 1 ? 2 : 1;
-  const int cpg = mode == 2 ? 8 : 4;      // channels per 16-byte granule (bf16 : tf32)
+  q.planes = (mode == 1 || mode == 3) ? 2 : 1;
+  const int cpg = mode >= 2 ? 8 : 4;      // channels per 16-byte operand granule (bf16 : tf32)
   q.kbg = kbg;
   q.mt = mt;
   q.BN = BN;
@@ -93,6 +93,8 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN,
 
 // MODE 0: one tf32 MMA per K step (operands rounded to nearest tf32).
 // MODE 2: bf16 operands (rounded to nearest even by the producers / the host), kind::f16, 8 channels per granule.
+// MODE 3: "bf16x3" fp32-class emulation: x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 significant bits), three kind::f16 MMAs per
+//                 K = 16 step (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi): ~1e-5 relative at half the tensor-core / weight-stream cost of 3xTF32.
 // MODE 1: "3xTF32" fp32 emulation: x = hi + lo with hi = tf32(x), lo = tf32(x - hi);
 //                 a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the dropped lo*lo term is 2^-22 relative),
 //                 three MMAs per K step into the same fp32 TMEM accumulator.  Weights arrive pre-split
@@ -103,8 +105,9 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN,
 template <int MODE, int MT, int KBG, int PDLM>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Plan pl) {
   constexpr bool SPLIT3 = (MODE == 1);
-  constexpr bool BF16 = (MODE == 2);
-  constexpr int PLANES = SPLIT3 ? 2 : 1;
+  constexpr bool X3B = (MODE == 3);       // "bf16x3": fp32 operands split into bf16 hi + lo planes, three kind::f16 MMAs per K = 16 step
+  constexpr bool BF16 = (MODE == 2) || X3B;      // the staged operands are bf16 (8 channels per granule)
+  constexpr int PLANES = (SPLIT3 || X3B) ? 2 : 1;
   constexpr int CPG = BF16 ? 8 : 4;       // channels per 16-byte granule
   constexpr int KB = CPG * KBG;
   constexpr int GSH = (KBG == 8 ? 3 : 2);
@@ -331,6 +334,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
                 q.x = pack_bf16(t0.x, t0.y); q.y = pack_bf16(t0.z, t0.w);
                 q.z = pack_bf16(t1.x, t1.y); q.w = pack_bf16(t1.z, t1.w);
                 *reinterpret_cast<uint4*>(d) = q;
+                if (X3B) {      // lo plane: what the bf16 rounding dropped (8 more significant bits)
+                  uint4 l;
+                  l.x = pack_bf16(t0.x - __uint_as_float(q.x << 16), t0.y - __uint_as_float(q.x & 0xffff0000u));
+                  l.y = pack_bf16(t0.z - __uint_as_float(q.y << 16), t0.w - __uint_as_float(q.y & 0xffff0000u));
+                  l.z = pack_bf16(t1.x - __uint_as_float(q.z << 16), t1.y - __uint_as_float(q.z & 0xffff0000u));
+                  l.w = pack_bf16(t1.z - __uint_as_float(q.w << 16), t1.w - __uint_as_float(q.w & 0xffff0000u));
+                  *reinterpret_cast<uint4*>(d + pl.a_plane_bytes) = l;
+                }
               } else {
                 const float4 t = v[u * NW];
                 // round-to-nearest tf32 (the MMA would otherwise truncate the low 13 mantissa bits)
@@ -398,6 +409,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
                     umma_tf32(d, a_lo, b_hi, idesc, first);     // small terms first
                     umma_tf32(d, a_hi, b_lo, idesc, 1u);
                     umma_tf32(d, a_hi, b_hi, idesc, 1u);
+                  } else if (X3B) {
+                    const uint64_t a_lo = desc_advance(a_hi, (uint32_t)pl.a_plane_bytes);
+                    const uint64_t b_lo = desc_advance(b_hi, (uint32_t)pl.b_plane_bytes);
+                    umma_bf16(d, a_lo, b_hi, idesc, first);
+                    umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                    umma_bf16(d, a_hi, b_hi, idesc, 1u);
                   } else if (BF16) {
                     umma_bf16(d, a_hi, b_hi, idesc, first);
                   } else {
@@ -425,7 +442,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
       // (4 fp32 or 8 bf16 per granule; granule-major inside a tile)
       const int cin4 = p.Cin / CPG;
       const int bnp = p.Cout < 128 ? p.Cout : 128;
-      const size_t plane = (size_t)p.K * p.Cin * p.Cout;
+      const size_t plane = (size_t)p.K * cin4 * p.Cout * 4;         // 4-byte words per plane (fp32 or packed bf16 granules)
       const size_t tile_stride = (size_t)p.K * cin4 * bnp * 4;      // floats per packed N tile
       int b_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
@@ -445,11 +462,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
             if (nt == bnp) {
               // the CTA's N tile is a whole packed tile: the stage's granules are adjacent in memory -> ONE bulk copy per plane
               bulk_g2s(dst, src, (uint32_t)(ngran * nt * 16), b_full(sb));
-              if (SPLIT3) bulk_g2s(dst + (uint32_t)pl.b_plane_bytes, src + plane, (uint32_t)(ngran * nt * 16), b_full(sb));
+              if (PLANES == 2) bulk_g2s(dst + (uint32_t)pl.b_plane_bytes, src + plane, (uint32_t)(ngran * nt * 16), b_full(sb));
             } else {
               for (int g = 0; g < ngran; ++g) {
                 bulk_g2s(dst + (uint32_t)(g * BN * 16), src + (size_t)g * bnp * 4, (uint32_t)(nt * 16), b_full(sb));
-                if (SPLIT3) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane + (size_t)g * bnp * 4, (uint32_t)(nt * 16), b_full(sb));
+                if (PLANES == 2) bulk_g2s(dst + (uint32_t)(pl.b_plane_bytes + g * BN * 16), src + plane + (size_t)g * bnp * 4, (uint32_t)(nt * 16), b_full(sb));
               }
             }
           }
@@ -556,6 +573,7 @@ static void preload_tc_mode() {
 }
 void preload_conv1d_tc() {      // see conv1d_gp.cu: preload_conv1d_gp (the default, non-PDL instantiations)
   preload_tc_mode<0, 4>(); preload_tc_mode<0, 8>(); preload_tc_mode<1, 4>(); preload_tc_mode<2, 4>(); preload_tc_mode<2, 8>();
+  preload_tc_mode<3, 4>(); preload_tc_mode<3, 8>();
   cudaFuncAttributes fa;
   cudaFuncGetAttributes(&fa, tc::splitk_reduce_kernel<false>);
   cudaGetLastError();
@@ -563,7 +581,7 @@ void preload_conv1d_tc() {      // see conv1d_gp.cu: preload_conv1d_gp (the defa
 
 static int validate_conv1d_tc(const ConvParams& p, int mode) {
   EV_CHECK_ARG(p.B > 0 && p.L > 0, "conv1d_tc: bad problem B=%d L=%d", p.B, p.L);
-  EV_CHECK_ARG(p.Cin % (mode == 2 ? 16 : 8) == 0, "conv1d_tc: Cin=%d must be a multiple of %d", p.Cin, mode == 2 ? 16 : 8);
+  EV_CHECK_ARG(p.Cin % (mode >= 2 ? 16 : 8) == 0, "conv1d_tc: Cin=%d must be a multiple of %d", p.Cin, mode >= 2 ? 16 : 8);
   EV_CHECK_ARG(p.Cout % 16 == 0 && (p.Cout <= 128 || p.Cout % 128 == 0), "conv1d_tc: Cout=%d must be a multiple of 16, and of 128 above 128", p.Cout);
   EV_CHECK_ARG(p.K >= 1 && (p.K & 1) && p.dil >= 1, "conv1d_tc: K=%d must be odd, dil=%d >= 1", p.K, p.dil);
   EV_CHECK_ARG(p.in_act == EV_ACT_NONE || p.in_act == EV_ACT_LRELU, "conv1d_tc: unsupported input activation");
@@ -587,7 +605,7 @@ static int apply_ksplit(const ConvParams& p, int mode, tc::Plan* pl) {
   const size_t per = (size_t)p.B * p.L * p.Cout;
   if (p.ksplit > 1 && (p.splitk_ws || p.splitk_cap == (size_t)-1)) {
     int S = p.ksplit;
-    const int cpg = mode == 2 ? 8 : 4;
+    const int cpg = mode >= 2 ? 8 : 4;
     const int n_cb = (p.Cin + cpg * pl->kbg - 1) / (cpg * pl->kbg);
     if (S > n_cb) S = n_cb;
     if ((size_t)S * per > p.splitk_cap) { set_error("conv1d_tc: split-K scratch too small (%zu < %zu floats)", p.splitk_cap, (size_t)S * per); return EV_EWORKSPACE; }
@@ -639,6 +657,7 @@ int debug_tc_plan(const ConvParams& p, int mode, int* v) {
 
 static int dispatch_tc(const ConvParams& p, int mode, const tc::Plan& pl, cudaStream_t st, int pdl = 0) {
   if (mode == 1) return launch_tc_mt<1, 4>(p, pl, st, pdl);
+  if (mode == 3) return pl.kbg == 8 ? launch_tc_mt<3, 8>(p, pl, st, pdl) : launch_tc_mt<3, 4>(p, pl, st, pdl);
   if (mode == 2) return pl.kbg == 8 ? launch_tc_mt<2, 8>(p, pl, st, pdl) : launch_tc_mt<2, 4>(p, pl, st, pdl);
   return pl.kbg == 8 ? launch_tc_mt<0, 8>(p, pl, st, pdl) : launch_tc_mt<0, 4>(p, pl, st, pdl);
 }

@@ -83,6 +83,7 @@ struct EncLayerW {
   const float *ln1w, *ln1b, *wqkv, *bqkv, *wo, *bo, *ln2w, *ln2b, *w1, *b1, *w2, *b2;
   const float *wqkv_tc = nullptr, *wo_tc = nullptr, *w1_tc = nullptr, *w2_tc = nullptr;   // tensor-core layout (optional)
   const float *wqkv_h = nullptr, *wo_h = nullptr, *w1_h = nullptr, *w2_h = nullptr;       // bf16 tensor-core layout (optional)
+  const float *wqkv_x2 = nullptr, *wo_x2 = nullptr, *w1_x2 = nullptr, *w2_x2 = nullptr;   // two bf16 planes (bf16x3 emulation; decoder only)
 };
 struct StackW {
   const float* alpha;
@@ -119,6 +120,7 @@ struct ev_ctx {
   int precision = EV_PREC_FP32;
   const float* mel_w_tc = nullptr;
   const float* mel_w_h = nullptr;
+  const float* mel_w_x2 = nullptr;
   const float* cond_wx_tc = nullptr;   // a blob may carry only one half (PromptTTS / Generator used alone)
   std::unordered_map<std::string, ev::Tensor> tensors;
   const float* pe = nullptr;
@@ -256,6 +258,10 @@ static int resolve_stack(ev_ctx* c, const char* pre, int n_layers, StackW* s) {
     l.wo_h = find_opt(c, q + ".wo.tc16", H * H / 2);
     l.w1_h = find_opt(c, q + ".w1.tc16", K * H * 4 * H / 2);
     l.w2_h = find_opt(c, q + ".w2.tc16", K * 4 * H * H / 2);
+    l.wqkv_x2 = find_opt(c, q + ".wqkv.tc16x2", H * 3 * H);
+    l.wo_x2 = find_opt(c, q + ".wo.tc16x2", H * H);
+    l.w1_x2 = find_opt(c, q + ".w1.tc16x2", K * H * 4 * H);
+    l.w2_x2 = find_opt(c, q + ".w2.tc16x2", K * 4 * H * H);
   }
   EV_TRY(find(c, p + ".lnf.w", H, &s->lnfw));
   EV_TRY(find(c, p + ".lnf.b", H, &s->lnfb));
@@ -311,6 +317,7 @@ static int resolve_all(ev_ctx* c) {
   EV_TRY(find(c, "to_mel.b", g.n_mels, &c->mel_b));
   c->mel_w_tc = find_opt(c, "to_mel.w.tc", 2 * H * g.n_mels);
   c->mel_w_h = find_opt(c, "to_mel.w.tc16", H * g.n_mels / 2);
+  c->mel_w_x2 = find_opt(c, "to_mel.w.tc16x2", H * g.n_mels);
   return EV_OK;
 }
 
@@ -394,20 +401,28 @@ struct SplitWs {
 };
 static thread_local SplitWs g_split_ws;   // set by the phase entry points for the convs they launch
 
+// bf16x3 in the decoder (fp32 mode): EV_AM_FP32=tf32x3 keeps 3xTF32 there as well
+static inline bool am_bf16x3_enabled() {
+  static const int v = [] { const char* e = getenv("EV_AM_FP32"); return (e && e[0] == 't') ? 0 : 1; }();
+  return v == 1;
+}
+// w_x2: two bf16 planes; when given (decoder layers only) and the mode is the fp32-accurate one (3), the layer runs the bf16x3
+// emulation instead of 3xTF32.  The duration-critical prefix never passes it.
 static int conv_x(int mode, const float* w_tc, const float* w_h, const float* x, const float* w, const float* bias,
                   long long bias_bs, const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
                   const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act, int acc, float div,
-                  cudaStream_t st) {
+                  cudaStream_t st, const float* w_x2 = nullptr) {
+  const bool x3b = mode == 3 && w_x2 && (Cin % 16) == 0 && am_bf16x3_enabled();
   if (mode == 2 && (!w_h || (Cin % 16))) mode = 3;
   if (mode == 0 || (mode != 2 && !w_tc) || (Cin % 8) || (Cout % 16) || (Cout > 128 && Cout % 128))
     return conv(x, w, bias, bias_bs, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul, in_act, in_slope, out_act, acc, div, st);
   ConvParams p;
-  p.x = x; p.w = (mode == 2) ? w_h : w_tc; p.bias = bias; p.res = res; p.out = out; p.bias_bs = bias_bs;
+  p.x = x; p.w = x3b ? w_x2 : ((mode == 2) ? w_h : w_tc); p.bias = bias; p.res = res; p.out = out; p.bias_bs = bias_bs;
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil;
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope;
   p.out_act = out_act; p.acc = acc; p.div = div;
   p.splitk_ws = g_split_ws.p; p.splitk_cap = g_split_ws.cap; p.ksplit = g_split_ws.ksplit;
-  return launch_conv1d_tc(p, mode == 3 ? 1 : (mode == 2 ? 2 : 0), st);
+  return launch_conv1d_tc(p, x3b ? 3 : (mode == 3 ? 1 : (mode == 2 ? 2 : 0)), st);
 }
 
 // HiFi-GAN convolution on granule-planar activations (conv1d_gp.cu).  mode as conv_x: 1 = tf32, 2 = bf16 (bf16 activations), 3 = 3xTF32.
@@ -476,7 +491,7 @@ static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float
       EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln1w, l.ln1b, y, B * L, L, H, st));
     g_split_ws.ksplit = 2;   // K = H: two slices
     EV_TRY(conv_x(mode, l.wqkv_tc, l.wqkv_h, y, l.wqkv, l.bqkv, 0, nullptr, qkv, B, L, H, 3 * H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
-                  EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+                  EV_ACT_NONE, EV_ACC_STORE, 1.f, st, l.wqkv_x2));
     // QK^T / softmax / PV: tcgen05 (3xTF32 where the layer runs fp32-accurate, one tf32 MMA otherwise) for d_k = 48; the fp32 FFMA
     // flash kernel in the "fp32_ffma" mode, for other head sizes, or with EV_ATTN=ffma (A/B measurements)
     if (mode != 0 && H / heads == 48 && attn_tc_enabled())
@@ -484,14 +499,14 @@ static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float
     else
       EV_TRY(launch_attention(qkv, key_lens, ctxb, B, L, H, heads, st));
     EV_TRY(conv_x(mode, l.wo_tc, l.wo_h, ctxb, l.wo, l.bo, 0, x, x, B, L, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
-                  EV_ACC_STORE, 1.f, st));
+                  EV_ACC_STORE, 1.f, st, l.wo_x2));
     EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln2w, l.ln2b, y, B * L, L, H, st));
     g_split_ws.ksplit = 2;
     EV_TRY(conv_x(mode, l.w1_tc, l.w1_h, y, l.w1, l.b1, 0, nullptr, h, B, L, H, 4 * H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_GELU,
-                  EV_ACC_STORE, 1.f, st));
+                  EV_ACC_STORE, 1.f, st, l.w1_x2));
     g_split_ws.ksplit = 4;   // K = 3 * 4H: four slices
     EV_TRY(conv_x(mode, l.w2_tc, l.w2_h, h, l.w2, l.b2, 0, x, x, B, L, 4 * H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
-                  EV_ACC_STORE, 1.f, st));
+                  EV_ACC_STORE, 1.f, st, l.w2_x2));
   }
   g_split_ws.ksplit = 2;
   EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, s.lnfw, s.lnfb, y, B * L, L, H, st));
@@ -696,7 +711,7 @@ int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens,
   EV_TRY(run_stack(ctx, ctx->dec, b.x, b.y, b.qkv, b.ctx, b.h, B, F, flens, flens, false, mode, st));
   // to_mel (model_open_source.py:147)
   EV_TRY(conv_x(mode, ctx->mel_w_tc, ctx->mel_w_h, b.y, ctx->mel_w, ctx->mel_b, 0, nullptr, mel_out, B, F, H, g.n_mels, 1, 1, flens, 1,
-                EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st));
+                EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st, ctx->mel_w_x2));
   return EV_OK;
 }
 
@@ -838,7 +853,15 @@ int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* 
   EV_TRY(use_device_of(x));
   EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0 && (Cout <= 128 || Cout % 128 == 0),
                "ev_op_conv1d_tc: needs Cin %% 8 == 0, Cout %% 16 == 0 and Cout <= 128 or a multiple of 128 (Cin=%d Cout=%d)", Cin, Cout);
-  EV_CHECK_ARG(split3 != 2 || Cin % 16 == 0, "ev_op_conv1d_tc: the bf16 mode needs Cin %% 16 == 0 (Cin=%d)", Cin);
+  EV_CHECK_ARG(split3 < 2 || Cin % 16 == 0, "ev_op_conv1d_tc: the bf16 / bf16x3 modes need Cin %% 16 == 0 (Cin=%d)", Cin);
+  if (split3 == 3) {      // bf16x3: w_tc holds the two bf16 planes
+    ConvParams p;
+    p.x = x; p.w = w_tc; p.bias = bias; p.res = res; p.out = out; p.bias_bs = (long long)bias_bstride;
+    p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope;
+    p.out_act = out_act; p.acc = acc; p.div = div;
+    p.splitk_ws = g_split_ws.p; p.splitk_cap = g_split_ws.cap; p.ksplit = g_split_ws.ksplit;
+    return launch_conv1d_tc(p, 3, reinterpret_cast<cudaStream_t>(stream));
+  }
   return conv_x(split3 == 2 ? 2 : (split3 ? 3 : 1), w_tc, w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul,
                 in_act, in_slope, out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));
 }

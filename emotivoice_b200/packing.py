@@ -110,7 +110,7 @@ def add_tc_weights(packed):
             extra[k + ".tc"] = to_tc_layout(v)
         if (is_stack and k.startswith("dec.")) or is_voc or k == "to_mel.w":      # layers the bf16 mode runs in bf16
             extra[k + ".tc16"] = to_tc16_layout(v)
-        if is_voc:                                                                  # the vocoder's fp32 mode: bf16x3 emulation
+        if is_voc or (is_stack and k.startswith("dec.")) or k == "to_mel.w":     # the fp32 mode past the duration prefix: bf16x3 emulation
             extra[k + ".tc16x2"] = to_tc16x2_layout(v)
     packed.update(extra)
     return packed

@@ -153,3 +153,27 @@ def test_tf32_mode_is_batch_invariant(model, dev):
             assert torch.equal(single["wav_predictions"][0, 0], out["wav_predictions"][b, 0, :Fb * 256])
     finally:
         model.precision = "fp32"
+
+
+@pytest.mark.parametrize("B,L,Cin,Cout,K", [(1, 537, 384, 1152, 1), (1, 537, 384, 1536, 3), (2, 130, 1536, 384, 3), (1, 537, 384, 80, 1), (3, 700, 128, 128, 3)])
+def test_conv1d_tc_bf16x3_is_fp32_class(lib, dev, B, L, Cin, Cout, K):
+    """MODE 3 of conv1d_tc ("bf16x3": fp32 operands split into bf16 hi + lo, three kind::f16 MMAs per K = 16 step) -- what the
+    decoder's GEMM-shaped layers run in the "fp32" precision.  Against an fp64 torch reference: <= 5e-5 of max|ref|
+    (16 significant bits per operand; 3xTF32 is held to the same bound), with the GELU / residual epilogue and K-split."""
+    g = torch.Generator().manual_seed(B + L + Cin + Cout + K)
+    x = torch.randn(B, Cin, L, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / math.sqrt(Cin * K)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn(B, L, Cout, generator=g)
+    ref = F.gelu(F.conv1d(x.double(), w.double(), b.double(), padding=(K - 1) // 2)).transpose(1, 2) + res.double()
+    xd, bd, rd = x.transpose(1, 2).contiguous().to(dev), b.to(dev), res.to(dev)
+    wd = packing.to_tc16x2_layout(packing._conv_w(w)).to(dev)
+    for ws_floats in (0, 4 * B * L * Cout):
+        ws = torch.empty(ws_floats, device=dev) if ws_floats else None
+        out = torch.full((B, L, Cout), float("nan"), device=dev)
+        _abi.check(lib.ev_op_conv1d_tc(_ptr(xd), _ptr(wd), 3, _ptr(bd), 0, _ptr(rd), _ptr(out), B, L, Cin, Cout, K, 1, None, 1, _abi.ACT_NONE, 0.0,
+                                       _abi.ACT_GELU, _abi.ACC_STORE, 1.0, _ptr(ws), ws_floats, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        err = float((out.cpu().double() - ref).abs().max() / ref.abs().max())
+        print("conv1d_tc bf16x3", (B, L, Cin, Cout, K), "ksplit" if ws_floats else "plain", "rel-max err %.2e" % err)
+        assert err <= 5e-5
