@@ -276,39 +276,44 @@ def timed_forwards(fn, n, flush):
 
 def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
     """The single most expensive layer shape of the step: the k=11 ResBlock convolutions of HiFi-GAN stage 2 (C=128,
-    L=64*F; 22% of all FLOPs).  Timed live with CUDA events on the launching stream, L2 flushed before every launch."""
-    from emotivoice_b200 import _abi, packing
+    L=64*F; 22% of all FLOPs), through the kernel and mode the engine runs it in (conv1d_gp: bf16x3 in the "fp32" precision,
+    tf32, or bf16 with bf16 activations).  Timed live with CUDA events on the launching stream, L2 flushed before every launch."""
+    from emotivoice_b200 import _abi, layout, packing
     C, K, L = 128, 11, 64 * frames
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, L, C, generator=g).to(dev)
+    x = torch.randn(1, L, C, generator=g)
     w = torch.randn(K, C, C, generator=g) / math.sqrt(C * K)
-    use_tc = precision in ("fp32", "tf32", "bf16")
-    if use_tc:
-        w = packing.to_tc16_layout(w) if precision == "bf16" else packing.to_tc_layout(w)
-    w = w.to(dev)
-    split3 = {"fp32": 1, "tf32": 0, "bf16": 2}.get(precision, 0)
     b = torch.randn(C, generator=g).to(dev)
-    res = torch.randn(1, L, C, generator=g).to(dev)
-    out = torch.empty(1, L, C, device=dev)
+    res = torch.randn(1, L, C, generator=g)
     st = torch.cuda.current_stream().cuda_stream
     times = []
+    if precision == "fp32_ffma":
+        xd, wd, rd, out = x.to(dev), w.to(dev), res.to(dev), torch.empty(1, L, C, device=dev)
+        call = lambda: lib.ev_op_conv1d(xd.data_ptr(), wd.data_ptr(), b.data_ptr(), 0, rd.data_ptr(), out.data_ptr(), 1, L, C, C, K, 1, None, 1,
+                                        _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, st)
+        kname, esize, mma_mult, rate = "conv1d_tm (fp32 FFMA)", 4, 1, None
+    else:
+        gmode = {"fp32": 3, "tf32": 0, "bf16": 2}[precision]
+        bf = precision == "bf16"
+        wd = (packing.to_tc16x2_layout(w) if gmode == 3 else (packing.to_tc16_layout(w) if bf else packing.to_tc_layout(w))).to(dev)
+        xd, rd = layout.to_gp(x, bf).to(dev), layout.to_gp(res, bf).to(dev)
+        out = torch.empty_like(xd)
+        call = lambda: lib.ev_op_conv1d_gp(xd.data_ptr(), wd.data_ptr(), gmode, b.data_ptr(), rd.data_ptr(), out.data_ptr(), 1, L, C, C, K, 1, 1, None, 1,
+                                           _abi.ACT_LRELU, 0.1, _abi.ACC_STORE, 1.0, st)
+        kname = "conv1d_gp " + {3: "bf16x3 (fp32 activations, 3 bf16 MMAs per K=16)", 0: "tf32", 2: "bf16 (bf16 activations)"}[gmode]
+        esize, mma_mult, rate = (2 if bf else 4), (3 if gmode == 3 else 1), ("tf32 = half the bf16 rate" if gmode == 0 else "bf16 rate")
     for i in range(13):
         flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if use_tc:
-            _abi.check(lib.ev_op_conv1d_tc(x.data_ptr(), w.data_ptr(), split3, b.data_ptr(), 0, res.data_ptr(), out.data_ptr(), 1, L, C, C,
-                                           K, 1, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, None, 0, st))
-        else:
-            _abi.check(lib.ev_op_conv1d(x.data_ptr(), w.data_ptr(), b.data_ptr(), 0, res.data_ptr(), out.data_ptr(), 1, L, C, C,
-                                        K, 1, None, 1, _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, st))
+        _abi.check(call())
         e1.record()
         e1.synchronize()
         if i >= 3:
             times.append(e0.elapsed_time(e1) * 1e-3)
     t = statistics.mean(times)
     flops = 2.0 * L * C * C * K
-    alg_bytes = 4.0 * (L * C * 3) + 4.0 * K * C * C
+    alg_bytes = float(esize) * (L * C * 3) + 4.0 * K * C * C
     achieved = flops / t / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes/launch from the committed ncu --set full capture
@@ -317,13 +322,13 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
             traffic = json.load(open(tpath)).get(precision, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    mma_mult = 3 if precision == "fp32" else 1
+    exec_frac = mma_mult * (2 if precision == "tf32" else 1) * achieved / peaks["bf16_tflops"]
     roof = {"bound": "tensor", "achieved": _r(achieved), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-            "kernel": "conv C=128 k=11 L=%d %s" % (L, precision), "ms": _r(t * 1e3),
-            "peak_is": "%s bf16 burst; tf32 MMAs run at half that rate and this mode executes %dx the algorithmic FLOPs" % (peaks["source"], mma_mult),
-            "frac_vs_tf32_executed": _r(2 * mma_mult * achieved / peaks["bf16_tflops"]) if precision in ("fp32", "tf32") else None,
-            "alg_gbs": _r(alg_bytes / t / 1e9)}
+            "kernel": "%s, C=128 k=11 L=%d" % (kname, L), "ms": _r(t * 1e3),
+            "peak_is": "%s bf16 burst (cuBLAS); `achieved` counts ALGORITHMIC flops, the mode executes %dx of them at the %s"
+                       % (peaks["source"], mma_mult, rate),
+            "tensor_pipe_frac_est": _r(exec_frac), "alg_gbs": _r(alg_bytes / t / 1e9)}
     full = dict(roof, flops_per_launch=flops, algorithmic_bytes_per_launch=alg_bytes, times_ms=[x * 1e3 for x in times])
     return roof, full
 
@@ -569,8 +574,8 @@ def main():
             "metric": "mel_frames_per_sec", "value": _r(value, 6), "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": _r(dev_s / args.steps * 1e3, 5), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": {"fp32": "fp32 (3xTF32 on tcgen05, fp32 accumulate)", "tf32": "tf32", "bf16": "bf16 (fp32 accumulate)",
-                      "fp32_ffma": "fp32 (FFMA)"}[args.precision],
+            "dtype": {"fp32": "fp32 (fp32 storage + accumulate; tcgen05 fp32 emulation: 3xTF32 prefix, bf16x3 after it)", "tf32": "tf32",
+                      "bf16": "bf16 (fp32 accumulate)", "fp32_ffma": "fp32 (FFMA)"}[args.precision],
             "data": "synthetic", "config": CONFIG,
             "rtf": _r(dev_s / audio_s), "x_realtime": _r(audio_s / dev_s),
             "clocks": clocks,

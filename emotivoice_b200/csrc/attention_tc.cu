@@ -3,11 +3,12 @@
 // and sums are thread-local -- no shuffles, no (L x L) tensor in memory.  Replaces encoder.py:84-109
 // (scores = q k^T / sqrt(d_k); key-padding mask; softmax; p v) for d_k = 48 (EmotiVoice: 384 / 8).
 //
-// One CTA = 128 queries of one (batch item, head); keys are walked in tiles of 64, TWICE:
-//   pass 1:  S_j = Q K_j^T  ->  m = max_j rowmax(S_j)                       (exact row maximum, like torch.softmax)
-//   pass 2:  S_j again      ->  P_j = exp(S_j / sqrt(d_k) - m), l += rowsum(P_j), O += P_j V_j        (no rescaling of O)
-// Recomputing S costs one extra K=48 MMA chain per tile (the tensor pipe idles most of the time anyway: the exponentials are
-// the bound) and removes the online-softmax correction pass over O in TMEM.  Final: ctx = O / l.
+// One CTA = 128 queries of one (batch item, head); keys are walked ONCE in tiles of 64 with a lazily rescaled online softmax:
+//   S_j = Q K_j^T  ->  P_j = exp(S_j / sqrt(d_k) - m), l += rowsum(P_j), O += P_j V_j
+// m is the running row maximum; it only moves (and O, l are only rescaled by exp(m_old - m_new), a TMEM load / multiply / store of
+// the row's 48 accumulator columns) when a tile's maximum exceeds it by more than 8: until then P_j <= e^8, harmless in fp32 and
+// in the relative precision of the tf32 operand.  Softmax is shift invariant, so the result is the reference's up to rounding.
+// Final: ctx = O / l.
 //
 // Operands are staged in shared memory in the no-swizzle K-major UMMA layout of conv1d_tc.cu (element (row r, 16-byte
 // granule g) at (g * rows_pad + r) * 16):  Q [12 granules][128 rows], K_j [12][64 rows] (B operand of S), V_j^T [16 key
@@ -18,7 +19,7 @@
 //
 // Roles (288 threads): warps 0-3 softmax (warp w <-> TMEM lanes 32w..), warps 4-7 loaders, warp 8 TMEM alloc + MMA issue.
 // mbarriers: q_ready, kv_full/kv_empty[2], s_full/s_empty[2] (S is double buffered in TMEM: Q K_{j+1}^T runs under the
-// softmax of tile j), p_full/p_empty, o_full.
+// softmax of tile j), p_full/p_empty (the O rescale sits between p_empty -- P V_{j-1} has completed -- and p_full), o_full.
 #include "ev_common.cuh"
 #include "tc_common.cuh"
 
@@ -97,46 +98,61 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const floa
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float inv_sqrt_dk = 1.0f / sqrtf((float)DK);
     float m = -INFINITY, l = 0.f;
-    int cnt = 0;
     float v[64];
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int j = 0; j < nkt; ++j, ++cnt) {
-        const int sb = cnt & 1;
-        mbar_wait(s_full(sb), (cnt >> 1) & 1);
-        tc_fence_after();
-        tmem_ld32(lane_addr + (uint32_t)(sb * BKT), 32, v);
-        tmem_ld32(lane_addr + (uint32_t)(sb * BKT + 32), 32, v + 32);
-        tc_fence_before();
-        mbar_arrive(s_empty(sb));                  // S_j is in registers: the buffer may take Q K_{j+2}^T
-        const int nvalid = min(BKT, klen - j * BKT);
-        if (pass == 0) {
+    constexpr float RESCALE_AT = 8.0f;
+    for (int j = 0; j < nkt; ++j) {
+      const int sb = j & 1;
+      mbar_wait(s_full(sb), (j >> 1) & 1);
+      tc_fence_after();
+      tmem_ld32(lane_addr + (uint32_t)(sb * BKT), 32, v);
+      tmem_ld32(lane_addr + (uint32_t)(sb * BKT + 32), 32, v + 32);
+      tc_fence_before();
+      mbar_arrive(s_empty(sb));                  // S_j is in registers: the buffer may take Q K_{j+2}^T
+      const int nvalid = min(BKT, klen - j * BKT);
+      float mt = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < BKT; ++c)
-            if (c < nvalid) m = fmaxf(m, v[c] * inv_sqrt_dk);
-        } else {
-          mbar_wait(p_empty, ((j & 1) ^ 1));       // the MMAs of tile j-1 have read P
+      for (int c = 0; c < BKT; ++c) {
+        v[c] *= inv_sqrt_dk;
+        if (c < nvalid) mt = fmaxf(mt, v[c]);
+      }
+      mbar_wait(p_empty, ((j & 1) ^ 1));         // the MMAs of tile j-1 have read P and have finished accumulating into O
+      tc_fence_after();
+      // lazy rescale: tcgen05.ld / st are warp collectives, so the warp decides together and rows that need nothing scale by 1
+      const bool need = (j > 0) && (mt > m + RESCALE_AT);
+      if (j == 0) m = mt;
+      if (__any_sync(0xffffffffu, need)) {
+        const float f = need ? expf(m - mt) : 1.0f;
+        if (need) { m = mt; l *= f; }
+        float o[64];
+        tmem_ld32(lane_addr + 128u, 32, o);
+        tmem_ld32(lane_addr + 160u, 16, o + 32);      // columns 32..47 (the helper zero-fills o[48..63])
 #pragma unroll
-          for (int g = 0; g < GK; ++g) {
-            float p[4];
+        for (int c = 0; c < DK; ++c) o[c] *= f;
+        tmem_st32(lane_addr + 128u, o);
+        tmem_st16(lane_addr + 160u, o + 32);
+        tmem_st_wait();
+      }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = 4 * g + e;
-              const float x = v[c] * inv_sqrt_dk - m;
-              p[e] = c < nvalid ? (SPLIT3 ? expf(x) : __expf(x)) : 0.f;
-            }
-            const float4 hi = make_float4(to_tf32(p[0]), to_tf32(p[1]), to_tf32(p[2]), to_tf32(p[3]));
-            // the denominator sums exactly what the tensor core multiplies: p (= hi + lo) in the 3xTF32 mode, the rounded hi otherwise
-            l += SPLIT3 ? (p[0] + p[1]) + (p[2] + p[3]) : (hi.x + hi.y) + (hi.z + hi.w);
-            *reinterpret_cast<float4*>(p_s + ((size_t)g * BQ + r) * 16) = hi;
-            if (SPLIT3) {
-              const float4 lo = make_float4(to_tf32(p[0] - hi.x), to_tf32(p[1] - hi.y), to_tf32(p[2] - hi.z), to_tf32(p[3] - hi.w));
-              *reinterpret_cast<float4*>(p_s + S::p_plane + ((size_t)g * BQ + r) * 16) = lo;
-            }
-          }
-          fence_proxy_async();
-          mbar_arrive(p_full);
+      for (int g = 0; g < GK; ++g) {
+        float p[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 4 * g + e;
+          const float x = v[c] - m;
+          p[e] = c < nvalid ? (SPLIT3 ? expf(x) : __expf(x)) : 0.f;
+        }
+        const float4 hi = make_float4(to_tf32(p[0]), to_tf32(p[1]), to_tf32(p[2]), to_tf32(p[3]));
+        // the denominator sums exactly what the tensor core multiplies: p (= hi + lo) in the 3xTF32 mode, the rounded hi otherwise
+        l += SPLIT3 ? (p[0] + p[1]) + (p[2] + p[3]) : (hi.x + hi.y) + (hi.z + hi.w);
+        *reinterpret_cast<float4*>(p_s + ((size_t)g * BQ + r) * 16) = hi;
+        if (SPLIT3) {
+          const float4 lo = make_float4(to_tf32(p[0] - hi.x), to_tf32(p[1] - hi.y), to_tf32(p[2] - hi.z), to_tf32(p[3] - hi.w));
+          *reinterpret_cast<float4*>(p_s + S::p_plane + ((size_t)g * BQ + r) * 16) = lo;
         }
       }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_full);
     }
     // ctx = O / l   (an item without keys -- rejected by the module's input validation -- yields zeros instead of a hang)
     float o[64];
@@ -178,9 +194,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const floa
     }
     fence_proxy_async();
     mbar_arrive(q_ready);
-    int cnt = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int j = 0; j < nkt; ++j, ++cnt) {
+    {
+      for (int j = 0; j < nkt; ++j) {
+        const int cnt = j;
         const int s = cnt & 1;
         const int k0 = j * BKT;
         mbar_wait(kv_empty(s), ((cnt >> 1) & 1) ^ 1);
@@ -197,7 +213,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const floa
             *reinterpret_cast<float4*>(kd + S::k_plane + ((size_t)g * KPAD + r) * 16) = lo;
           }
         }
-        if (pass == 1) {
+        {
           // V_j^T: thread = (key granule gk, channel group d4): a 4 keys x 4 channels block, transposed in registers
           uint8_t* vd = v_s + (size_t)s * PL * S::v_plane;
           for (int idx = lt; idx < GK * G; idx += NLW * 32) {
@@ -240,7 +256,6 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const floa
       const uint64_t k_desc0 = make_desc(0u, k_lbo, 128u), v_desc0 = make_desc(0u, v_lbo, 128u);
       mbar_wait(q_ready, 0);
       tc_fence_after();
-      int cnt = 0;
       auto issue_qk = [&](int c, bool release_kv) {       // S[c & 1] = Q K^T with the K tile in stage c & 1
         const int s = c & 1;
         mbar_wait(kv_full(s), (c >> 1) & 1);
@@ -268,9 +283,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const floa
         }
         __syncwarp();
       };
-      // pass 1: maxima only; the K stage is free as soon as its MMAs have completed
-      for (int j = 0; j < nkt; ++j, ++cnt) issue_qk(cnt, true);
-      // pass 2
+      int cnt = 0;
       if (nkt > 0) issue_qk(cnt, false);
       for (int j = 0; j < nkt; ++j) {
         const int c = cnt + j, s = c & 1;

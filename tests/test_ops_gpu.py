@@ -212,6 +212,34 @@ def test_attention_tc(lib, dev, B, L, masked, tc_mode, tol):
         assert torch.equal(one[0], out[1, :n])
 
 
+@pytest.mark.parametrize("tc_mode,tol", [(1, 2e-5), (0, 3e-3)], ids=["3xtf32", "tf32"])
+def test_attention_tc_lazy_rescale_path(lib, dev, tc_mode, tol):
+    """The online softmax only rescales O / l when a key tile's row maximum exceeds the running one by more than 8.  Random
+    scores never do, so this case makes them: the keys grow by a factor per 64-key tile (every tile after the first triggers
+    the TMEM load / multiply / store of the accumulator), for some rows only (the warp-collective decision must leave the
+    other rows exact), with a ragged second item."""
+    H, heads, dk, B, L = 384, 8, 48, 2, 400
+    g = torch.Generator().manual_seed(77)
+    qkv = torch.randn(B, L, 3 * H, generator=g)
+    scale = (1.0 + 2.5 * (torch.arange(L) // 64).float())[None, :, None]            # keys of later tiles are larger
+    qkv[:, :, H:2 * H] *= scale
+    qkv[:, 1::3, :H] *= 0.05                                                          # a third of the queries barely see it
+    lens = torch.tensor([L, 333], dtype=torch.int32)
+    q, k, v = [t.reshape(B, L, heads, dk).transpose(1, 2) for t in qkv.split(H, dim=-1)]
+    scores = q.double() @ k.double().transpose(-2, -1) / math.sqrt(dk)
+    m = (torch.arange(L)[None, :] >= lens[:, None])[:, None, None, :]
+    attn = torch.softmax(scores.masked_fill(m, float("-inf")), -1)
+    ref = (attn @ v.double()).transpose(1, 2).reshape(B, L, H).float()
+    assert (scores.amax(-1) > 60).any()                                               # the jumps really exceed the threshold
+    out = torch.full((B, L, H), float("nan"), device=dev)
+    qd, ld = qkv.to(dev), lens.to(dev)
+    _abi.check(lib.ev_op_attention_tc(qd.data_ptr(), ld.data_ptr(), out.data_ptr(), B, L, H, heads, tc_mode, _stream()))
+    torch.cuda.synchronize()
+    err = rel_max(out.cpu(), ref)
+    print("attention_tc rescale path", tc_mode, "rel-max err %.2e" % err)
+    assert err <= tol
+
+
 @pytest.mark.parametrize("invariant", [0, 1])
 def test_gauss_upsample(lib, dev, invariant):
     """alignment.py:180-211 incl. the cumsum; literal padded batch vs per-item semantics."""

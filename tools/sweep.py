@@ -38,6 +38,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--corner", action="store_true", help="add the B=128, F=4096 corner of cfg4")
+    ap.add_argument("--no-cfg3", action="store_true")
     ap.add_argument("--precisions", default="fp32,tf32", help="comma separated: fp32,tf32,bf16")
     args = ap.parse_args()
     precisions = tuple(args.precisions.split(","))
@@ -58,7 +60,7 @@ def main():
     rng = np.random.default_rng(32)
     lens = sorted(rng.integers(20, 201, size=32).tolist(), reverse=True)
     batch = {k: v.to(dev) for k, v in synth.make_batch(lens, seed=3232).items()}
-    for prec in precisions:
+    for prec in ([] if args.no_cfg3 else precisions):
         model.precision = prec
         t, out = timed(lambda: model(**batch), 5, flush)
         frames = int(out["mel_lengths"].sum())
@@ -74,13 +76,20 @@ def main():
         print("cfg3", prec, json.dumps({k: v for k, v in res["cfg3"][prec].items() if k != "phonemes"}), flush=True)
 
     # ---- cfg4: vocoder-only sweep ------------------------------------------------------------
-    points = [(1, 256), (1, 1024), (1, 4096), (8, 1024), (32, 512), (32, 1024)] if args.quick else \
+    points = [(1, 256), (1, 1024), (1, 4096), (8, 1024), (32, 1024)] if args.quick else \
         [(1, 256), (1, 512), (1, 1024), (1, 2048), (1, 4096), (4, 1024), (8, 1024), (16, 1024), (32, 512), (32, 1024), (64, 512), (128, 256)]
+    if args.corner:
+        points = points + [(128, 4096)]          # BASELINE.json configs[3]'s largest point: 86 GB of vocoder workspace in the fp32-storage modes
     for prec in precisions:
         model.precision = prec
         for B, F in points:
             mel = synth.make_mel(B, F, seed=B * 7 + F).to(dev)
-            t, _ = timed(lambda: model.generator(mel), 3, flush)
+            try:
+                t, _ = timed(lambda: model.generator(mel), 2 if B * F > 100000 else 3, flush)
+            except Exception as e:          # an out-of-memory at the corner must not cost the other points
+                print("cfg4", json.dumps({"precision": prec, "batch": B, "frames": F, "error": repr(e)[:200]}), flush=True)
+                torch.cuda.empty_cache()
+                continue
             fr = B * F
             # note: model.generator is the stand-alone Generator module (its own engine, fp32 precision attr set below)
             row = {"precision": prec, "batch": B, "frames": F, "seconds": t, "mel_frames_per_sec": fr / t,
