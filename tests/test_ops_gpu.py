@@ -212,8 +212,8 @@ def test_attention_tc(lib, dev, B, L, masked, tc_mode, tol):
         assert torch.equal(one[0], out[1, :n])
 
 
-@pytest.mark.parametrize("tc_mode,tol", [(1, 2e-5), (0, 3e-3)], ids=["3xtf32", "tf32"])
-def test_attention_tc_lazy_rescale_path(lib, dev, tc_mode, tol):
+@pytest.mark.parametrize("tc_mode,tol", [(1, 2e-5), (0, 2e-2)], ids=["3xtf32", "tf32"])      # tf32: scores up to ~100 carry 2^-11 * 100 ~ 0.05
+def test_attention_tc_lazy_rescale_path(lib, dev, tc_mode, tol):                               # in the exponent (inherent to tf32 operands)
     """The online softmax only rescales O / l when a key tile's row maximum exceeds the running one by more than 8.  Random
     scores never do, so this case makes them: the keys grow by a factor per 64-key tile (every tile after the first triggers
     the TMEM load / multiply / store of the accumulator), for some rows only (the warp-collective decision must leave the
