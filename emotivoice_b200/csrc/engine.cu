@@ -481,15 +481,23 @@ static inline bool attn_tc_enabled() {
 
 // Encoder.forward (encoder.py:316-324) minus the positional prologue (done by the caller of this
 // function): n x [ x += W_o Attn(LN1 x) ; x += Conv2(GELU(Conv1(LN2 x))) ], then after_norm -> y.
+// K-split factors of a stack's four GEMM-shaped layers.  They are part of the layer's definition (they fix the order of each output
+// element's reduction), never a function of batch or length.  The encoder runs on ~100 tokens per utterance -- one or two row tiles --
+// so its launches have only (N tiles x S) CTAs to stream the layer's weights with: more slices.  The decoder has ~5 row tiles per
+// utterance.  Measured at batch 1: 32 us -> ~12 us per encoder GEMM; at batch 32 the extra partial-sum traffic is ~1 % of the step.
+struct StackSplits { int qkv, wo, ffn1, ffn2; };
+static const StackSplits kEncSplits = {4, 8, 4, 16};
+static const StackSplits kDecSplits = {2, 4, 4, 8};
+
 static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float* qkv, float* ctxb, float* h,
                      int B, int L, const int32_t* key_lens, const int32_t* conv_lens, bool first_ln_done, int mode,
-                     cudaStream_t st) {
+                     const StackSplits& sp, cudaStream_t st) {
   const int H = c->cfg.hidden, K = c->cfg.ffn_kernel, heads = c->cfg.n_heads;
   for (size_t i = 0; i < s.layers.size(); ++i) {
     const EncLayerW& l = s.layers[i];
     if (!(i == 0 && first_ln_done))
       EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln1w, l.ln1b, y, B * L, L, H, st));
-    g_split_ws.ksplit = 2;   // K = H: two slices
+    g_split_ws.ksplit = sp.qkv;
     EV_TRY(conv_x(mode, l.wqkv_tc, l.wqkv_h, y, l.wqkv, l.bqkv, 0, nullptr, qkv, B, L, H, 3 * H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
                   EV_ACT_NONE, EV_ACC_STORE, 1.f, st, l.wqkv_x2));
     // QK^T / softmax / PV: tcgen05 (3xTF32 where the layer runs fp32-accurate, one tf32 MMA otherwise) for d_k = 48; the fp32 FFMA
@@ -498,13 +506,14 @@ static int run_stack(const ev_ctx* c, const StackW& s, float* x, float* y, float
       EV_TRY(launch_attention_tc(qkv, key_lens, ctxb, B, L, H, heads, mode == 3 ? 1 : 0, st));
     else
       EV_TRY(launch_attention(qkv, key_lens, ctxb, B, L, H, heads, st));
+    g_split_ws.ksplit = sp.wo;
     EV_TRY(conv_x(mode, l.wo_tc, l.wo_h, ctxb, l.wo, l.bo, 0, x, x, B, L, H, H, 1, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
                   EV_ACC_STORE, 1.f, st, l.wo_x2));
     EV_TRY(launch_layernorm(x, nullptr, nullptr, nullptr, nullptr, nullptr, l.ln2w, l.ln2b, y, B * L, L, H, st));
-    g_split_ws.ksplit = 2;
+    g_split_ws.ksplit = sp.ffn1;
     EV_TRY(conv_x(mode, l.w1_tc, l.w1_h, y, l.w1, l.b1, 0, nullptr, h, B, L, H, 4 * H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_GELU,
                   EV_ACC_STORE, 1.f, st, l.w1_x2));
-    g_split_ws.ksplit = 4;   // K = 3 * 4H: four slices
+    g_split_ws.ksplit = sp.ffn2;
     EV_TRY(conv_x(mode, l.w2_tc, l.w2_h, h, l.w2, l.b2, 0, x, x, B, L, 4 * H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f, EV_ACT_NONE,
                   EV_ACC_STORE, 1.f, st, l.w2_x2));
   }
@@ -518,7 +527,7 @@ static int run_predictor(const ev_ctx* c, const PredW& p, const float* in, float
                          const int32_t* lens, const int32_t* conv_lens, int mode, float* out_f, int64_t* out_i,
                          int cmode, cudaStream_t st) {
   const int H = c->cfg.hidden, K = c->cfg.pred_kernel;
-  g_split_ws.ksplit = 2;
+  g_split_ws.ksplit = 8;      // K = 3H on ~100 tokens and 3 N tiles: eight slices (see StackSplits)
   const float* cur = in;
   for (size_t i = 0; i < p.w.size(); ++i) {
     EV_TRY(conv_x(cmode, p.w_tc[i], nullptr, cur, p.w[i], p.b[i], 0, nullptr, t1, B, T, H, H, K, 1, conv_lens, 1, EV_ACT_NONE, 0.f,
@@ -662,7 +671,8 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   // encoder: x = word_emb[ids] + alpha*pe (model_open_source.py:107, encoder.py:257-261), fused with LN1 of layer 0
   EV_TRY(launch_layernorm(nullptr, ling, ctx->emb_word, ctx->pe, ctx->enc.alpha, b.x, ctx->enc.layers[0].ln1w,
                           ctx->enc.layers[0].ln1b, b.y, B * T, T, H, st, g.n_vocab));
-  EV_TRY(run_stack(ctx, ctx->enc, b.x, b.y, b.qkv, b.ctx, b.h, B, T, lens, conv_lens, true, prefix_mode, st));
+  EV_TRY(run_stack(ctx, ctx->enc, b.x, b.y, b.qkv, b.ctx, b.h, B, T, lens, conv_lens, true, prefix_mode, kEncSplits, st));
+  g_split_ws.ksplit = 4;
   // conditioning (model_open_source.py:109-111): per-utterance bias + W_x x
   EV_TRY(launch_cond_gather(spk, ctx->emb_spk, style, content, b.cond_in, B, H, g.bert_dim, g.n_speaker, st));
   EV_TRY(launch_cond_gemv(b.cond_in, ctx->cond_wc, ctx->cond_b, b.cond_bias, B, H + 2 * g.bert_dim, H, st));
@@ -708,7 +718,8 @@ int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens,
   EV_TRY(launch_gauss_upsample(b1.hs, b1.centers, lens, mel_lens, B, T, H, F, invariant, ctx->pe, ctx->dec.alpha, b.x, st));
   // decoder (model_open_source.py:146: mask None in the reference; per-item lengths under the invariant contract)
   const int mode = body_mode(ctx);
-  EV_TRY(run_stack(ctx, ctx->dec, b.x, b.y, b.qkv, b.ctx, b.h, B, F, flens, flens, false, mode, st));
+  EV_TRY(run_stack(ctx, ctx->dec, b.x, b.y, b.qkv, b.ctx, b.h, B, F, flens, flens, false, mode, kDecSplits, st));
+  g_split_ws.ksplit = 2;
   // to_mel (model_open_source.py:147)
   EV_TRY(conv_x(mode, ctx->mel_w_tc, ctx->mel_w_h, b.y, ctx->mel_w, ctx->mel_b, 0, nullptr, mel_out, B, F, H, g.n_mels, 1, 1, flens, 1,
                 EV_ACT_NONE, 0.f, EV_ACT_NONE, EV_ACC_STORE, 1.f, st, ctx->mel_w_x2));
