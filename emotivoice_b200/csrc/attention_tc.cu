@@ -179,70 +179,91 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const floa
     // ================================ loaders =====================================================================
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lt = (warp - W_LOAD) * 32 + lane;        // 0..127
-    // Q tile: (row, granule) pairs, granule fastest -> coalesced 192-byte head rows; rows >= L are zeros
-    for (int idx = lt; idx < BQ * G; idx += NLW * 32) {
-      const int r = idx / G, g = idx - r * G;
-      const int row = q0 + r;
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < L) t = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * ld + h * DK + g * 4));
+    // Every tile is loaded in batches of independent 16-byte loads issued back to back (memory-level parallelism: one latency
+    // per batch instead of one per element -- the first version of this loop serialised them and was loader bound), then
+    // rounded / split and stored in operand layout.
+    auto store_split = [&](uint8_t* dst, int plane_bytes, const float4& t) {
       const float4 hi = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
-      *reinterpret_cast<float4*>(q_s + ((size_t)g * QPAD + r) * 16) = hi;
+      *reinterpret_cast<float4*>(dst) = hi;
       if (SPLIT3) {
         const float4 lo = make_float4(to_tf32(t.x - hi.x), to_tf32(t.y - hi.y), to_tf32(t.z - hi.z), to_tf32(t.w - hi.w));
-        *reinterpret_cast<float4*>(q_s + S::q_plane + ((size_t)g * QPAD + r) * 16) = lo;
+        *reinterpret_cast<float4*>(dst + plane_bytes) = lo;
+      }
+    };
+    constexpr int NT = NLW * 32;
+    constexpr int QB = 6;                                  // loads in flight per thread
+    static_assert((BQ * G) % (NT * QB) == 0 && (BKT * G) == NT * QB, "loader batching assumes d_k = 48, 128 loader threads");
+    // Q tile: (row, granule) pairs, granule fastest -> coalesced 192-byte head rows; rows >= L are zeros
+    for (int base_idx = 0; base_idx < BQ * G; base_idx += NT * QB) {
+      float4 t[QB];
+#pragma unroll
+      for (int u = 0; u < QB; ++u) {
+        const int idx = base_idx + u * NT + lt;
+        const int r = idx / G, g = idx - r * G;
+        const int row = q0 + r;
+        t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < L) t[u] = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * ld + h * DK + g * 4));
+      }
+#pragma unroll
+      for (int u = 0; u < QB; ++u) {
+        const int idx = base_idx + u * NT + lt;
+        const int r = idx / G, g = idx - r * G;
+        store_split(q_s + ((size_t)g * QPAD + r) * 16, S::q_plane, t[u]);
       }
     }
     fence_proxy_async();
     mbar_arrive(q_ready);
-    {
-      for (int j = 0; j < nkt; ++j) {
-        const int cnt = j;
-        const int s = cnt & 1;
-        const int k0 = j * BKT;
-        mbar_wait(kv_empty(s), ((cnt >> 1) & 1) ^ 1);
-        uint8_t* kd = k_s + (size_t)s * PL * S::k_plane;
-        for (int idx = lt; idx < BKT * G; idx += NLW * 32) {
-          const int r = idx / G, g = idx - r * G;
-          const int row = k0 + r;
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < klen) t = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * ld + H + h * DK + g * 4));
-          const float4 hi = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
-          *reinterpret_cast<float4*>(kd + ((size_t)g * KPAD + r) * 16) = hi;
-          if (SPLIT3) {
-            const float4 lo = make_float4(to_tf32(t.x - hi.x), to_tf32(t.y - hi.y), to_tf32(t.z - hi.z), to_tf32(t.w - hi.w));
-            *reinterpret_cast<float4*>(kd + S::k_plane + ((size_t)g * KPAD + r) * 16) = lo;
-          }
-        }
-        {
-          // V_j^T: thread = (key granule gk, channel group d4): a 4 keys x 4 channels block, transposed in registers
-          uint8_t* vd = v_s + (size_t)s * PL * S::v_plane;
-          for (int idx = lt; idx < GK * G; idx += NLW * 32) {
-            const int gk = idx / G, d4 = idx - gk * G;
-            float4 t[4];
+    for (int j = 0; j < nkt; ++j) {
+      const int s = j & 1;
+      const int k0 = j * BKT;
+      // all global loads of the tile first (K: 6 per thread; V: one or two 4-key x 4-channel blocks = 4 or 8 per thread) ...
+      float4 kt[QB];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int row = k0 + 4 * gk + i;
-              t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (row < klen) t[i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * ld + 2 * H + h * DK + d4 * 4));
-            }
-            const float col[4][4] = {{t[0].x, t[1].x, t[2].x, t[3].x}, {t[0].y, t[1].y, t[2].y, t[3].y},
-                                     {t[0].z, t[1].z, t[2].z, t[3].z}, {t[0].w, t[1].w, t[2].w, t[3].w}};
-#pragma unroll
-            for (int dd = 0; dd < 4; ++dd) {
-              const float4 hi = make_float4(to_tf32(col[dd][0]), to_tf32(col[dd][1]), to_tf32(col[dd][2]), to_tf32(col[dd][3]));
-              uint8_t* d = vd + ((size_t)gk * VPAD + d4 * 4 + dd) * 16;
-              *reinterpret_cast<float4*>(d) = hi;
-              if (SPLIT3) {
-                const float4 lo = make_float4(to_tf32(col[dd][0] - hi.x), to_tf32(col[dd][1] - hi.y), to_tf32(col[dd][2] - hi.z),
-                                              to_tf32(col[dd][3] - hi.w));
-                *reinterpret_cast<float4*>(d + S::v_plane) = lo;
-              }
-            }
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(kv_full(s));
+      for (int u = 0; u < QB; ++u) {
+        const int idx = u * NT + lt;
+        const int r = idx / G, g = idx - r * G;
+        const int row = k0 + r;
+        kt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < klen) kt[u] = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * ld + H + h * DK + g * 4));
       }
+      constexpr int VB = (GK * G + NT - 1) / NT;         // blocks per thread (2 for d_k = 48; the second only for lt < 64)
+      float4 vt[VB][4];
+#pragma unroll
+      for (int u = 0; u < VB; ++u) {
+        const int idx = u * NT + lt;
+        const int gk = idx / G, d4 = idx - gk * G;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = k0 + 4 * gk + i;
+          vt[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < GK * G && row < klen) vt[u][i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * ld + 2 * H + h * DK + d4 * 4));
+        }
+      }
+      // ... then wait for the ring slot and store
+      mbar_wait(kv_empty(s), ((j >> 1) & 1) ^ 1);
+      uint8_t* kd = k_s + (size_t)s * PL * S::k_plane;
+#pragma unroll
+      for (int u = 0; u < QB; ++u) {
+        const int idx = u * NT + lt;
+        const int r = idx / G, g = idx - r * G;
+        store_split(kd + ((size_t)g * KPAD + r) * 16, S::k_plane, kt[u]);
+      }
+      // V_j^T: a 4 keys x 4 channels block per (key granule gk, channel group d4), transposed in registers
+      uint8_t* vd = v_s + (size_t)s * PL * S::v_plane;
+#pragma unroll
+      for (int u = 0; u < VB; ++u) {
+        const int idx = u * NT + lt;
+        if (idx < GK * G) {
+          const int gk = idx / G, d4 = idx - gk * G;
+          const float4* t = vt[u];
+          store_split(vd + ((size_t)gk * VPAD + d4 * 4 + 0) * 16, S::v_plane, make_float4(t[0].x, t[1].x, t[2].x, t[3].x));
+          store_split(vd + ((size_t)gk * VPAD + d4 * 4 + 1) * 16, S::v_plane, make_float4(t[0].y, t[1].y, t[2].y, t[3].y));
+          store_split(vd + ((size_t)gk * VPAD + d4 * 4 + 2) * 16, S::v_plane, make_float4(t[0].z, t[1].z, t[2].z, t[3].z));
+          store_split(vd + ((size_t)gk * VPAD + d4 * 4 + 3) * 16, S::v_plane, make_float4(t[0].w, t[1].w, t[2].w, t[3].w));
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(kv_full(s));
     }
   } else {
     // ================================ MMA issuer ===================================================================
