@@ -90,7 +90,8 @@ __host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int 
   return true;
 }
 
-__device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
+// LeakyReLU for 0 <= slope <= 1 as max(v, v*slope): two instructions (FMUL + FMNMX) instead of compare / multiply / select; same bits
+__device__ __forceinline__ float lrelu_f(float v, float slope) { return fmaxf(v, v * slope); }
 
 // MODE 0: one tf32 MMA per K step; 1: 3xTF32 fp32 emulation (hi/lo planes, three MMAs per K step); 2: bf16 operands,
 // bf16 activations in HBM (kind::f16, 8 channels per granule); 3: "bf16x3": fp32 activations in HBM, every operand split

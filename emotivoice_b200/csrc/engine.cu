@@ -451,6 +451,10 @@ static inline bool fuse_res_enabled() {
 static bool try_gp_pair(int mode, const ConvW& c1, const ConvW& c2, const void* src, void* dst, int B, int L, int C, const int32_t* lens, int lens_mul,
                         int acc, float div, cudaStream_t st, int* rc) {
   if (!fuse_res_enabled() || c1.K != c2.K || c2.dil != 1) return false;
+  // Fused and unfused are bitwise equal, so the choice may depend on the batch: measured (profiles/r02_fused_vs_unfused.jsonl) the fused
+  // layer wins 1.1-1.8x on the HBM-bound shapes (k <= 7, or 32 channels) and wherever the launch count matters (batch 1), and loses
+  // ~25 % on 64 channels x 11 taps once the batch is large enough to be tensor / issue bound.
+  if (C >= 64 && c1.K > 7 && (long long)B * L > 4ll * 70000) return false;
   const bool x3b = mode == 3 && c1.w_x2 && c2.w_x2 && voc_bf16x3_enabled();
   const int gm = x3b ? 3 : (mode == 3 ? 1 : (mode == 2 ? 2 : 0));
   GpPairParams p;

@@ -78,7 +78,8 @@ __host__ __device__ inline bool make_pplan(const GpPairParams& p, int mode, int 
   return true;
 }
 
-__device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
+// LeakyReLU for 0 <= slope <= 1 as max(v, v*slope): two instructions (FMUL + FMNMX) instead of compare / multiply / select; same bits
+__device__ __forceinline__ float lrelu_f(float v, float slope) { return fmaxf(v, v * slope); }
 
 // MODE as conv1d_gp.cu: 0 tf32, 1 3xTF32, 2 bf16 activations + operands, 3 bf16x3 on fp32 activations.
 template <int MODE, int MT, int KBG>
