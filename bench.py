@@ -24,6 +24,7 @@ per rank.
     cfg5 = configs[4]: a fixed 256-utterance-per-GPU... see `cfg5_block` -- corpus sharded over the ranks in B=32
            buckets, wall-clock end to end (pinned int16 D2H), with a digest that is identical for every world size iff
            every utterance's PCM is bit-identical.
+    cfg5_strong = the same pipeline on a FIXED 2048-utterance corpus (strong scaling 1 -> N; digest over all of it).
 * --impl reference: the reference's algorithm on the host CPU (oracle/jets_oracle.py, the torch-CPU restatement pinned
   bit-exactly to the unmodified reference, which is Python and cannot travel to the GPU box), all usable host threads,
   same corpus, same unit (B=1 per step as every reference caller runs), rank 0 only.
@@ -199,7 +200,7 @@ def emit(line, detail=None, n_gpus=1):
     """ONE compact JSON line on stdout (the driver parses the last line); the long form to gpurun_out/ and stderr."""
     s = json.dumps(line, separators=(",", ":"))
     if len(s) >= MAX_LINE:       # never let a secondary block cost the headline: drop the optional sub-objects, largest first
-        for k in sorted(("cfg5", "voc", "b32", "b1", "parity"), key=lambda k: -len(json.dumps(line.get(k, None)))):
+        for k in sorted(("cfg5_strong", "cfg5", "voc", "b32", "b1", "parity"), key=lambda k: -len(json.dumps(line.get(k, None)))):
             if k in line:
                 line[k] = {"dropped": "line too long; see bench_detail"}
                 s = json.dumps(line, separators=(",", ":"))
@@ -617,6 +618,17 @@ def main():
         except Exception as e:
             if rank == 0:
                 line["cfg5"] = {"error": repr(e)[:200]}
+        try:
+            # the same pipeline on a FIXED 2048-utterance corpus (strong scaling: the shard shrinks as N grows); the digest
+            # covers every utterance, so equal digests across world sizes = the whole corpus is bit-identical
+            c5s, recs = cfg5_block(model, dev, rank, world, dist, per_gpu=2048, total_fixed=2048)
+            if rank == 0:
+                line["cfg5_strong"] = {"utts": c5s["utts"], "wall_s": c5s["wall_s"], "utt_per_s": c5s["utt_per_s"], "fps": c5s["fps"],
+                                       "rank_wall_min_s": c5s["rank_wall_min_s"], "digest": c5s["digest_first2048"]}
+                detail["cfg5_strong_ranks"] = [{k: v for k, v in r.items() if k != "pairs"} for r in recs]
+        except Exception as e:
+            if rank == 0:
+                line["cfg5_strong"] = {"error": repr(e)[:200]}
 
     if dist is not None:
         dist.barrier()

@@ -60,6 +60,8 @@ def _build_locked(force, verbose):
     stamp = os.path.join(LIB_DIR, "build.stamp")
     dig = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        if verbose:
+            print("emotivoice_b200.build: up to date (sources digest %s), not recompiled" % dig[:12], flush=True)
         return LIB_PATH
     objs = []
     procs = []
@@ -84,6 +86,8 @@ def _build_locked(force, verbose):
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(dig)
+    if verbose:
+        print("emotivoice_b200.build: compiled %d sources with nvcc for sm_100a (digest %s)" % (len(objs), dig[:12]), flush=True)
     return LIB_PATH
 
 

@@ -1,7 +1,7 @@
 """Launch one conv shape through the C ABI a few times (for ncu / timing).
 
 usage: python tools/profile_conv.py MODE C K DIL L [B] [reps]
-  MODE in {ffma, tf32, fp32, bf16}            round-1 time-major kernels (conv1d_tm / conv1d_tc)
+  MODE in {ffma, tf32, fp32, bf16, bf16x3}    time-major kernels (conv1d_tm / conv1d_tc: what the acoustic model runs); env KSPLIT=n splits K
           {gp:tf32, gp:fp32, gp:bf16, gp:bf16x3}   granule-planar kernel (conv1d_gp), the vocoder's default path
                                               (gp:fp32 = 3xTF32; gp:bf16x3 = the fp32 mode's default emulation)
   C may be "Cin:Cout" (or "Cin:Cout:rate" for the polyphase ConvTranspose1d form, gp only).
@@ -39,6 +39,8 @@ if gp:
     out = torch.empty_like(layout.to_gp(torch.zeros(B, L * rate, coutR), prec == "bf16")).to(dev)
 else:
     xd, rd, out = x.to(dev), res.to(dev), torch.empty(B, L, Cout, device=dev)
+ksplit = int(os.environ.get("KSPLIT", "0"))
+ws = torch.empty(ksplit * B * (L + 256) * Cout, device=dev) if ksplit > 1 and not gp else None
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 ptr = lambda t: None if t is None else t.data_ptr()
@@ -53,8 +55,8 @@ for i in range(reps):
     elif mode == "ffma":
         _abi.check(lib.ev_op_conv1d(ptr(xd), ptr(wd), ptr(b), 0, ptr(rd), ptr(out), B, L, Cin, Cout, K, dil, None, 1, 1, 0.1, 0, 0, 1.0, st))
     else:
-        _abi.check(lib.ev_op_conv1d_tc(ptr(xd), ptr(wd), {"fp32": 1, "tf32": 0, "bf16": 2}[mode], ptr(b), 0, ptr(rd), ptr(out), B, L, Cin, Cout, K, dil,
-                                       None, 1, 1, 0.1, 0, 0, 1.0, None, 0, st))
+        _abi.check(lib.ev_op_conv1d_tc(ptr(xd), ptr(wd), {"fp32": 1, "tf32": 0, "bf16": 2, "bf16x3": 3}[mode], ptr(b), 0, ptr(rd), ptr(out), B, L, Cin, Cout, K, dil,
+                                       None, 1, 1, 0.1, 0, 0, 1.0, ptr(ws), 0 if ws is None else ws.numel(), st))
     e1.record()
     e1.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
