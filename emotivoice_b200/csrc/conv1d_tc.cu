@@ -100,7 +100,7 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN,
 //                 three MMAs per K step into the same fp32 TMEM accumulator.  Weights arrive pre-split
 //                 (two planes, packing.to_tc_layout); activations are split by the producer warps.
 // MT: 128-row accumulators per tile.  KBG: 16-byte K granules (4 tf32 or 8 bf16 channels each) per pipeline stage.
-// PDLM: programmatic dependent launch mode (EV_PDL): 0 = plain launch (the default path; no extra instructions),
+// PDLM: programmatic dependent launch mode (EV_PDL): 0 = plain launch (no extra instructions),
 //       1 = convolutions only, 2 = every kernel of the engine launches this way (see the note after the set-up below).
 template <int MODE, int MT, int KBG, int PDLM>
 __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Plan pl) {
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Programmatic dependent launch (opt-in, EV_PDL).  The grid is persistent (<= one CTA per SM, all resident), so it lets
+  // Programmatic dependent launch (EV_PDL, default 2).  The grid is persistent (<= one CTA per SM, all resident), so it lets
   // the NEXT launch in the stream start as soon as SMs free up: that kernel's CTAs run their set-up (barriers, TMEM) while
   // this grid's tail is still running.  Everything that touches activations (producers: x; epilogue: res / out / split-K
   // partials) first executes griddepcontrol.wait, which returns once the preceding grid has completed and its writes are
@@ -668,7 +668,7 @@ int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st) {
   tc::Plan pl;
   EV_TRY(plan_conv1d_tc(p, mode, &pl));
   const size_t per = (size_t)p.B * p.L * p.Cout;
-  const int rc = dispatch_tc(p, mode, pl, st, pdl_mode());      // EV_PDL: opt-in until it has been measured on hardware
+  const int rc = dispatch_tc(p, mode, pl, st, pdl_mode());      // EV_PDL (default 2)
   if (rc != EV_OK || pl.ksplit == 1) return rc;
   const size_t n4 = per / 4;
   launch_k(tc::splitk_reduce_kernel<true>, tc::splitk_reduce_kernel<false>, (unsigned)((n4 + 255) / 256), 256, 0, st, p, pl.ksplit);

@@ -70,7 +70,7 @@ int use_device_of(const void* dev_ptr) {
   return EV_OK;
 }
 int pdl_mode() {
-  static const int v = [] { const char* e = getenv("EV_PDL"); return (e && *e) ? atoi(e) : 0; }();
+  static const int v = [] { const char* e = getenv("EV_PDL"); return (e && *e) ? atoi(e) : 2; }();
   return v;
 }
 

@@ -68,11 +68,9 @@ __global__ void __launch_bounds__(CP_BT) conv_post_kernel(const float* __restric
   const int t = t0 + threadIdx.x;
   if (t >= L) return;
   float acc = 0.f;
-  for (int j = 0; j < K; ++j) {
-    const float* xr = xs + (threadIdx.x + j) * ld;
-    const float* wr = ws + j * C;
-#pragma unroll 8
-    for (int c = 0; c < C; ++c) acc = fmaf(xr[c], wr[c], acc);
+  for (int c = 0; c < C; ++c) {       // channel-major reduction order, shared with the granule-planar conv_post kernels (conv1d_gp.cu)
+    const float* xr = xs + threadIdx.x * ld + c;
+    for (int j = 0; j < K; ++j) acc = fmaf(xr[j * ld], ws[j * C + c], acc);
   }
   wav[(size_t)b * L + t] = t < len ? tanhf(acc + bias[0]) : 0.f;
 }

@@ -206,6 +206,18 @@ def main():
         okp = e < (2e-2 if bf else 1e-5) and z
         print(json.dumps({"conv_post_gp_max_abs_err": e, "pad_zero": z, "bf16": bf, "ok": okp}), flush=True)
         ok_all = ok_all and okp
+    # odd length (scalar stores), no lengths, the generic-K kernel (K = 5) beside the K = 7 one
+    for K in (7, 5):
+        x = torch.randn(1, 1001, 32, generator=g)
+        w = torch.randn(K, 32, generator=g) * 0.1
+        ref = torch.tanh(F.conv1d(F.leaky_relu(x, 0.01).transpose(1, 2), w.t().unsqueeze(0), b1, padding=K // 2))[:, 0]
+        xg, w_d = layout.to_gp(x, False).to(dev), w.to(dev)
+        wav = torch.empty(1, 1001, device=dev)
+        _abi.check(lib.ev_op_conv_post_gp(ptr(xg), 0, ptr(w_d), ptr(b1_d), None, 1, 1, 1001, 32, K, 0.01, ptr(wav), st))
+        torch.cuda.synchronize()
+        e = float((wav.cpu() - ref).abs().max())
+        print(json.dumps({"conv_post_gp_odd_len_K": K, "max_abs_err": e, "ok": e < 1e-5}), flush=True)
+        ok_all = ok_all and e < 1e-5
     print("GP_CHECK_" + ("OK" if ok_all else "FAILED"), flush=True)
     sys.exit(0 if ok_all else 1)
 

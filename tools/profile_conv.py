@@ -45,8 +45,12 @@ flush = torch.empty(64 * 1024 * 1024, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 ptr = lambda t: None if t is None else t.data_ptr()
 ts = []
+warm = os.environ.get("WARM", "none")      # none: everything cold (L2 flushed); w: weights re-read after the flush (L2 warm); all: no flush
 for i in range(reps):
-    flush.zero_()
+    if warm != "all":
+        flush.zero_()
+    if warm == "w":
+        wd.view(torch.uint8).sum().item()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if gp:
@@ -63,5 +67,5 @@ for i in range(reps):
 fl = 2.0 * B * L * Cin * Cout * K
 by = esize * B * L * (Cin + Cout * (2 if res is not None else 1)) + 4.0 * K * Cin * Cout
 best = min(ts[1:]) if len(ts) > 1 else ts[0]
-print(json.dumps({"mode": mode, "Cin": Cin, "Cout": Cout, "rate": rate, "K": K, "dil": dil, "L": L, "B": B, "us": [round(t, 1) for t in ts],
+print(json.dumps({"warm": warm, "mode": mode, "Cin": Cin, "Cout": Cout, "rate": rate, "K": K, "dil": dil, "L": L, "B": B, "us": [round(t, 1) for t in ts],
                   "best_us": round(best, 1), "tflops": round(fl / best / 1e6, 1), "layer_gbs": round(by / best / 1e3, 1)}))
