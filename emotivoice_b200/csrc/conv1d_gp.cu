@@ -53,7 +53,10 @@ struct GPlan {
   int smem_total;
 };
 
-__host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int BN, int mt, int kbg, GPlan* o) {
+// span = (K-1)*dil of the widest member and kmin = the fewest taps of a grouped launch (ng convolutions); -1 / 0: p's own
+__host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int BN, int mt, int kbg, GPlan* o, int span = -1, int kmin = 0, int ng = 1) {
+  if (span < 0) span = (p.K - 1) * p.dil;
+  if (kmin <= 0) kmin = p.K;
   GPlan q;
   q.planes = mode == 1 ? 2 : 1;          // A planes in shared memory (mode 3 keeps hi / lo interleaved in ONE plane, in place)
   const int b_planes = (mode == 1 || mode == 3) ? 2 : 1;
@@ -63,7 +66,7 @@ __host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int 
   if (2 * mt * BN > 512) return false;
   q.tmem_cols = 32;
   while (q.tmem_cols < 2 * mt * BN) q.tmem_cols <<= 1;
-  const int rows = BM * mt + (p.K - 1) * p.dil;
+  const int rows = BM * mt + span;
   q.rows_pad = (rows + 7) / 8 * 8;
   q.a_plane_bytes = kbg * q.rows_pad * 16;
   q.b_plane_bytes = (kbg * cpg / wcpg) * BN * 16;
@@ -71,7 +74,7 @@ __host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int 
   q.b_stage_bytes = b_planes * q.b_plane_bytes;
   const int budget = 227 * 1024 - SMEM_HEAD;
   const int n_cb = (p.Cin + cpg * kbg - 1) / (cpg * kbg);
-  const int b_max = n_cb * p.K < MAX_B ? n_cb * p.K : MAX_B;
+  const int b_max = n_cb * kmin < MAX_B ? n_cb * kmin : MAX_B;
   q.a_stages = 2;
   q.b_stages = b_max < 2 ? b_max : 2;
   if (q.a_stages * q.a_stage_bytes + q.b_stages * q.b_stage_bytes > budget) return false;
@@ -84,7 +87,7 @@ __host__ __device__ inline bool make_gplan(const GpConvParams& p, int mode, int 
   while (q.a_stages < MAX_A && fits(q.a_stages + 1, q.b_stages)) ++q.a_stages;
   q.tiles_m = (p.L + BM * mt - 1) / (BM * mt);
   q.tiles_n = (p.Cout + BN - 1) / BN;
-  q.total_tiles = p.B * q.tiles_m * q.tiles_n;
+  q.total_tiles = ng * p.B * q.tiles_m * q.tiles_n;
   q.smem_total = SMEM_HEAD + q.a_stages * q.a_stage_bytes + q.b_stages * q.b_stage_bytes;
   *o = q;
   return true;
@@ -98,7 +101,8 @@ __device__ __forceinline__ float lrelu_f(float v, float slope) { return fmaxf(v,
 // into bf16 hi + lo (16 significant bits), three kind::f16 MMAs per K = 16 step -- an fp32-class result (~1e-5 relative) at
 // half the tensor-core and shared-memory cost of 3xTF32.  Accumulation is fp32 in TMEM in every mode.
 template <int MODE, int MT, int KBG>
-__global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p, GPlan pl) {
+__global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(const __grid_constant__ GpConvParams p, const __grid_constant__ GPlan pl,
+                                                                  const __grid_constant__ GpGroups gs) {
   constexpr bool SPLIT3 = (MODE == 1);     // 3xTF32: hi / lo tf32 planes
   constexpr bool BF16 = (MODE == 2);       // bf16 activations in HBM, bf16 operands
   constexpr bool X3B = (MODE == 3);        // fp32 activations in HBM, operands split into bf16 hi + lo: three kind::f16 MMAs per K=16 step
@@ -148,12 +152,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int n_cb = (p.Cin + KB - 1) / KB;
-  const int halo = ((p.K - 1) / 2) * p.dil;
-  const int rows_a = BM * MT + (p.K - 1) * p.dil;
   const int tiles_per_b = pl.tiles_m * pl.tiles_n;
-  const int gin = p.Cin / CPG;                // input granule planes per item
+  const int tiles_per_g = p.B * tiles_per_b;  // a launch may carry up to three convolutions of one shape (different taps, dilations,
+  const int gin = p.Cin / CPG;                // weights and tensors): tile -> (convolution, item, row tile, column tile)
 
-  auto decode = [&](int tile, int& b, int& t0, int& n0, int& len) {
+  auto decode = [&](int tile, int& gi, int& b, int& t0, int& n0, int& len) {
+    gi = tile / tiles_per_g;
+    tile -= gi * tiles_per_g;
     b = tile / tiles_per_b;
     const int r = tile - b * tiles_per_b;
     const int tm = r / pl.tiles_n, tn = r - tm * pl.tiles_n;
@@ -171,13 +176,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
     const int gout = coutR / CPG;              // output granule planes per item
     const size_t Lout = (size_t)p.L * p.rate;
     const int accm = p.acc;
-    const bool has_res = p.res != nullptr;
     int tile_cnt = 0;
     for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
-      int b, t0, n0, len;
-      decode(tile, b, t0, n0, len);
+      int gi, b, t0, n0, len;
+      decode(tile, gi, b, t0, n0, len);
       if (t0 >= len) continue;                 // padding tile: no MMA work was issued, nothing is stored (rows >= len are undefined)
       const int buf = tile_cnt & 1;
+      const GpGroup& G = gs.g[gi];
+      const bool has_res = G.res != nullptr;
       bool waited = false;
 #pragma unroll 1
       for (int item = half; item < MT * nchunks; item += 2) {
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
 #pragma unroll
           for (int q = 0; q < NG; ++q) {
             rq[q] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok) rq[q] = *(reinterpret_cast<const uint4*>(p.res) + gbase + (size_t)q * Lout);
+            if (ok) rq[q] = *(reinterpret_cast<const uint4*>(G.res) + gbase + (size_t)q * Lout);
           }
         }
         if (!waited) {
@@ -206,10 +212,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * MT * BN + mt * BN + c), 32, v);
         if (ok) {
-          if (p.bias) {
+          if (G.bias) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(G.bias + n) + q);
               v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
             }
           }
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
           if (accm != EV_ACC_STORE) {     // the xs += / xs /= n accumulation of the last layer of a ResBlock (2 launches in 18): loaded late to keep
             uint4 oq[NG];                 // the common path's register footprint small
 #pragma unroll
-            for (int q = 0; q < NG; ++q) oq[q] = *(reinterpret_cast<const uint4*>(p.out) + gbase + (size_t)q * Lout);
+            for (int q = 0; q < NG; ++q) oq[q] = *(reinterpret_cast<const uint4*>(G.out) + gbase + (size_t)q * Lout);
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
               if (BF16) {
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
               o.x = __float_as_uint(v[4 * q]); o.y = __float_as_uint(v[4 * q + 1]);
               o.z = __float_as_uint(v[4 * q + 2]); o.w = __float_as_uint(v[4 * q + 3]);
             }
-            *(reinterpret_cast<uint4*>(p.out) + gbase + (size_t)q * Lout) = o;
+            *(reinterpret_cast<uint4*>(G.out) + gbase + (size_t)q * Lout) = o;
           }
         }
       }
@@ -283,10 +289,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
     const float slope = p.in_slope;
     int a_cnt = 0;
     for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
-      int b, t0, n0, len;
-      decode(tile, b, t0, n0, len);
+      int gi, b, t0, n0, len;
+      decode(tile, gi, b, t0, n0, len);
       if (t0 >= len) continue;
-      const int row0 = t0 - halo;
+      const int span = (gs.g[gi].K - 1) * gs.g[gi].dil;
+      const int rows_a = BM * MT + span;
+      const int row0 = t0 - span / 2;
       for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
         const int s = a_cnt % pl.a_stages;
         const int ngran = min(KB, p.Cin - cb * KB) / CPG;
@@ -367,14 +375,16 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
       asm volatile("griddepcontrol.wait;" ::: "memory");
       int a_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
-        int b, t0, n0, len;
-        decode(tile, b, t0, n0, len);
+        int gi, b, t0, n0, len;
+        decode(tile, gi, b, t0, n0, len);
         if (t0 >= len) continue;
+        const int span = (gs.g[gi].K - 1) * gs.g[gi].dil;
+        const int halo = span / 2, rows_a = BM * MT + span;
         const int r_lo = max(t0 - halo, 0);
         const int r_hi = min(t0 - halo + rows_a, len);      // len <= L: never past the plane
         const uint32_t nbytes = (uint32_t)(r_hi - r_lo) * 16u;
         const uint32_t roff = (uint32_t)(r_lo - (t0 - halo)) * 16u;
-        const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x) + ((size_t)b * gin * p.L + r_lo) * 16;
+        const uint8_t* xb = reinterpret_cast<const uint8_t*>(gs.g[gi].x) + ((size_t)b * gin * p.L + r_lo) * 16;
         for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
           const int s = a_cnt % pl.a_stages;
           const int ngran = min(KB, p.Cin - cb * KB) / CPG;
@@ -394,18 +404,19 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
       // w layout: [plane (hi, lo)][N tile of BNp = min(Cout,128)][tap][Cin/WCPG granules][BNp][16 bytes] (fp32 or bf16 granules)
       const int bnp = p.Cout < 128 ? p.Cout : 128;
       const int win = p.Cin / WCPG;                                  // weight granules along C_in
-      const size_t plane = (size_t)p.K * win * p.Cout * 4;          // 4-byte words per plane
-      const size_t tile_stride = (size_t)p.K * win * bnp * 4;       // 4-byte words per packed N tile
       constexpr int KBGW = KBG * CPG / WCPG;                         // weight granules per pipeline stage
       int b_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
-        int b, t0, n0, len;
-        decode(tile, b, t0, n0, len);
+        int gi, b, t0, n0, len;
+        decode(tile, gi, b, t0, n0, len);
         if (t0 >= len) continue;
-        const float* wt = p.w + (size_t)(n0 / bnp) * tile_stride + (size_t)(n0 % bnp) * 4;
+        const int K = gs.g[gi].K;
+        const size_t plane = (size_t)K * win * p.Cout * 4;          // 4-byte words per plane
+        const size_t tile_stride = (size_t)K * win * bnp * 4;       // 4-byte words per packed N tile
+        const float* wt = gs.g[gi].w + (size_t)(n0 / bnp) * tile_stride + (size_t)(n0 % bnp) * 4;
         for (int cb = 0; cb < n_cb; ++cb) {
           const int ngran = min(KB, p.Cin - cb * KB) / WCPG;          // weight granules of this stage
-          for (int j = 0; j < p.K; ++j, ++b_cnt) {
+          for (int j = 0; j < K; ++j, ++b_cnt) {
             const int sb = b_cnt % pl.b_stages;
             mbar_wait(b_empty(sb), ((b_cnt / pl.b_stages) & 1) ^ 1);
             mbar_expect_tx(b_full(sb), (uint32_t)(BPLANES * ngran * BN * 16));
@@ -434,14 +445,15 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       // bf16x3: the two K granules of one MMA are two slots apart (hi in the even slots, lo in the odd ones), one K step = 4 slots
       const uint64_t a_desc0 = make_desc(0u, X3B ? 2u * a_lbo : a_lbo, 128u), b_desc0 = make_desc(0u, b_lbo, 128u);
-      const uint32_t a_tap = (uint32_t)p.dil * 16u;                    // bytes per tap shift
       const uint32_t a_k8 = (X3B ? 4u : 2u) * a_lbo, b_k8 = 2u * b_lbo;   // bytes per K step
       const uint32_t a_lo_off = X3B ? a_lbo : (uint32_t)pl.a_plane_bytes;
       int a_cnt = 0, b_cnt = 0, tile_cnt = 0;
       for (int tile = blockIdx.x; tile < pl.total_tiles; tile += gridDim.x) {
-        int b, t0, n0, len;
-        decode(tile, b, t0, n0, len);
+        int gi, b, t0, n0, len;
+        decode(tile, gi, b, t0, n0, len);
         if (t0 >= len) continue;
+        const int K = gs.g[gi].K;
+        const uint32_t a_tap = (uint32_t)gs.g[gi].dil * 16u;          // bytes per tap shift
         const int buf = tile_cnt & 1;
         mbar_wait(acc_empty(buf), ((tile_cnt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator set
         tc_fence_after();
@@ -451,7 +463,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
           const int nk8 = min(KB, p.Cin - cb * KB) / (2 * WCPG);  // MMA K steps: two 16-byte operand granules each
           mbar_wait(a_ready(sa), (a_cnt / pl.a_stages) & 1);
           const uint64_t a_hi0 = desc_advance(a_desc0, smem_u32(a_tiles + sa * pl.a_stage_bytes));
-          for (int j = 0; j < p.K; ++j, ++b_cnt) {
+          for (int j = 0; j < K; ++j, ++b_cnt) {
             const int sb = b_cnt % pl.b_stages;
             mbar_wait(b_full(sb), (b_cnt / pl.b_stages) & 1);
             tc_fence_after();
@@ -486,7 +498,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) conv1d_gp_kernel(GpConvParams p
                 }
               }
               umma_commit(b_empty(sb));               // weight stage free once these MMAs have read it
-              if (j == p.K - 1) {
+              if (j == K - 1) {
                 umma_commit(a_empty(sa));             // activation stage free
                 if (cb == n_cb - 1) umma_commit(acc_full(buf));   // accumulators of this tile complete -> epilogue
               }
@@ -687,11 +699,15 @@ static int gp_shape_kbg(const GpConvParams& p, int mode) {
 //   activations HBM -> shared memory -> HBM:        MT * 128 rows * (Cin + 2 Cout) * esize at ~23 B/cycle/SM
 // plus a fixed pipeline fill / drain per tile; the launch takes ceil(tiles / SMs) such tile times.  More accumulators per tile
 // (MT) amortise the weight stream and the halo rows, a narrower N tile fills idle SMs (HiFi-GAN stage 1 at batch 1).
-static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out) {
+// A grouped launch (ng convolutions of one shape, ksum = the sum of their taps, span / kmin as in make_gplan) is planned like one
+// convolution with the mean number of taps and ng times the tiles; kbg must be the members' own (checked by the caller).
+static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out, int ng = 1, int ksum = 0, int span = -1, int kmin = 0, int kbg_forced = 0) {
   EV_TRY(validate_gp(p, mode));
   const int nsm = sm_count();
-  const int kbg = gp_shape_kbg(p, mode);
-  const double kc8 = (double)p.K * p.Cin / 8.0;
+  const int kbg = kbg_forced ? kbg_forced : gp_shape_kbg(p, mode);
+  if (ksum <= 0) ksum = p.K;
+  if (span < 0) span = (p.K - 1) * p.dil;
+  const double kc8 = (double)ksum / ng * p.Cin / 8.0;
   const double n_mma = ((mode == 1 || mode == 3) ? 3.0 : 1.0) * (mode >= 2 ? 0.5 : 1.0) * kc8;     // MMA instructions per accumulator and tile
   const double w_per_n = ((mode == 1 || mode == 3) ? 2.0 : 1.0) * (mode >= 2 ? 16.0 : 32.0) / 42.0;
   const double esize = mode == 2 ? 2.0 : 4.0;
@@ -705,14 +721,14 @@ static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out) {
     if (p.Cout % BN || BN % 32) continue;
     for (int mt = 4; mt >= 1; mt >>= 1) {
       gp::GPlan pl;
-      if (!gp::make_gplan(p, mode, BN, mt, kbg, &pl)) continue;
+      if (!gp::make_gplan(p, mode, BN, mt, kbg, &pl, span, kmin, ng)) continue;
       // per MMA instruction: BN/2 tensor cycles, but both operands come from shared memory (128 B/cycle): (128 + BN) rows x 32 B
       // = 32 + BN/4 cycles -- the binding term below BN = 128 (a 64-wide tile costs 1.5x per FLOP, a 32-wide one 2.5x)
       double c_mma = BN / 2.0;
       if (32.0 + BN / 4.0 > c_mma) c_mma = 32.0 + BN / 4.0;
       const double t_mma = mt * n_mma * c_mma;
       const double t_w = w_per_n * BN * kc8;
-      const double t_hbm = (double)mt * tc::BM * ((double)p.Cin * (mt * tc::BM + (p.K - 1) * p.dil) / (mt * tc::BM) + 2.0 * BN) * esize / 23.0;
+      const double t_hbm = (double)mt * tc::BM * ((double)p.Cin * (mt * tc::BM + span) / (mt * tc::BM) + 2.0 * BN) * esize / 23.0;
       double t = t_mma > t_w ? t_mma : t_w;
       if (t_hbm > t) t = t_hbm;
       const double waves = (double)((pl.total_tiles + nsm - 1) / nsm);
@@ -725,6 +741,11 @@ static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out) {
   return EV_OK;
 }
 
+int gp_solo_tiles(const GpConvParams& p, int mode) {
+  gp::GPlan pl;
+  return plan_gp(p, mode, &pl) == EV_OK ? pl.total_tiles : 0;
+}
+
 int debug_gp_plan(const GpConvParams& p, int mode, int* v) {
   gp::GPlan pl;
   const int rc = plan_gp(p, mode, &pl);
@@ -735,37 +756,92 @@ int debug_gp_plan(const GpConvParams& p, int mode, int* v) {
 }
 
 template <int MODE, int MT, int KBG>
-static int launch_gp_variant(const GpConvParams& p, const gp::GPlan& pl, cudaStream_t st) {
+static int launch_gp_variant(const GpConvParams& p, const gp::GPlan& pl, const GpGroups& gs, cudaStream_t st) {
   static std::atomic<uint64_t> attr_devs{0};
   if (first_use_on_device(attr_devs))
     cudaFuncSetAttribute(gp::conv1d_gp_kernel<MODE, MT, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   const int nsm = sm_count();
   const int grid = pl.total_tiles < nsm ? pl.total_tiles : nsm;
   if (pdl_mode()) {
-    const cudaError_t e = launch_with_pdl(gp::conv1d_gp_kernel<MODE, MT, KBG>, dim3((unsigned)grid), dim3(gp::GP_THREADS), (size_t)pl.smem_total, st, p, pl);
+    const cudaError_t e = launch_with_pdl(gp::conv1d_gp_kernel<MODE, MT, KBG>, dim3((unsigned)grid), dim3(gp::GP_THREADS), (size_t)pl.smem_total, st, p, pl, gs);
     if (e != cudaSuccess) { set_error("conv1d_gp_kernel (PDL launch): %s", cudaGetErrorString(e)); return EV_ECUDA; }
     count_launch();
     return EV_OK;
   }
-  gp::conv1d_gp_kernel<MODE, MT, KBG><<<grid, gp::GP_THREADS, pl.smem_total, st>>>(p, pl);
+  gp::conv1d_gp_kernel<MODE, MT, KBG><<<grid, gp::GP_THREADS, pl.smem_total, st>>>(p, pl, gs);
   EV_CUDA_LAUNCH_CHECK("conv1d_gp_kernel");
   return EV_OK;
 }
 
 template <int MODE, int KBG>
-static int launch_gp_mt(const GpConvParams& p, const gp::GPlan& pl, cudaStream_t st) {
-  if (pl.mt == 4) return launch_gp_variant<MODE, 4, KBG>(p, pl, st);
-  if (pl.mt == 2) return launch_gp_variant<MODE, 2, KBG>(p, pl, st);
-  return launch_gp_variant<MODE, 1, KBG>(p, pl, st);
+static int launch_gp_mt(const GpConvParams& p, const gp::GPlan& pl, const GpGroups& gs, cudaStream_t st) {
+  if (pl.mt == 4) return launch_gp_variant<MODE, 4, KBG>(p, pl, gs, st);
+  if (pl.mt == 2) return launch_gp_variant<MODE, 2, KBG>(p, pl, gs, st);
+  return launch_gp_variant<MODE, 1, KBG>(p, pl, gs, st);
+}
+
+static int dispatch_gp(const GpConvParams& p, const gp::GPlan& pl, const GpGroups& gs, int mode, cudaStream_t st) {
+  if (mode == 1) return launch_gp_mt<1, 4>(p, pl, gs, st);
+  if (mode == 3) return pl.kbg == 8 ? launch_gp_mt<3, 8>(p, pl, gs, st) : launch_gp_mt<3, 4>(p, pl, gs, st);
+  if (mode == 2) return pl.kbg == 8 ? launch_gp_mt<2, 8>(p, pl, gs, st) : launch_gp_mt<2, 4>(p, pl, gs, st);
+  return pl.kbg == 8 ? launch_gp_mt<0, 8>(p, pl, gs, st) : launch_gp_mt<0, 4>(p, pl, gs, st);
 }
 
 int launch_conv1d_gp(const GpConvParams& p, int mode, cudaStream_t st) {
   gp::GPlan pl;
   EV_TRY(plan_gp(p, mode, &pl));
-  if (mode == 1) return launch_gp_mt<1, 4>(p, pl, st);
-  if (mode == 3) return pl.kbg == 8 ? launch_gp_mt<3, 8>(p, pl, st) : launch_gp_mt<3, 4>(p, pl, st);
-  if (mode == 2) return pl.kbg == 8 ? launch_gp_mt<2, 8>(p, pl, st) : launch_gp_mt<2, 4>(p, pl, st);
-  return pl.kbg == 8 ? launch_gp_mt<0, 8>(p, pl, st) : launch_gp_mt<0, 4>(p, pl, st);
+  GpGroups gs{};
+  gs.ng = 1;
+  gs.g[0] = GpGroup{p.x, p.w, p.bias, p.res, p.out, p.K, p.dil};
+  return dispatch_gp(p, pl, gs, mode, st);
+}
+
+// ---- grouped launch ------------------------------------------------------------------------------------------------------
+static bool group_shapes_match(const GpConvParams* ps, int n, int mode, int* kbg) {
+  if (n < 1 || n > 3) return false;
+  const GpConvParams& a = ps[0];
+  int kb = 0;
+  for (int i = 0; i < n; ++i) {
+    const GpConvParams& q = ps[i];
+    if (q.B != a.B || q.L != a.L || q.Cin != a.Cin || q.Cout != a.Cout || q.rate != 1 || q.lens != a.lens || q.lens_mul != a.lens_mul ||
+        q.in_act != a.in_act || q.in_slope != a.in_slope || q.acc != EV_ACC_STORE || !q.x || !q.w || !q.out)
+      return false;
+    if (q.K < 1 || !(q.K & 1) || q.dil < 1) return false;
+    for (int j = 0; j < i; ++j)
+      if (ps[j].out == q.out) return false;                 // every member writes its own tensor
+    const int k = gp_shape_kbg(q, mode);                    // the reduction order of each member must be its own launch's
+    if (i == 0) kb = k;
+    else if (k != kb) return false;
+  }
+  *kbg = kb;
+  return true;
+}
+bool gp_group_supported(const GpConvParams* ps, int n, int mode) {
+  int kbg = 0;
+  if (mode < 0 || mode > 3 || !group_shapes_match(ps, n, mode, &kbg)) return false;
+  return validate_gp(ps[0], mode) == EV_OK;
+}
+int launch_conv1d_gp_group(const GpConvParams* ps, int n, int mode, cudaStream_t st) {
+  int kbg = 0;
+  EV_CHECK_ARG(ps && group_shapes_match(ps, n, mode, &kbg), "conv1d_gp group: the %d convolutions do not share a launch shape", n);
+  // heaviest member first: with static round-robin tiles the CTAs that take a second (third) tile then take a light one
+  int order[3] = {0, 1, 2};
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+      if (ps[order[j]].K > ps[order[i]].K) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+  GpGroups gs{};
+  gs.ng = n;
+  int ksum = 0, span = 0, kmin = 1 << 30;
+  for (int i = 0; i < n; ++i) {
+    const GpConvParams& q = ps[order[i]];
+    gs.g[i] = GpGroup{q.x, q.w, q.bias, q.res, q.out, q.K, q.dil};
+    ksum += q.K;
+    span = (q.K - 1) * q.dil > span ? (q.K - 1) * q.dil : span;
+    kmin = q.K < kmin ? q.K : kmin;
+  }
+  gp::GPlan pl;
+  EV_TRY(plan_gp(ps[0], mode, &pl, n, ksum, span, kmin, kbg));
+  return dispatch_gp(ps[0], pl, gs, mode, st);
 }
 
 // Load every instantiation's code now (CUDA loads kernels lazily, at their first launch: tens of milliseconds for a kernel of this

@@ -169,6 +169,7 @@ struct VocBufs {
   float *X, *ACC, *part;
   size_t part_cap;
   float *Tm, *R1, *R2;   // ResBlock chain scratch
+  float *G0, *G1, *G2;   // small batches only: the three parallel ResBlocks of a stage advance together (grouped launches)
 };
 
 static void carve_phase1(const ev_ctx* c, Carver& cv, int B, int T, Phase1Bufs* o) {
@@ -198,6 +199,12 @@ static void carve_phase2(const ev_ctx* c, Carver& cv, int B, int F, Phase2Bufs* 
   o->part_cap = 8 * n * 4 * H;
   o->part = cv.take(o->part_cap);
 }
+// Grouped launches (one kernel for the same-index convolutions of the three parallel ResBlocks of a stage) need three more stage-sized
+// buffers; they only pay while one convolution has too few tiles for the machine, i.e. up to a few thousand batch-frames.
+static inline bool voc_group_frames(int B, int F) {
+  static const int v = [] { const char* e = getenv("EV_VOC_GROUP"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v == 1 && (long long)B * F <= 2400;
+}
 static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
   const size_t n = (size_t)B * F * (size_t)c->max_stage_width;
   o->X = cv.take(n);
@@ -207,6 +214,8 @@ static void carve_voc(const ev_ctx* c, Carver& cv, int B, int F, VocBufs* o) {
   o->Tm = cv.take(n);
   o->R1 = cv.take(n);
   o->R2 = cv.take(n);
+  o->G0 = o->G1 = o->G2 = nullptr;
+  if (voc_group_frames(B, F)) { o->G0 = cv.take(n); o->G1 = cv.take(n); o->G2 = cv.take(n); }
 }
 
 static int find(ev_ctx* c, const std::string& name, uint64_t expect, const float** out) {
@@ -432,15 +441,22 @@ static inline bool voc_bf16x3_enabled() {
   static const int v = [] { const char* e = getenv("EV_VOC_FP32"); return (e && e[0] == 't') ? 0 : 1; }();
   return v == 1;
 }
-static int conv_gp(int mode, const float* w_tc, const float* w_h, const float* w_x2, const void* x, const float* bias, const void* res, void* out,
-                   int B, int L, int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act, float in_slope, int acc,
-                   float div, cudaStream_t st) {
-  GpConvParams p;
+static int gp_params(int mode, const float* w_tc, const float* w_h, const float* w_x2, const void* x, const float* bias, const void* res, void* out,
+                     int B, int L, int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act, float in_slope, int acc,
+                     float div, GpConvParams* o) {      // returns the kernel mode
+  GpConvParams& p = *o;
   const bool x3b = mode == 3 && w_x2 && voc_bf16x3_enabled();
   p.x = x; p.w = x3b ? w_x2 : ((mode == 2) ? w_h : w_tc); p.bias = bias; p.res = res; p.out = out;
   p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.rate = rate;
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope; p.acc = acc; p.div = div;
-  return launch_conv1d_gp(p, x3b ? 3 : (mode == 3 ? 1 : (mode == 2 ? 2 : 0)), st);
+  return x3b ? 3 : (mode == 3 ? 1 : (mode == 2 ? 2 : 0));
+}
+static int conv_gp(int mode, const float* w_tc, const float* w_h, const float* w_x2, const void* x, const float* bias, const void* res, void* out,
+                   int B, int L, int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act, float in_slope, int acc,
+                   float div, cudaStream_t st) {
+  GpConvParams p;
+  const int gm = gp_params(mode, w_tc, w_h, w_x2, x, bias, res, out, B, L, Cin, Cout, K, dil, rate, lens, lens_mul, in_act, in_slope, acc, div, &p);
+  return launch_conv1d_gp(p, gm, st);
 }
 
 // One ResBlock layer through the fused kernel (resblock_gp.cu) where it takes the shape (C <= 128); EV_FUSE_RES=0 keeps two launches.
@@ -449,7 +465,7 @@ static inline bool fuse_res_enabled() {
   return v == 1;
 }
 static bool try_gp_pair(int mode, const ConvW& c1, const ConvW& c2, const void* src, void* dst, int B, int L, int C, const int32_t* lens, int lens_mul,
-                        int acc, float div, cudaStream_t st, int* rc) {
+                        int acc, float div, cudaStream_t st, int* rc, bool dry_run = false) {
   if (!fuse_res_enabled() || c1.K != c2.K || c2.dil != 1) return false;
   // Fused and unfused are bitwise equal, so the choice may depend on the batch: measured (profiles/r02_fused_vs_unfused.jsonl) the fused
   // layer wins 1.1-1.8x on the HBM-bound shapes (k <= 7, or 32 channels) and wherever the launch count matters (batch 1), and loses
@@ -463,7 +479,66 @@ static bool try_gp_pair(int mode, const ConvW& c1, const ConvW& c2, const void* 
   p.w2 = x3b ? c2.w_x2 : (mode == 2 ? c2.w_h : c2.w_tc);
   p.B = B; p.L = L; p.C = C; p.K = c1.K; p.dil = c1.dil; p.lens = lens; p.lens_mul = lens_mul; p.slope = 0.1f; p.acc = acc; p.div = div;
   if (!p.w1 || !p.w2 || !gp_pair_supported(p, gm)) return false;
-  *rc = launch_gp_pair(p, gm, st);
+  if (!dry_run) *rc = launch_gp_pair(p, gm, st);
+  return true;
+}
+
+// One HiFi-GAN stage's ResBlocks (hifigan/models.py:120-126) with the three parallel blocks advancing together: the same-index
+// convolutions of the blocks (different taps / dilations / weights, one shape) are ONE launch.  Used while a single convolution has
+// fewer than two waves of tiles (batch 1: 68 / 135 tiles on 148 SMs); every tile is computed as in the ungrouped launches, so the
+// result is bitwise the same.  The last c2 of each block accumulates into xs in block order (three plain launches).
+// Returns false (nothing launched) when the stage does not qualify.
+static bool try_grouped_stage(ev_ctx* ctx, const VocBufs& v, int mode, size_t rb0, int B, int L, int C, const int32_t* lens, int mul, cudaStream_t st, int* rc) {
+  const ev_config& g = ctx->cfg;
+  const int J = g.n_resk, D = g.n_dil;
+  if (!v.G0 || J < 2 || J > 3 || D < 1) return false;
+  void* T[3] = {v.Tm, v.G0, v.G1};
+  void* Y[3] = {v.R1, v.R2, v.G2};
+  int frc = EV_OK;
+  // qualify: no layer of the stage takes the fused-pair kernel, every step's members can share a launch, and one member alone is small
+  GpConvParams ps[3];
+  int gm = 0;
+  for (int l = 0; l < D; ++l) {
+    for (int j = 0; j < J; ++j) {
+      const ConvW& c1 = ctx->rb_c1[rb0 + (size_t)j * D + l];
+      const ConvW& c2 = ctx->rb_c2[rb0 + (size_t)j * D + l];
+      if (try_gp_pair(mode, c1, c2, v.X, Y[j], B, L, C, lens, mul, EV_ACC_STORE, 1.f, st, &frc, true)) return false;
+      gm = gp_params(mode, c1.w_tc, c1.w_h, c1.w_x2, v.X, c1.b, nullptr, T[j], B, L, C, C, c1.K, c1.dil, 1, lens, mul, EV_ACT_LRELU, 0.1f, EV_ACC_STORE, 1.f, &ps[j]);
+      if (!ps[j].w) return false;
+    }
+    if (!gp_group_supported(ps, J, gm)) return false;
+    for (int j = 0; j < J; ++j) {
+      const ConvW& c2 = ctx->rb_c2[rb0 + (size_t)j * D + l];
+      gp_params(mode, c2.w_tc, c2.w_h, c2.w_x2, T[j], c2.b, v.X, Y[j], B, L, C, C, c2.K, 1, 1, lens, mul, EV_ACT_LRELU, 0.1f, EV_ACC_STORE, 1.f, &ps[j]);
+      if (!ps[j].w) return false;
+    }
+    if (!gp_group_supported(ps, J, gm)) return false;
+  }
+  if (gp_solo_tiles(ps[0], gm) >= 2 * sm_count()) return false;
+  *rc = EV_OK;
+  for (int l = 0; l < D && *rc == EV_OK; ++l) {
+    const bool last = (l == D - 1);
+    for (int j = 0; j < J; ++j) {      // xt_j = c1_j(lrelu(x_j))
+      const ConvW& c1 = ctx->rb_c1[rb0 + (size_t)j * D + l];
+      gp_params(mode, c1.w_tc, c1.w_h, c1.w_x2, l == 0 ? (const void*)v.X : Y[j], c1.b, nullptr, T[j], B, L, C, C, c1.K, c1.dil, 1, lens, mul, EV_ACT_LRELU, 0.1f,
+                EV_ACC_STORE, 1.f, &ps[j]);
+    }
+    *rc = launch_conv1d_gp_group(ps, J, gm, st);
+    if (*rc != EV_OK) break;
+    for (int j = 0; j < J; ++j) {      // x_j = c2_j(lrelu(xt_j)) + x_j  (in place from the second layer on: a thread reads and writes its own elements)
+      const ConvW& c2 = ctx->rb_c2[rb0 + (size_t)j * D + l];
+      const void* res = l == 0 ? (const void*)v.X : Y[j];
+      int acc = EV_ACC_STORE;
+      if (last && j > 0) acc = (j == J - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;       // xs += ...; x = xs / n
+      gp_params(mode, c2.w_tc, c2.w_h, c2.w_x2, T[j], c2.b, res, last ? (void*)v.ACC : Y[j], B, L, C, C, c2.K, 1, 1, lens, mul, EV_ACT_LRELU, 0.1f, acc,
+                (float)J, &ps[j]);
+    }
+    if (!last) {
+      *rc = launch_conv1d_gp_group(ps, J, gm, st);
+    } else {
+      for (int j = 0; j < J && *rc == EV_OK; ++j) *rc = launch_conv1d_gp(ps[j], gm, st);
+    }
+  }
   return true;
 }
 
@@ -763,6 +838,12 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
                      EV_ACC_STORE, 1.f, st));
       L *= u.rate; mul *= u.rate;
       const int C = u.cout;
+      int grc = EV_OK;
+      if (try_grouped_stage(ctx, v, mode, rb, B, L, C, mel_lens, mul, st, &grc)) {
+        EV_TRY(grc);
+        rb += (size_t)g.n_resk * g.n_dil;
+        continue;
+      }
       for (int j = 0; j < g.n_resk; ++j) {
         const float* src = v.X;
         for (int l = 0; l < g.n_dil; ++l, ++rb) {
@@ -897,6 +978,22 @@ int ev_op_conv1d_gp(const void* x, const float* w, int mode, const float* bias, 
   p.x = x; p.w = w; p.bias = bias; p.res = res; p.out = out; p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.rate = rate;
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope; p.acc = acc; p.div = div;
   return launch_conv1d_gp(p, mode, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_conv1d_gp_group(int n, const void* const* x, const float* const* w, int mode, const float* const* bias, const void* const* res, void* const* out,
+                          const int* K, const int* dil, int B, int L, int Cin, int Cout, const int32_t* lens, int lens_mul, int in_act, float in_slope,
+                          void* stream) {
+  EV_CHECK_ARG(n >= 1 && n <= 3 && x && w && out && K && dil, "ev_op_conv1d_gp_group: 1..3 convolutions, non-null tables");
+  GpConvParams ps[3];
+  for (int i = 0; i < n; ++i) {
+    GpConvParams& p = ps[i];
+    EV_CHECK_ARG(x[i] && w[i] && out[i], "ev_op_conv1d_gp_group: null tensor in member %d", i);
+    p.x = x[i]; p.w = w[i]; p.bias = bias ? bias[i] : nullptr; p.res = res ? res[i] : nullptr; p.out = out[i];
+    p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K[i]; p.dil = dil[i]; p.rate = 1;
+    p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope; p.acc = EV_ACC_STORE; p.div = 1.f;
+  }
+  EV_TRY(use_device_of(x[0]));
+  return launch_conv1d_gp_group(ps, n, mode, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ev_op_resblock_gp(const void* x, const float* w1, const float* b1, const float* w2, const float* b2, int mode, void* out, int B, int L, int C, int K,

@@ -150,7 +150,27 @@ struct GpConvParams {
   int acc;             // EV_ACC_*
   float div;
 };
+// What differs between the (up to three) convolutions of one grouped launch; the kernel's view of every launch (a single
+// convolution is a group of one, filled from the scalar fields above).
+struct GpGroup {
+  const void* x;
+  const float* w;
+  const float* bias;
+  const void* res;
+  void* out;
+  int K, dil;
+};
+struct GpGroups {
+  int ng;
+  GpGroup g[3];
+};
 int launch_conv1d_gp(const GpConvParams& p, int mode, cudaStream_t st);    // mode 0: tf32, 1: 3xTF32 (fp32 activations); 2: bf16 activations
+// n <= 3 convolutions that share B, L, Cin, Cout, lens, the input activation and rate == 1, acc == STORE, as ONE launch (the three
+// parallel ResBlocks of a HiFi-GAN stage at small batch, where a single convolution has too few tiles for the machine).  Every tile is
+// computed exactly as in the convolution's own launch: bitwise equal.  EV_EINVAL (nothing launched) if the shapes cannot share a launch.
+int launch_conv1d_gp_group(const GpConvParams* ps, int n, int mode, cudaStream_t st);
+bool gp_group_supported(const GpConvParams* ps, int n, int mode);
+int gp_solo_tiles(const GpConvParams& p, int mode);       // tiles of the convolution's own launch (0 if it cannot be planned)
 int debug_gp_plan(const GpConvParams& p, int mode, int* v11);
 // fp32 in[b*sb + t*st + c*sc] -> GP (fp32, or bf16 when bf16 != 0)
 int launch_to_gp(const float* in, long long sb, long long st_, long long sc, void* out, int B, int L, int C, int bf16, cudaStream_t st);

@@ -200,6 +200,13 @@ EV_API int ev_debug_tc_plan(int B, int L, int Cin, int Cout, int K, int dil, int
 EV_API int ev_op_conv1d_gp(const void* x, const float* w, int mode, const float* bias, const void* res, void* out, int B, int L,
                            int Cin, int Cout, int K, int dil, int rate, const int32_t* lens, int lens_mul, int in_act,
                            float in_slope, int acc, float div, void* stream);
+/* n <= 3 convolutions of ONE shape (B, L, Cin -> Cout, rate 1, plain store) but different taps / dilations / weights / tensors as ONE
+ * launch: the same-index convolutions of the three parallel ResBlocks of a HiFi-GAN stage (hifigan/models.py:120-126), which at small
+ * batch have too few tiles each to fill the machine.  Tables of n entries; bias / res may be null (or hold nulls).  Every tile is
+ * computed as in the member's own ev_op_conv1d_gp launch: bitwise equal.  EV_EINVAL if the members cannot share a launch. */
+EV_API int ev_op_conv1d_gp_group(int n, const void* const* x, const float* const* w, int mode, const float* const* bias,
+                                 const void* const* res, void* const* out, const int* K, const int* dil, int B, int L, int Cin,
+                                 int Cout, const int32_t* lens, int lens_mul, int in_act, float in_slope, void* stream);
 /* One ResBlock1 layer (hifigan/models.py:50-57) as ONE kernel on granule-planar activations (csrc/resblock_gp.cu):
  * out = [acc]( x + c2(lrelu(c1(lrelu(x), dil)), 1) ), C -> C channels (C in {32, 64, 128}), slope 0.1, both weights in the layout of
  * `mode` (as ev_op_conv1d_gp).  Bitwise equal to the two ev_op_conv1d_gp launches it replaces; EV_EINVAL for shapes it does not take

@@ -230,6 +230,7 @@ def sim_gp(seed, tiles, n_cb, K, a_stages, b_stages, n_work_items=2, skip_idle_w
     work items (MT * BN/32) per lane quadrant; warp `half` of a quadrant takes items half, half+2, ...: with one item the
     second warp of each quadrant has nothing to read but must still follow the accumulator phases."""
     sim = Sim(seed)
+    taps = (lambda ti: K[ti]) if isinstance(K, (list, tuple)) else (lambda ti: K)     # grouped launch: the taps differ from tile to tile
     a_full = [Bar(1) for _ in range(a_stages)]
     a_ready = [Bar(NTW) for _ in range(a_stages)]           # one arrival per transform warp here (the kernel: per thread)
     a_empty = [Bar(1) for _ in range(a_stages)]
@@ -270,7 +271,7 @@ def sim_gp(seed, tiles, n_cb, K, a_stages, b_stages, n_work_items=2, skip_idle_w
             if not active:
                 continue
             for cb in range(n_cb):
-                for j in range(K):
+                for j in range(taps(ti)):
                     sb = b_cnt % b_stages
                     yield ("wait", b_empty[sb], ((b_cnt // b_stages) & 1) ^ 1)
                     yield ("write", ("B", sb), (ti, cb, j))
@@ -287,7 +288,7 @@ def sim_gp(seed, tiles, n_cb, K, a_stages, b_stages, n_work_items=2, skip_idle_w
             for cb in range(n_cb):
                 sa = a_cnt % a_stages
                 yield ("wait", a_ready[sa], (a_cnt // a_stages) & 1)
-                for j in range(K):
+                for j in range(taps(ti)):
                     sb = b_cnt % b_stages
                     yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
                     yield ("mma_read", ("A", sa), ("op", ti, cb))
@@ -364,6 +365,18 @@ def test_gp_summation_order_parameters_do_not_depend_on_batch_or_length(lib):
         for mode in (0, 1, 2):
             kbgs = {_gp_plan(lib, B, L, Cin, Cout, K, dil, rate, mode)["KBG"] for (B, L) in [(1, 64), (1, 5000), (3, 70000), (32, 300000)]}
             assert len(kbgs) == 1, (Cin, Cout, K, dil, mode, kbgs)
+
+
+def test_gp_grouped_launch_protocol():
+    """A grouped launch (conv1d_gp_group: the same-index convolutions of three parallel ResBlocks in one kernel) changes the number of
+    taps -- weight stages per activation stage -- from tile to tile; the weight loader and the MMA issuer derive it from the same
+    tile decode, so the rings stay in step for any mix and any ring depth."""
+    for seed in range(30):
+        rng = random.Random(seed)
+        n = rng.randint(2, 7)
+        tiles = [rng.random() > 0.15 for _ in range(n)]
+        taps = [rng.choice((3, 7, 11)) for _ in range(n)]
+        sim_gp(seed, tiles, rng.randint(1, 4), taps, rng.randint(2, 4), rng.randint(2, 8), n_work_items=rng.choice((1, 2, 4)))
 
 
 def test_gp_protocol_model_is_sensitive():

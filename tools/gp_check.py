@@ -178,6 +178,57 @@ def main():
                 row["ok"] = False
             ok_all = ok_all and row["ok"]
             print(json.dumps(row), flush=True)
+    # ---- grouped launch (up to three convolutions of one shape in one kernel) against each member's own launch: BITWISE ----
+    import ctypes
+    GROUPS = [
+        # B, L, C, Ks, dils, use_res (in place: out == res), ragged
+        (1, 4296, 256, (3, 7, 11), (1, 3, 5), 0, 0),      # HiFi-GAN stage 1 at batch 1: c1 of the three ResBlocks
+        (1, 4296, 256, (11, 3, 7), (1, 1, 1), 1, 0),      # ... c2, residual in place, members not sorted by taps
+        (2, 3000, 128, (3, 7, 11), (5, 5, 5), 1, 1),
+        (3, 900, 64, (7, 3), (3, 1), 0, 1),               # two members
+        (1, 34368, 128, (3, 7, 11), (3, 3, 3), 0, 0),     # stage 2 at batch 1: 3 x 135 tiles
+    ]
+    for case in (GROUPS[:2] if quick else GROUPS):
+        B, L, C, Ks, dils, use_res, ragged = case
+        n = len(Ks)
+        g = torch.Generator().manual_seed(B + L + C + sum(Ks))
+        xs = [torch.randn(B, L, C, generator=g) for _ in range(n)]
+        ws = [torch.randn(K, C, C, generator=g) / math.sqrt(C * K) for K in Ks]
+        bs = [torch.randn(C, generator=g).to(dev) for _ in range(n)]
+        prev = [torch.randn(B, L, C, generator=g) for _ in range(n)]
+        lens = torch.tensor([max(1, L // 2 - 5 * b) for b in range(B)], dtype=torch.int32, device=dev) if ragged else None
+        lens_mul = 2 if ragged else 1
+        valid = [L] * B if lens is None else [min(L, int(v) * lens_mul) for v in lens.tolist()]
+        for mode in (1, 0, 2, 3):
+            bf = mode == 2
+            pack = packing.to_tc16x2_layout if mode == 3 else (packing.to_tc16_layout if bf else packing.to_tc_layout)
+            wd = [pack(w).to(dev) for w in ws]
+            xg = [layout.to_gp(x, bf).to(dev) for x in xs]
+            solo = [layout.to_gp(q, bf).to(dev) for q in prev]
+            grp = [layout.to_gp(q, bf).to(dev) for q in prev]
+            for i in range(n):       # with use_res the output tensor is also the residual (the engine's in-place x_j += c2(...))
+                _abi.check(lib.ev_op_conv1d_gp(ptr(xg[i]), ptr(wd[i]), mode, ptr(bs[i]), ptr(solo[i]) if use_res else None, ptr(solo[i]), B, L, C, C, Ks[i], dils[i], 1,
+                                               ptr(lens), lens_mul, _abi.ACT_LRELU, 0.1, _abi.ACC_STORE, 1.0, st))
+            VP, FP = ctypes.c_void_p * n, ctypes.c_void_p * n
+            IA = ctypes.c_int * n
+            rc = lib.ev_op_conv1d_gp_group(n, VP(*[ptr(t) for t in xg]), FP(*[ptr(t) for t in wd]), mode, FP(*[ptr(t) for t in bs]),
+                                           VP(*[ptr(t) for t in grp]) if use_res else None, VP(*[ptr(t) for t in grp]), IA(*Ks), IA(*dils), B, L, C, C,
+                                           ptr(lens), lens_mul, _abi.ACT_LRELU, 0.1, st)
+            torch.cuda.synchronize()
+            row = {"group": [B, L, C, list(Ks), list(dils), use_res, ragged], "mode": mode, "rc": rc}
+            if rc == 0:
+                eq, pad, fin = True, True, True
+                for i in range(n):
+                    a, r = layout.from_gp(grp[i].cpu()), layout.from_gp(solo[i].cpu())
+                    pg = layout.from_gp(layout.to_gp(prev[i], bf))
+                    eq = eq and all(torch.equal(a[b, :valid[b]], r[b, :valid[b]]) for b in range(B))
+                    fin = fin and all(bool(torch.isfinite(a[b, :valid[b]]).all()) for b in range(B))
+                    pad = pad and all(torch.equal(a[b, valid[b]:], pg[b, valid[b]:]) for b in range(B))
+                row.update(bitwise_vs_own_launches=eq, finite=fin, pad_rows_untouched=pad, ok=bool(eq and fin and pad))
+            else:
+                row.update(err=lib.ev_last_error().decode(), ok=False)
+            ok_all = ok_all and row["ok"]
+            print(json.dumps(row), flush=True)
     # boundary kernels
     g = torch.Generator().manual_seed(5)
     mel = torch.randn(2, 80, 37, generator=g)
