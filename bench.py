@@ -275,47 +275,65 @@ def timed_forwards(fn, n, flush):
     return [a.elapsed_time(b) * 1e-3 for a, b in ev], outs
 
 
-def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
-    """The single most expensive layer shape of the step: the k=11 ResBlock convolutions of HiFi-GAN stage 2 (C=128,
-    L=64*F; 22% of all FLOPs), through the kernel and mode the engine runs it in (conv1d_gp: bf16x3 in the "fp32" precision,
-    tf32, or bf16 with bf16 activations).  Timed live with CUDA events on the launching stream, L2 flushed before every launch."""
+def dominant_launch(lib, dev, frames, precision="fp32"):
+    """The most expensive launch of the batch-1 step, as the engine issues it: the k = 3 / 7 / 11 convolutions of the three parallel
+    ResBlocks of HiFi-GAN stage 2 (C = 128, L = 64 F; about 42 % of the step's FLOPs sit in this stage) as ONE grouped launch (conv1d_gp: bf16x3
+    in the "fp32" precision, tf32, or bf16 with bf16 activations), here the c2 step with its residual.  Returns the launch closure
+    and its algorithmic work; tools/profile_dominant.py runs the same closure under ncu."""
+    import ctypes
     from emotivoice_b200 import _abi, layout, packing
-    C, K, L = 128, 11, 64 * frames
+    C, Ks, L = 128, (11, 7, 3), 64 * frames
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, L, C, generator=g)
-    w = torch.randn(K, C, C, generator=g) / math.sqrt(C * K)
-    b = torch.randn(C, generator=g).to(dev)
-    res = torch.randn(1, L, C, generator=g)
+    xs = [torch.randn(1, L, C, generator=g) for _ in Ks]
+    ws = [torch.randn(K, C, C, generator=g) / math.sqrt(C * K) for K in Ks]
+    bs = [torch.randn(C, generator=g).to(dev) for _ in Ks]
+    res = [torch.randn(1, L, C, generator=g) for _ in Ks]
     st = torch.cuda.current_stream().cuda_stream
-    times = []
+    keep = []
     if precision == "fp32_ffma":
-        xd, wd, rd, out = x.to(dev), w.to(dev), res.to(dev), torch.empty(1, L, C, device=dev)
-        call = lambda: lib.ev_op_conv1d(xd.data_ptr(), wd.data_ptr(), b.data_ptr(), 0, rd.data_ptr(), out.data_ptr(), 1, L, C, C, K, 1, None, 1,
+        K = 11
+        xd, wd, rd, out = xs[0].to(dev), ws[0].to(dev), res[0].to(dev), torch.empty(1, L, C, device=dev)
+        keep = [xd, wd, rd, out, bs]
+        call = lambda: lib.ev_op_conv1d(xd.data_ptr(), wd.data_ptr(), bs[0].data_ptr(), 0, rd.data_ptr(), out.data_ptr(), 1, L, C, C, K, 1, None, 1,
                                         _abi.ACT_LRELU, 0.1, _abi.ACT_NONE, _abi.ACC_STORE, 1.0, st)
-        kname, esize, mma_mult, rate = "conv1d_tm (fp32 FFMA)", 4, 1, None
-    else:
-        gmode = {"fp32": 3, "tf32": 0, "bf16": 2}[precision]
-        bf = precision == "bf16"
-        wd = (packing.to_tc16x2_layout(w) if gmode == 3 else (packing.to_tc16_layout(w) if bf else packing.to_tc_layout(w))).to(dev)
-        xd, rd = layout.to_gp(x, bf).to(dev), layout.to_gp(res, bf).to(dev)
-        out = torch.empty_like(xd)
-        call = lambda: lib.ev_op_conv1d_gp(xd.data_ptr(), wd.data_ptr(), gmode, b.data_ptr(), rd.data_ptr(), out.data_ptr(), 1, L, C, C, K, 1, 1, None, 1,
-                                           _abi.ACT_LRELU, 0.1, _abi.ACC_STORE, 1.0, st)
-        kname = "conv1d_gp " + {3: "bf16x3 (fp32 activations, 3 bf16 MMAs per K=16)", 0: "tf32", 2: "bf16 (bf16 activations)"}[gmode]
-        esize, mma_mult, rate = (2 if bf else 4), (3 if gmode == 3 else 1), ("tf32 = half the bf16 rate" if gmode == 0 else "bf16 rate")
+        return dict(call=call, keep=keep, kname="conv1d_tm (fp32 FFMA), C=128 k=11 L=%d" % L, flops=2.0 * L * C * C * K,
+                    alg_bytes=4.0 * (L * C * 3) + 4.0 * K * C * C, mma_mult=1, rate=None, L=L)
+    gmode = {"fp32": 3, "tf32": 0, "bf16": 2}[precision]
+    bf = precision == "bf16"
+    pack = packing.to_tc16x2_layout if gmode == 3 else (packing.to_tc16_layout if bf else packing.to_tc_layout)
+    wd = [pack(w).to(dev) for w in ws]
+    xd = [layout.to_gp(x, bf).to(dev) for x in xs]
+    od = [layout.to_gp(r, bf).to(dev) for r in res]          # residual and output (in place, as the engine's x_j += c2_j(...))
+    n = len(Ks)
+    VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
+    tabs = dict(x=VP(*[t.data_ptr() for t in xd]), w=VP(*[t.data_ptr() for t in wd]), b=VP(*[t.data_ptr() for t in bs]),
+                o=VP(*[t.data_ptr() for t in od]), K=IA(*Ks), d=IA(*([1] * n)))
+    keep = [wd, xd, od, bs, tabs]
+    call = lambda: lib.ev_op_conv1d_gp_group(n, tabs["x"], tabs["w"], gmode, tabs["b"], tabs["o"], tabs["o"], tabs["K"], tabs["d"], 1, L, C, C, None, 1,
+                                             _abi.ACT_LRELU, 0.1, st)
+    esize = 2 if bf else 4
+    kname = "conv1d_gp grouped launch (3 ResBlock convolutions k=11,7,3; %s), C=128 L=%d" % (
+        {3: "bf16x3: fp32 activations, 3 bf16 MMAs per K=16", 0: "tf32", 2: "bf16 activations"}[gmode], L)
+    return dict(call=call, keep=keep, kname=kname, flops=2.0 * L * C * C * sum(Ks), alg_bytes=float(esize) * (L * C * 3) * n + 4.0 * sum(Ks) * C * C,
+                mma_mult=3 if gmode == 3 else 1, rate="tf32 = half the bf16 rate" if gmode == 0 else "bf16 rate", L=L)
+
+
+def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
+    """`roofline` of the bench line: dominant_launch() timed live with CUDA events on the launching stream, L2 flushed before every launch."""
+    from emotivoice_b200 import _abi
+    d = dominant_launch(lib, dev, frames, precision)
+    times = []
     for i in range(13):
         flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _abi.check(call())
+        _abi.check(d["call"]())
         e1.record()
         e1.synchronize()
         if i >= 3:
             times.append(e0.elapsed_time(e1) * 1e-3)
     t = statistics.mean(times)
-    flops = 2.0 * L * C * C * K
-    alg_bytes = float(esize) * (L * C * 3) + 4.0 * K * C * C
-    achieved = flops / t / 1e12
+    achieved = d["flops"] / t / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes/launch from the committed ncu --set full capture
     if os.path.exists(tpath):
@@ -323,14 +341,14 @@ def dominant_kernel_roofline(lib, dev, frames, peaks, flush, precision="fp32"):
             traffic = json.load(open(tpath)).get(precision, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    exec_frac = mma_mult * (2 if precision == "tf32" else 1) * achieved / peaks["bf16_tflops"]
+    exec_frac = d["mma_mult"] * (2 if precision == "tf32" else 1) * achieved / peaks["bf16_tflops"]
     roof = {"bound": "tensor", "achieved": _r(achieved), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-            "kernel": "%s, C=128 k=11 L=%d" % (kname, L), "ms": _r(t * 1e3),
+            "kernel": d["kname"], "ms": _r(t * 1e3),
             "peak_is": "%s bf16 burst (cuBLAS); `achieved` counts ALGORITHMIC flops, the mode executes %dx of them at the %s"
-                       % (peaks["source"], mma_mult, rate),
-            "tensor_pipe_frac_est": _r(exec_frac), "alg_gbs": _r(alg_bytes / t / 1e9)}
-    full = dict(roof, flops_per_launch=flops, algorithmic_bytes_per_launch=alg_bytes, times_ms=[x * 1e3 for x in times])
+                       % (peaks["source"], d["mma_mult"], d["rate"]),
+            "tensor_pipe_frac_est": _r(exec_frac), "alg_gbs": _r(d["alg_bytes"] / t / 1e9)}
+    full = dict(roof, flops_per_launch=d["flops"], algorithmic_bytes_per_launch=d["alg_bytes"], times_ms=[x * 1e3 for x in times])
     return roof, full
 
 

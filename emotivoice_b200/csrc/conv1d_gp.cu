@@ -701,7 +701,8 @@ static int gp_shape_kbg(const GpConvParams& p, int mode) {
 // (MT) amortise the weight stream and the halo rows, a narrower N tile fills idle SMs (HiFi-GAN stage 1 at batch 1).
 // A grouped launch (ng convolutions of one shape, ksum = the sum of their taps, span / kmin as in make_gplan) is planned like one
 // convolution with the mean number of taps and ng times the tiles; kbg must be the members' own (checked by the caller).
-static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out, int ng = 1, int ksum = 0, int span = -1, int kmin = 0, int kbg_forced = 0) {
+static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out, int ng = 1, int ksum = 0, int span = -1, int kmin = 0, int kbg_forced = 0,
+                   const int* gK = nullptr) {
   EV_TRY(validate_gp(p, mode));
   const int nsm = sm_count();
   const int kbg = kbg_forced ? kbg_forced : gp_shape_kbg(p, mode);
@@ -731,8 +732,22 @@ static int plan_gp(const GpConvParams& p, int mode, gp::GPlan* out, int ng = 1, 
       const double t_hbm = (double)mt * tc::BM * ((double)p.Cin * (mt * tc::BM + span) / (mt * tc::BM) + 2.0 * BN) * esize / 23.0;
       double t = t_mma > t_w ? t_mma : t_w;
       if (t_hbm > t) t = t_hbm;
-      const double waves = (double)((pl.total_tiles + nsm - 1) / nsm);
-      const double cost = waves * (t + 3000.0);
+      double cost;
+      if (ng > 1 && gK) {
+        // grouped launch: the members' tiles cost in proportion to their taps and are dealt round-robin in member order (heaviest
+        // first); the launch takes as long as its busiest CTA
+        const int tg = pl.total_tiles / ng;
+        const int ncta = pl.total_tiles < nsm ? pl.total_tiles : nsm;
+        cost = 0.0;
+        for (int c = 0; c < ncta; ++c) {
+          double sum = 0.0;
+          for (int i = c; i < pl.total_tiles; i += nsm) sum += t * gK[i / tg] * ng / (double)ksum + 3000.0;
+          if (sum > cost) cost = sum;
+        }
+      } else {
+        const double waves = (double)((pl.total_tiles + nsm - 1) / nsm);
+        cost = waves * (t + 3000.0);
+      }
       if (cost < best * 0.97) { best = cost; best_pl = pl; found = true; }     // widest N / most accumulators first; 3 % hysteresis
     }
   }
@@ -821,7 +836,24 @@ bool gp_group_supported(const GpConvParams* ps, int n, int mode) {
   if (mode < 0 || mode > 3 || !group_shapes_match(ps, n, mode, &kbg)) return false;
   return validate_gp(ps[0], mode) == EV_OK;
 }
+static int plan_group(const GpConvParams* ps, int n, int mode, GpGroups* gs_out, gp::GPlan* pl_out);
+int debug_gp_group_plan(const GpConvParams* ps, int n, int mode, int* v) {
+  GpGroups gs{};
+  gp::GPlan pl;
+  EV_TRY(plan_group(ps, n, mode, &gs, &pl));
+  v[0] = pl.BN; v[1] = pl.mt; v[2] = pl.kbg; v[3] = pl.a_stages; v[4] = pl.b_stages; v[5] = gp::NTW;
+  v[6] = pl.planes; v[7] = pl.tmem_cols; v[8] = pl.smem_total; v[9] = pl.total_tiles; v[10] = pl.rows_pad;
+  return EV_OK;
+}
 int launch_conv1d_gp_group(const GpConvParams* ps, int n, int mode, cudaStream_t st) {
+  GpGroups gs{};
+  gp::GPlan pl;
+  EV_TRY(plan_group(ps, n, mode, &gs, &pl));
+  return dispatch_gp(ps[0], pl, gs, mode, st);
+}
+static int plan_group(const GpConvParams* ps, int n, int mode, GpGroups* gs_out, gp::GPlan* pl_out) {
+  GpGroups& gs = *gs_out;
+  gp::GPlan& pl = *pl_out;
   int kbg = 0;
   EV_CHECK_ARG(ps && group_shapes_match(ps, n, mode, &kbg), "conv1d_gp group: the %d convolutions do not share a launch shape", n);
   // heaviest member first: with static round-robin tiles the CTAs that take a second (third) tile then take a light one
@@ -829,7 +861,7 @@ int launch_conv1d_gp_group(const GpConvParams* ps, int n, int mode, cudaStream_t
   for (int i = 0; i < n; ++i)
     for (int j = i + 1; j < n; ++j)
       if (ps[order[j]].K > ps[order[i]].K) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
-  GpGroups gs{};
+  gs = GpGroups{};
   gs.ng = n;
   int ksum = 0, span = 0, kmin = 1 << 30;
   for (int i = 0; i < n; ++i) {
@@ -839,9 +871,9 @@ int launch_conv1d_gp_group(const GpConvParams* ps, int n, int mode, cudaStream_t
     span = (q.K - 1) * q.dil > span ? (q.K - 1) * q.dil : span;
     kmin = q.K < kmin ? q.K : kmin;
   }
-  gp::GPlan pl;
-  EV_TRY(plan_gp(ps[0], mode, &pl, n, ksum, span, kmin, kbg));
-  return dispatch_gp(ps[0], pl, gs, mode, st);
+  int gK[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i) gK[i] = gs.g[i].K;
+  return plan_gp(ps[0], mode, &pl, n, ksum, span, kmin, kbg, gK);
 }
 
 // Load every instantiation's code now (CUDA loads kernels lazily, at their first launch: tens of milliseconds for a kernel of this

@@ -122,6 +122,10 @@ struct ConvParams {
   size_t splitk_cap = 0;
   int ksplit = 0;      // requested K-split factor (fixed per LAYER by the engine, never by batch size: keeps the
                        // summation order, hence every output bit, independent of how utterances are batched)
+  // optional: zero-initialised arrival counters, one per output tile.  With them the CTA whose slice of a tile lands last sums the
+  // slices (same fixed order) and runs the fused epilogue itself -- no separate reduce launch; the counters are left at zero.
+  int* splitk_cnt = nullptr;
+  int splitk_cnt_cap = 0;
 };
 int launch_conv1d(const ConvParams& p, cudaStream_t st);
 // tcgen05 variant (conv1d_tc.cu); p.w in the tensor-core layout [plane hi|lo][Cout/BNp][K][Cin/4][BNp][4], BNp = min(Cout,128);
@@ -170,6 +174,7 @@ int launch_conv1d_gp(const GpConvParams& p, int mode, cudaStream_t st);    // mo
 // computed exactly as in the convolution's own launch: bitwise equal.  EV_EINVAL (nothing launched) if the shapes cannot share a launch.
 int launch_conv1d_gp_group(const GpConvParams* ps, int n, int mode, cudaStream_t st);
 bool gp_group_supported(const GpConvParams* ps, int n, int mode);
+int debug_gp_group_plan(const GpConvParams* ps, int n, int mode, int* v11);
 int gp_solo_tiles(const GpConvParams& p, int mode);       // tiles of the convolution's own launch (0 if it cannot be planned)
 int debug_gp_plan(const GpConvParams& p, int mode, int* v11);
 // fp32 in[b*sb + t*st + c*sc] -> GP (fp32, or bf16 when bf16 != 0)

@@ -180,7 +180,8 @@ EV_API int ev_op_conv1d(const float* x, const float* w, const float* bias, size_
  * tensor-core layout (2 planes hi|lo, Cout/BNp N tiles, K, Cin/4, BNp = min(Cout,128), 4; packing.to_tc_layout);
  * split3 = 0: 1xTF32, 1: 3xTF32 fp32 emulation, 2: bf16 operands (w_tc then in the bf16 layout of
  * packing.to_tc16_layout; Cin % 16 == 0).  Requires Cin % 8 == 0, Cout % 16 == 0 and Cout <= 128 or Cout % 128 == 0.  splitk_ws (optional, splitk_floats floats of scratch) lets a
- * launch with few output tiles and a long reduction be split along K (deterministic two-pass). */
+ * launch with few output tiles and a long reduction be split along K (deterministic: the slices are summed in a fixed order, by a
+ * reduce kernel or -- when the scratch has 16384 words beyond the four slices, used as arrival counters -- by the CTA whose slice lands last). */
 EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* bias, size_t bias_bstride,
                            const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
                            const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
@@ -207,6 +208,8 @@ EV_API int ev_op_conv1d_gp(const void* x, const float* w, int mode, const float*
 EV_API int ev_op_conv1d_gp_group(int n, const void* const* x, const float* const* w, int mode, const float* const* bias,
                                  const void* const* res, void* const* out, const int* K, const int* dil, int B, int L, int Cin,
                                  int Cout, const int32_t* lens, int lens_mul, int in_act, float in_slope, void* stream);
+/* Host-only: the plan of a grouped launch, out11 as ev_debug_gp_plan (tiles = all members'). */
+EV_API int ev_debug_gp_group_plan(int n, const int* K, const int* dil, int B, int L, int Cin, int Cout, int mode, int* out11);
 /* One ResBlock1 layer (hifigan/models.py:50-57) as ONE kernel on granule-planar activations (csrc/resblock_gp.cu):
  * out = [acc]( x + c2(lrelu(c1(lrelu(x), dil)), 1) ), C -> C channels (C in {32, 64, 128}), slope 0.1, both weights in the layout of
  * `mode` (as ev_op_conv1d_gp).  Bitwise equal to the two ev_op_conv1d_gp launches it replaces; EV_EINVAL for shapes it does not take
