@@ -43,7 +43,6 @@ struct Plan {
   int ngroups;         // producer groups: largest of {6,3,2,1} that is <= a_stages
   int ksplit;          // K-split factor S: S CTAs share one output tile, each reducing a slice of the C_in blocks
                        // into a private partial buffer; splitk_reduce_kernel sums them in a fixed order
-  int fix;             // K-split only: the CTA that finishes an output tile's last slice reduces the tile itself (no reduce launch)
   int tmem_cols;
   int tiles_m, tiles_n, total_tiles;
   int smem_total;
@@ -86,7 +85,6 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN,
   q.tiles_m = (p.L + BM * mt - 1) / (BM * mt);
   q.tiles_n = (p.Cout + q.BN - 1) / q.BN;
   q.ksplit = 1;
-  q.fix = 0;
   q.total_tiles = p.B * q.tiles_m * q.tiles_n;
   q.smem_total = 1024 + STAGING_BYTES + q.a_stages * q.a_stage_bytes + q.b_stages * q.b_stage_bytes;
   *o = q;
@@ -95,12 +93,11 @@ __host__ __device__ inline bool make_plan(const ConvParams& p, int mode, int BN,
 
 // out[e..e+3] = epi( sum_z partial[z][e..e+3] ): the slices added in the fixed order z = 0..S-1 starting from zero (deterministic,
 // batch invariant), then bias / activation / residual / accumulate exactly like the fused epilogue; rows >= len are zeros.
-// Shared by splitk_reduce_kernel and by the in-kernel reduction of the last-arriving CTA (Plan::fix): identical bits.
 __device__ __forceinline__ void splitk_reduce_store(const ConvParams& p, int S, size_t per, size_t e, int b, int row, int col, int len) {
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
   if (row < len) {
     for (int z = 0; z < S; ++z) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.splitk_ws + (size_t)z * per + e));
+      const float4 v = *reinterpret_cast<const float4*>(p.splitk_ws + (size_t)z * per + e);
       o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
     }
     if (p.bias) {
@@ -211,7 +208,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
     if (PDLM) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int quad = warp & 3, chalf = warp >> 2;
     float* stg = reinterpret_cast<float*>(staging + warp * (32 * 32 * 4));
-    volatile int* fix_flag = reinterpret_cast<volatile int*>(smem_raw + 528);
     const int rr = lane >> 3, cq = lane & 7;         // coalesced phase: 4 rows x 8 float4 per instruction
     const bool split = pl.ksplit > 1;           // K-split: raw partial sums, the fused epilogue runs in the reduce kernel
     const bool has_res = p.res != nullptr && !split;
@@ -222,39 +218,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
       decode(tile, b, t0, n0, nt, len);
       float* ob = (split ? p.splitk_ws + (size_t)z_cur * p.B * p.L * p.Cout : p.out) + (size_t)b * p.L * p.Cout;   // may alias p.res
       const float* rb = has_res ? p.res + (size_t)b * p.L * p.Cout : nullptr;
-      // K-split with arrival counters: after this CTA's slice of the tile is in the scratch buffer (or skipped: padding tile), the 8
-      // epilogue warps count the slice in; the CTA that counts the LAST slice sums all of them in the fixed order and stores the tile.
-      auto finish_slice = [&]() {
-        if (!pl.fix) return;
-        __threadfence();                                       // this thread's partial stores are visible device-wide
-        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
-        const int otile = tile / pl.ksplit;
-        if (tid == 0) *fix_flag = atomicAdd(p.splitk_cnt + otile, 1) == pl.ksplit - 1;
-        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
-        if (*fix_flag) {
-          __threadfence();
-          const size_t per = (size_t)p.B * p.L * p.Cout;
-          const int nt4 = nt >> 2;
-          for (int i = tid; i < MT * BM * nt4; i += NEPI) {
-            const int r = i / nt4, c4 = i - r * nt4;
-            const int row = t0 + r;
-            if (row >= p.L) break;
-            const int col = n0 + c4 * 4;
-            splitk_reduce_store(p, pl.ksplit, per, ((size_t)b * p.L + row) * p.Cout + col, b, row, col, len);
-          }
-          if (tid == 0) p.splitk_cnt[otile] = 0;             // ready for the next launch
-        }
-      };
       if (t0 >= len) {   // padding tile: the batch-invariant contract stores zeros (no MMA work was issued)
-        if (!pl.fix)       // (with arrival counters the reducing CTA writes the zeros)
-          for (int mt = 0; mt < MT; ++mt)
-            for (int c = chalf * 32; c < nt; c += 64)
-              for (int it = 0; it < 8; ++it) {
-                const int row = t0 + mt * BM + quad * 32 + it * 4 + rr;
-                if (row < p.L && c + cq * 4 < nt)
-                  *reinterpret_cast<float4*>(ob + (size_t)row * p.Cout + n0 + c + cq * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-        finish_slice();
+        for (int mt = 0; mt < MT; ++mt)
+          for (int c = chalf * 32; c < nt; c += 64)
+            for (int it = 0; it < 8; ++it) {
+              const int row = t0 + mt * BM + quad * 32 + it * 4 + rr;
+              if (row < p.L && c + cq * 4 < nt)
+                *reinterpret_cast<float4*>(ob + (size_t)row * p.Cout + n0 + c + cq * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         continue;
       }
       const int buf = tile_cnt & 1;
@@ -328,7 +299,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
       ++tile_cnt;
-      finish_slice();
     }
   } else if (warp < MMA_WARP) {
     // ============================ A producers ===================================================
@@ -701,10 +671,8 @@ int launch_conv1d_tc(const ConvParams& p, int mode, cudaStream_t st) {
   tc::Plan pl;
   EV_TRY(plan_conv1d_tc(p, mode, &pl));
   const size_t per = (size_t)p.B * p.L * p.Cout;
-  static const int fix_on = env_int("EV_SPLITK_FIXUP", 1);
-  if (pl.ksplit > 1 && fix_on && p.splitk_cnt && pl.total_tiles / pl.ksplit <= p.splitk_cnt_cap) pl.fix = 1;
   const int rc = dispatch_tc(p, mode, pl, st, pdl_mode());      // EV_PDL (default 2)
-  if (rc != EV_OK || pl.ksplit == 1 || pl.fix) return rc;
+  if (rc != EV_OK || pl.ksplit == 1) return rc;
   const size_t n4 = per / 4;
   launch_k(tc::splitk_reduce_kernel<true>, tc::splitk_reduce_kernel<false>, (unsigned)((n4 + 255) / 256), 256, 0, st, p, pl.ksplit);
   EV_CUDA_LAUNCH_CHECK("splitk_reduce_kernel");

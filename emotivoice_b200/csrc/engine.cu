@@ -407,24 +407,12 @@ struct SplitWs {
   float* p = nullptr;
   size_t cap = 0;
   int ksplit = 0;     // K-split factor for the convs launched next (set per layer, see conv1d_tc.cu)
-  int* cnt = nullptr; // zeroed arrival counters (one per output tile) for the in-kernel split-K reduction, or null
-  int cnt_cap = 0;
 };
 static thread_local SplitWs g_split_ws;   // set by the phase entry points for the convs they launch
 
-// Point the K-split scratch of the convs launched next at `part` (cap floats).  With `st` given, its last kSplitCounters words
-// become the arrival counters of the in-kernel reduction and are zeroed on the stream (once per phase: the kernels leave them at zero).
-constexpr int kSplitCounters = 16384;
-static int set_split_ws(float* part, size_t cap, int ksplit, cudaStream_t st, bool counters, size_t min_floats = 0) {
+static int set_split_ws(float* part, size_t cap, int ksplit) {
   g_split_ws = SplitWs{};
   g_split_ws.p = part; g_split_ws.cap = part ? cap : 0; g_split_ws.ksplit = ksplit;
-  if (counters && part && cap > (size_t)kSplitCounters * 2 && cap - kSplitCounters >= min_floats) {
-    g_split_ws.cap = cap - kSplitCounters;
-    g_split_ws.cnt = reinterpret_cast<int*>(part + g_split_ws.cap);
-    g_split_ws.cnt_cap = kSplitCounters;
-    const cudaError_t e = cudaMemsetAsync(g_split_ws.cnt, 0, (size_t)kSplitCounters * sizeof(int), st);
-    if (e != cudaSuccess) { set_error("split-K counters: %s", cudaGetErrorString(e)); return EV_ECUDA; }
-  }
   return EV_OK;
 }
 
@@ -449,7 +437,6 @@ static int conv_x(int mode, const float* w_tc, const float* w_h, const float* x,
   p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope;
   p.out_act = out_act; p.acc = acc; p.div = div;
   p.splitk_ws = g_split_ws.p; p.splitk_cap = g_split_ws.cap; p.ksplit = g_split_ws.ksplit;
-  p.splitk_cnt = g_split_ws.cnt; p.splitk_cnt_cap = g_split_ws.cnt_cap;
   return launch_conv1d_tc(p, x3b ? 3 : (mode == 3 ? 1 : (mode == 2 ? 2 : 0)), st);
 }
 
@@ -757,7 +744,7 @@ int ev_am_phase1(ev_ctx* ctx, const int64_t* ling, const int64_t* lens64, const 
   carve_phase1(ctx, cv, B, T, &b);
   if (cv.off > workspace_bytes) { set_error("ev_am_phase1: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
   EV_TRY(use_device(ctx));
-  EV_TRY(set_split_ws(b.part, b.part_cap, 2, st, true));
+  EV_TRY(set_split_ws(b.part, b.part_cap, 2));
   // lengths -> int32, plus range checks of ids / speakers / lengths into the status word mel_lens_out[B + 1]
   EV_TRY(launch_validate_inputs(ling, lens64, spk, lens32_out, mel_lens_out + B + 1, B, T, g.n_vocab, g.n_speaker, st));
   const int32_t* lens = lens32_out;
@@ -810,7 +797,7 @@ int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t* lens,
   carve_phase2(ctx, cv, B, F, &b);
   if (cv.off > workspace_bytes) { set_error("ev_am_phase2: workspace %zu < %zu bytes", workspace_bytes, cv.off); return EV_EWORKSPACE; }
   const int32_t* flens = invariant ? mel_lens : nullptr;
-  EV_TRY(set_split_ws(b.part, b.part_cap, 2, st, true));
+  EV_TRY(set_split_ws(b.part, b.part_cap, 2));
   Range r_phase("ev:am_phase2");
   // length regulator + the decoder's positional encoding (alignment.py:198-211, encoder.py:257-261)
   EV_TRY(launch_gauss_upsample(b1.hs, b1.centers, lens, mel_lens, B, T, H, F, invariant, ctx->pe, ctx->dec.alpha, b.x, st));
@@ -892,7 +879,7 @@ int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t*
     // x = leaky_relu(x) [slope 0.01]; conv_post; tanh (:127-129)
     return launch_conv_post_gp(v.ACC, bf, ctx->post_w, ctx->post_b, mel_lens, mul, B, L, ctx->ups.back().cout, ctx->post_k, 0.01f, wav_out, st);
   }
-  EV_TRY(set_split_ws(v.part, v.part_cap, 0, st, false));
+  EV_TRY(set_split_ws(v.part, v.part_cap, 0));
   const float* m = mel;
   if (!mel_time_major) {
     EV_TRY(launch_transpose_cf_to_tm(mel, v.Tm, B, g.n_mels, F, st));
@@ -965,8 +952,7 @@ int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* 
                     void* stream) {
   EV_CHECK_ARG(x && w_tc && out, "ev_op_conv1d_tc: null argument");
   EV_TRY(use_device_of(x));
-  // (the arrival counters of the in-kernel reduction come out of the caller's scratch when it has room beyond the four slices)
-  EV_TRY(set_split_ws(splitk_ws, splitk_floats, splitk_ws ? 4 : 0, reinterpret_cast<cudaStream_t>(stream), true, 4 * (size_t)B * L * Cout));
+  EV_TRY(set_split_ws(splitk_ws, splitk_floats, splitk_ws ? 4 : 0));
   EV_CHECK_ARG(Cin % 8 == 0 && Cout % 16 == 0 && (Cout <= 128 || Cout % 128 == 0),
                "ev_op_conv1d_tc: needs Cin %% 8 == 0, Cout %% 16 == 0 and Cout <= 128 or a multiple of 128 (Cin=%d Cout=%d)", Cin, Cout);
   EV_CHECK_ARG(split3 < 2 || Cin % 16 == 0, "ev_op_conv1d_tc: the bf16 / bf16x3 modes need Cin %% 16 == 0 (Cin=%d)", Cin);
@@ -976,8 +962,7 @@ int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* 
     p.B = B; p.L = L; p.Cin = Cin; p.Cout = Cout; p.K = K; p.dil = dil; p.lens = lens; p.lens_mul = lens_mul; p.in_act = in_act; p.in_slope = in_slope;
     p.out_act = out_act; p.acc = acc; p.div = div;
     p.splitk_ws = g_split_ws.p; p.splitk_cap = g_split_ws.cap; p.ksplit = g_split_ws.ksplit;
-    p.splitk_cnt = g_split_ws.cnt; p.splitk_cnt_cap = g_split_ws.cnt_cap;
-    return launch_conv1d_tc(p, 3, reinterpret_cast<cudaStream_t>(stream));
+      return launch_conv1d_tc(p, 3, reinterpret_cast<cudaStream_t>(stream));
   }
   return conv_x(split3 == 2 ? 2 : (split3 ? 3 : 1), w_tc, w_tc, x, nullptr, bias, (long long)bias_bstride, res, out, B, L, Cin, Cout, K, dil, lens, lens_mul,
                 in_act, in_slope, out_act, acc, div, reinterpret_cast<cudaStream_t>(stream));

@@ -122,10 +122,6 @@ struct ConvParams {
   size_t splitk_cap = 0;
   int ksplit = 0;      // requested K-split factor (fixed per LAYER by the engine, never by batch size: keeps the
                        // summation order, hence every output bit, independent of how utterances are batched)
-  // optional: zero-initialised arrival counters, one per output tile.  With them the CTA whose slice of a tile lands last sums the
-  // slices (same fixed order) and runs the fused epilogue itself -- no separate reduce launch; the counters are left at zero.
-  int* splitk_cnt = nullptr;
-  int splitk_cnt_cap = 0;
 };
 int launch_conv1d(const ConvParams& p, cudaStream_t st);
 // tcgen05 variant (conv1d_tc.cu); p.w in the tensor-core layout [plane hi|lo][Cout/BNp][K][Cin/4][BNp][4], BNp = min(Cout,128);

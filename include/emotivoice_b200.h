@@ -180,8 +180,7 @@ EV_API int ev_op_conv1d(const float* x, const float* w, const float* bias, size_
  * tensor-core layout (2 planes hi|lo, Cout/BNp N tiles, K, Cin/4, BNp = min(Cout,128), 4; packing.to_tc_layout);
  * split3 = 0: 1xTF32, 1: 3xTF32 fp32 emulation, 2: bf16 operands (w_tc then in the bf16 layout of
  * packing.to_tc16_layout; Cin % 16 == 0).  Requires Cin % 8 == 0, Cout % 16 == 0 and Cout <= 128 or Cout % 128 == 0.  splitk_ws (optional, splitk_floats floats of scratch) lets a
- * launch with few output tiles and a long reduction be split along K (deterministic: the slices are summed in a fixed order, by a
- * reduce kernel or -- when the scratch has 16384 words beyond the four slices, used as arrival counters -- by the CTA whose slice lands last). */
+ * launch with few output tiles and a long reduction be split along K (deterministic two-pass). */
 EV_API int ev_op_conv1d_tc(const float* x, const float* w_tc, int split3, const float* bias, size_t bias_bstride,
                            const float* res, float* out, int B, int L, int Cin, int Cout, int K, int dil,
                            const int32_t* lens, int lens_mul, int in_act, float in_slope, int out_act,
