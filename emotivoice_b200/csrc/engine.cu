@@ -471,7 +471,7 @@ static inline bool fuse_res_enabled() {
   return v == 1;
 }
 static bool try_gp_pair(int mode, const ConvW& c1, const ConvW& c2, const void* src, void* dst, int B, int L, int C, const int32_t* lens, int lens_mul,
-                        int acc, float div, cudaStream_t st, int* rc, bool dry_run = false) {
+                        int acc, float div, cudaStream_t st, int* rc, bool dry_run = false, GpPairParams* p_out = nullptr, int* gm_out = nullptr) {
   if (!fuse_res_enabled() || c1.K != c2.K || c2.dil != 1) return false;
   // Fused and unfused are bitwise equal, so the choice may depend on the batch: measured (profiles/r02_fused_vs_unfused.jsonl) the fused
   // layer wins 1.1-1.8x on the HBM-bound shapes (k <= 7, or 32 channels) and wherever the launch count matters (batch 1), and loses
@@ -485,6 +485,8 @@ static bool try_gp_pair(int mode, const ConvW& c1, const ConvW& c2, const void* 
   p.w2 = x3b ? c2.w_x2 : (mode == 2 ? c2.w_h : c2.w_tc);
   p.B = B; p.L = L; p.C = C; p.K = c1.K; p.dil = c1.dil; p.lens = lens; p.lens_mul = lens_mul; p.slope = 0.1f; p.acc = acc; p.div = div;
   if (!p.w1 || !p.w2 || !gp_pair_supported(p, gm)) return false;
+  if (p_out) *p_out = p;
+  if (gm_out) *gm_out = gm;
   if (!dry_run) *rc = launch_gp_pair(p, gm, st);
   return true;
 }
@@ -501,14 +503,48 @@ static bool try_grouped_stage(ev_ctx* ctx, const VocBufs& v, int mode, size_t rb
   void* T[3] = {v.Tm, v.G0, v.G1};
   void* Y[3] = {v.R1, v.R2, v.G2};
   int frc = EV_OK;
-  // qualify: no layer of the stage takes the fused-pair kernel, every step's members can share a launch, and one member alone is small
+  // qualify: the stage's layers either all take the fused-pair kernel or none does, every step's members can share a launch, and
+  // one member alone is small
   GpConvParams ps[3];
-  int gm = 0;
+  GpPairParams pp[3];
+  int gm = 0, n_pair = 0;
+  for (int l = 0; l < D; ++l)
+    for (int j = 0; j < J; ++j)
+      n_pair += try_gp_pair(mode, ctx->rb_c1[rb0 + (size_t)j * D + l], ctx->rb_c2[rb0 + (size_t)j * D + l], v.X, Y[j], B, L, C, lens, mul, EV_ACC_STORE, 1.f, st,
+                            &frc, true) ? 1 : 0;
+  if (n_pair == J * D) {
+    // ---- fused layers: layer l of the three blocks is one launch (x -> Y, Y -> T, T -> Y, ...); the last layer accumulates into
+    // ---- xs block by block (three single launches) ----------------------------------------------------------------------------
+    for (int l = 0; l < D; ++l) {
+      for (int j = 0; j < J; ++j)
+        try_gp_pair(mode, ctx->rb_c1[rb0 + (size_t)j * D + l], ctx->rb_c2[rb0 + (size_t)j * D + l], v.X, Y[j], B, L, C, lens, mul, EV_ACC_STORE, 1.f, st, &frc, true,
+                    &pp[j], &gm);
+      if (!gp_pair_group_supported(pp, J, gm)) return false;
+    }
+    if (gp_pair_solo_tiles(pp[0], gm) >= 2 * sm_count()) return false;
+    *rc = EV_OK;
+    for (int l = 0; l < D && *rc == EV_OK; ++l) {
+      const bool last = (l == D - 1);
+      for (int j = 0; j < J; ++j) {
+        const void* src = l == 0 ? (const void*)v.X : ((l & 1) ? Y[j] : T[j]);
+        void* dst = last ? (void*)v.ACC : ((l & 1) ? T[j] : Y[j]);
+        int acc = EV_ACC_STORE;
+        if (last && j > 0) acc = (j == J - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;
+        try_gp_pair(mode, ctx->rb_c1[rb0 + (size_t)j * D + l], ctx->rb_c2[rb0 + (size_t)j * D + l], src, dst, B, L, C, lens, mul, acc, (float)J, st, &frc, true,
+                    &pp[j], &gm);
+      }
+      if (!last) {
+        *rc = launch_gp_pair_group(pp, J, gm, st);
+      } else {
+        for (int j = 0; j < J && *rc == EV_OK; ++j) *rc = launch_gp_pair(pp[j], gm, st);
+      }
+    }
+    return true;
+  }
+  if (n_pair != 0) return false;
   for (int l = 0; l < D; ++l) {
     for (int j = 0; j < J; ++j) {
       const ConvW& c1 = ctx->rb_c1[rb0 + (size_t)j * D + l];
-      const ConvW& c2 = ctx->rb_c2[rb0 + (size_t)j * D + l];
-      if (try_gp_pair(mode, c1, c2, v.X, Y[j], B, L, C, lens, mul, EV_ACC_STORE, 1.f, st, &frc, true)) return false;
       gm = gp_params(mode, c1.w_tc, c1.w_h, c1.w_x2, v.X, c1.b, nullptr, T[j], B, L, C, C, c1.K, c1.dil, 1, lens, mul, EV_ACT_LRELU, 0.1f, EV_ACC_STORE, 1.f, &ps[j]);
       if (!ps[j].w) return false;
     }
@@ -1022,6 +1058,20 @@ int ev_op_resblock_gp(const void* x, const float* w1, const float* b1, const flo
   p.x = x; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.out = out; p.B = B; p.L = L; p.C = C; p.K = K; p.dil = dil; p.lens = lens; p.lens_mul = lens_mul;
   p.slope = 0.1f; p.acc = acc; p.div = div;
   return launch_gp_pair(p, mode, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ev_op_resblock_gp_group(int n, const void* const* x, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2,
+                            int mode, void* const* out, int B, int L, int C, const int* K, const int* dil, const int32_t* lens, int lens_mul, void* stream) {
+  EV_CHECK_ARG(n >= 1 && n <= 3 && x && w1 && b1 && w2 && b2 && out && K && dil, "ev_op_resblock_gp_group: 1..3 layers, non-null tables");
+  GpPairParams ps[3];
+  for (int i = 0; i < n; ++i) {
+    GpPairParams& p = ps[i];
+    EV_CHECK_ARG(x[i] && w1[i] && b1[i] && w2[i] && b2[i] && out[i], "ev_op_resblock_gp_group: null tensor in member %d", i);
+    p.x = x[i]; p.w1 = w1[i]; p.b1 = b1[i]; p.w2 = w2[i]; p.b2 = b2[i]; p.out = out[i]; p.B = B; p.L = L; p.C = C; p.K = K[i]; p.dil = dil[i];
+    p.lens = lens; p.lens_mul = lens_mul; p.slope = 0.1f; p.acc = EV_ACC_STORE; p.div = 1.f;
+  }
+  EV_TRY(use_device_of(x[0]));
+  return launch_gp_pair_group(ps, n, mode, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ev_debug_resblock_gp_plan(int B, int L, int C, int K, int dil, int mode, int* out11) {

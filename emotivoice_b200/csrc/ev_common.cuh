@@ -191,8 +191,25 @@ struct GpPairParams {
   int acc;             // EV_ACC_*
   float div;
 };
+// The kernel's view: up to three layers of one shape in a launch (a single layer is a group of one).
+struct GpPairGroup {
+  const void* x;
+  const float *w1, *b1, *w2, *b2;
+  void* out;
+  int K, dil;
+  int R, tiles_m, tile0;   // output rows per tile (128*MT - (K-1)), row tiles per item, first tile index of the member
+};
+struct GpPairGroups {
+  int ng;
+  GpPairGroup g[3];
+};
 bool gp_pair_supported(const GpPairParams& p, int mode);
 int launch_gp_pair(const GpPairParams& p, int mode, cudaStream_t st);      // mode as launch_conv1d_gp
+// n <= 3 layers sharing B, L, C, lens, slope and acc == STORE as ONE launch (the same-index layers of HiFi-GAN's parallel ResBlocks
+// at small batch); every tile is computed as in the member's own launch: bitwise equal.
+bool gp_pair_group_supported(const GpPairParams* ps, int n, int mode);
+int launch_gp_pair_group(const GpPairParams* ps, int n, int mode, cudaStream_t st);
+int gp_pair_solo_tiles(const GpPairParams& p, int mode);
 int debug_gp_pair_plan(const GpPairParams& p, int mode, int* v11);
 int launch_conv_post_gp(const void* x, int bf16, const float* w, const float* bias, const int32_t* lens, int lens_mul, int B, int L, int C, int K,
                         float slope, float* wav, cudaStream_t st);

@@ -41,7 +41,10 @@ struct PPlan {
   int smem_total;
 };
 
-__host__ __device__ inline bool make_pplan(const GpPairParams& p, int mode, int mt, int kbg, PPlan* o) {
+// span1 = (K-1)*dil of the widest member and kmax = the most taps of a grouped launch (-1 / 0: p's own)
+__host__ __device__ inline bool make_pplan(const GpPairParams& p, int mode, int mt, int kbg, PPlan* o, int span1 = -1, int kmax = 0) {
+  if (span1 < 0) span1 = (p.K - 1) * p.dil;
+  if (kmax <= 0) kmax = p.K;
   PPlan q;
   q.mt = mt; q.kbg = kbg;
   const int C = p.C;
@@ -51,10 +54,10 @@ __host__ __device__ inline bool make_pplan(const GpPairParams& p, int mode, int 
   const int xplanes = mode == 1 ? 2 : 1;
   const int splitp = (mode == 1 || mode == 3) ? 2 : 1;
   q.R = BM * mt - (p.K - 1);
-  if (q.R < 32) return false;
-  const int rows1 = BM * mt + (p.K - 1) * p.dil;
+  if (BM * mt - (kmax - 1) < 32) return false;
+  const int rows1 = BM * mt + span1;
   q.rows1_pad = (rows1 + 7) / 8 * 8;
-  q.rows2_pad = (BM * mt + (p.K - 1) + 7) / 8 * 8;
+  q.rows2_pad = (BM * mt + (kmax - 1) + 7) / 8 * 8;
   q.x_plane_bytes = kbg * q.rows1_pad * 16;
   q.x_stage_bytes = xplanes * q.x_plane_bytes;
   q.a2_plane_bytes = (C / ocpg) * q.rows2_pad * 16;
@@ -83,7 +86,8 @@ __device__ __forceinline__ float lrelu_f(float v, float slope) { return fmaxf(v,
 
 // MODE as conv1d_gp.cu: 0 tf32, 1 3xTF32, 2 bf16 activations + operands, 3 bf16x3 on fp32 activations.
 template <int MODE, int MT, int KBG>
-__global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParams p, PPlan pl) {
+__global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(const __grid_constant__ GpPairParams p, const __grid_constant__ PPlan pl,
+                                                                     const __grid_constant__ GpPairGroups gs) {
   constexpr bool SPLIT3 = (MODE == 1), BF16 = (MODE == 2), X3B = (MODE == 3);
   constexpr bool OP16 = BF16 || X3B;
   constexpr int SPL = (SPLIT3 || X3B) ? 2 : 1;
@@ -132,17 +136,19 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int n_cb = (C + KB - 1) / KB;
-  const int h2 = (p.K - 1) / 2, h1 = h2 * p.dil;
-  const int rows1 = BM * MT + (p.K - 1) * p.dil;
   const int gC = C / CPG;                      // activation granule planes per item
-  const int R = pl.R;
   // TMEM columns: acc1[buf] at buf*MT*C, acc2[buf] at (2 + buf)*MT*C
-  auto tile_len = [&](int tile, int& b, int& t0) {
-    b = tile / pl.tiles_m;
-    t0 = (tile - b * pl.tiles_m) * R;
+  // A launch carries up to three layers of one shape (the same-index layers of HiFi-GAN's parallel ResBlocks: their own taps,
+  // dilation, weights, tensors, hence their own rows per tile and tile count); tiles are numbered member after member.
+  auto group_of = [&](int tile) { return (gs.ng > 1 && tile >= gs.g[1].tile0) ? ((gs.ng > 2 && tile >= gs.g[2].tile0) ? 2 : 1) : 0; };
+  auto tile_len = [&](int tile, int& gi, int& b, int& t0) {
+    gi = group_of(tile);
+    const int local = tile - gs.g[gi].tile0;
+    b = local / gs.g[gi].tiles_m;
+    t0 = (local - b * gs.g[gi].tiles_m) * gs.g[gi].R;
     return p.lens ? min(p.L, p.lens[b] * p.lens_mul) : p.L;
   };
-  auto active = [&](int tile) { int b, t0; const int len = tile_len(tile, b, t0); return t0 < len; };
+  auto active = [&](int tile) { int gi, b, t0; const int len = tile_len(tile, gi, b, t0); return t0 < len; };
   auto next_active = [&](int tile) {      // first active tile of this CTA at or after `tile` (stride gridDim.x); >= total when none
     while (tile < pl.total_tiles && !active(tile)) tile += gridDim.x;
     return tile;
@@ -156,8 +162,10 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
     constexpr int NG = 32 / CPG;
     int cnt = 0;
     for (int tile = next_active(blockIdx.x); tile < pl.total_tiles; tile = next_active(tile + gridDim.x), ++cnt) {
-      int b, t0;
-      const int len = tile_len(tile, b, t0);
+      int gi, b, t0;
+      const int len = tile_len(tile, gi, b, t0);
+      const GpPairGroup& G = gs.g[gi];
+      const int R = G.R;
       const int buf = cnt & 1;
       bool waited = false;
 #pragma unroll 1
@@ -171,7 +179,7 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
           rq[q] = make_uint4(0u, 0u, 0u, 0u);
-          if (ok) rq[q] = *(reinterpret_cast<const uint4*>(p.x) + gbase + (size_t)q * p.L);       // the residual: L2 hit (the x tile was just staged)
+          if (ok) rq[q] = *(reinterpret_cast<const uint4*>(G.x) + gbase + (size_t)q * p.L);       // the residual: L2 hit (the x tile was just staged)
         }
         if (!waited) {
           mbar_wait(acc2_full(buf), (cnt >> 1) & 1);
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
         if (ok) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + c) + q);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(G.b2 + c) + q);
             v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
           }
 #pragma unroll
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
           if (p.acc != EV_ACC_STORE) {
             uint4 oq[NG];
 #pragma unroll
-            for (int q = 0; q < NG; ++q) oq[q] = *(reinterpret_cast<const uint4*>(p.out) + gbase + (size_t)q * p.L);
+            for (int q = 0; q < NG; ++q) oq[q] = *(reinterpret_cast<const uint4*>(G.out) + gbase + (size_t)q * p.L);
 #pragma unroll
             for (int q = 0; q < NG; ++q) {
               if (BF16) {
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
             } else {
               o.x = __float_as_uint(v[4 * q]); o.y = __float_as_uint(v[4 * q + 1]); o.z = __float_as_uint(v[4 * q + 2]); o.w = __float_as_uint(v[4 * q + 3]);
             }
-            *(reinterpret_cast<uint4*>(p.out) + gbase + (size_t)q * p.L) = o;
+            *(reinterpret_cast<uint4*>(G.out) + gbase + (size_t)q * p.L) = o;
           }
         }
       }
@@ -241,8 +249,10 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
     const float slope = p.slope;
     int cnt = 0;
     for (int tile = next_active(blockIdx.x); tile < pl.total_tiles; tile = next_active(tile + gridDim.x), ++cnt) {
-      int b, t0;
-      const int len = tile_len(tile, b, t0);
+      int gi, b, t0;
+      const int len = tile_len(tile, gi, b, t0);
+      const int h2 = (gs.g[gi].K - 1) / 2;
+      const float* b1 = gs.g[gi].b1;
       const int buf = cnt & 1;
       mbar_wait(acc1_full(buf), (cnt >> 1) & 1);
       mbar_wait(a2_empty, (cnt & 1) ^ 1);                 // c2 of the previous tile has read the xt tile
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * MT * C + mt * C + c), 32, v);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b1 + c) + q);
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + c) + q);
           v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
         }
 #pragma unroll
@@ -305,9 +315,11 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
     const float slope = p.slope;
     int a_cnt = 0;
     for (int tile = next_active(blockIdx.x); tile < pl.total_tiles; tile = next_active(tile + gridDim.x)) {
-      int b, t0;
-      const int len = tile_len(tile, b, t0);
-      const int row0 = t0 - h2 - h1;
+      int gi, b, t0;
+      const int len = tile_len(tile, gi, b, t0);
+      const int span = (gs.g[gi].K - 1) * gs.g[gi].dil;
+      const int rows1 = BM * MT + span;
+      const int row0 = t0 - (gs.g[gi].K - 1) / 2 - span / 2;
       for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
         const int s = a_cnt % pl.a_stages;
         const int ngran = min(KB, C - cb * KB) / CPG;
@@ -369,12 +381,14 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
       asm volatile("griddepcontrol.wait;" ::: "memory");
       int a_cnt = 0;
       for (int tile = next_active(blockIdx.x); tile < pl.total_tiles; tile = next_active(tile + gridDim.x)) {
-        int b, t0;
-        const int len = tile_len(tile, b, t0);
-        const int row0 = t0 - h2 - h1;
+        int gi, b, t0;
+        const int len = tile_len(tile, gi, b, t0);
+        const int span = (gs.g[gi].K - 1) * gs.g[gi].dil;
+        const int rows1 = BM * MT + span;
+        const int row0 = t0 - (gs.g[gi].K - 1) / 2 - span / 2;
         const int r_lo = max(row0, 0), r_hi = min(row0 + rows1, len);
         const uint32_t nbytes = (uint32_t)(r_hi - r_lo) * 16u, roff = (uint32_t)(r_lo - row0) * 16u;
-        const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x) + ((size_t)b * gC * p.L + r_lo) * 16;
+        const uint8_t* xb = reinterpret_cast<const uint8_t*>(gs.g[gi].x) + ((size_t)b * gC * p.L + r_lo) * 16;
         for (int cb = 0; cb < n_cb; ++cb, ++a_cnt) {
           const int s = a_cnt % pl.a_stages;
           const int ngran = min(KB, C - cb * KB) / CPG;
@@ -391,12 +405,12 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
     // ============================ weight loader: the MMA issuer's order  C1(0) | C1(i+1), C2(i) ====================
     if (lane == 0) {
       const int win = C / OCPG;
-      const size_t plane = (size_t)p.K * win * C * 4;        // 4-byte words per plane
       int b_cnt = 0;
-      auto stream = [&](const float* w) {
+      auto stream = [&](const float* w, int K) {
+        const size_t plane = (size_t)K * win * C * 4;        // 4-byte words per plane
         for (int cb = 0; cb < n_cb; ++cb) {
           const int ngran = min(KB, C - cb * KB) / OCPG;
-          for (int j = 0; j < p.K; ++j, ++b_cnt) {
+          for (int j = 0; j < K; ++j, ++b_cnt) {
             const int sb = b_cnt % pl.b_stages;
             mbar_wait(b_empty(sb), ((b_cnt / pl.b_stages) & 1) ^ 1);
             mbar_expect_tx(b_full(sb), (uint32_t)(SPL * ngran * C * 16));
@@ -408,11 +422,11 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
         }
       };
       int tile = next_active(blockIdx.x);
-      if (tile < pl.total_tiles) stream(p.w1);
+      if (tile < pl.total_tiles) stream(gs.g[group_of(tile)].w1, gs.g[group_of(tile)].K);
       while (tile < pl.total_tiles) {
         const int nxt = next_active(tile + gridDim.x);
-        if (nxt < pl.total_tiles) stream(p.w1);
-        stream(p.w2);
+        if (nxt < pl.total_tiles) stream(gs.g[group_of(nxt)].w1, gs.g[group_of(nxt)].K);
+        stream(gs.g[group_of(tile)].w2, gs.g[group_of(tile)].K);
         tile = nxt;
       }
     }
@@ -437,7 +451,8 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
         umma_tf32(d, a_hi, b_hi, idesc, first);
       }
     };
-    auto conv1 = [&](int cnt) {          // acc1[cnt & 1] = c1 over the staged x tile of the cnt-th active tile
+    auto conv1 = [&](int cnt, int tile) {          // acc1[cnt & 1] = c1 over the staged x tile of the cnt-th active tile
+      const int K = gs.g[group_of(tile)].K, dil = gs.g[group_of(tile)].dil;
       const int buf = cnt & 1;
       mbar_wait(acc1_empty(buf), ((cnt >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -447,12 +462,12 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
         const int nk = min(KB, C - cb * KB) / (2 * OCPG);
         mbar_wait(a_ready(sa), (a_cnt / pl.a_stages) & 1);
         const uint64_t x0 = desc_advance(x_desc0, smem_u32(x_tiles + sa * pl.x_stage_bytes));
-        for (int j = 0; j < p.K; ++j, ++b_cnt) {
+        for (int j = 0; j < K; ++j, ++b_cnt) {
           const int sb = b_cnt % pl.b_stages;
           mbar_wait(b_full(sb), (b_cnt / pl.b_stages) & 1);
           tc_fence_after();
           const uint64_t b0 = desc_advance(b_desc0, smem_u32(b_tiles + sb * pl.b_stage_bytes));
-          const uint64_t xj = desc_advance(x0, (uint32_t)(j * p.dil) * 16u);
+          const uint64_t xj = desc_advance(x0, (uint32_t)(j * dil) * 16u);
           if (elect_one()) {
             for (int k = 0; k < nk; ++k) {
               const uint64_t b_hi = desc_advance(b0, (uint32_t)k * 2u * b_lbo);
@@ -466,7 +481,7 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
               }
             }
             umma_commit(b_empty(sb));
-            if (j == p.K - 1) {
+            if (j == K - 1) {
               umma_commit(a_empty(sa));
               if (cb == n_cb - 1) umma_commit(acc1_full(buf));
             }
@@ -475,7 +490,8 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
         }
       }
     };
-    auto conv2 = [&](int cnt) {          // acc2[cnt & 1] = c2 over the xt tile epi1 wrote for the cnt-th active tile
+    auto conv2 = [&](int cnt, int tile) {          // acc2[cnt & 1] = c2 over the xt tile epi1 wrote for the cnt-th active tile
+      const int K = gs.g[group_of(tile)].K;
       const int buf = cnt & 1;
       mbar_wait(a2_full, cnt & 1);
       mbar_wait(acc2_empty(buf), ((cnt >> 1) & 1) ^ 1);
@@ -484,7 +500,7 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
       for (int cb = 0; cb < n_cb; ++cb) {
         const int nk = min(KB, C - cb * KB) / (2 * OCPG);
         const uint64_t a0 = desc_advance(a2_desc0, (uint32_t)(cb * KBGW) * a2_lbo);
-        for (int j = 0; j < p.K; ++j, ++b_cnt) {
+        for (int j = 0; j < K; ++j, ++b_cnt) {
           const int sb = b_cnt % pl.b_stages;
           mbar_wait(b_full(sb), (b_cnt / pl.b_stages) & 1);
           tc_fence_after();
@@ -503,18 +519,18 @@ __global__ void __launch_bounds__(GPP_THREADS, 1) resblock_gp_kernel(GpPairParam
               }
             }
             umma_commit(b_empty(sb));
-            if (j == p.K - 1 && cb == n_cb - 1) { umma_commit(a2_empty); umma_commit(acc2_full(buf)); }
+            if (j == K - 1 && cb == n_cb - 1) { umma_commit(a2_empty); umma_commit(acc2_full(buf)); }
           }
           __syncwarp();
         }
       }
     };
     int tile = next_active(blockIdx.x), cnt = 0;
-    if (tile < pl.total_tiles) conv1(0);
+    if (tile < pl.total_tiles) conv1(0, tile);
     while (tile < pl.total_tiles) {
       const int nxt = next_active(tile + gridDim.x);
-      if (nxt < pl.total_tiles) conv1(cnt + 1);          // runs under epi1 / c2 / epi2 of the current tile
-      conv2(cnt);
+      if (nxt < pl.total_tiles) conv1(cnt + 1, nxt);     // runs under epi1 / c2 / epi2 of the current tile
+      conv2(cnt, tile);
       tile = nxt;
       ++cnt;
     }
@@ -575,28 +591,34 @@ int debug_gp_pair_plan(const GpPairParams& p, int mode, int* v) {
 }
 
 template <int MODE, int MT, int KBG>
-static int launch_pair_variant(const GpPairParams& p, const gpp::PPlan& pl, cudaStream_t st) {
+static int launch_pair_variant(const GpPairParams& p, const gpp::PPlan& pl, const GpPairGroups& gs, cudaStream_t st) {
   static std::atomic<uint64_t> attr_devs{0};
   if (first_use_on_device(attr_devs))
     cudaFuncSetAttribute(gpp::resblock_gp_kernel<MODE, MT, KBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   const int nsm = sm_count();
   const int grid = pl.total_tiles < nsm ? pl.total_tiles : nsm;
   if (pdl_mode()) {
-    const cudaError_t e = launch_with_pdl(gpp::resblock_gp_kernel<MODE, MT, KBG>, dim3((unsigned)grid), dim3(gpp::GPP_THREADS), (size_t)pl.smem_total, st, p, pl);
+    const cudaError_t e = launch_with_pdl(gpp::resblock_gp_kernel<MODE, MT, KBG>, dim3((unsigned)grid), dim3(gpp::GPP_THREADS), (size_t)pl.smem_total, st, p, pl, gs);
     if (e != cudaSuccess) { set_error("resblock_gp_kernel (PDL launch): %s", cudaGetErrorString(e)); return EV_ECUDA; }
     count_launch();
     return EV_OK;
   }
-  gpp::resblock_gp_kernel<MODE, MT, KBG><<<grid, gpp::GPP_THREADS, pl.smem_total, st>>>(p, pl);
+  gpp::resblock_gp_kernel<MODE, MT, KBG><<<grid, gpp::GPP_THREADS, pl.smem_total, st>>>(p, pl, gs);
   EV_CUDA_LAUNCH_CHECK("resblock_gp_kernel");
   return EV_OK;
 }
 
 template <int MODE, int KBG>
-static int launch_pair_mt(const GpPairParams& p, const gpp::PPlan& pl, cudaStream_t st) {
-  if (pl.mt == 4) return launch_pair_variant<MODE, 4, KBG>(p, pl, st);
-  if (pl.mt == 2) return launch_pair_variant<MODE, 2, KBG>(p, pl, st);
-  return launch_pair_variant<MODE, 1, KBG>(p, pl, st);
+static int launch_pair_mt(const GpPairParams& p, const gpp::PPlan& pl, const GpPairGroups& gs, cudaStream_t st) {
+  if (pl.mt == 4) return launch_pair_variant<MODE, 4, KBG>(p, pl, gs, st);
+  if (pl.mt == 2) return launch_pair_variant<MODE, 2, KBG>(p, pl, gs, st);
+  return launch_pair_variant<MODE, 1, KBG>(p, pl, gs, st);
+}
+static int dispatch_pair(const GpPairParams& p, const gpp::PPlan& pl, const GpPairGroups& gs, int mode, cudaStream_t st) {
+  if (mode == 1) return launch_pair_mt<1, 4>(p, pl, gs, st);
+  if (mode == 3) return pl.kbg == 8 ? launch_pair_mt<3, 8>(p, pl, gs, st) : launch_pair_mt<3, 4>(p, pl, gs, st);
+  if (mode == 2) return pl.kbg == 8 ? launch_pair_mt<2, 8>(p, pl, gs, st) : launch_pair_mt<2, 4>(p, pl, gs, st);
+  return pl.kbg == 8 ? launch_pair_mt<0, 8>(p, pl, gs, st) : launch_pair_mt<0, 4>(p, pl, gs, st);
 }
 
 template <int MODE, int KBG>
@@ -614,10 +636,70 @@ void preload_resblock_gp() {      // see preload_conv1d_gp
 int launch_gp_pair(const GpPairParams& p, int mode, cudaStream_t st) {
   gpp::PPlan pl;
   if (!plan_pair(p, mode, &pl)) { set_error("resblock_gp: shape not supported (C=%d K=%d dil=%d mode=%d)", p.C, p.K, p.dil, mode); return EV_EINVAL; }
-  if (mode == 1) return launch_pair_mt<1, 4>(p, pl, st);
-  if (mode == 3) return pl.kbg == 8 ? launch_pair_mt<3, 8>(p, pl, st) : launch_pair_mt<3, 4>(p, pl, st);
-  if (mode == 2) return pl.kbg == 8 ? launch_pair_mt<2, 8>(p, pl, st) : launch_pair_mt<2, 4>(p, pl, st);
-  return pl.kbg == 8 ? launch_pair_mt<0, 8>(p, pl, st) : launch_pair_mt<0, 4>(p, pl, st);
+  GpPairGroups gs{};
+  gs.ng = 1;
+  gs.g[0] = GpPairGroup{p.x, p.w1, p.b1, p.w2, p.b2, p.out, p.K, p.dil, pl.R, pl.tiles_m, 0};
+  return dispatch_pair(p, pl, gs, mode, st);
+}
+
+int gp_pair_solo_tiles(const GpPairParams& p, int mode) {
+  gpp::PPlan pl;
+  return plan_pair(p, mode, &pl) ? pl.total_tiles : 0;
+}
+
+// ---- grouped launch: members ordered heaviest first; one MT for all (the smallest any member's own plan takes, >= 2), stage sizes from
+// ---- the widest halos; each member keeps its own rows per tile R = 128*MT - (K-1) and tile count ------------------------------------
+static bool plan_pair_group(const GpPairParams* ps, int n, int mode, GpPairGroups* gs, gpp::PPlan* out) {
+  if (!ps || n < 1 || n > 3) return false;
+  const GpPairParams& a = ps[0];
+  int kbg = 0, span1 = 0, kmax = 0;
+  for (int i = 0; i < n; ++i) {
+    const GpPairParams& q = ps[i];
+    if (q.B != a.B || q.L != a.L || q.C != a.C || q.lens != a.lens || q.lens_mul != a.lens_mul || q.slope != a.slope || q.acc != EV_ACC_STORE) return false;
+    if (!q.x || !q.out || !q.w1 || !q.w2 || !q.b1 || !q.b2 || q.x == q.out) return false;
+    for (int j = 0; j < n; ++j)
+      if (j != i && (ps[j].out == q.out || ps[j].out == q.x)) return false;       // a member's output is nobody's input
+    gpp::PPlan solo;
+    if (!plan_pair(q, mode, &solo) || solo.mt < 2) return false;
+    if (i == 0) kbg = solo.kbg;
+    else if (solo.kbg != kbg) return false;
+    span1 = (q.K - 1) * q.dil > span1 ? (q.K - 1) * q.dil : span1;
+    kmax = q.K > kmax ? q.K : kmax;
+  }
+  int order[3] = {0, 1, 2};
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+      if (ps[order[j]].K > ps[order[i]].K) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+  const int nsm = sm_count();
+  for (int mt = 4; mt >= 2; mt >>= 1) {
+    gpp::PPlan pl;
+    if (!gpp::make_pplan(a, mode, mt, kbg, &pl, span1, kmax)) continue;
+    int total = 0;
+    gs->ng = n;
+    for (int i = 0; i < n; ++i) {
+      const GpPairParams& q = ps[order[i]];
+      const int R = tc::BM * mt - (q.K - 1);
+      const int tm = (q.L + R - 1) / R;
+      gs->g[i] = GpPairGroup{q.x, q.w1, q.b1, q.w2, q.b2, q.out, q.K, q.dil, R, tm, total};
+      total += q.B * tm;
+    }
+    if (mt > 2 && total < 2 * nsm) continue;          // keep about two tiles per SM: prefer the smaller tile
+    pl.total_tiles = total;
+    *out = pl;
+    return true;
+  }
+  return false;
+}
+bool gp_pair_group_supported(const GpPairParams* ps, int n, int mode) {
+  GpPairGroups gs{};
+  gpp::PPlan pl;
+  return plan_pair_group(ps, n, mode, &gs, &pl);
+}
+int launch_gp_pair_group(const GpPairParams* ps, int n, int mode, cudaStream_t st) {
+  GpPairGroups gs{};
+  gpp::PPlan pl;
+  if (!plan_pair_group(ps, n, mode, &gs, &pl)) { set_error("resblock_gp group: the %d layers do not share a launch shape", n); return EV_EINVAL; }
+  return dispatch_pair(ps[0], pl, gs, mode, st);
 }
 
 }  // namespace ev

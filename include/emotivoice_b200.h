@@ -215,6 +215,12 @@ EV_API int ev_debug_gp_group_plan(int n, const int* K, const int* dil, int B, in
  * (the engine then runs the pair unfused). */
 EV_API int ev_op_resblock_gp(const void* x, const float* w1, const float* b1, const float* w2, const float* b2, int mode, void* out, int B,
                              int L, int C, int K, int dil, const int32_t* lens, int lens_mul, int acc, float div, void* stream);
+/* n <= 3 such layers of ONE shape (B, L, C; plain store) with their own taps / dilations / weights / tensors as ONE launch: the
+ * same-index layers of HiFi-GAN's three parallel ResBlocks at small batch.  Bitwise equal to the members' own launches; EV_EINVAL if
+ * they cannot share a launch (each member must itself be a shape ev_op_resblock_gp takes with at least two accumulators per tile). */
+EV_API int ev_op_resblock_gp_group(int n, const void* const* x, const float* const* w1, const float* const* b1, const float* const* w2,
+                                   const float* const* b2, int mode, void* const* out, int B, int L, int C, const int* K, const int* dil,
+                                   const int32_t* lens, int lens_mul, void* stream);
 /* Host-only: out11 = {MT, KBG, x stages, weight stages, transform warps, tmem columns, smem bytes, tiles, rows per tile, rows1_pad, rows2_pad}. */
 EV_API int ev_debug_resblock_gp_plan(int B, int L, int C, int K, int dil, int mode, int* out11);
 /* Host-only: out11 = {BN, MT, KBG, a_stages, b_stages, transform warps, planes, tmem columns, smem bytes, tiles, rows_pad}. */

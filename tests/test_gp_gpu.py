@@ -29,7 +29,7 @@ def test_gp_operator_check_tool(lib):
     rows = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert r.returncode == 0 and "GP_CHECK_OK" in r.stdout, [x for x in rows if not x.get("ok", True)]
     assert len([x for x in rows if "case" in x]) == 52 and len([x for x in rows if "pair" in x]) == 24
-    assert len([x for x in rows if "group" in x]) == 20
+    assert len([x for x in rows if "group" in x]) == 20 and len([x for x in rows if "pair_group" in x]) == 16
 
 
 _TM_CHILD = r"""

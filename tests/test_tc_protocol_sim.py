@@ -379,6 +379,15 @@ def test_gp_grouped_launch_protocol():
         sim_gp(seed, tiles, rng.randint(1, 4), taps, rng.randint(2, 4), rng.randint(2, 8), n_work_items=rng.choice((1, 2, 4)))
 
 
+def test_resblock_gp_grouped_launch_protocol():
+    """Grouped fused-ResBlock launch: consecutive tiles of a CTA may belong to layers with different taps; the weight loader streams
+    w1 of the NEXT tile's layer, then w2 of the current one, exactly as the MMA issuer consumes them."""
+    for seed in range(30):
+        rng = random.Random(seed)
+        n = rng.randint(1, 6)
+        sim_pair(seed, n, rng.randint(1, 3), [rng.choice((3, 7, 11)) for _ in range(n)], rng.randint(2, 4), rng.randint(2, 8))
+
+
 def test_gp_protocol_model_is_sensitive():
     """The model must fail when an epilogue warp without work items releases an accumulator set it never waited for
     (the round-1 hang), which is why the kernel's idle warps still wait on acc_full."""
@@ -392,6 +401,7 @@ def test_gp_protocol_model_is_sensitive():
 # ------------------------------------------------------------------------------------------------------------------
 def sim_pair(seed, n_tiles, n_cb, K, a_stages, b_stages):
     sim = Sim(seed)
+    taps = (lambda ti: K[ti]) if isinstance(K, (list, tuple)) else (lambda ti: K)     # grouped launch: the taps differ from tile to tile
     a_full = [Bar(1) for _ in range(a_stages)]
     a_ready = [Bar(NTW) for _ in range(a_stages)]
     a_empty = [Bar(1) for _ in range(a_stages)]
@@ -435,7 +445,7 @@ def sim_pair(seed, n_tiles, n_cb, K, a_stages, b_stages):
         b_cnt = 0
         for which, ti in order():
             for cb in range(n_cb):
-                for j in range(K):
+                for j in range(taps(ti)):
                     sb = b_cnt % b_stages
                     yield ("wait", b_empty[sb], ((b_cnt // b_stages) & 1) ^ 1)
                     yield ("write", ("B", sb), (which, ti, cb, j))
@@ -451,7 +461,7 @@ def sim_pair(seed, n_tiles, n_cb, K, a_stages, b_stages):
                 for cb in range(n_cb):
                     sa = a_cnt % a_stages
                     yield ("wait", a_ready[sa], (a_cnt // a_stages) & 1)
-                    for j in range(K):
+                    for j in range(taps(ti)):
                         sb = b_cnt % b_stages
                         yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
                         yield ("mma_read", ("X", sa), ("op", ti, cb))
@@ -466,7 +476,7 @@ def sim_pair(seed, n_tiles, n_cb, K, a_stages, b_stages):
                 yield ("wait", a2_full, ti & 1)
                 yield ("wait", acc2_empty[buf], ((ti >> 1) & 1) ^ 1)
                 for cb in range(n_cb):
-                    for j in range(K):
+                    for j in range(taps(ti)):
                         sb = b_cnt % b_stages
                         yield ("wait", b_full[sb], (b_cnt // b_stages) & 1)
                         yield ("mma_read", ("A2",), ti)

@@ -229,6 +229,54 @@ def main():
                 row.update(err=lib.ev_last_error().decode(), ok=False)
             ok_all = ok_all and row["ok"]
             print(json.dumps(row), flush=True)
+    # ---- grouped fused ResBlock layers against each member's own ev_op_resblock_gp launch: BITWISE ----
+    PGROUPS = [
+        # B, L, C, Ks, dils, ragged
+        (1, 68736, 64, (3, 7, 11), (1, 3, 5), 0),         # HiFi-GAN stage 3 at batch 1
+        (1, 137472, 32, (11, 3, 7), (5, 5, 5), 0),        # stage 4, members not sorted by taps
+        (2, 20000, 32, (3, 7, 11), (3, 3, 3), 1),
+        (3, 20000, 64, (7, 3), (1, 1), 1),
+    ]
+    for case in (PGROUPS[:1] if quick else PGROUPS):
+        B, L, C, Ks, dils, ragged = case
+        n = len(Ks)
+        g = torch.Generator().manual_seed(B + L + C + sum(Ks) + 7)
+        xs = [torch.randn(B, L, C, generator=g) for _ in range(n)]
+        w1s = [torch.randn(K, C, C, generator=g) / math.sqrt(C * K) for K in Ks]
+        w2s = [torch.randn(K, C, C, generator=g) / math.sqrt(C * K) for K in Ks]
+        b1s = [torch.randn(C, generator=g).to(dev) for _ in range(n)]
+        b2s = [torch.randn(C, generator=g).to(dev) for _ in range(n)]
+        prev = [torch.randn(B, L, C, generator=g) for _ in range(n)]
+        lens = torch.tensor([max(1, L // 2 - 5 * b) for b in range(B)], dtype=torch.int32, device=dev) if ragged else None
+        lens_mul = 2 if ragged else 1
+        valid = [L] * B if lens is None else [min(L, int(v) * lens_mul) for v in lens.tolist()]
+        for mode in (1, 0, 2, 3):
+            bf = mode == 2
+            pack = packing.to_tc16x2_layout if mode == 3 else (packing.to_tc16_layout if bf else packing.to_tc_layout)
+            w1d, w2d = [pack(w).to(dev) for w in w1s], [pack(w).to(dev) for w in w2s]
+            xg = [layout.to_gp(x, bf).to(dev) for x in xs]
+            solo = [layout.to_gp(q, bf).to(dev) for q in prev]
+            grp = [layout.to_gp(q, bf).to(dev) for q in prev]
+            rcs = [lib.ev_op_resblock_gp(ptr(xg[i]), ptr(w1d[i]), ptr(b1s[i]), ptr(w2d[i]), ptr(b2s[i]), mode, ptr(solo[i]), B, L, C, Ks[i], dils[i], ptr(lens), lens_mul,
+                                         _abi.ACC_STORE, 1.0, st) for i in range(n)]
+            VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
+            tab = lambda ts: VP(*[ptr(t) for t in ts])
+            rc = lib.ev_op_resblock_gp_group(n, tab(xg), tab(w1d), tab(b1s), tab(w2d), tab(b2s), mode, tab(grp), B, L, C, IA(*Ks), IA(*dils), ptr(lens), lens_mul, st)
+            torch.cuda.synchronize()
+            row = {"pair_group": [B, L, C, list(Ks), list(dils), ragged], "mode": mode, "rc": rc, "solo_rc": rcs}
+            if rc == 0 and not any(rcs):
+                eq, pad, fin = True, True, True
+                for i in range(n):
+                    a, r = layout.from_gp(grp[i].cpu()), layout.from_gp(solo[i].cpu())
+                    pg = layout.from_gp(layout.to_gp(prev[i], bf))
+                    eq = eq and all(torch.equal(a[b, :valid[b]], r[b, :valid[b]]) for b in range(B))
+                    fin = fin and all(bool(torch.isfinite(a[b, :valid[b]]).all()) for b in range(B))
+                    pad = pad and all(torch.equal(a[b, valid[b]:], pg[b, valid[b]:]) for b in range(B))
+                row.update(bitwise_vs_own_launches=eq, finite=fin, pad_rows_untouched=pad, ok=bool(eq and fin and pad))
+            else:
+                row.update(err=lib.ev_last_error().decode(), ok=False)
+            ok_all = ok_all and row["ok"]
+            print(json.dumps(row), flush=True)
     # boundary kernels
     g = torch.Generator().manual_seed(5)
     mel = torch.randn(2, 80, 37, generator=g)
