@@ -545,6 +545,24 @@ __global__ void __launch_bounds__(256) to_gp_kernel(const float* __restrict__ in
   reinterpret_cast<uint4*>(out)[i] = o;
 }
 
+// out = ((b + a) [+ c]) / div over whole fp32 granule-planar tensors: the `xs += ...; x = xs / n` of a HiFi-GAN stage
+// (hifigan/models.py:120-126) when the three ResBlocks' last layers ran as one grouped launch into their own tensors.  Same additions
+// in the same order as the accumulate modes of the epilogue (a stored, then b + a, then c + that, then / div): identical bits.
+template <int N>
+__global__ void __launch_bounds__(256) gp_sum_div_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ c,
+                                                         float4* __restrict__ out, size_t n4, float div) {
+  asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 va = a[i], vb = b[i];
+  float4 t = make_float4(vb.x + va.x, vb.y + va.y, vb.z + va.z, vb.w + va.w);
+  if (N == 3) {
+    const float4 vc = c[i];
+    t = make_float4(vc.x + t.x, vc.y + t.y, vc.z + t.z, vc.w + t.w);
+  }
+  out[i] = make_float4(t.x / div, t.y / div, t.z / div, t.w / div);
+}
+
 // wav[b,t] = tanh( bias + sum_j sum_c w[j][c] * lrelu(x[b, t+j-(K-1)/2, c]) ) on a GP input (hifigan/models.py:127-129:
 // F.leaky_relu default slope 0.01, Conv1d(C,1,7,pad 3), tanh).  HBM-bound: each CTA stages (256 + K - 1) rows once, already
 // activated; rows >= len read as zero padding and are written as zeros.  Same summation order as conv_post_kernel.  Generic shapes;
@@ -912,6 +930,26 @@ int launch_to_gp(const float* in, long long sb, long long st_, long long sc, voi
   }
   park_launch_error(e);
   EV_CUDA_LAUNCH_CHECK("to_gp_kernel");
+  return EV_OK;
+}
+
+int launch_gp_sum_div(const float* a, const float* b, const float* c, float* out, size_t n_floats, float div, cudaStream_t st) {
+  EV_CHECK_ARG(a && b && out && n_floats % 4 == 0, "gp_sum_div: bad arguments");
+  const size_t n4 = n_floats / 4;
+  const unsigned grid = (unsigned)((n4 + 255) / 256);
+  const float4 *a4 = reinterpret_cast<const float4*>(a), *b4 = reinterpret_cast<const float4*>(b), *c4 = reinterpret_cast<const float4*>(c);
+  float4* o4 = reinterpret_cast<float4*>(out);
+  cudaError_t e = cudaSuccess;
+  if (pdl_mode()) {
+    e = c ? launch_with_pdl(gp::gp_sum_div_kernel<3>, dim3(grid), dim3(256), 0, st, a4, b4, c4, o4, n4, div)
+          : launch_with_pdl(gp::gp_sum_div_kernel<2>, dim3(grid), dim3(256), 0, st, a4, b4, c4, o4, n4, div);
+  } else if (c) {
+    gp::gp_sum_div_kernel<3><<<grid, 256, 0, st>>>(a4, b4, c4, o4, n4, div);
+  } else {
+    gp::gp_sum_div_kernel<2><<<grid, 256, 0, st>>>(a4, b4, c4, o4, n4, div);
+  }
+  park_launch_error(e);
+  EV_CUDA_LAUNCH_CHECK("gp_sum_div_kernel");
   return EV_OK;
 }
 

@@ -525,16 +525,22 @@ static bool try_grouped_stage(ev_ctx* ctx, const VocBufs& v, int mode, size_t rb
     *rc = EV_OK;
     for (int l = 0; l < D && *rc == EV_OK; ++l) {
       const bool last = (l == D - 1);
+      // fp32 storage: the last layer is grouped too, into the blocks' own tensors, and one elementwise pass forms ((y1 + y0) + y2) / n
+      // -- the additions of the accumulate modes in their order, identical bits.  (With bf16 storage xs is rounded after every
+      // accumulation, which that pass cannot reproduce: three single launches.)
+      const bool sum_pass = last && gm != 2 && D >= 2;
       for (int j = 0; j < J; ++j) {
         const void* src = l == 0 ? (const void*)v.X : ((l & 1) ? Y[j] : T[j]);
-        void* dst = last ? (void*)v.ACC : ((l & 1) ? T[j] : Y[j]);
+        void* dst = (last && !sum_pass) ? (void*)v.ACC : ((l & 1) ? T[j] : Y[j]);
         int acc = EV_ACC_STORE;
-        if (last && j > 0) acc = (j == J - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;
+        if (last && !sum_pass && j > 0) acc = (j == J - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;
         try_gp_pair(mode, ctx->rb_c1[rb0 + (size_t)j * D + l], ctx->rb_c2[rb0 + (size_t)j * D + l], src, dst, B, L, C, lens, mul, acc, (float)J, st, &frc, true,
                     &pp[j], &gm);
       }
-      if (!last) {
+      if (!last || sum_pass) {
         *rc = launch_gp_pair_group(pp, J, gm, st);
+        if (sum_pass && *rc == EV_OK)
+          *rc = launch_gp_sum_div((const float*)pp[0].out, (const float*)pp[1].out, J == 3 ? (const float*)pp[2].out : nullptr, v.ACC, (size_t)B * L * C, (float)J, st);
       } else {
         for (int j = 0; j < J && *rc == EV_OK; ++j) *rc = launch_gp_pair(pp[j], gm, st);
       }
@@ -560,6 +566,7 @@ static bool try_grouped_stage(ev_ctx* ctx, const VocBufs& v, int mode, size_t rb
   *rc = EV_OK;
   for (int l = 0; l < D && *rc == EV_OK; ++l) {
     const bool last = (l == D - 1);
+    const bool sum_pass = last && gm != 2 && D >= 2;      // see the fused path above
     for (int j = 0; j < J; ++j) {      // xt_j = c1_j(lrelu(x_j))
       const ConvW& c1 = ctx->rb_c1[rb0 + (size_t)j * D + l];
       gp_params(mode, c1.w_tc, c1.w_h, c1.w_x2, l == 0 ? (const void*)v.X : Y[j], c1.b, nullptr, T[j], B, L, C, C, c1.K, c1.dil, 1, lens, mul, EV_ACT_LRELU, 0.1f,
@@ -572,11 +579,14 @@ static bool try_grouped_stage(ev_ctx* ctx, const VocBufs& v, int mode, size_t rb
       const void* res = l == 0 ? (const void*)v.X : Y[j];
       int acc = EV_ACC_STORE;
       if (last && j > 0) acc = (j == J - 1) ? EV_ACC_ADD_DIV : EV_ACC_ADD;       // xs += ...; x = xs / n
-      gp_params(mode, c2.w_tc, c2.w_h, c2.w_x2, T[j], c2.b, res, last ? (void*)v.ACC : Y[j], B, L, C, C, c2.K, 1, 1, lens, mul, EV_ACT_LRELU, 0.1f, acc,
+      if (sum_pass) acc = EV_ACC_STORE;
+      gp_params(mode, c2.w_tc, c2.w_h, c2.w_x2, T[j], c2.b, res, (last && !sum_pass) ? (void*)v.ACC : Y[j], B, L, C, C, c2.K, 1, 1, lens, mul, EV_ACT_LRELU, 0.1f, acc,
                 (float)J, &ps[j]);
     }
-    if (!last) {
+    if (!last || sum_pass) {
       *rc = launch_conv1d_gp_group(ps, J, gm, st);
+      if (sum_pass && *rc == EV_OK)
+        *rc = launch_gp_sum_div((const float*)Y[0], (const float*)Y[1], J == 3 ? (const float*)Y[2] : nullptr, v.ACC, (size_t)B * L * C, (float)J, st);
     } else {
       for (int j = 0; j < J && *rc == EV_OK; ++j) *rc = launch_conv1d_gp(ps[j], gm, st);
     }

@@ -211,6 +211,8 @@ bool gp_pair_group_supported(const GpPairParams* ps, int n, int mode);
 int launch_gp_pair_group(const GpPairParams* ps, int n, int mode, cudaStream_t st);
 int gp_pair_solo_tiles(const GpPairParams& p, int mode);
 int debug_gp_pair_plan(const GpPairParams& p, int mode, int* v11);
+// out = ((b + a) [+ c]) / div on whole fp32 tensors (c may be null): the stage-level `xs / n` after a grouped last layer
+int launch_gp_sum_div(const float* a, const float* b, const float* c, float* out, size_t n_floats, float div, cudaStream_t st);
 int launch_conv_post_gp(const void* x, int bf16, const float* w, const float* bias, const int32_t* lens, int lens_mul, int B, int L, int C, int K,
                         float slope, float* wav, cudaStream_t st);
 

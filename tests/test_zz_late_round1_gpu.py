@@ -182,7 +182,7 @@ m = JETSGenerator(conf).to("cuda:0"); m.load_state_dict(synth.make_state_dict(co
 z = np.load(sys.argv[2])
 keys = ("inputs_ling", "input_lengths", "inputs_speaker", "inputs_style_embedding", "inputs_content_embedding")
 res = {}
-for prec in ("fp32", "tf32"):
+for prec in ("fp32", "tf32", "bf16"):
     m.precision = prec
     for rep in range(3):                      # back-to-back forwards: launches of one forward overlap the tail of the previous one
         out = m(**{k: torch.from_numpy(z[k]).cuda() for k in keys})
@@ -209,7 +209,7 @@ def _check_knobs_bitwise(model, dev, tmp_path, knobs):
     got = np.load(dst)
     g = load_golden("b3_padded")
     try:
-        for prec in ("fp32", "tf32"):
+        for prec in ("fp32", "tf32", "bf16"):
             model.precision = prec
             out = model(**{k: g[k].to(dev) for k in KEYS})
             assert np.array_equal(out["dec_outputs"].cpu().numpy(), got[prec + "_mel"])

@@ -264,7 +264,12 @@ def main():
             rc = lib.ev_op_resblock_gp_group(n, tab(xg), tab(w1d), tab(b1s), tab(w2d), tab(b2s), mode, tab(grp), B, L, C, IA(*Ks), IA(*dils), ptr(lens), lens_mul, st)
             torch.cuda.synchronize()
             row = {"pair_group": [B, L, C, list(Ks), list(dils), ragged], "mode": mode, "rc": rc, "solo_rc": rcs}
-            if rc == 0 and not any(rcs):
+            # a member whose own plan keeps fewer than two accumulators per tile (3xTF32 at 64 channels) is not grouped: EV_EINVAL expected
+            v11 = (ctypes.c_int * 11)()
+            mts = [v11[0] if lib.ev_debug_resblock_gp_plan(B, L, C, Ks[i], dils[i], mode, v11) == 0 else 0 for i in range(n)]
+            if min(mts) < 2:
+                row.update(member_mt=mts, ok=bool(rc != 0))
+            elif rc == 0 and not any(rcs):
                 eq, pad, fin = True, True, True
                 for i in range(n):
                     a, r = layout.from_gp(grp[i].cpu()), layout.from_gp(solo[i].cpu())

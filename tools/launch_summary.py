@@ -1,5 +1,7 @@
 """Summarise an ncu launch list (`ncu --metrics gpu__time_duration.sum --csv --log-file X ...`): per-kernel launches, total and
-share of device time; with --per-step N divides by N forward passes.   python tools/launch_summary.py gpurun_out/launches.csv [--per-step N]"""
+share of device time; with --per-step N divides by N forward passes; with --steps-by KERNEL the window is trimmed to the whole steps
+between the first and the last launch of KERNEL (e.g. validate_inputs_kernel, the first launch of a forward) and divided by their number.
+   python tools/launch_summary.py gpurun_out/launches.csv [--per-step N | --steps-by validate_inputs]"""
 import csv
 import re
 import sys
@@ -21,6 +23,12 @@ def main():
         v = float(r[vi].replace(",", ""))
         v = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}.get(r[ui], 1.0)
         rows.append((re.sub(r"\(.*", "", r[ki]).replace("void ", "").strip(), v))
+    if "--steps-by" in sys.argv:
+        mk = sys.argv[sys.argv.index("--steps-by") + 1]
+        idx = [i for i, (k, _) in enumerate(rows) if mk in k]
+        if len(idx) >= 2:
+            rows = rows[idx[0]:idx[-1]]
+            per = len(idx) - 1
     agg = OrderedDict()
     for k, v in rows:
         a = agg.setdefault(k, [0, 0.0])
