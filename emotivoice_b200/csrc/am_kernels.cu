@@ -557,9 +557,10 @@ int launch_duration_scan(const int64_t* dur, const int32_t* lens, int invariant,
 // invariant != 0: frames >= mel_lens[b] are written as zeros (B=1 semantics per item);
 // otherwise all F frames are computed like the reference's padded batch does.
 // ---------------------------------------------------------------------------------------------
-constexpr int GU_FT = 16;   // frames per CTA
 constexpr int GU_TT = 16;   // tokens per smem chunk
-template <int NC, bool PDL>           // channels per thread: H = NC * 128
+// GU_FT frames per CTA (16, or 8 when the launch would otherwise leave most SMs idle: batch 1; the per-output token order, hence every
+// bit, does not depend on it)
+template <int NC, int GU_FT, bool PDL>           // channels per thread: H = NC * 128
 __global__ void __launch_bounds__(128) gauss_upsample_kernel(const float* __restrict__ hs, const float* __restrict__ centers,
                                                              const int32_t* __restrict__ lens,
                                                              const int32_t* __restrict__ mel_lens, int T, int F,
@@ -664,13 +665,19 @@ int launch_gauss_upsample(const float* hs, const float* centers, const int32_t* 
   EV_CHECK_ARG(H % 128 == 0 && H <= 512, "gauss_upsample: H=%d", H);
   EV_CHECK_ARG(F > 0 && T > 0, "gauss_upsample: F=%d T=%d", F, T);
   EV_CHECK_ARG(B <= 65535, "gauss_upsample: B too large");
-  dim3 grid((F + GU_FT - 1) / GU_FT, B);
+  const bool small = (long long)B * ((F + 15) / 16) < 2 * sm_count();
+  const int ft = small ? 8 : 16;
+  dim3 grid((F + ft - 1) / ft, B);
+#define EV_GU(NC)                                                                                                                              \
+  if (small) launch_k(gauss_upsample_kernel<NC, 8, true>, gauss_upsample_kernel<NC, 8, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); \
+  else launch_k(gauss_upsample_kernel<NC, 16, true>, gauss_upsample_kernel<NC, 16, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out);
   switch (H / 128) {
-    case 1: launch_k(gauss_upsample_kernel<1, true>, gauss_upsample_kernel<1, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
-    case 2: launch_k(gauss_upsample_kernel<2, true>, gauss_upsample_kernel<2, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
-    case 3: launch_k(gauss_upsample_kernel<3, true>, gauss_upsample_kernel<3, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
-    default: launch_k(gauss_upsample_kernel<4, true>, gauss_upsample_kernel<4, false>, grid, 128, 0, st, hs, centers, lens, mel_lens, T, F, invariant, pe, alpha, out); break;
+    case 1: EV_GU(1) break;
+    case 2: EV_GU(2) break;
+    case 3: EV_GU(3) break;
+    default: EV_GU(4) break;
   }
+#undef EV_GU
   EV_CUDA_LAUNCH_CHECK("gauss_upsample_kernel");
   return EV_OK;
 }
