@@ -57,8 +57,6 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const floa
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
-  const int klen = key_lens ? min(L, key_lens[b]) : L;
-  const int nkt = (klen + BKT - 1) / BKT;
   const size_t ld = (size_t)3 * H;
   const float* base = qkv + (size_t)b * L * ld;
 
@@ -89,7 +87,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const floa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Programmatic dependent launch: the set-up above ran under the predecessor's tail; EVERY thread now waits for the preceding grids
+  // before anything is read -- including key_lens, which in the encoder is written by validate_inputs_kernel a few launches upstream
+  // (a role that decoded its tile count from stale lengths would desynchronise the pipeline).
+  asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+  const int klen = key_lens ? min(L, key_lens[b]) : L;
+  const int nkt = (klen + BKT - 1) / BKT;
 
   if (warp < NSW) {
     // ================================ softmax: thread = query row ================================================

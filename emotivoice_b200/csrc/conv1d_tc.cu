@@ -179,9 +179,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   // the NEXT launch in the stream start as soon as SMs free up: that kernel's CTAs run their set-up (barriers, TMEM) while
   // this grid's tail is still running.  Everything that touches activations (producers: x; epilogue: res / out / split-K
   // partials) first executes griddepcontrol.wait, which returns once the preceding grid has completed and its writes are
-  // visible.  The weight loader and the MMA issuer read only weights and p.lens and do not wait: the first weight stages are
-  // prefetched under the predecessor's tail.  Contract: p.lens is not written by an engine kernel that may still be running
-  // (the engine's length vectors are inputs, or are read back by the host between phase 1 and phase 2).
+  // visible.  PDLM == 1 (only the convolutions launch this way, so the launch before a convolution's predecessor has fully
+  // completed): the loader and the MMA issuer, which read only weights and p.lens, do not wait and the first weight stages
+  // are prefetched under the predecessor's tail.  PDLM == 2 (every kernel launches this way): p.lens may come from a grid that
+  // is still running TWO launches upstream (validate_inputs_kernel writes the int32 lengths, LayerNorm starts early and waits,
+  // this kernel starts early too) -- a role that decoded tiles from stale lengths would walk a different tile sequence than
+  // the others and the pipeline would deadlock (seen once: a bench run whose batches had different lengths hung).  Every role waits.
   if (PDLM) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int n_cb = (p.Cin + KB - 1) / KB;
@@ -393,6 +396,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
     // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues the tcgen05 instructions
     // (descriptors stay in uniform registers: no vote loop / R2UR per MMA, see tc_common.cuh: elect_one).
     {
+      if (PDLM == 2) asm volatile("griddepcontrol.wait;" ::: "memory");      // p.lens (see the note after the set-up)
       const uint32_t a_lbo = (uint32_t)pl.rows_pad * 16u, b_lbo = (uint32_t)BN * 16u;
       const uint64_t a_desc0 = make_desc(0u, a_lbo, 128u), b_desc0 = make_desc(0u, b_lbo, 128u);
       const uint32_t a_tap = (uint32_t)p.dil * 16u, a_k8 = 2u * a_lbo, b_k8 = 2u * b_lbo;
@@ -465,6 +469,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(ConvParams p, Pl
   } else {
     // ============================ weight loader ==================================================
     if (lane == 0) {
+      if (PDLM == 2) asm volatile("griddepcontrol.wait;" ::: "memory");      // p.lens (see the note after the set-up)
       // w_tc layout: [plane (hi, lo)][N tile of BNp = min(Cout,128)][tap][Cin/CPG granules][BNp][16 bytes]
       // (4 fp32 or 8 bf16 per granule; granule-major inside a tile)
       const int cin4 = p.Cin / CPG;

@@ -224,6 +224,45 @@ def test_launch_modes_are_bitwise_identical(model, dev, tmp_path, knobs):
     _check_knobs_bitwise(model, dev, tmp_path, knobs)
 
 
+_ALTERNATE_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from emotivoice_b200 import synth
+from emotivoice_b200.config import default_config
+from emotivoice_b200.modules import JETSGenerator
+conf = default_config()
+m = JETSGenerator(conf).to("cuda:0"); m.load_state_dict(synth.make_state_dict(conf)); m.eval()
+batches = [synth.make_batch(lens, seed=11 + i) for i, lens in enumerate(([100], [23, 180, 61, 9], [150, 40], [12], [200, 199, 198, 20, 21, 22, 90, 91]))]
+batches = [{k: v.cuda() for k, v in b.items()} for b in batches]
+ok = True
+for prec in ("fp32", "bf16"):
+    m.precision = prec
+    first = {}
+    for rep in range(6):
+        for i, b in enumerate(batches):          # no synchronisation between forwards of different shapes and lengths
+            out = m(**b)
+            w = out["wav_predictions"]
+            if i not in first:
+                first[i] = w.clone()
+            else:
+                ok = ok and bool(torch.equal(w, first[i]))
+torch.cuda.synchronize()
+print("ALTERNATE_OK" if ok else "ALTERNATE_MISMATCH", flush=True)
+"""
+
+
+def test_back_to_back_batches_of_different_lengths():
+    """Programmatic dependent launch lets a kernel start while its predecessors still run; the int32 lengths are written by the first
+    kernel of a forward.  A role that read them before griddepcontrol.wait would decode tiles from the PREVIOUS batch's lengths: wrong
+    results or -- roles disagreeing on the tile sequence -- a deadlock (that happened once: tcgen05 roles that skipped the wait).
+    Alternating batches of very different lengths without host synchronisation must reproduce their first results bit for bit."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, "-c", _ALTERNATE_CHILD, ROOT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALTERNATE_OK" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
 def test_alignment_module_and_segments_match_reference_fixture(lib, dev):
     """The rest of SURVEY.md s8f rank 4: AlignmentModule.forward (five 3xTF32 convolutions on tcgen05 + the distance /
     log-softmax kernel + the host-built prior) against the unmodified reference module's output (1e-4 on finite entries, the

@@ -42,10 +42,13 @@ def main():
                 "| CPU baseline in the same run (oracle port, %d threads) | 1.34-1.36 k frames/s | %.0f frames/s |" % (b["cpu_baseline"]["cores"], b["cpu_baseline"]["value"]),
                 ""]
         rf = b["roofline"]
-        out += ["Dominant layer, timed live inside bench.py: %s: %.1f us, %.0f algorithmic TFLOP/s = **%.3f** of the measured bf16 peak (%.0f), "
-                "executing 3x that in bf16 MMAs (tensor-pipe estimate %.2f; ncu: 50.8 %% active, `r02_ncu_gp_bf16x3_c128k11_details.csv`); DRAM traffic %.1f MB "
-                "per launch vs %.1f MB algorithmic.  Round 1: 0.083 (88 us)." % (rf["kernel"], rf["ms"] * 1e3, rf["achieved"], rf["frac"], rf["peak"],
-                                                                              rf.get("tensor_pipe_frac_est", 0), (rf.get("traffic") or 0) / 1e6, 53.5), ""]
+        tr = json.load(open(os.path.join(P, "dominant_kernel_traffic.json"))).get("fp32", {})
+        out += ["Dominant launch, timed live inside bench.py: %s: %.1f us, %.0f algorithmic TFLOP/s = **%.3f** of the measured bf16 peak (%.0f), "
+                "executing 3x that in bf16 MMAs (tensor-pipe estimate %.2f; ncu of the same launch: tensor pipe %.1f %% active, %.1f us, DRAM traffic %.1f MB "
+                "vs %.1f MB algorithmic -- the in-place outputs stay in L2; `%s`).  Round 1: one convolution of this stage at 0.083 (88 us); the same single "
+                "convolution this round: 0.153 (41-46 us)." % (rf["kernel"], rf["ms"] * 1e3, rf["achieved"], rf["frac"], rf["peak"], rf.get("tensor_pipe_frac_est", 0),
+                                                            tr.get("tensor_pipe_pct", 0), tr.get("duration_us", 0), (rf.get("traffic") or 0) / 1e6,
+                                                            tr.get("algorithmic_bytes_per_launch", 0) / 1e6, tr.get("source", "").split(" ")[0]), ""]
         if "b1" in b:
             out += ["Fixture utterance (537 frames, 8.59 s of audio): %.2f ms = %.0fx real time (round 1: 6.28 ms)." % (b["b1"]["ms"], b["b1"]["x_rt"]), ""]
         if "b32" in b and "bf16" in b["b32"]:
@@ -82,7 +85,8 @@ def main():
         for r in d["cfg4"]:
             if "seconds" in r:
                 out.append("| %s | %d | %d | %.2f | %.0f | %.3f |" % (r["precision"], r["batch"], r["frames"], r["seconds"] * 1e3, r["mel_frames_per_sec"], r["frac_hbm"]))
-        out += ["", "(measured before the last kernel changes of the round; round 1 saturated at 230 k (fp32) / 403 k (tf32) frames/s = 0.17 / 0.31.)", ""]
+        out += ["", "(round 1 saturated at 230 k (fp32) / 403 k (tf32) frames/s = 0.17 / 0.31; `hbm_frac` uses SURVEY.md s8d's fp32 byte count for every "
+                    "mode, so the bf16 rows -- whose activations are stored as bf16 -- move half those bytes: their DRAM utilisation is about half the figure.)", ""]
 
     for name, title in (("r02_layer_sweep_b8_f1024.jsonl", "B=8, F=1024 (the cfg4 point)"), ("r02_layer_sweep_b1_f537.jsonl", "B=1, F=537 (the cfg2 utterance)")):
         rows = jl(name)
@@ -102,7 +106,7 @@ def main():
         for r in rows:
             out.append("| %s | %d | %d | %d | %d | %.1f | %.1f | **%.2f** | %.0f |" % (r["mode"], r["C"], r["K"], r["dil"], r["B"], r["fused_us"], r["unfused_us"], r["speedup"], r["fused_tflops"]))
         out += ["", "Round 1's fused kernel was 10-21 % SLOWER than its unfused path.  The engine fuses the 32-channel layers always and the 64-channel ones except "
-                    "k = 11 at large batch (both paths are bitwise equal, so the choice may depend on the batch).", ""]
+                    "k = 11 at large batch (both paths are bitwise equal, so the choice may depend on the batch).  (Measured mid-round, before PDL and the grouped launches.)", ""]
     rows = jl("r02_attention_tc_vs_ffma.jsonl")
     if rows:
         out += ["## Attention: tcgen05 kernel vs the fp32 FFMA flash kernel (`r02_attention_tc_vs_ffma.jsonl`, `tools/profile_attn.py`)", "",
@@ -111,10 +115,37 @@ def main():
             t, f = min(r["us"]["tc"][1:]), min(r["us"]["ffma"][1:])
             out.append("| %d | %d | %s | %.1f | %.1f | %.2f |" % (r["B"], r["L"], "3xTF32" if r["tc_mode"] else "tf32", t, f, f / t))
         out.append("")
+    pk = os.path.join(P, "r02_packed_batch_layer_shapes.json")
+    if os.path.exists(pk):
+        d = json.load(open(pk))
+        out += ["## Acoustic-model GEMM shapes at packed-batch size, time-major kernel conv1d_tc (`r02_packed_batch_layer_shapes.json`)", "", d["what"] + ".  " + d["peak_note"] + ".", "",
+                "| mode | layer | us | algorithmic TFLOP/s | tensor-pipe fraction (executed) |", "|---|---|---|---|---|"]
+        for r in d["rows"]:
+            out.append("| %s | %s | %.1f | %.0f | %.2f |" % (r["mode"], r["layer"], r["us"], r["tflops_algorithmic"], r["tensor_pipe_frac_est"]))
+        out += ["", "Round 1 (`r01_packed_batch_layer_shapes.json`): 3xTF32 0.34 / 0.62 / 0.52, tf32 0.13 / 0.36 / 0.30.  The >= 60 % target is met by the fp32-class "
+                    "modes' conv-FFN layers (0.73 / 0.67 3xTF32, 0.63 / 0.56 bf16x3) and missed by the 1x modes (tf32 0.40, bf16 0.28): this kernel still stages "
+                    "A through registers (the vocoder's granule-planar operand path was not ported to the acoustic model).", ""]
+    for name, title in (("r02_pdl_modes.log", "Programmatic dependent launch (EV_PDL = 0 / 1 / 2; before the grouped launches)"),
+                        ("r02_grouped_launches_b1.log", "Grouped launches on / off, fixture utterance, final code (`EV_VOC_GROUP`)"),
+                        ("r02_dominant_launch.log", "The dominant launch standalone (`tools/profile_dominant.py`: the grouped stage-2 convolutions, L2 flushed)")):
+        path = os.path.join(P, name)
+        if os.path.exists(path):
+            out += ["## %s (`%s`)" % (title, name), "", "```"] + [l.rstrip()[:230] for l in open(path).read().splitlines()] + ["```", ""]
+    wc = jl("r02_warm_vs_cold_b1.jsonl")
+    if wc:
+        out += ["## Batch-1 layers: L2-cold vs weights-warm vs everything-warm (`r02_warm_vs_cold_b1.jsonl`): weight fetch is not the limiter", "",
+                "| mode | C_in | C_out | k | L | cold us | weights warm us | all warm us |", "|---|---|---|---|---|---|---|---|"]
+        key = lambda r: (r["mode"], r["Cin"], r["Cout"], r["K"], r["L"])
+        tab = {}
+        for r in wc:
+            tab.setdefault(key(r), {})[r["warm"]] = r["best_us"]
+        for k, v in tab.items():
+            out.append("| %s | %d | %d | %d | %d | %.1f | %.1f | %.1f |" % (k + (v.get("none", 0), v.get("w", 0), v.get("all", 0))))
+        out.append("")
     for name, per, title in (("r02_launches_b1_fp32.csv", 3, "one B=1 fp32 step (cfg2 fixture utterance)"), ("r02_launches_b32_bf16.csv", 2, "one B=32 bf16 step (cfg3 batch)")):
         path = os.path.join(P, name)
         if os.path.exists(path):
-            txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), path, "--per-step", str(per)], capture_output=True, text=True).stdout
+            txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), path, "--steps-by", "validate_inputs"], capture_output=True, text=True).stdout
             out += ["## ncu launch list of %s (`%s`; cold-cache, serialised: compare shares)" % (title, name), "", "```"] + txt.splitlines()[:16] + ["```", ""]
     open(os.path.join(P, "r02_summary.md"), "w").write("\n".join(out) + "\n")
     print("\n".join(out[:40]))
