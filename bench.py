@@ -98,6 +98,16 @@ class ClockSampler:
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        # nvidia-smi's own start-up (driver handshake, ~100 ms) stalls kernel launches of this process; it must not overlap the timed
+        # region: wait for the first sample line (at most 3 s), the steady 100 ms sampling that follows does not disturb the device
+        t0 = time.perf_counter()
+        while self.proc is not None and time.perf_counter() - t0 < 3.0:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                break
+            time.sleep(0.02)
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
