@@ -273,15 +273,20 @@ def parity_vs_fixture(model, dev):
     return res
 
 
-def timed_forwards(fn, n, flush):
-    """n x (flush; event; fn(i); event) -> list of seconds; synchronises once at the end."""
+def timed_forwards(fn, n, flush, keep_last=False):
+    """n x (flush; event; fn(i); event) -> list of seconds; synchronises once at the end.  keep_last: only the last result is kept
+    (results that hold device tensors would otherwise pile up and force fresh cudaMallocs inside the timed steps)."""
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
     outs = []
     for i, (a, b) in enumerate(ev):
         flush()
         a.record()
-        outs.append(fn(i))
+        r = fn(i)
         b.record()
+        if keep_last:
+            outs = [r]
+        else:
+            outs.append(r)
     torch.cuda.synchronize()
     return [a.elapsed_time(b) * 1e-3 for a, b in ev], outs
 
@@ -375,7 +380,7 @@ def b32_block(model, dev, flush, headline_precision, conf, sd_cpu):
         model.precision = prec
         for _ in range(2):
             out = model(**batch)
-        ts, outs = timed_forwards(lambda i: model(**batch), 5, flush)
+        ts, outs = timed_forwards(lambda i: model(**batch), 5, flush, keep_last=True)
         out = outs[-1]
         t = statistics.median(ts)
         valid = int(out["mel_lengths_host"].sum())
@@ -407,7 +412,7 @@ def voc_block(model, dev, flush, peaks, headline_precision, lean):
         for (B, F) in points:
             mel = synth.make_mel(B, F, seed=B * 7 + F).to(dev)
             model.generator(mel)
-            ts, _ = timed_forwards(lambda i: model.generator(mel), 3, flush)
+            ts, _ = timed_forwards(lambda i: model.generator(mel), 3, flush, keep_last=True)
             t = statistics.median(ts)
             res["%s_b%d_f%d" % (prec, B, F)] = {"ms": _r(t * 1e3), "fps": _r(B * F / t), "tflops": _r(B * F * VOC_FLOP_PER_FRAME / t / 1e12),
                                                "hbm_frac": _r(B * F * VOC_BYTES_PER_FRAME / t / 1e9 / peaks["hbm_gbs"], 3)}
@@ -554,13 +559,17 @@ def main():
     barrier()
     l0 = _abi.launch_count()
     wall0 = time.perf_counter()
-    ts, outs = timed_forwards(lambda s: model(**dev_batches[args.warmup + s]), args.steps, flush)
+    def value_step(s):      # the outputs are dropped at once (only their shapes are kept): holding 20 waveforms would make torch's allocator
+        o = model(**dev_batches[args.warmup + s])      # cudaMalloc fresh segments inside the timed region (a device-synchronising call)
+        return int(o["dec_outputs"].shape[1]), int(o["wav_predictions"].shape[-1])
+
+    ts, outs = timed_forwards(value_step, args.steps, flush)
     barrier()
     wall = time.perf_counter() - wall0
     launches = _abi.launch_count() - l0
     dev_s = sum(ts)
-    frames = sum(int(o["dec_outputs"].shape[1]) for o in outs)
-    n_samples = sum(int(o["wav_predictions"].shape[-1]) for o in outs)
+    frames = sum(o[0] for o in outs)
+    n_samples = sum(o[1] for o in outs)
     del outs
 
     # ---- timed: end to end from host data (collate -> pinned -> H2D -> forward -> wav D2H pinned) --------
@@ -685,7 +694,7 @@ def b1_block(model, dev, flush, parity):
     batch = {k: torch.from_numpy(z[k]).to(dev) for k in keys}
     for _ in range(2):
         out = model(**batch)
-    ts, outs = timed_forwards(lambda i: model(**batch), 10, flush)
+    ts, outs = timed_forwards(lambda i: model(**batch), 10, flush, keep_last=True)
     frames = int(outs[-1]["dec_outputs"].shape[1])
     t = statistics.median(ts)
     return {"frames": frames, "ms": _r(t * 1e3), "x_rt": _r(frames * HOP / SR / t), "ms_min": _r(min(ts) * 1e3)}

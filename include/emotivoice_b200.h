@@ -150,7 +150,11 @@ EV_API int ev_am_phase2(ev_ctx* ctx, const void* phase1_workspace, const int32_t
 
 /* Replaces: Generator.forward (hifigan/models.py:115-131).
  *   mel (B,F,n_mels) time-major if mel_time_major else (B,n_mels,F) (the reference layout);
- *   mel_lens (B) i32 or NULL (literal padded semantics); wav_out (B, F*prod(up_rates)) f32. */
+ *   mel_lens (B) i32 or NULL (literal padded semantics); wav_out (B, F*prod(up_rates)) f32.
+ *   mel_lens must be COMPLETE when this is called (not pending in a kernel still running on the stream): the vocoder's kernels start
+ *   under their predecessors' tails (programmatic dependent launch) and read the lengths before they wait.  The engine's own flow
+ *   satisfies this by construction -- the host reads mel_lens_out back to learn F before it can call ev_am_phase2 / ev_vocoder.  The
+ *   same holds for the `lens` argument of the ev_op_*_gp entry points below. */
 EV_API int ev_vocoder(ev_ctx* ctx, const float* mel, int mel_time_major, const int32_t* mel_lens, int B, int F,
                       float* wav_out, void* workspace, size_t workspace_bytes, void* stream);
 
