@@ -17,6 +17,7 @@ ABI in include/emotivoice_b200.h.  PyTorch provides device memory and the stream
 is no CPU path: calling ``forward`` on CPU tensors raises.
 """
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -31,6 +32,10 @@ class _Holder(nn.Module):
 
     def forward(self, *a, **k):  # pragma: no cover
         raise RuntimeError("parameter holder: compute happens in libemotivoice_b200.so")
+
+
+_HOST_WAIT_BLOCK = os.environ.get("EV_HOST_WAIT", "") == "block"
+_TLS = threading.local()          # per-thread pinned read-back buffer + event
 
 
 def _bucket(nbytes):
@@ -131,6 +136,21 @@ class _Engine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _read_back(self, t):
+        """Device int32 vector -> host tensor, waiting by polling (EV_HOST_WAIT=block: a blocking copy)."""
+        if _HOST_WAIT_BLOCK:
+            return t.cpu()
+        tl = _TLS
+        n = t.numel()
+        if getattr(tl, "pin", None) is None or tl.pin.numel() < n:
+            tl.pin = torch.empty((max(n, 1024),), dtype=torch.int32).pin_memory()
+            tl.ev = torch.cuda.Event()
+        tl.pin[:n].copy_(t, non_blocking=True)
+        tl.ev.record(torch.cuda.current_stream(self.device))
+        while not tl.ev.query():
+            pass
+        return tl.pin[:n].clone()
+
     def acoustic(self, ling, lens, spk, style, content, invariant):
         lib, dev = self.lib, self.device
         B, T = ling.shape
@@ -147,8 +167,10 @@ class _Engine:
         _abi.check(lib.ev_am_phase1(self.handle, ling.data_ptr(), lens.data_ptr(), spk.data_ptr(), style.data_ptr(),
                                     content.data_ptr(), B, T, int(invariant), dur.data_ptr(), pitch.data_ptr(),
                                     energy.data_ptr(), lens32_ptr, mel_lens_ptr, ws1.data_ptr(), n1, st))
-        # the path's single host sync: the output length is data dependent (alignment.py:194-195)
-        mel_lens_host = meta[B:].cpu()
+        # the path's single host sync: the output length is data dependent (alignment.py:194-195).  Asynchronous copy into pinned
+        # memory + a polled event instead of a blocking .cpu(): a blocking wait of a few milliseconds puts the thread to sleep, and its
+        # wake-up latency (measured: 5-15 ms now and then on a busy host) would sit in the middle of the forward with the GPU idle.
+        mel_lens_host = self._read_back(meta[B:])
         status = int(mel_lens_host[B + 1])
         if status:      # what nn.Embedding / the mask construction raise in the reference (checked on the device, read with the lengths)
             if status & 1:
