@@ -54,7 +54,8 @@ WORKLOAD = ("cfg2: batch=1, one 100-phoneme utterance per step (distinct seeded 
             "PromptTTS AM + HiFi-GAN")
 # identical on both arms (the driver compares it): everything arm-specific lives in `detail`
 CONFIG = {"workload": WORKLOAD, "batch": 1, "phonemes_per_utterance": N_PHONEMES, "corpus_seed": 1234,
-          "l2": "flushed between timed steps", "timing": "per-step CUDA events, max over ranks"}
+          "l2": "flushed between timed steps", "timing": "per-step CUDA events, max over ranks",
+          "workspace": "arena reserved at start-up for 1 x 1024 frames (JETSGenerator.reserve), grow-only afterwards"}
 VOC_FLOP_PER_FRAME = 614105088.0
 VOC_BYTES_PER_FRAME = 5010752.0        # layer-granular fp32 activation traffic per mel frame
 MAX_LINE = 4096
@@ -545,6 +546,9 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # serving set-up: size the workspace arena once (no device allocation inside the timed steps when a longer utterance arrives)
+    model.reserve(batch=1, phonemes=N_PHONEMES + 28, frames=1024)
 
     # ---- warm-up -----------------------------------------------------------------------
     for s in range(args.warmup):

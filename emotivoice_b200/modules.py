@@ -107,6 +107,8 @@ class _Engine:
                                             ctypes.cast(self.index, ctypes.c_void_p), len(self.index)))
         self.set_precision(precision)
         self.pe = None
+        self._arena = {}              # (stream, kind) -> uint8 workspace, grow-only
+        self.call_lock = threading.RLock()      # one forward at a time enqueues on an engine (its workspaces are reused, stream-ordered)
         self.ensure_pe(5000)          # PositionalEncoding max_len=5000 (encoder.py:206)
         self.total_up = int(np.prod([self.cfg.up_rates[i] for i in range(self.cfg.n_ups)]))
 
@@ -136,6 +138,30 @@ class _Engine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _ws(self, kind, nbytes):
+        """Grow-only workspace arena, one buffer per (stream, kind): after the largest request has been seen (or `reserve`d) no call
+        allocates device memory any more -- a fresh cudaMalloc in the middle of a forward is a device-synchronising stall of
+        milliseconds.  Reuse across calls is safe because every use is ordered on the stream the buffer belongs to."""
+        key = (self._stream(), kind)
+        t = self._arena.get(key)
+        if t is None or t.numel() < nbytes:
+            self._arena.pop(key, None)
+            t = None
+            t = torch.empty((_bucket(nbytes),), dtype=torch.uint8, device=self.device)
+            self._arena[key] = t
+        return t
+
+    def reserve(self, batch, phonemes, frames):
+        """Pre-size the arena of the current stream for requests up to (batch, phonemes, frames)."""
+        lib = self.lib
+        fs = {int(frames)}
+        if batch * frames > 2400:                 # small batches carry extra grouped-launch buffers: cover the largest of those shapes too
+            fs.add(max(1, 2400 // int(batch)))
+        with self.call_lock:
+            self.ensure_pe(max(int(frames), int(phonemes)))
+            self._ws("p1", lib.ev_phase1_workspace_bytes(self.handle, int(batch), int(phonemes)))
+            self._ws("p2", max(lib.ev_phase2_workspace_bytes(self.handle, int(batch), f) for f in fs))
+
     def _read_back(self, t):
         """Device int32 vector -> host tensor, waiting by polling (EV_HOST_WAIT=block: a blocking copy)."""
         if _HOST_WAIT_BLOCK:
@@ -159,8 +185,8 @@ class _Engine:
         pitch = torch.empty((B, T), dtype=torch.float32, device=dev)
         energy = torch.empty((B, T), dtype=torch.float32, device=dev)
         meta = torch.empty((2 * B + 2,), dtype=torch.int32, device=dev)      # lens32 (B) | mel_lens (B) | max | input status
-        n1 = _bucket(lib.ev_phase1_workspace_bytes(self.handle, B, T))
-        ws1 = torch.empty((n1,), dtype=torch.uint8, device=dev)
+        ws1 = self._ws("p1", lib.ev_phase1_workspace_bytes(self.handle, B, T))
+        n1 = ws1.numel()
         st = self._stream()
         lens32_ptr = meta.data_ptr()
         mel_lens_ptr = meta.data_ptr() + 4 * B
@@ -180,8 +206,8 @@ class _Engine:
             raise RuntimeError("input_lengths must lie in [1, %d] (the padded width of inputs_ling)" % T)
         F = int(mel_lens_host[B])
         self.ensure_pe(F)
-        n2 = _bucket(lib.ev_phase2_workspace_bytes(self.handle, B, F))
-        ws2 = torch.empty((n2,), dtype=torch.uint8, device=dev)
+        ws2 = self._ws("p2", lib.ev_phase2_workspace_bytes(self.handle, B, F))
+        n2 = ws2.numel()
         mel = torch.empty((B, F, int(self.cfg.n_mels)), dtype=torch.float32, device=dev)
         _abi.check(lib.ev_am_phase2(self.handle, ws1.data_ptr(), lens32_ptr, mel_lens_ptr, B, T, F, int(invariant),
                                     mel.data_ptr(), ws2.data_ptr(), n2, st))
@@ -195,8 +221,8 @@ class _Engine:
         else:
             B, _, F = mel.shape
         if ws is None:
-            n = _bucket(lib.ev_phase2_workspace_bytes(self.handle, B, F))
-            ws = torch.empty((n,), dtype=torch.uint8, device=dev)
+            ws = self._ws("p2", lib.ev_phase2_workspace_bytes(self.handle, B, F))
+            n = ws.numel()
         wav = torch.empty((B, 1, F * self.total_up), dtype=torch.float32, device=dev)
         _abi.check(lib.ev_vocoder(self.handle, mel.data_ptr(), int(bool(time_major)), mel_lens_ptr, B, F,
                                   wav.data_ptr(), ws.data_ptr(), n, self._stream()))
@@ -310,7 +336,8 @@ class Generator(_EngineOwner):
     def forward(self, x):
         eng = self._engine()
         x = _prep(x, torch.float32, eng.device)
-        return eng.vocode(x, time_major=False, mel_lens_ptr=None)
+        with eng.call_lock:
+            return eng.vocode(x, time_major=False, mel_lens_ptr=None)
 
     def remove_weight_norm(self):
         """hifigan/models.py:133-140 (broken on torch >= 2.1 in the reference):
@@ -352,8 +379,9 @@ class PromptTTS(_EngineOwner):
         if mel_targets is not None:
             raise NotImplementedError("training-mode forward (teacher forcing) is out of scope for this engine")
         eng = self._engine()
-        return _am_forward(eng, inputs_ling, input_lengths, inputs_speaker, inputs_style_embedding,
-                           inputs_content_embedding, not self.compat_padded_batch)[0]
+        with eng.call_lock:
+            return _am_forward(eng, inputs_ling, input_lengths, inputs_speaker, inputs_style_embedding,
+                               inputs_content_embedding, not self.compat_padded_batch)[0]
 
 
 def _am_forward(eng, inputs_ling, input_lengths, inputs_speaker, style, content, invariant):
@@ -423,6 +451,16 @@ class JETSGenerator(_EngineOwner):
             raise NotImplementedError("training-mode forward (teacher forcing / random segments) is out of scope")
         eng = self._engine()
         invariant = not self.compat_padded_batch
+        with eng.call_lock:
+            return self._forward_locked(eng, invariant, inputs_ling, input_lengths, inputs_speaker, inputs_style_embedding, inputs_content_embedding)
+
+    def reserve(self, batch=1, phonemes=256, frames=2048):
+        """Serving set-up: pre-size the engine's workspace arena (current CUDA stream) for requests up to this shape, so that no
+        forward allocates device memory afterwards.  Without it the arena simply grows when a larger request arrives (one allocation
+        stall per new maximum)."""
+        self._engine().reserve(batch, phonemes, frames)
+
+    def _forward_locked(self, eng, invariant, inputs_ling, input_lengths, inputs_speaker, inputs_style_embedding, inputs_content_embedding):
         outputs, r = _am_forward(eng, inputs_ling, input_lengths, inputs_speaker, inputs_style_embedding,
                                  inputs_content_embedding, invariant)
         B = r["mel"].shape[0]
