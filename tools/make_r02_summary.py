@@ -68,14 +68,19 @@ def main():
             c = b["cfg5"]
             out += ["cfg5 block (256 utterances per GPU, B=32 buckets, pinned int16 D2H, wall clock): %.0f utterances/s, %.0f frames/s at N=1 "
                     "(host collate %.1f ms, trim + sha1 %.0f ms of %.0f ms)." % (c["utt_per_s"], c["fps"], c["host_collate_s"] * 1e3, c["host_finish_s"] * 1e3, c["wall_s"] * 1e3), ""]
+        if "cfg5_strong" in b:
+            c = b["cfg5_strong"]
+            out += ["cfg5_strong (the same pipeline on a FIXED 2048-utterance corpus; strong scaling): %.0f utterances/s, %.0f frames/s at N=1 (%.2f s)."
+                    % (c["utt_per_s"], c["fps"], c["wall_s"]), ""]
     for n in (2, 4, 8):
         bn = last_json("r02_bench_n%d.json" % n)
         if bn and b:
             out += ["N=%d (`r02_bench_n%d.json`): value %.0f frames/s (%.2fx N=1), e2e %.0f (%.2fx); cfg5 %.0f utt/s (%.2fx), digest of utterances 0..255 %s "
-                    "(N=1: %s); weight distribution: raw %.0f ms + pack-and-blob %.0f ms (%.0f MB)."
+                    "(N=1: %s); cfg5_strong (2048 utterances, fixed) %.0f utt/s (%.2fx), digest over all of them %s (N=1: %s); weight distribution: raw %.0f ms + pack-and-blob %.0f ms (%.0f MB)."
                     % (n, n, bn["value"], bn["value"] / b["value"], bn["e2e"]["value"], bn["e2e"]["value"] / b["e2e"]["value"], bn["cfg5"]["utt_per_s"],
                        bn["cfg5"]["utt_per_s"] / b["cfg5"]["utt_per_s"], bn["cfg5"].get("digest_first256"), b["cfg5"].get("digest_first256"),
-                       bn["weights"]["raw_ms"], bn["weights"]["pack_and_blob_ms"], bn["weights"]["blob_mb"]), ""]
+                       bn["cfg5_strong"]["utt_per_s"], bn["cfg5_strong"]["utt_per_s"] / b["cfg5_strong"]["utt_per_s"], bn["cfg5_strong"].get("digest"),
+                       b["cfg5_strong"].get("digest"), bn["weights"]["raw_ms"], bn["weights"]["pack_and_blob_ms"], bn["weights"]["blob_mb"]), ""]
 
     sw = os.path.join(P, "r02_sweep_cfg4_with_corner.json")
     if os.path.exists(sw):
