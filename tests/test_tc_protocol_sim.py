@@ -367,6 +367,43 @@ def test_gp_summation_order_parameters_do_not_depend_on_batch_or_length(lib):
             assert len(kbgs) == 1, (Cin, Cout, K, dil, mode, kbgs)
 
 
+def _gp_group_plan(lib, Ks, dils, B, L, Cin, Cout, mode):
+    n = len(Ks)
+    v = (ctypes.c_int * 11)()
+    IA = ctypes.c_int * n
+    assert lib.ev_debug_gp_group_plan(n, IA(*Ks), IA(*dils), B, L, Cin, Cout, mode, v) == 0, lib.ev_last_error()
+    return dict(zip("BN MT KBG a_stages b_stages ntw planes tmem smem tiles rows_pad".split(), list(v)))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(1, 4296, 256), (1, 34368, 128), (2, 3000, 128), (3, 900, 64)])
+def test_gp_grouped_launch_plans(lib, shape, mode):
+    """The grouped launch (three convolutions of one shape in a kernel) must use each member's own K granules per stage (the
+    reduction order: bitwise equality with the members' own launches), size its stages for the widest halo, and carry every
+    member's tiles; and it must fit the same hardware limits as a single launch."""
+    B, L, C = shape
+    Ks, dils = (3, 7, 11), (1, 3, 5)
+    g = _gp_group_plan(lib, Ks, dils, B, L, C, C, mode)
+    solo = [_gp_plan(lib, B, L, C, C, K, d, 1, mode) for K, d in zip(Ks, dils)]
+    assert {p["KBG"] for p in solo} == {g["KBG"]}
+    assert g["smem"] <= 227 * 1024 and 2 * g["MT"] * g["BN"] <= g["tmem"] <= 512
+    assert g["rows_pad"] >= 128 * g["MT"] + (11 - 1) * 5 and g["rows_pad"] % 8 == 0
+    tiles_one = B * -(-L // (128 * g["MT"])) * (C // g["BN"])
+    assert g["tiles"] == 3 * tiles_one
+    n_cb = -(-C // ((8 if mode == 2 else 4) * g["KBG"]))
+    for seed in range(3):
+        rng = random.Random(seed)
+        n = rng.randint(2, 6)
+        sim_gp(seed, [True] * n, min(n_cb, 4), [rng.choice(Ks) for _ in range(n)], g["a_stages"], g["b_stages"], n_work_items=g["MT"] * (g["BN"] // 32))
+
+
+def test_gp_grouped_launch_plan_fills_the_machine_at_batch_1(lib):
+    """HiFi-GAN stage 1 at batch 1 in the fp32 mode: 3 x 68 one-accumulator tiles (204 > 148 SMs) instead of 3 x 34 two-accumulator
+    ones -- the plan is picked by simulating the round-robin deal, where the k = 11 member's double tile would be the critical path."""
+    g = _gp_group_plan(lib, (3, 7, 11), (1, 3, 5), 1, 4296, 256, 256, 3)
+    assert g["MT"] == 1 and g["tiles"] == 204
+
+
 def test_gp_grouped_launch_protocol():
     """A grouped launch (conv1d_gp_group: the same-index convolutions of three parallel ResBlocks in one kernel) changes the number of
     taps -- weight stages per activation stage -- from tile to tile; the weight loader and the MMA issuer derive it from the same
