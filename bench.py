@@ -99,9 +99,8 @@ class ClockSampler:
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
-        # nvidia-smi's own start-up (driver handshake, ~100 ms) stalls kernel launches of this process; it must not overlap the timed
-        # region: wait for the first sample line (at most 3 s).  Every later sample (the recipe's 200 ms interval) still costs the step it lands
-        # in ~10 ms -- the query waits for the device, and with programmatic dependent launches there is no idle gap between kernels
+        # nvidia-smi's own start-up (driver handshake, ~100 ms) should not overlap the timed region: wait for the first sample line
+        # (at most 3 s); the samples that follow come at the recipe's 200 ms interval
         t0 = time.perf_counter()
         while self.proc is not None and time.perf_counter() - t0 < 3.0:
             try:
