@@ -1084,6 +1084,18 @@ int ev_op_resblock_gp_group(int n, const void* const* x, const float* const* w1,
   return launch_gp_pair_group(ps, n, mode, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int ev_debug_resblock_gp_group_plan(int n, const int* K, const int* dil, int B, int L, int C, int mode, int* out16) {
+  EV_CHECK_ARG(out16 && K && dil && n >= 1 && n <= 3, "ev_debug_resblock_gp_group_plan: bad arguments");
+  static float dummy_in[3], dummy_out[3], dummy_w;
+  GpPairParams ps[3];
+  for (int i = 0; i < n; ++i) {
+    ps[i] = GpPairParams{};
+    ps[i].x = &dummy_in[i]; ps[i].out = &dummy_out[i]; ps[i].w1 = ps[i].w2 = ps[i].b1 = ps[i].b2 = &dummy_w;
+    ps[i].B = B; ps[i].L = L; ps[i].C = C; ps[i].K = K[i]; ps[i].dil = dil[i]; ps[i].lens_mul = 1; ps[i].slope = 0.1f; ps[i].acc = EV_ACC_STORE; ps[i].div = 1.f;
+  }
+  return debug_gp_pair_group_plan(ps, n, mode, out16);
+}
+
 int ev_debug_resblock_gp_plan(int B, int L, int C, int K, int dil, int mode, int* out11) {
   EV_CHECK_ARG(out11, "ev_debug_resblock_gp_plan: null output");
   static float dummy_in, dummy_out;

@@ -210,6 +210,7 @@ int launch_gp_pair(const GpPairParams& p, int mode, cudaStream_t st);      // mo
 bool gp_pair_group_supported(const GpPairParams* ps, int n, int mode);
 int launch_gp_pair_group(const GpPairParams* ps, int n, int mode, cudaStream_t st);
 int gp_pair_solo_tiles(const GpPairParams& p, int mode);
+int debug_gp_pair_group_plan(const GpPairParams* ps, int n, int mode, int* v16);
 int debug_gp_pair_plan(const GpPairParams& p, int mode, int* v11);
 // out = ((b + a) [+ c]) / div on whole fp32 tensors (c may be null): the stage-level `xs / n` after a grouped last layer
 int launch_gp_sum_div(const float* a, const float* b, const float* c, float* out, size_t n_floats, float div, cudaStream_t st);

@@ -690,6 +690,18 @@ static bool plan_pair_group(const GpPairParams* ps, int n, int mode, GpPairGroup
   }
   return false;
 }
+int debug_gp_pair_group_plan(const GpPairParams* ps, int n, int mode, int* v) {      // v[16]
+  GpPairGroups gs{};
+  gpp::PPlan pl;
+  if (!plan_pair_group(ps, n, mode, &gs, &pl)) { set_error("resblock_gp group: the %d layers do not share a launch shape", n); return EV_EINVAL; }
+  v[0] = pl.mt; v[1] = pl.kbg; v[2] = pl.total_tiles; v[3] = pl.rows1_pad; v[4] = pl.rows2_pad; v[5] = pl.smem_total; v[6] = pl.tmem_cols;
+  for (int i = 0; i < 3; ++i) {
+    v[7 + 3 * i] = i < gs.ng ? gs.g[i].K : 0;
+    v[8 + 3 * i] = i < gs.ng ? gs.g[i].tiles_m : 0;
+    v[9 + 3 * i] = i < gs.ng ? gs.g[i].tile0 : 0;
+  }
+  return EV_OK;
+}
 bool gp_pair_group_supported(const GpPairParams* ps, int n, int mode) {
   GpPairGroups gs{};
   gpp::PPlan pl;

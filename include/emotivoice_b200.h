@@ -225,6 +225,9 @@ EV_API int ev_op_resblock_gp(const void* x, const float* w1, const float* b1, co
 EV_API int ev_op_resblock_gp_group(int n, const void* const* x, const float* const* w1, const float* const* b1, const float* const* w2,
                                    const float* const* b2, int mode, void* const* out, int B, int L, int C, const int* K, const int* dil,
                                    const int32_t* lens, int lens_mul, void* stream);
+/* Host-only: the plan of a grouped fused launch: out16 = {MT, KBG, tiles (all members), rows1_pad, rows2_pad, smem bytes, tmem columns,
+ * then per member in launch order (heaviest first) {K, row tiles per item, first tile index}}. */
+EV_API int ev_debug_resblock_gp_group_plan(int n, const int* K, const int* dil, int B, int L, int C, int mode, int* out16);
 /* Host-only: out11 = {MT, KBG, x stages, weight stages, transform warps, tmem columns, smem bytes, tiles, rows per tile, rows1_pad, rows2_pad}. */
 EV_API int ev_debug_resblock_gp_plan(int B, int L, int C, int K, int dil, int mode, int* out11);
 /* Host-only: out11 = {BN, MT, KBG, a_stages, b_stages, transform warps, planes, tmem columns, smem bytes, tiles, rows_pad}. */

@@ -397,6 +397,18 @@ def test_gp_grouped_launch_plans(lib, shape, mode):
         sim_gp(seed, [True] * n, min(n_cb, 4), [rng.choice(Ks) for _ in range(n)], g["a_stages"], g["b_stages"], n_work_items=g["MT"] * (g["BN"] // 32))
 
 
+@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("C,mul", [(256, 8), (128, 64)])
+def test_gp_grouped_launch_plans_over_utterance_lengths(lib, C, mul, mode):
+    """The grouped convolution plan over every length a batch-1 step can have: members' own K granules, all tiles carried, limits kept."""
+    for F in range(40, 2401, 17):
+        L = F * mul
+        g = _gp_group_plan(lib, (3, 7, 11), (1, 3, 5), 1, L, C, C, mode)
+        assert g["KBG"] == _gp_plan(lib, 1, L, C, C, 11, 5, 1, mode)["KBG"] == _gp_plan(lib, 1, L, C, C, 3, 1, 1, mode)["KBG"]
+        assert g["tiles"] == 3 * -(-L // (128 * g["MT"])) * (C // g["BN"]) and g["MT"] in (1, 2, 4)
+        assert g["smem"] <= 227 * 1024 and 2 * g["MT"] * g["BN"] <= g["tmem"] <= 512 and g["rows_pad"] >= 128 * g["MT"] + 50
+
+
 def test_gp_grouped_launch_plan_fills_the_machine_at_batch_1(lib):
     """HiFi-GAN stage 1 at batch 1 in the fp32 mode: 3 x 68 one-accumulator tiles (204 > 148 SMs) instead of 3 x 34 two-accumulator
     ones -- the plan is picked by simulating the round-robin deal, where the k = 11 member's double tile would be the critical path."""
@@ -414,6 +426,44 @@ def test_gp_grouped_launch_protocol():
         tiles = [rng.random() > 0.15 for _ in range(n)]
         taps = [rng.choice((3, 7, 11)) for _ in range(n)]
         sim_gp(seed, tiles, rng.randint(1, 4), taps, rng.randint(2, 4), rng.randint(2, 8), n_work_items=rng.choice((1, 2, 4)))
+
+
+@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("C,mul", [(64, 128), (32, 256)])
+def test_resblock_gp_grouped_launch_plans_over_utterance_lengths(lib, C, mul, mode):
+    """Host logic of the grouped fused launch over the lengths a batch-1 step can have (every frame count from 40 to 2400 in steps of
+    13): members in launch order heaviest first, each with ITS OWN rows per tile R = 128 MT - (K - 1) and row-tile count, tile
+    ranges contiguous and complete, stage sizes for the widest halo, hardware limits respected.  A wrong first-tile index or tile
+    count would make the roles of the kernel walk different tile sequences (a hang), so this is checked here, on the CPU."""
+    Ks, dils = (3, 7, 11), (1, 3, 5)
+    IA = ctypes.c_int * 3
+    seen_mt = set()
+    for F in range(40, 2401, 13):
+        L = F * mul
+        v = (ctypes.c_int * 16)()
+        rc = lib.ev_debug_resblock_gp_group_plan(3, IA(*Ks), IA(*dils), 1, L, C, mode, v)
+        solo = []
+        for K, d in zip(Ks, dils):
+            w = (ctypes.c_int * 11)()
+            solo.append(list(w) if lib.ev_debug_resblock_gp_plan(1, L, C, K, d, mode, w) == 0 else None)
+        if any(x is None or x[0] < 2 for x in solo):
+            assert rc != 0          # a member that would not be fused on its own is never grouped
+            continue
+        assert rc == 0, lib.ev_last_error()
+        mt, kbg, total, rows1_pad, rows2_pad, smem, tmem = list(v)[:7]
+        members = [tuple(v[7 + 3 * i: 10 + 3 * i]) for i in range(3)]
+        seen_mt.add(mt)
+        assert mt in (2, 4) and {x[1] for x in solo} == {kbg}
+        assert [m[0] for m in members] == [11, 7, 3]                      # heaviest first
+        t0 = 0
+        for K, tiles_m, tile0 in members:
+            R = 128 * mt - (K - 1)
+            assert tiles_m == -(-L // R) and tile0 == t0
+            t0 += tiles_m
+        assert total == t0
+        assert rows1_pad >= 128 * mt + 10 * 5 and rows2_pad >= 128 * mt + 10 and rows1_pad % 8 == 0 and rows2_pad % 8 == 0
+        assert smem <= 227 * 1024 and 4 * mt * C <= tmem <= 512
+    assert seen_mt
 
 
 def test_resblock_gp_grouped_launch_protocol():
