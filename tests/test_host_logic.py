@@ -44,6 +44,21 @@ def test_forward_without_cuda_fails_loudly(conf):
     m = JETSGenerator(conf)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(**synth.make_batch([5]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.reserve(1, 128, 1024)          # the serving set-up call builds the engine too: same failure, no silent no-op
+
+
+def test_workspace_buckets_are_monotonic_and_coarse():
+    """Arena sizes are rounded up to a geometric series so that requests of similar size share a buffer."""
+    from emotivoice_b200.modules import _bucket
+    prev = 0
+    seen = set()
+    for n in range(1, 400 << 20, 3 << 20):
+        b = _bucket(n)
+        assert b >= n and b >= prev and b % (2 << 20) == 0
+        prev = b
+        seen.add(b)
+    assert len(seen) < 60 and _bucket(100 << 20) / (100 << 20) <= 1.2
 
 
 def test_training_mode_arguments_are_rejected(conf):
